@@ -1,0 +1,1496 @@
+// Small JavaScript interpreter for the metric plugin scripts. See minijs.hpp.
+#include "minijs.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+
+namespace minijs {
+
+// ------------------------------------------------------------------------------------------
+// Lexer
+// ------------------------------------------------------------------------------------------
+enum class Tok { End, Num, Str, Ident, Keyword, Punct, Template };
+
+struct Token {
+    Tok type = Tok::End;
+    std::string text;
+    double num = 0;
+    int line = 1;
+    bool nl_before = false;
+};
+
+static const std::set<std::string> kKeywords = {
+    "var", "let", "const", "function", "return", "if", "else", "for", "while", "do", "break",
+    "continue", "new", "typeof", "this", "true", "false", "null", "undefined", "in", "of",
+    "throw", "try", "catch", "finally", "void", "delete", "instanceof", "class", "switch",
+    "case", "default"};
+
+struct Lexer {
+    const std::string& src;
+    std::string name;
+    size_t pos = 0;
+    int line = 1;
+    std::vector<Token> toks;
+
+    Lexer(const std::string& s, const std::string& n) : src(s), name(n) {}
+
+    [[noreturn]] void fail(const std::string& msg) {
+        throw JsError(name + ":" + std::to_string(line) + ": SyntaxError: " + msg);
+    }
+
+    void run() {
+        static const char* puncts[] = {
+            ">>>=", "===", "!==", "**=", "<<=", ">>=", ">>>", "...", "=>", "==", "!=", "<=", ">=",
+            "&&", "||", "??", "++", "--", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=", "**",
+            "<<", ">>", "{", "}", "(", ")", "[", "]", ";", ",", "<", ">", "+", "-", "*", "/", "%",
+            "&", "|", "^", "!", "~", "?", ":", "=", "."};
+        bool nl = false;
+        while (true) {
+            // whitespace and comments
+            while (pos < src.size()) {
+                char c = src[pos];
+                if (c == '\n') { line++; nl = true; pos++; }
+                else if (c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v') pos++;
+                else if ((unsigned char)c == 0xEF && pos + 2 < src.size() && (unsigned char)src[pos + 1] == 0xBB) pos += 3;  // BOM
+                else if (c == '/' && pos + 1 < src.size() && src[pos + 1] == '/') {
+                    while (pos < src.size() && src[pos] != '\n') pos++;
+                } else if (c == '/' && pos + 1 < src.size() && src[pos + 1] == '*') {
+                    pos += 2;
+                    while (pos + 1 < src.size() && !(src[pos] == '*' && src[pos + 1] == '/')) {
+                        if (src[pos] == '\n') { line++; nl = true; }
+                        pos++;
+                    }
+                    if (pos + 1 >= src.size()) fail("unterminated comment");
+                    pos += 2;
+                } else break;
+            }
+            Token t;
+            t.line = line;
+            t.nl_before = nl;
+            nl = false;
+            if (pos >= src.size()) { t.type = Tok::End; toks.push_back(t); return; }
+            char c = src[pos];
+            if (isdigit((unsigned char)c) || (c == '.' && pos + 1 < src.size() && isdigit((unsigned char)src[pos + 1]))) {
+                if (c == '0' && pos + 1 < src.size() && (src[pos + 1] == 'x' || src[pos + 1] == 'X')) {
+                    char* end;
+                    t.num = (double)strtoull(src.c_str() + pos, &end, 16);
+                    pos = end - src.c_str();
+                } else {
+                    char* end;
+                    t.num = strtod(src.c_str() + pos, &end);
+                    pos = end - src.c_str();
+                    if (pos < src.size() && src[pos] == 'n') pos++;  // BigInt suffix: treat as number
+                }
+                t.type = Tok::Num;
+            } else if (isalpha((unsigned char)c) || c == '_' || c == '$') {
+                size_t s = pos;
+                while (pos < src.size() && (isalnum((unsigned char)src[pos]) || src[pos] == '_' || src[pos] == '$')) pos++;
+                t.text = src.substr(s, pos - s);
+                t.type = kKeywords.count(t.text) ? Tok::Keyword : Tok::Ident;
+            } else if (c == '"' || c == '\'' || c == '`') {
+                char q = c;
+                pos++;
+                std::string out;
+                while (pos < src.size() && src[pos] != q) {
+                    char ch = src[pos++];
+                    if (ch == '\n') { if (q != '`') fail("unterminated string"); line++; }
+                    if (ch == '\\' && pos < src.size()) {
+                        char e = src[pos++];
+                        switch (e) {
+                            case 'n': out += '\n'; break;
+                            case 't': out += '\t'; break;
+                            case 'r': out += '\r'; break;
+                            case '0': out += '\0'; break;
+                            case '\n': line++; break;
+                            default: out += e;
+                        }
+                    } else out += ch;
+                }
+                if (pos >= src.size()) fail("unterminated string");
+                pos++;
+                t.type = Tok::Str;
+                t.text = out;
+            } else {
+                bool found = false;
+                for (const char* p : puncts) {
+                    size_t n = strlen(p);
+                    if (src.compare(pos, n, p) == 0) {
+                        t.type = Tok::Punct;
+                        t.text = p;
+                        pos += n;
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) fail(std::string("unexpected character '") + c + "'");
+            }
+            toks.push_back(t);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// AST
+// ------------------------------------------------------------------------------------------
+enum class K {
+    Num, Str, Ident, ArrayLit, ObjectLit, Func, Member, Index, Call, New, Unary, Update, Binary,
+    Logical, Assign, Cond, Comma, This, Literal,
+    VarDecl, FuncDecl, Return, If, For, ForIn, ForOf, While, DoWhile, Break, Continue, Block,
+    ExprStmt, Empty, Throw, Try
+};
+
+struct Node;
+using NodeP = std::unique_ptr<Node>;
+
+struct FuncDef {
+    std::string name;
+    std::vector<std::string> params;
+    NodeP body;             // Block, or an expression for concise arrows
+    bool is_arrow = false;
+    bool expr_body = false;
+    std::vector<std::string> hoisted_vars;
+    std::vector<const Node*> hoisted_funcs;
+};
+
+struct Node {
+    K k;
+    int line = 0;
+    std::string s;          // identifier / operator / string / decl kind
+    double num = 0;
+    bool flag = false;      // Update: prefix; Literal: bool value
+    std::vector<NodeP> kids;
+    std::unique_ptr<FuncDef> fn;
+    Node(K kind, int ln) : k(kind), line(ln) {}
+};
+
+struct Program {
+    std::string name;
+    std::vector<NodeP> body;
+    FuncDef top;  // holds hoisting info for the top level
+};
+
+static void collect_hoisted(const Node* n, FuncDef& into, bool top) {
+    if (!n) return;
+    switch (n->k) {
+        case K::Func: return;  // do not descend into nested functions
+        case K::FuncDecl:
+            into.hoisted_funcs.push_back(n);
+            return;
+        case K::VarDecl:
+            if (n->s == "var")
+                for (auto& d : n->kids) into.hoisted_vars.push_back(d->s);
+            for (auto& d : n->kids) for (auto& kk : d->kids) collect_hoisted(kk.get(), into, false);
+            return;
+        case K::ForIn: case K::ForOf:
+            if (n->flag && n->num == 0) into.hoisted_vars.push_back(n->s);  // `for (var x in ..)`
+            break;
+        default: break;
+    }
+    for (auto& kk : n->kids) collect_hoisted(kk.get(), into, false);
+    (void)top;
+}
+
+// ------------------------------------------------------------------------------------------
+// Parser
+// ------------------------------------------------------------------------------------------
+struct Parser {
+    std::vector<Token>& t;
+    std::string name;
+    size_t p = 0;
+    Parser(std::vector<Token>& toks, const std::string& n) : t(toks), name(n) {}
+
+    [[noreturn]] void fail(const std::string& msg) {
+        throw JsError(name + ":" + std::to_string(t[p].line) + ": SyntaxError: " + msg +
+                      (t[p].type == Tok::End ? " (at end of input)" : " (near '" + t[p].text + "')"));
+    }
+    const Token& cur() { return t[p]; }
+    bool is_punct(const char* s) { return t[p].type == Tok::Punct && t[p].text == s; }
+    bool is_kw(const char* s) { return t[p].type == Tok::Keyword && t[p].text == s; }
+    bool eat_punct(const char* s) { if (is_punct(s)) { p++; return true; } return false; }
+    bool eat_kw(const char* s) { if (is_kw(s)) { p++; return true; } return false; }
+    void expect_punct(const char* s) { if (!eat_punct(s)) fail(std::string("expected '") + s + "'"); }
+    NodeP mk(K k) { return std::make_unique<Node>(k, t[p].line); }
+
+    void consume_semicolon() {
+        if (eat_punct(";")) return;
+        if (is_punct("}") || t[p].type == Tok::End || t[p].nl_before) return;  // ASI
+        fail("expected ';'");
+    }
+
+    std::string ident_name() {
+        if (t[p].type == Tok::Ident) return t[p++].text;
+        // contextual keywords usable as identifiers
+        if (t[p].type == Tok::Keyword && (t[p].text == "of" || t[p].text == "undefined")) return t[p++].text;
+        fail("expected identifier");
+    }
+    std::string property_name() {
+        if (t[p].type == Tok::Ident || t[p].type == Tok::Keyword) return t[p++].text;
+        if (t[p].type == Tok::Str) return t[p++].text;
+        if (t[p].type == Tok::Num) {
+            char buf[32];
+            double d = t[p++].num;
+            if (d == std::floor(d)) snprintf(buf, sizeof buf, "%lld", (long long)d);
+            else snprintf(buf, sizeof buf, "%.17g", d);
+            return buf;
+        }
+        fail("expected property name");
+    }
+
+    std::unique_ptr<Program> parse_program() {
+        auto prog = std::make_unique<Program>();
+        prog->name = name;
+        while (t[p].type != Tok::End) prog->body.push_back(statement());
+        for (auto& s : prog->body) collect_hoisted(s.get(), prog->top, true);
+        return prog;
+    }
+
+    std::unique_ptr<FuncDef> function_rest(const std::string& fname) {
+        auto f = std::make_unique<FuncDef>();
+        f->name = fname;
+        expect_punct("(");
+        while (!is_punct(")")) {
+            f->params.push_back(ident_name());
+            if (eat_punct("=")) fail("default parameters are not supported");
+            if (!eat_punct(",")) break;
+        }
+        expect_punct(")");
+        f->body = block();
+        collect_hoisted(f->body.get(), *f, true);
+        return f;
+    }
+
+    NodeP block() {
+        auto b = mk(K::Block);
+        expect_punct("{");
+        while (!is_punct("}")) {
+            if (t[p].type == Tok::End) fail("unterminated block");
+            b->kids.push_back(statement());
+        }
+        expect_punct("}");
+        return b;
+    }
+
+    NodeP var_decl(bool need_semicolon) {
+        auto d = mk(K::VarDecl);
+        d->s = t[p++].text;  // var/let/const
+        do {
+            auto one = mk(K::Ident);
+            one->s = ident_name();
+            if (eat_punct("=")) one->kids.push_back(assignment());
+            d->kids.push_back(std::move(one));
+        } while (eat_punct(","));
+        if (need_semicolon) consume_semicolon();
+        return d;
+    }
+
+    NodeP statement() {
+        if (is_punct("{")) return block();
+        if (is_punct(";")) { auto e = mk(K::Empty); p++; return e; }
+        if (is_kw("var") || is_kw("let") || is_kw("const")) return var_decl(true);
+        if (is_kw("function")) {
+            auto n = mk(K::FuncDecl);
+            p++;
+            n->s = ident_name();
+            n->fn = function_rest(n->s);
+            return n;
+        }
+        if (is_kw("return")) {
+            auto n = mk(K::Return);
+            p++;
+            if (!is_punct(";") && !is_punct("}") && t[p].type != Tok::End && !t[p].nl_before)
+                n->kids.push_back(expression());
+            consume_semicolon();
+            return n;
+        }
+        if (is_kw("if")) {
+            auto n = mk(K::If);
+            p++;
+            expect_punct("(");
+            n->kids.push_back(expression());
+            expect_punct(")");
+            n->kids.push_back(statement());
+            if (eat_kw("else")) n->kids.push_back(statement());
+            return n;
+        }
+        if (is_kw("for")) {
+            int ln = t[p].line;
+            p++;
+            expect_punct("(");
+            // for-in / for-of detection
+            size_t save = p;
+            if (is_kw("var") || is_kw("let") || is_kw("const") || t[p].type == Tok::Ident) {
+                bool decl = t[p].type == Tok::Keyword;
+                std::string declkind = decl ? t[p].text : "";
+                if (decl) p++;
+                if (t[p].type == Tok::Ident) {
+                    std::string vname = t[p].text;
+                    p++;
+                    if (is_kw("in") || is_kw("of")) {
+                        auto n = std::make_unique<Node>(t[p].text == "in" ? K::ForIn : K::ForOf, ln);
+                        p++;
+                        n->s = vname;
+                        n->flag = decl;
+                        n->num = (declkind == "var") ? 0 : 1;
+                        n->kids.push_back(expression());
+                        expect_punct(")");
+                        n->kids.push_back(statement());
+                        return n;
+                    }
+                }
+                p = save;
+            }
+            auto n = std::make_unique<Node>(K::For, ln);
+            if (is_punct(";")) n->kids.push_back(mk(K::Empty));
+            else if (is_kw("var") || is_kw("let") || is_kw("const")) n->kids.push_back(var_decl(false));
+            else { auto e = mk(K::ExprStmt); e->kids.push_back(expression()); n->kids.push_back(std::move(e)); }
+            expect_punct(";");
+            if (is_punct(";")) n->kids.push_back(mk(K::Empty)); else n->kids.push_back(expression());
+            expect_punct(";");
+            if (is_punct(")")) n->kids.push_back(mk(K::Empty)); else n->kids.push_back(expression());
+            expect_punct(")");
+            n->kids.push_back(statement());
+            return n;
+        }
+        if (is_kw("while")) {
+            auto n = mk(K::While);
+            p++;
+            expect_punct("(");
+            n->kids.push_back(expression());
+            expect_punct(")");
+            n->kids.push_back(statement());
+            return n;
+        }
+        if (is_kw("do")) {
+            auto n = mk(K::DoWhile);
+            p++;
+            n->kids.push_back(statement());
+            if (!eat_kw("while")) fail("expected 'while'");
+            expect_punct("(");
+            n->kids.push_back(expression());
+            expect_punct(")");
+            eat_punct(";");
+            return n;
+        }
+        if (is_kw("break")) { auto n = mk(K::Break); p++; consume_semicolon(); return n; }
+        if (is_kw("continue")) { auto n = mk(K::Continue); p++; consume_semicolon(); return n; }
+        if (is_kw("throw")) {
+            auto n = mk(K::Throw);
+            p++;
+            n->kids.push_back(expression());
+            consume_semicolon();
+            return n;
+        }
+        if (is_kw("try")) {
+            auto n = mk(K::Try);
+            p++;
+            n->kids.push_back(block());
+            if (eat_kw("catch")) {
+                if (eat_punct("(")) { n->s = ident_name(); expect_punct(")"); }
+                n->kids.push_back(block());
+            } else n->kids.push_back(mk(K::Empty));
+            if (eat_kw("finally")) n->kids.push_back(block());
+            return n;
+        }
+        if (is_kw("class") || is_kw("switch")) fail("'" + t[p].text + "' is not supported by the metric script interpreter");
+        auto e = mk(K::ExprStmt);
+        e->kids.push_back(expression());
+        consume_semicolon();
+        return e;
+    }
+
+    NodeP expression() {
+        auto e = assignment();
+        if (is_punct(",")) {
+            auto c = mk(K::Comma);
+            c->kids.push_back(std::move(e));
+            while (eat_punct(",")) c->kids.push_back(assignment());
+            return c;
+        }
+        return e;
+    }
+
+    // arrow function lookahead: `ident =>` or `( ... ) =>`
+    bool looks_like_arrow() {
+        if (t[p].type == Tok::Ident && t[p + 1].type == Tok::Punct && t[p + 1].text == "=>") return true;
+        if (!is_punct("(")) return false;
+        size_t q = p + 1;
+        int depth = 1;
+        while (q < t.size() && depth > 0) {
+            if (t[q].type == Tok::End) return false;
+            if (t[q].type == Tok::Punct) {
+                if (t[q].text == "(") depth++;
+                else if (t[q].text == ")") depth--;
+            }
+            q++;
+        }
+        return q < t.size() && t[q].type == Tok::Punct && t[q].text == "=>";
+    }
+
+    NodeP arrow_function() {
+        auto n = mk(K::Func);
+        auto f = std::make_unique<FuncDef>();
+        f->is_arrow = true;
+        if (t[p].type == Tok::Ident) f->params.push_back(t[p++].text);
+        else {
+            expect_punct("(");
+            while (!is_punct(")")) {
+                f->params.push_back(ident_name());
+                if (!eat_punct(",")) break;
+            }
+            expect_punct(")");
+        }
+        expect_punct("=>");
+        if (is_punct("{")) f->body = block();
+        else { f->body = assignment(); f->expr_body = true; }
+        collect_hoisted(f->body.get(), *f, true);
+        n->fn = std::move(f);
+        return n;
+    }
+
+    NodeP assignment() {
+        if (looks_like_arrow()) return arrow_function();
+        auto lhs = conditional();
+        static const char* ops[] = {"=", "+=", "-=", "*=", "/=", "%=", "**=", "&=", "|=", "^=", "<<=", ">>=", ">>>="};
+        for (const char* op : ops) {
+            if (is_punct(op)) {
+                if (lhs->k != K::Ident && lhs->k != K::Member && lhs->k != K::Index) fail("invalid assignment target");
+                auto n = mk(K::Assign);
+                n->s = op;
+                p++;
+                n->kids.push_back(std::move(lhs));
+                n->kids.push_back(assignment());
+                return n;
+            }
+        }
+        return lhs;
+    }
+
+    NodeP conditional() {
+        auto c = binary(0);
+        if (is_punct("?")) {
+            auto n = mk(K::Cond);
+            p++;
+            n->kids.push_back(std::move(c));
+            n->kids.push_back(assignment());
+            expect_punct(":");
+            n->kids.push_back(assignment());
+            return n;
+        }
+        return c;
+    }
+
+    static int prec(const Token& tk) {
+        if (tk.type == Tok::Keyword) {
+            if (tk.text == "instanceof" || tk.text == "in") return 9;
+            return -1;
+        }
+        if (tk.type != Tok::Punct) return -1;
+        const std::string& s = tk.text;
+        if (s == "??") return 1;
+        if (s == "||") return 2;
+        if (s == "&&") return 3;
+        if (s == "|") return 4;
+        if (s == "^") return 5;
+        if (s == "&") return 6;
+        if (s == "==" || s == "!=" || s == "===" || s == "!==") return 8;
+        if (s == "<" || s == ">" || s == "<=" || s == ">=") return 9;
+        if (s == "<<" || s == ">>" || s == ">>>") return 10;
+        if (s == "+" || s == "-") return 11;
+        if (s == "*" || s == "/" || s == "%") return 12;
+        if (s == "**") return 13;
+        return -1;
+    }
+
+    NodeP binary(int min_prec) {
+        auto lhs = unary();
+        while (true) {
+            int pr = prec(t[p]);
+            if (pr < 0 || pr < min_prec) break;
+            std::string op = t[p].text;
+            int ln = t[p].line;
+            p++;
+            NodeP rhs = (op == "**") ? binary(pr) : binary(pr + 1);  // ** is right associative
+            auto n = std::make_unique<Node>((op == "&&" || op == "||" || op == "??") ? K::Logical : K::Binary, ln);
+            n->s = op;
+            n->kids.push_back(std::move(lhs));
+            n->kids.push_back(std::move(rhs));
+            lhs = std::move(n);
+        }
+        return lhs;
+    }
+
+    NodeP unary() {
+        if (t[p].type == Tok::Punct && (t[p].text == "-" || t[p].text == "+" || t[p].text == "!" || t[p].text == "~")) {
+            auto n = mk(K::Unary);
+            n->s = t[p++].text;
+            n->kids.push_back(unary());
+            return n;
+        }
+        if (is_kw("typeof") || is_kw("void") || is_kw("delete")) {
+            auto n = mk(K::Unary);
+            n->s = t[p++].text;
+            n->kids.push_back(unary());
+            return n;
+        }
+        if (is_punct("++") || is_punct("--")) {
+            auto n = mk(K::Update);
+            n->s = t[p++].text;
+            n->flag = true;
+            n->kids.push_back(unary());
+            return n;
+        }
+        auto e = postfix();
+        return e;
+    }
+
+    NodeP postfix() {
+        auto e = call_member();
+        if ((is_punct("++") || is_punct("--")) && !t[p].nl_before) {
+            auto n = mk(K::Update);
+            n->s = t[p++].text;
+            n->flag = false;
+            n->kids.push_back(std::move(e));
+            return n;
+        }
+        return e;
+    }
+
+    void arguments(Node& call) {
+        expect_punct("(");
+        while (!is_punct(")")) {
+            call.kids.push_back(assignment());
+            if (!eat_punct(",")) break;
+        }
+        expect_punct(")");
+    }
+
+    NodeP call_member() {
+        NodeP e;
+        if (is_kw("new")) {
+            auto n = mk(K::New);
+            p++;
+            // callee without call parens
+            NodeP callee = primary();
+            while (true) {
+                if (eat_punct(".")) {
+                    auto m = mk(K::Member);
+                    m->s = property_name();
+                    m->kids.push_back(std::move(callee));
+                    callee = std::move(m);
+                } else break;
+            }
+            n->kids.push_back(std::move(callee));
+            if (is_punct("(")) arguments(*n);
+            e = std::move(n);
+        } else e = primary();
+        while (true) {
+            if (is_punct(".")) {
+                auto m = mk(K::Member);
+                p++;
+                m->s = property_name();
+                m->kids.push_back(std::move(e));
+                e = std::move(m);
+            } else if (is_punct("[")) {
+                auto m = mk(K::Index);
+                p++;
+                m->kids.push_back(std::move(e));
+                m->kids.push_back(expression());
+                expect_punct("]");
+                e = std::move(m);
+            } else if (is_punct("(")) {
+                auto c = mk(K::Call);
+                c->kids.push_back(std::move(e));
+                arguments(*c);
+                e = std::move(c);
+            } else break;
+        }
+        return e;
+    }
+
+    NodeP primary() {
+        const Token& tk = t[p];
+        if (tk.type == Tok::Num) { auto n = mk(K::Num); n->num = tk.num; p++; return n; }
+        if (tk.type == Tok::Str) { auto n = mk(K::Str); n->s = tk.text; p++; return n; }
+        if (tk.type == Tok::Ident) { auto n = mk(K::Ident); n->s = tk.text; p++; return n; }
+        if (tk.type == Tok::Keyword) {
+            if (tk.text == "this") { auto n = mk(K::This); p++; return n; }
+            if (tk.text == "true" || tk.text == "false") { auto n = mk(K::Literal); n->s = "bool"; n->flag = tk.text == "true"; p++; return n; }
+            if (tk.text == "null") { auto n = mk(K::Literal); n->s = "null"; p++; return n; }
+            if (tk.text == "undefined") { auto n = mk(K::Literal); n->s = "undefined"; p++; return n; }
+            if (tk.text == "of") { auto n = mk(K::Ident); n->s = tk.text; p++; return n; }
+            if (tk.text == "function") {
+                auto n = mk(K::Func);
+                p++;
+                std::string fname;
+                if (t[p].type == Tok::Ident) fname = t[p++].text;
+                n->fn = function_rest(fname);
+                return n;
+            }
+        }
+        if (is_punct("(")) {
+            p++;
+            auto e = expression();
+            expect_punct(")");
+            return e;
+        }
+        if (is_punct("[")) {
+            auto a = mk(K::ArrayLit);
+            p++;
+            while (!is_punct("]")) {
+                if (is_punct(",")) { a->kids.push_back(mk(K::Literal)); a->kids.back()->s = "hole"; p++; continue; }
+                a->kids.push_back(assignment());
+                if (!eat_punct(",")) break;
+            }
+            expect_punct("]");
+            return a;
+        }
+        if (is_punct("{")) {
+            auto o = mk(K::ObjectLit);
+            p++;
+            while (!is_punct("}")) {
+                auto key = mk(K::Str);
+                bool was_ident = t[p].type == Tok::Ident;
+                key->s = property_name();
+                if (is_punct("(")) {  // method shorthand
+                    auto fnode = mk(K::Func);
+                    fnode->fn = function_rest(key->s);
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(std::move(fnode));
+                } else if (was_ident && (is_punct(",") || is_punct("}"))) {  // {x}
+                    auto id = mk(K::Ident);
+                    id->s = key->s;
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(std::move(id));
+                } else {
+                    expect_punct(":");
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(assignment());
+                }
+                if (!eat_punct(",")) break;
+            }
+            expect_punct("}");
+            return o;
+        }
+        fail("unexpected token");
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Evaluator
+// ------------------------------------------------------------------------------------------
+enum class Comp { Normal, Break, Continue, Return };
+
+struct Thrown {
+    Value v;
+};
+
+struct Evaluator {
+    Interp& in;
+    std::string name;
+    Value ret;         // value carried by Return
+    Value completion;  // completion value of the last expression statement
+    Evaluator(Interp& i, const std::string& n) : in(i), name(n) {}
+
+    [[noreturn]] void fail(const Node* n, const std::string& msg) {
+        throw JsError(name + ":" + std::to_string(n ? n->line : 0) + ": " + msg);
+    }
+    void tick(const Node* n) {
+        if (++in.steps > 50000000L) fail(n, "script exceeded the execution step limit");
+    }
+
+    // ---- environments ----
+    static EnvP new_env(EnvP parent, bool fn_scope) {
+        auto e = std::make_shared<Env>();
+        e->parent = std::move(parent);
+        e->function_scope = fn_scope;
+        if (e->parent) e->this_val = e->parent->this_val;
+        return e;
+    }
+    Env* lookup_env(Env* e, const std::string& nm) {
+        for (; e; e = e->parent.get())
+            if (e->vars.count(nm)) return e;
+        return nullptr;
+    }
+    Value get_var(const Node* n, EnvP& env, const std::string& nm) {
+        Env* e = lookup_env(env.get(), nm);
+        if (e) return e->vars[nm];
+        auto g = in.global_getters.find(nm);
+        if (g != in.global_getters.end()) return g->second(in);
+        fail(n, "ReferenceError: '" + nm + "' is not defined");
+    }
+    void set_var(const Node* n, EnvP& env, const std::string& nm, const Value& v) {
+        Env* e = lookup_env(env.get(), nm);
+        if (!e) {
+            if (in.global_getters.count(nm)) return;  // e.g. `$cfg = ...`: setter is a no-op in the reference
+            in.globals->vars[nm] = v;                 // sloppy-mode implicit global
+            return;
+        }
+        if (e->is_const.count(nm) && e->is_const[nm]) fail(n, "TypeError: assignment to constant variable '" + nm + "'");
+        e->vars[nm] = v;
+    }
+    void hoist(const FuncDef& f, EnvP& env) {
+        for (auto& v : f.hoisted_vars)
+            if (!env->vars.count(v)) env->vars[v] = Value();
+        for (const Node* fd : f.hoisted_funcs) env->vars[fd->s] = make_closure(fd->fn.get(), env);
+    }
+    Value make_closure(const FuncDef* def, EnvP& env) {
+        auto o = std::make_shared<Object>();
+        o->kind = Object::Function;
+        o->def = def;
+        o->env = env;
+        if (def->is_arrow) { o->is_arrow = true; o->bound_this = env->this_val; }
+        return Value(o);
+    }
+
+    // ---- property access ----
+    static bool array_index(const std::string& key, size_t& idx) {
+        if (key.empty() || key.size() > 10) return false;
+        for (char c : key) if (!isdigit((unsigned char)c)) return false;
+        idx = (size_t)strtoull(key.c_str(), nullptr, 10);
+        return true;
+    }
+    std::string key_of(const Value& v) {
+        if (v.type == Value::Number) {
+            char buf[32];
+            if (v.num == std::floor(v.num) && std::fabs(v.num) < 1e15) snprintf(buf, sizeof buf, "%lld", (long long)v.num);
+            else snprintf(buf, sizeof buf, "%.17g", v.num);
+            return buf;
+        }
+        return in.to_string(v);
+    }
+    Value get_prop(const Node* n, const Value& objv, const std::string& key);
+    void set_prop(const Node* n, const Value& objv, const std::string& key, const Value& v);
+    Value array_method(const Node* n, const ObjP& a, const std::string& key);
+
+    // ---- operators ----
+    bool is_host(const Value& v) { return v.type == Value::Obj && v.obj->kind == Object::Host; }
+    Value binary_op(const Node* n, const std::string& op, const Value& a, const Value& b);
+    bool loose_equal(const Value& a, const Value& b);
+    bool strict_equal(const Value& a, const Value& b);
+
+    Value eval(const Node* n, EnvP& env);
+    Comp exec(const Node* n, EnvP& env);
+    Comp exec_block(const std::vector<NodeP>& body, EnvP& env);
+    Value call_function(const Node* n, const Value& fn, const Value& self, std::vector<Value>& args);
+    void assign_to(const Node* target, EnvP& env, const Value& v);
+};
+
+Value Evaluator::array_method(const Node* n, const ObjP& a, const std::string& key) {
+    std::weak_ptr<Object> wa = a;
+    auto self = [wa]() { return wa.lock(); };
+    if (key == "push") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        for (auto& v : args) s->arr.push_back(v);
+        return Value((double)s->arr.size());
+    });
+    if (key == "pop") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>&) {
+        auto s = self();
+        if (s->arr.empty()) return Value();
+        Value v = s->arr.back();
+        s->arr.pop_back();
+        return v;
+    });
+    if (key == "slice") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        long len = (long)s->arr.size();
+        long b = args.size() > 0 ? (long)Interp::to_number(args[0]) : 0;
+        long e = args.size() > 1 && !args[1].is_undefined() ? (long)Interp::to_number(args[1]) : len;
+        if (b < 0) b += len;
+        if (e < 0) e += len;
+        b = std::max(0L, std::min(b, len));
+        e = std::max(b, std::min(e, len));
+        return Value(Interp::make_array(std::vector<Value>(s->arr.begin() + b, s->arr.begin() + e)));
+    });
+    if (key == "concat") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        std::vector<Value> out = s->arr;
+        for (auto& v : args) {
+            if (v.type == Value::Obj && v.obj->kind == Object::Array) out.insert(out.end(), v.obj->arr.begin(), v.obj->arr.end());
+            else out.push_back(v);
+        }
+        return Value(Interp::make_array(out));
+    });
+    if (key == "fill") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        for (auto& v : s->arr) v = args.empty() ? Value() : args[0];
+        return Value(s);
+    });
+    if (key == "indexOf") return Interp::make_native([self, this](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        for (size_t i = 0; i < s->arr.size(); i++)
+            if (!args.empty() && strict_equal(s->arr[i], args[0])) return Value((double)i);
+        return Value(-1.0);
+    });
+    if (key == "join") return Interp::make_native([self](Interp& ip, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        std::string sep = args.empty() ? "," : ip.to_string(args[0]);
+        std::string out;
+        for (size_t i = 0; i < s->arr.size(); i++) { if (i) out += sep; out += ip.to_string(s->arr[i]); }
+        return Value(out);
+    });
+    if (key == "map" || key == "forEach" || key == "filter" || key == "reduce" || key == "some" || key == "every")
+        return Interp::make_native([self, key](Interp& ip, const Value&, std::vector<Value>& args) {
+            auto s = self();
+            if (args.empty()) throw JsError("TypeError: callback required");
+            std::vector<Value> out;
+            Value acc;
+            size_t start = 0;
+            if (key == "reduce") {
+                if (args.size() > 1) acc = args[1];
+                else { if (s->arr.empty()) throw JsError("TypeError: reduce of empty array"); acc = s->arr[0]; start = 1; }
+            }
+            for (size_t i = start; i < s->arr.size(); i++) {
+                if (key == "reduce") { acc = ip.call(args[0], Value(), {acc, s->arr[i], Value((double)i), Value(s)}); continue; }
+                Value r = ip.call(args[0], Value(), {s->arr[i], Value((double)i), Value(s)});
+                if (key == "map") out.push_back(r);
+                else if (key == "filter") { if (Interp::to_boolean(r)) out.push_back(s->arr[i]); }
+                else if (key == "some") { if (Interp::to_boolean(r)) return Value(true); }
+                else if (key == "every") { if (!Interp::to_boolean(r)) return Value(false); }
+            }
+            if (key == "map" || key == "filter") return Value(Interp::make_array(out));
+            if (key == "reduce") return acc;
+            if (key == "some") return Value(false);
+            if (key == "every") return Value(true);
+            return Value();
+        });
+    (void)n;
+    return Value();
+}
+
+Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& key) {
+    if (objv.type == Value::Undefined || objv.type == Value::Null)
+        fail(n, "TypeError: cannot read property '" + key + "' of " + (objv.type == Value::Null ? "null" : "undefined"));
+    if (objv.type == Value::String) {
+        if (key == "length") return Value((double)objv.str.size());
+        size_t idx;
+        if (array_index(key, idx) && idx < objv.str.size()) return Value(std::string(1, objv.str[idx]));
+        return Value();
+    }
+    if (objv.type != Value::Obj) return Value();
+    const ObjP& o = objv.obj;
+    if (o->get_hook) {
+        Value out;
+        if (o->get_hook(in, key, out)) return out;
+    }
+    if (o->kind == Object::Array) {
+        if (key == "length") return Value((double)o->arr.size());
+        size_t idx;
+        if (array_index(key, idx)) return idx < o->arr.size() ? o->arr[idx] : Value();
+        auto it = o->props.find(key);
+        if (it != o->props.end()) return it->second;
+        return array_method(n, o, key);
+    }
+    auto it = o->props.find(key);
+    if (it != o->props.end()) return it->second;
+    if ((o->kind == Object::Function || o->kind == Object::Native) && key == "call") {
+        Value fn = objv;
+        return Value(Interp::make_native([fn](Interp& ip, const Value&, std::vector<Value>& args) {
+            Value self = args.empty() ? Value() : args[0];
+            std::vector<Value> rest(args.size() > 1 ? args.begin() + 1 : args.end(), args.end());
+            return ip.call(fn, self, rest);
+        }));
+    }
+    return Value();
+}
+
+void Evaluator::set_prop(const Node* n, const Value& objv, const std::string& key, const Value& v) {
+    if (objv.type != Value::Obj) fail(n, "TypeError: cannot set property '" + key + "' on a non-object");
+    const ObjP& o = objv.obj;
+    if (o->set_hook && o->set_hook(in, key, v)) return;
+    if (o->kind == Object::Array) {
+        if (key == "length") {
+            double d = Interp::to_number(v);
+            if (d < 0 || d > 1e7) fail(n, "RangeError: invalid array length");
+            o->arr.resize((size_t)d);
+            return;
+        }
+        size_t idx;
+        if (array_index(key, idx)) {
+            if (idx > 10000000) fail(n, "RangeError: array index too large");
+            if (idx >= o->arr.size()) o->arr.resize(idx + 1);
+            o->arr[idx] = v;
+            return;
+        }
+    }
+    o->props[key] = v;
+}
+
+bool Evaluator::strict_equal(const Value& a, const Value& b) {
+    if (a.type != b.type) return false;
+    switch (a.type) {
+        case Value::Undefined: case Value::Null: return true;
+        case Value::Bool: return a.b == b.b;
+        case Value::Number: return a.num == b.num;
+        case Value::String: return a.str == b.str;
+        case Value::Obj: return a.obj == b.obj;
+    }
+    return false;
+}
+
+bool Evaluator::loose_equal(const Value& a, const Value& b) {
+    if (a.type == b.type) return strict_equal(a, b);
+    bool an = a.type == Value::Undefined || a.type == Value::Null;
+    bool bn = b.type == Value::Undefined || b.type == Value::Null;
+    if (an || bn) return an && bn;
+    if (a.type == Value::Obj || b.type == Value::Obj) return false;
+    return Interp::to_number(a) == Interp::to_number(b);
+}
+
+Value Evaluator::binary_op(const Node* n, const std::string& op, const Value& a, const Value& b) {
+    if (is_host(a) || is_host(b)) {
+        if (op == "===" ) return Value(strict_equal(a, b));
+        if (op == "!==") return Value(!strict_equal(a, b));
+        if (!in.host_operator) fail(n, "TypeError: no operator overloads installed");
+        return in.host_operator(in, op, a, b);
+    }
+    if (op == "+") {
+        bool as = a.type == Value::String || (a.type == Value::Obj), bs = b.type == Value::String || (b.type == Value::Obj);
+        if (as || bs) return Value(in.to_string(a) + in.to_string(b));
+        return Value(Interp::to_number(a) + Interp::to_number(b));
+    }
+    if (op == "===") return Value(strict_equal(a, b));
+    if (op == "!==") return Value(!strict_equal(a, b));
+    if (op == "==") return Value(loose_equal(a, b));
+    if (op == "!=") return Value(!loose_equal(a, b));
+    if (a.type == Value::String && b.type == Value::String) {
+        if (op == "<") return Value(a.str < b.str);
+        if (op == ">") return Value(a.str > b.str);
+        if (op == "<=") return Value(a.str <= b.str);
+        if (op == ">=") return Value(a.str >= b.str);
+    }
+    if (op == "in") {
+        if (b.type != Value::Obj) fail(n, "TypeError: 'in' needs an object");
+        std::string k = key_of(a);
+        size_t idx;
+        if (b.obj->kind == Object::Array && array_index(k, idx)) return Value(idx < b.obj->arr.size());
+        return Value(b.obj->props.count(k) > 0);
+    }
+    if (op == "instanceof") return Value(false);
+    double x = Interp::to_number(a), y = Interp::to_number(b);
+    if (op == "-") return Value(x - y);
+    if (op == "*") return Value(x * y);
+    if (op == "/") return Value(x / y);
+    if (op == "%") return Value(std::fmod(x, y));
+    if (op == "**") return Value(std::pow(x, y));
+    if (op == "<") return Value(x < y);
+    if (op == ">") return Value(x > y);
+    if (op == "<=") return Value(x <= y);
+    if (op == ">=") return Value(x >= y);
+    auto i32 = [](double d) -> int32_t { return std::isfinite(d) ? (int32_t)(int64_t)d : 0; };
+    if (op == "&") return Value((double)(i32(x) & i32(y)));
+    if (op == "|") return Value((double)(i32(x) | i32(y)));
+    if (op == "^") return Value((double)(i32(x) ^ i32(y)));
+    if (op == "<<") return Value((double)(i32(x) << (i32(y) & 31)));
+    if (op == ">>") return Value((double)(i32(x) >> (i32(y) & 31)));
+    if (op == ">>>") return Value((double)((uint32_t)i32(x) >> (i32(y) & 31)));
+    fail(n, "unsupported operator '" + op + "'");
+}
+
+void Evaluator::assign_to(const Node* target, EnvP& env, const Value& v) {
+    if (target->k == K::Ident) set_var(target, env, target->s, v);
+    else if (target->k == K::Member) set_prop(target, eval(target->kids[0].get(), env), target->s, v);
+    else if (target->k == K::Index) {
+        Value o = eval(target->kids[0].get(), env);
+        Value k = eval(target->kids[1].get(), env);
+        set_prop(target, o, key_of(k), v);
+    } else fail(target, "invalid assignment target");
+}
+
+Value Evaluator::call_function(const Node* n, const Value& fn, const Value& self, std::vector<Value>& args) {
+    if (fn.type != Value::Obj || (fn.obj->kind != Object::Function && fn.obj->kind != Object::Native))
+        fail(n, "TypeError: value is not a function");
+    if (fn.obj->kind == Object::Native) return fn.obj->native(in, self, args);
+    if (++in.call_depth > 200) { in.call_depth--; fail(n, "RangeError: call stack too deep"); }
+    const FuncDef* def = fn.obj->def;
+    EnvP env = new_env(fn.obj->env, true);
+    env->this_val = fn.obj->is_arrow ? fn.obj->bound_this : self;
+    for (size_t i = 0; i < def->params.size(); i++) env->vars[def->params[i]] = i < args.size() ? args[i] : Value();
+    if (!def->is_arrow) env->vars["arguments"] = Value(Interp::make_array(args));
+    hoist(*def, env);
+    Value result;
+    try {
+        if (def->expr_body) result = eval(def->body.get(), env);
+        else {
+            Value saved_ret = ret;
+            ret = Value();
+            Comp c = exec_block(def->body->kids, env);
+            if (c == Comp::Return) result = ret;
+            ret = saved_ret;
+        }
+    } catch (...) {
+        in.call_depth--;
+        throw;
+    }
+    in.call_depth--;
+    return result;
+}
+
+Value Evaluator::eval(const Node* n, EnvP& env) {
+    tick(n);
+    switch (n->k) {
+        case K::Num: return Value(n->num);
+        case K::Str: return Value(n->s);
+        case K::Literal:
+            if (n->s == "bool") return Value(n->flag);
+            if (n->s == "null") return Value::null();
+            return Value();
+        case K::This: return env->this_val;
+        case K::Ident: return get_var(n, env, n->s);
+        case K::ArrayLit: {
+            std::vector<Value> items;
+            for (auto& k : n->kids) items.push_back(eval(k.get(), env));
+            return Value(Interp::make_array(items));
+        }
+        case K::ObjectLit: {
+            auto o = Interp::make_object();
+            for (size_t i = 0; i + 1 < n->kids.size(); i += 2) o->props[n->kids[i]->s] = eval(n->kids[i + 1].get(), env);
+            return Value(o);
+        }
+        case K::Func: return make_closure(n->fn.get(), env);
+        case K::Member: return get_prop(n, eval(n->kids[0].get(), env), n->s);
+        case K::Index: {
+            Value o = eval(n->kids[0].get(), env);
+            Value k = eval(n->kids[1].get(), env);
+            return get_prop(n, o, key_of(k));
+        }
+        case K::Call: {
+            const Node* callee = n->kids[0].get();
+            Value self, fn;
+            if (callee->k == K::Member) {
+                self = eval(callee->kids[0].get(), env);
+                fn = get_prop(callee, self, callee->s);
+                if (fn.is_undefined()) fail(n, "TypeError: '" + callee->s + "' is not a function");
+            } else if (callee->k == K::Index) {
+                self = eval(callee->kids[0].get(), env);
+                fn = get_prop(callee, self, key_of(eval(callee->kids[1].get(), env)));
+            } else fn = eval(callee, env);
+            std::vector<Value> args;
+            for (size_t i = 1; i < n->kids.size(); i++) args.push_back(eval(n->kids[i].get(), env));
+            if (fn.type != Value::Obj) fail(n, "TypeError: " + (callee->k == K::Ident ? "'" + callee->s + "'" : std::string("expression")) + " is not a function");
+            return call_function(n, fn, self, args);
+        }
+        case K::New: {
+            Value ctor = eval(n->kids[0].get(), env);
+            std::vector<Value> args;
+            for (size_t i = 1; i < n->kids.size(); i++) args.push_back(eval(n->kids[i].get(), env));
+            if (ctor.type != Value::Obj) fail(n, "TypeError: not a constructor");
+            if (ctor.obj->kind == Object::Native) return ctor.obj->native(in, Value(), args);
+            Value self(Interp::make_object());
+            Value r = call_function(n, ctor, self, args);
+            return r.type == Value::Obj ? r : self;
+        }
+        case K::Unary: {
+            if (n->s == "typeof") {
+                Value v;
+                if (n->kids[0]->k == K::Ident && !lookup_env(env.get(), n->kids[0]->s) && !in.global_getters.count(n->kids[0]->s)) return Value("undefined");
+                v = eval(n->kids[0].get(), env);
+                switch (v.type) {
+                    case Value::Undefined: return Value("undefined");
+                    case Value::Null: return Value("object");
+                    case Value::Bool: return Value("boolean");
+                    case Value::Number: return Value("number");
+                    case Value::String: return Value("string");
+                    case Value::Obj: return Value((v.obj->kind == Object::Function || v.obj->kind == Object::Native) ? "function" : "object");
+                }
+            }
+            Value v = eval(n->kids[0].get(), env);
+            if (n->s == "void") return Value();
+            if (n->s == "delete") return Value(true);
+            if (n->s == "!") return Value(!Interp::to_boolean(v));
+            if (is_host(v)) {
+                if (!in.host_operator) fail(n, "TypeError: no operator overloads installed");
+                if (n->s == "-") return in.host_operator(in, "neg", v, Value());
+                if (n->s == "+") return in.host_operator(in, "pos", v, Value());
+                fail(n, "TypeError: unsupported unary operator on number object");
+            }
+            if (n->s == "-") return Value(-Interp::to_number(v));
+            if (n->s == "+") return Value(Interp::to_number(v));
+            if (n->s == "~") return Value((double)(~(int32_t)(int64_t)Interp::to_number(v)));
+            fail(n, "unsupported unary operator");
+        }
+        case K::Update: {
+            const Node* target = n->kids[0].get();
+            Value old = eval(target, env);
+            Value one(1.0);
+            Value nv = is_host(old) ? binary_op(n, n->s == "++" ? "+" : "-", old, one)
+                                    : Value(Interp::to_number(old) + (n->s == "++" ? 1.0 : -1.0));
+            assign_to(target, env, nv);
+            return n->flag ? nv : (is_host(old) ? old : Value(Interp::to_number(old)));
+        }
+        case K::Binary: {
+            Value a = eval(n->kids[0].get(), env);
+            Value b = eval(n->kids[1].get(), env);
+            return binary_op(n, n->s, a, b);
+        }
+        case K::Logical: {
+            Value a = eval(n->kids[0].get(), env);
+            if (n->s == "&&") return Interp::to_boolean(a) ? eval(n->kids[1].get(), env) : a;
+            if (n->s == "||") return Interp::to_boolean(a) ? a : eval(n->kids[1].get(), env);
+            return (a.type == Value::Undefined || a.type == Value::Null) ? eval(n->kids[1].get(), env) : a;
+        }
+        case K::Assign: {
+            const Node* target = n->kids[0].get();
+            if (n->s == "=") {
+                // evaluate target object before the value, as JavaScript does
+                if (target->k == K::Ident) {
+                    Value v = eval(n->kids[1].get(), env);
+                    set_var(target, env, target->s, v);
+                    return v;
+                }
+                Value o = eval(target->kids[0].get(), env);
+                std::string key = target->k == K::Member ? target->s : key_of(eval(target->kids[1].get(), env));
+                Value v = eval(n->kids[1].get(), env);
+                set_prop(target, o, key, v);
+                return v;
+            }
+            Value old = eval(target, env);
+            Value rhs = eval(n->kids[1].get(), env);
+            Value nv = binary_op(n, n->s.substr(0, n->s.size() - 1), old, rhs);
+            assign_to(target, env, nv);
+            return nv;
+        }
+        case K::Cond:
+            return Interp::to_boolean(eval(n->kids[0].get(), env)) ? eval(n->kids[1].get(), env) : eval(n->kids[2].get(), env);
+        case K::Comma: {
+            Value v;
+            for (auto& k : n->kids) v = eval(k.get(), env);
+            return v;
+        }
+        default: fail(n, "internal: statement node in expression position");
+    }
+}
+
+Comp Evaluator::exec_block(const std::vector<NodeP>& body, EnvP& env) {
+    for (auto& s : body) {
+        Comp c = exec(s.get(), env);
+        if (c != Comp::Normal) return c;
+    }
+    return Comp::Normal;
+}
+
+Comp Evaluator::exec(const Node* n, EnvP& env) {
+    tick(n);
+    switch (n->k) {
+        case K::Empty: return Comp::Normal;
+        case K::ExprStmt: completion = eval(n->kids[0].get(), env); return Comp::Normal;
+        case K::VarDecl: {
+            for (auto& d : n->kids) {
+                if (n->s == "var") {
+                    if (!d->kids.empty()) set_var(d.get(), env, d->s, eval(d->kids[0].get(), env));
+                } else {
+                    Value v = d->kids.empty() ? Value() : eval(d->kids[0].get(), env);
+                    env->vars[d->s] = v;
+                    env->is_const[d->s] = (n->s == "const");
+                }
+            }
+            return Comp::Normal;
+        }
+        case K::FuncDecl: return Comp::Normal;  // hoisted
+        case K::Return:
+            ret = n->kids.empty() ? Value() : eval(n->kids[0].get(), env);
+            return Comp::Return;
+        case K::If:
+            if (Interp::to_boolean(eval(n->kids[0].get(), env))) return exec(n->kids[1].get(), env);
+            if (n->kids.size() > 2) return exec(n->kids[2].get(), env);
+            return Comp::Normal;
+        case K::Block: {
+            EnvP inner = new_env(env, false);
+            // block-level function declarations are visible in the block
+            for (auto& s : n->kids)
+                if (s->k == K::FuncDecl && !lookup_env(env.get(), s->s)) inner->vars[s->s] = make_closure(s->fn.get(), inner);
+            return exec_block(n->kids, inner);
+        }
+        case K::For: {
+            EnvP loop = new_env(env, false);
+            exec(n->kids[0].get(), loop);
+            while (true) {
+                if (n->kids[1]->k != K::Empty && !Interp::to_boolean(eval(n->kids[1].get(), loop))) break;
+                Comp c = exec(n->kids[3].get(), loop);
+                if (c == Comp::Break) break;
+                if (c == Comp::Return) return c;
+                if (n->kids[2]->k != K::Empty) eval(n->kids[2].get(), loop);
+            }
+            return Comp::Normal;
+        }
+        case K::ForIn: case K::ForOf: {
+            Value it = eval(n->kids[0].get(), env);
+            std::vector<Value> items;
+            if (it.type == Value::Obj) {
+                if (n->k == K::ForOf) {
+                    if (it.obj->kind != Object::Array) fail(n, "TypeError: for-of needs an array");
+                    items = it.obj->arr;
+                } else {
+                    if (it.obj->kind == Object::Array) for (size_t i = 0; i < it.obj->arr.size(); i++) items.push_back(Value(std::to_string(i)));
+                    for (auto& kv : it.obj->props) items.push_back(Value(kv.first));
+                }
+            }
+            for (auto& item : items) {
+                EnvP loop = new_env(env, false);
+                if (n->flag && n->num != 0) loop->vars[n->s] = item;
+                else set_var(n, loop, n->s, item);
+                Comp c = exec(n->kids[1].get(), loop);
+                if (c == Comp::Break) break;
+                if (c == Comp::Return) return c;
+            }
+            return Comp::Normal;
+        }
+        case K::While:
+            while (Interp::to_boolean(eval(n->kids[0].get(), env))) {
+                Comp c = exec(n->kids[1].get(), env);
+                if (c == Comp::Break) break;
+                if (c == Comp::Return) return c;
+            }
+            return Comp::Normal;
+        case K::DoWhile:
+            do {
+                Comp c = exec(n->kids[0].get(), env);
+                if (c == Comp::Break) break;
+                if (c == Comp::Return) return c;
+            } while (Interp::to_boolean(eval(n->kids[1].get(), env)));
+            return Comp::Normal;
+        case K::Break: return Comp::Break;
+        case K::Continue: return Comp::Continue;
+        case K::Throw: throw Thrown{eval(n->kids[0].get(), env)};
+        case K::Try: {
+            Comp c = Comp::Normal;
+            auto run_finally = [&]() { if (n->kids.size() > 2) exec(n->kids[2].get(), env); };
+            try {
+                c = exec(n->kids[0].get(), env);
+            } catch (Thrown& th) {
+                if (n->kids[1]->k == K::Empty) { run_finally(); throw; }
+                EnvP h = new_env(env, false);
+                if (!n->s.empty()) h->vars[n->s] = th.v;
+                c = exec(n->kids[1].get(), h);
+            } catch (JsError& e) {
+                if (n->kids[1]->k == K::Empty) { run_finally(); throw; }
+                EnvP h = new_env(env, false);
+                auto eo = Interp::make_object();
+                eo->props["message"] = Value(std::string(e.what()));
+                if (!n->s.empty()) h->vars[n->s] = Value(eo);
+                c = exec(n->kids[1].get(), h);
+            }
+            run_finally();
+            return c;
+        }
+        default:
+            completion = eval(n, env);
+            return Comp::Normal;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Interp
+// ------------------------------------------------------------------------------------------
+ObjP Interp::make_object() { return std::make_shared<Object>(); }
+ObjP Interp::make_array(std::vector<Value> items) {
+    auto o = std::make_shared<Object>();
+    o->kind = Object::Array;
+    o->arr = std::move(items);
+    return o;
+}
+ObjP Interp::make_native(NativeFn fn) {
+    auto o = std::make_shared<Object>();
+    o->kind = Object::Native;
+    o->native = std::move(fn);
+    return o;
+}
+ObjP Interp::make_host(int tag, std::shared_ptr<void> payload) {
+    auto o = std::make_shared<Object>();
+    o->kind = Object::Host;
+    o->host_tag = tag;
+    o->host = std::move(payload);
+    return o;
+}
+
+double Interp::to_number(const Value& v) {
+    switch (v.type) {
+        case Value::Undefined: return NAN;
+        case Value::Null: return 0;
+        case Value::Bool: return v.b ? 1 : 0;
+        case Value::Number: return v.num;
+        case Value::String: {
+            if (v.str.empty()) return 0;
+            char* end;
+            double d = strtod(v.str.c_str(), &end);
+            while (*end == ' ') end++;
+            return *end ? NAN : d;
+        }
+        case Value::Obj:
+            if (v.obj->kind == Object::Array && v.obj->arr.size() == 1) return to_number(v.obj->arr[0]);
+            if (v.obj->kind == Object::Array && v.obj->arr.empty()) return 0;
+            return NAN;
+    }
+    return NAN;
+}
+bool Interp::to_boolean(const Value& v) {
+    switch (v.type) {
+        case Value::Undefined: case Value::Null: return false;
+        case Value::Bool: return v.b;
+        case Value::Number: return v.num != 0 && !std::isnan(v.num);
+        case Value::String: return !v.str.empty();
+        case Value::Obj: return true;
+    }
+    return false;
+}
+std::string Interp::to_string(const Value& v) {
+    switch (v.type) {
+        case Value::Undefined: return "undefined";
+        case Value::Null: return "null";
+        case Value::Bool: return v.b ? "true" : "false";
+        case Value::Number: {
+            if (std::isnan(v.num)) return "NaN";
+            if (std::isinf(v.num)) return v.num > 0 ? "Infinity" : "-Infinity";
+            char buf[40];
+            if (v.num == std::floor(v.num) && std::fabs(v.num) < 1e21) snprintf(buf, sizeof buf, "%.0f", v.num);
+            else snprintf(buf, sizeof buf, "%.17g", v.num);
+            // shortest round-trip
+            if (!(v.num == std::floor(v.num))) {
+                for (int prec = 1; prec <= 17; prec++) {
+                    snprintf(buf, sizeof buf, "%.*g", prec, v.num);
+                    if (strtod(buf, nullptr) == v.num) break;
+                }
+            }
+            return buf;
+        }
+        case Value::String: return v.str;
+        case Value::Obj:
+            if (v.obj->kind == Object::Array) {
+                std::string out;
+                for (size_t i = 0; i < v.obj->arr.size(); i++) {
+                    if (i) out += ",";
+                    if (v.obj->arr[i].type != Value::Undefined && v.obj->arr[i].type != Value::Null) out += to_string(v.obj->arr[i]);
+                }
+                return out;
+            }
+            if (v.obj->kind == Object::Function || v.obj->kind == Object::Native) return "function";
+            return "[object Object]";
+    }
+    return "";
+}
+
+static Value math1(double (*f)(double), std::vector<Value>& a) { return Value(f(a.empty() ? NAN : Interp::to_number(a[0]))); }
+
+Interp::Interp() {
+    globals = std::make_shared<Env>();
+    globals->function_scope = true;
+    auto math = make_object();
+#define M1(nm, fn) math->props[nm] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return math1(fn, a); }))
+    M1("sin", std::sin); M1("cos", std::cos); M1("tan", std::tan); M1("asin", std::asin); M1("acos", std::acos);
+    M1("atan", std::atan); M1("sqrt", std::sqrt); M1("cbrt", std::cbrt); M1("exp", std::exp); M1("log", std::log);
+    M1("log2", std::log2); M1("log10", std::log10); M1("abs", std::fabs); M1("floor", std::floor); M1("ceil", std::ceil);
+    M1("trunc", std::trunc); M1("sinh", std::sinh); M1("cosh", std::cosh); M1("tanh", std::tanh);
+#undef M1
+    math->props["round"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::floor((a.empty() ? NAN : to_number(a[0])) + 0.5)); }));
+    math->props["sign"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { double x = a.empty() ? NAN : to_number(a[0]); return Value(x > 0 ? 1.0 : (x < 0 ? -1.0 : x)); }));
+    math->props["atan2"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::atan2(a.size() > 0 ? to_number(a[0]) : NAN, a.size() > 1 ? to_number(a[1]) : NAN)); }));
+    math->props["pow"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::pow(a.size() > 0 ? to_number(a[0]) : NAN, a.size() > 1 ? to_number(a[1]) : NAN)); }));
+    math->props["hypot"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { double s = 0; for (auto& v : a) { double x = to_number(v); s += x * x; } return Value(std::sqrt(s)); }));
+    math->props["min"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { double m = INFINITY; for (auto& v : a) { double x = to_number(v); if (std::isnan(x)) return Value(NAN); m = std::min(m, x); } return Value(m); }));
+    math->props["max"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { double m = -INFINITY; for (auto& v : a) { double x = to_number(v); if (std::isnan(x)) return Value(NAN); m = std::max(m, x); } return Value(m); }));
+    math->props["PI"] = Value(3.14159265358979323846);
+    math->props["E"] = Value(2.7182818284590452354);
+    math->props["LN2"] = Value(0.69314718055994530942);
+    math->props["LN10"] = Value(2.30258509299404568402);
+    math->props["LOG2E"] = Value(1.4426950408889634074);
+    math->props["LOG10E"] = Value(0.43429448190325182765);
+    math->props["SQRT2"] = Value(1.41421356237309504880);
+    math->props["SQRT1_2"] = Value(0.70710678118654752440);
+    globals->vars["Math"] = Value(math);
+    globals->vars["NaN"] = Value(NAN);
+    globals->vars["Infinity"] = Value(INFINITY);
+    globals->vars["isNaN"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::isnan(a.empty() ? NAN : to_number(a[0]))); }));
+    globals->vars["isFinite"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value((bool)std::isfinite(a.empty() ? NAN : to_number(a[0]))); }));
+    globals->vars["parseFloat"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? NAN : strtod(ip.to_string(a[0]).c_str(), nullptr)); }));
+    globals->vars["parseInt"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? NAN : std::trunc(strtod(ip.to_string(a[0]).c_str(), nullptr))); }));
+    globals->vars["Number"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(a.empty() ? 0.0 : to_number(a[0])); }));
+    globals->vars["String"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? std::string() : ip.to_string(a[0])); }));
+    globals->vars["Boolean"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && to_boolean(a[0])); }));
+    auto array_ctor = make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        if (a.size() == 1 && a[0].type == Value::Number) {
+            if (a[0].num < 0 || a[0].num > 1e7) throw JsError("RangeError: invalid array length");
+            return Value(make_array(std::vector<Value>((size_t)a[0].num)));
+        }
+        return Value(make_array(a));
+    });
+    array_ctor->props["isArray"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Obj && a[0].obj->kind == Object::Array); }));
+    globals->vars["Array"] = Value(array_ctor);
+    auto object_ctor = make_native([](Interp&, const Value&, std::vector<Value>&) { return Value(make_object()); });
+    object_ctor->props["keys"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        std::vector<Value> keys;
+        if (!a.empty() && a[0].type == Value::Obj) {
+            if (a[0].obj->kind == Object::Array) for (size_t i = 0; i < a[0].obj->arr.size(); i++) keys.push_back(Value(std::to_string(i)));
+            for (auto& kv : a[0].obj->props) keys.push_back(Value(kv.first));
+        }
+        return Value(make_array(keys));
+    }));
+    globals->vars["Object"] = Value(object_ctor);
+    auto console = make_object();
+    auto logfn = make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        std::string line;
+        for (size_t i = 0; i < a.size(); i++) { if (i) line += " "; line += ip.to_string(a[i]); }
+        if (getenv("GRT_JS_CONSOLE")) fprintf(stderr, "[js] %s\n", line.c_str());
+        return Value();
+    });
+    console->props["log"] = Value(logfn);
+    console->props["warn"] = Value(logfn);
+    console->props["error"] = Value(logfn);
+    globals->vars["console"] = Value(console);
+    globals->vars["print"] = Value(logfn);
+    globals->vars["globalThis"] = Value(make_object());
+}
+
+Interp::~Interp() {
+    // break closure <-> environment reference cycles
+    std::set<Env*> seen;
+    std::function<void(Env*)> clear = [&](Env* e) {
+        if (!e || !seen.insert(e).second) return;
+        auto vars = std::move(e->vars);
+        e->vars.clear();
+        for (auto& kv : vars)
+            if (kv.second.type == Value::Obj && kv.second.obj->env) clear(kv.second.obj->env.get());
+    };
+    clear(globals.get());
+}
+
+void Interp::set_global(const std::string& name, const Value& v) { globals->vars[name] = v; }
+Value Interp::get_global(const std::string& name) {
+    auto it = globals->vars.find(name);
+    return it == globals->vars.end() ? Value() : it->second;
+}
+void Interp::set_global_getter(const std::string& name, std::function<Value(Interp&)> getter) {
+    global_getters[name] = std::move(getter);
+}
+
+Value Interp::eval(const std::string& source, const std::string& name) {
+    Lexer lx(source, name);
+    lx.run();
+    Parser ps(lx.toks, name);
+    programs.push_back(ps.parse_program());
+    Program* prog = programs.back().get();
+    Evaluator ev(*this, name);
+    steps = 0;
+    try {
+        ev.hoist(prog->top, globals);
+        Comp c = ev.exec_block(prog->body, globals);
+        (void)c;
+    } catch (Thrown& th) {
+        std::string msg = th.v.type == Value::Obj && th.v.obj->props.count("message") ? to_string(th.v.obj->props["message"]) : to_string(th.v);
+        throw JsError(name + ": uncaught exception: " + msg);
+    }
+    return ev.completion;
+}
+
+Value Interp::call(const Value& fn, const Value& self, std::vector<Value> args) {
+    Evaluator ev(*this, "<call>");
+    try {
+        return ev.call_function(nullptr, fn, self, args);
+    } catch (Thrown& th) {
+        std::string msg = th.v.type == Value::Obj && th.v.obj->props.count("message") ? to_string(th.v.obj->props["message"]) : to_string(th.v);
+        throw JsError("uncaught exception: " + msg);
+    }
+}
+
+}  // namespace minijs

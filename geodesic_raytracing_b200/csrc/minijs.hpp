@@ -1,0 +1,116 @@
+// A small JavaScript interpreter - just enough of ES5/ES6 to run the reference's metric plugin
+// scripts unchanged (scripts/*.js, scripts/coordinates/*.js, scripts/origins/*.js).
+//
+// The reference embeds QuickJS (2020-04-12, CONFIG_BIGNUM) and gets `a * b` on `number` objects
+// through `Operators.create` in /root/reference/number.js:4-71.  This image has no JavaScript
+// engine and the reference's vendored one must not be copied, so the plugin boundary
+//  is served by this interpreter: operator overloading on host objects is a
+// first-class hook instead of the bignum extension, everything else is plain JavaScript:
+// var/let/const with hoisting, functions/closures/arrows, if/for/while/do, arrays, objects,
+// Math.*, the usual operators, automatic semicolon insertion.  The completion value of a
+// script (the value of its last expression statement) is what `eval` returns, which is how the
+// reference obtains the metric function (/root/reference/js_interop.cpp:738-742).
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace minijs {
+
+struct Object;
+struct Interp;
+using ObjP = std::shared_ptr<Object>;
+
+struct Value {
+    enum Type { Undefined, Null, Bool, Number, String, Obj } type = Undefined;
+    double num = 0;
+    bool b = false;
+    std::string str;
+    ObjP obj;
+    Value() {}
+    Value(double d) : type(Number), num(d) {}
+    Value(int d) : type(Number), num(d) {}
+    Value(bool v) : type(Bool), b(v) {}
+    Value(const std::string& s) : type(String), str(s) {}
+    Value(const char* s) : type(String), str(s) {}
+    Value(ObjP o) : type(Obj), obj(std::move(o)) {}
+    static Value null() { Value v; v.type = Null; return v; }
+    bool is_undefined() const { return type == Undefined; }
+    bool is_number() const { return type == Number; }
+    bool is_bool() const { return type == Bool; }
+    bool is_object() const { return type == Obj; }
+};
+
+struct JsError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+using NativeFn = std::function<Value(Interp&, const Value& self, std::vector<Value>& args)>;
+
+struct FuncDef;  // AST
+struct Env;
+using EnvP = std::shared_ptr<Env>;
+
+struct Object {
+    enum Kind { Plain, Array, Function, Native, Host } kind = Plain;
+    std::map<std::string, Value> props;
+    std::vector<Value> arr;                 // Array
+    const FuncDef* def = nullptr;           // Function
+    EnvP env;                               // Function closure
+    Value bound_this;                       // arrow functions capture `this`
+    bool is_arrow = false;
+    NativeFn native;                        // Native
+    int host_tag = 0;                       // Host: type tag chosen by the embedder
+    std::shared_ptr<void> host;             // Host payload
+    // property hooks for Host objects (return true when handled)
+    std::function<bool(Interp&, const std::string&, Value&)> get_hook;
+    std::function<bool(Interp&, const std::string&, const Value&)> set_hook;
+};
+
+struct Env {
+    std::unordered_map<std::string, Value> vars;
+    std::unordered_map<std::string, bool> is_const;
+    EnvP parent;
+    bool function_scope = false;
+    Value this_val;
+};
+
+struct Program;  // parsed script (owns its AST)
+
+struct Interp {
+    Interp();
+    ~Interp();
+    // Parse + run; returns the completion value. Throws JsError (message carries the line).
+    Value eval(const std::string& source, const std::string& name = "<script>");
+    Value call(const Value& fn, const Value& self, std::vector<Value> args);
+    void set_global(const std::string& name, const Value& v);
+    Value get_global(const std::string& name);
+    // global with a getter (the reference installs `$cfg` this way, js_interop.cpp:841-846)
+    void set_global_getter(const std::string& name, std::function<Value(Interp&)> getter);
+
+    static ObjP make_object();
+    static ObjP make_array(std::vector<Value> items = {});
+    static ObjP make_native(NativeFn fn);
+    static ObjP make_host(int tag, std::shared_ptr<void> payload);
+
+    // operator overloading: called when either operand is a Host object.
+    // op is one of "+", "-", "*", "/", "%", "**", "neg", "pos", "<", "<=", ">", ">=", "==", "!=".
+    std::function<Value(Interp&, const std::string& op, const Value& a, const Value& b)> host_operator;
+
+    // conversions (ECMAScript semantics for the primitive cases)
+    static double to_number(const Value& v);
+    static bool to_boolean(const Value& v);
+    std::string to_string(const Value& v);
+
+    EnvP globals;
+    std::vector<std::unique_ptr<Program>> programs;  // keep ASTs alive for closures
+    std::unordered_map<std::string, std::function<Value(Interp&)>> global_getters;
+    int call_depth = 0;
+    long steps = 0;  // runaway-script guard
+};
+
+}  // namespace minijs

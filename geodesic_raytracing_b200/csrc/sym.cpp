@@ -1,0 +1,486 @@
+// Symbolic expression DAG: hash-consing, simplification, differentiation, emission.
+// See sym.hpp for what this replaces in the reference.
+#include "sym.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <set>
+#include <stdexcept>
+
+namespace sym {
+
+static thread_local Graph* g_cur = nullptr;
+Graph* Graph::cur() {
+    if (!g_cur) throw std::runtime_error("sym: no current graph");
+    return g_cur;
+}
+void Graph::set_cur(Graph* g) { g_cur = g; }
+
+Graph::Graph() { nodes_.reserve(4096); }
+
+int Graph::intern(const Node& n) {
+    char buf[96];
+    std::string key;
+    if (n.op == Op::Const) {
+        uint64_t bits;
+        double v = n.val;
+        if (v == 0.0) v = 0.0;  // merge -0 and +0
+        memcpy(&bits, &v, 8);
+        snprintf(buf, sizeof buf, "c%llx", (unsigned long long)bits);
+        key = buf;
+    } else if (n.op == Op::Var || n.op == Op::Param) {
+        key = (n.op == Op::Var ? "v:" : "p:") + n.name;
+    } else {
+        snprintf(buf, sizeof buf, "o%d:%d:%d:%d", (int)n.op, n.a, n.b, n.c);
+        key = buf;
+    }
+    auto it = table_.find(key);
+    if (it != table_.end()) return it->second;
+    int id = (int)nodes_.size();
+    nodes_.push_back(n);
+    table_.emplace(std::move(key), id);
+    return id;
+}
+
+int Graph::constant(double v) {
+    Node n;
+    n.op = Op::Const;
+    n.val = (v == 0.0) ? 0.0 : v;
+    return intern(n);
+}
+int Graph::var(const std::string& name) {
+    Node n;
+    n.op = Op::Var;
+    n.name = name;
+    return intern(n);
+}
+int Graph::param(const std::string& name) {
+    Node n;
+    n.op = Op::Param;
+    n.name = name;
+    return intern(n);
+}
+
+static bool is_commutative(Op op) {
+    return op == Op::Add || op == Op::Mul || op == Op::Min || op == Op::Max || op == Op::Eq;
+}
+
+static double fold1(Op op, double a) {
+    switch (op) {
+        case Op::Neg: return -a;
+        case Op::Sin: return std::sin(a);
+        case Op::Cos: return std::cos(a);
+        case Op::Tan: return std::tan(a);
+        case Op::Asin: return std::asin(a);
+        case Op::Acos: return std::acos(a);
+        case Op::Atan: return std::atan(a);
+        case Op::Fabs: return std::fabs(a);
+        case Op::Log: return std::log(a);
+        case Op::Sqrt: return std::sqrt(a);
+        case Op::Exp: return std::exp(a);
+        case Op::Sinh: return std::sinh(a);
+        case Op::Cosh: return std::cosh(a);
+        case Op::Tanh: return std::tanh(a);
+        case Op::Sign: return a > 0 ? 1.0 : (a < 0 ? -1.0 : 0.0);
+        default: throw std::runtime_error("sym: fold1 bad op");
+    }
+}
+static double fold2(Op op, double a, double b) {
+    switch (op) {
+        case Op::Add: return a + b;
+        case Op::Sub: return a - b;
+        case Op::Mul: return a * b;
+        case Op::Div: return a / b;
+        case Op::Atan2: return std::atan2(a, b);
+        case Op::Pow: return std::pow(a, b);
+        case Op::Lt: return a < b ? 1.0 : 0.0;
+        case Op::Lte: return a <= b ? 1.0 : 0.0;
+        case Op::Eq: return a == b ? 1.0 : 0.0;
+        case Op::Gt: return a > b ? 1.0 : 0.0;
+        case Op::Gte: return a >= b ? 1.0 : 0.0;
+        case Op::Fmod: return std::fmod(a, b);
+        case Op::Min: return std::min(a, b);
+        case Op::Max: return std::max(a, b);
+        default: throw std::runtime_error("sym: fold2 bad op");
+    }
+}
+
+// Returns a node id when the expression collapses (done=true), else done=false and the caller interns.
+int Graph::simplify(Op op, int a, int b, int c, bool& done) {
+    done = true;
+    const bool ca = a >= 0 && is_const(a), cb = b >= 0 && is_const(b);
+    auto isneg = [&](int id) { return nodes_[id].op == Op::Neg; };
+    switch (op) {
+        case Op::Add:
+            if (ca && cb) return constant(cval(a) + cval(b));
+            if (is_const(a, 0.0)) return b;
+            if (is_const(b, 0.0)) return a;
+            if (isneg(b)) return make(Op::Sub, a, nodes_[b].a);
+            if (isneg(a)) return make(Op::Sub, b, nodes_[a].a);
+            break;
+        case Op::Sub:
+            if (ca && cb) return constant(cval(a) - cval(b));
+            if (is_const(b, 0.0)) return a;
+            if (is_const(a, 0.0)) return make(Op::Neg, b);
+            if (a == b) return constant(0.0);
+            if (isneg(b)) return make(Op::Add, a, nodes_[b].a);
+            if (isneg(a)) return make(Op::Neg, make(Op::Add, nodes_[a].a, b));
+            break;
+        case Op::Mul:
+            if (ca && cb) return constant(cval(a) * cval(b));
+            if (is_const(a, 0.0) || is_const(b, 0.0)) return constant(0.0);
+            if (is_const(a, 1.0)) return b;
+            if (is_const(b, 1.0)) return a;
+            if (is_const(a, -1.0)) return make(Op::Neg, b);
+            if (is_const(b, -1.0)) return make(Op::Neg, a);
+            if (isneg(a) && isneg(b)) return make(Op::Mul, nodes_[a].a, nodes_[b].a);
+            if (isneg(a)) return make(Op::Neg, make(Op::Mul, nodes_[a].a, b));
+            if (isneg(b)) return make(Op::Neg, make(Op::Mul, a, nodes_[b].a));
+            // fold constants through nested products: c1 * (c2 * x) -> (c1*c2) * x
+            if (ca && nodes_[b].op == Op::Mul && is_const(nodes_[b].a))
+                return make(Op::Mul, constant(cval(a) * cval(nodes_[b].a)), nodes_[b].b);
+            if (cb && nodes_[a].op == Op::Mul && is_const(nodes_[a].a))
+                return make(Op::Mul, constant(cval(b) * cval(nodes_[a].a)), nodes_[a].b);
+            if (ca && cval(a) < 0) return make(Op::Neg, make(Op::Mul, constant(-cval(a)), b));
+            if (cb && cval(b) < 0) return make(Op::Neg, make(Op::Mul, a, constant(-cval(b))));
+            break;
+        case Op::Div:
+            if (ca && cb) return constant(cval(a) / cval(b));
+            if (is_const(a, 0.0)) return constant(0.0);
+            if (is_const(b, 1.0)) return a;
+            if (is_const(b, -1.0)) return make(Op::Neg, a);
+            if (a == b) return constant(1.0);
+            if (isneg(a) && isneg(b)) return make(Op::Div, nodes_[a].a, nodes_[b].a);
+            if (isneg(a)) return make(Op::Neg, make(Op::Div, nodes_[a].a, b));
+            if (isneg(b)) return make(Op::Neg, make(Op::Div, a, nodes_[b].a));
+            if (cb) return make(Op::Mul, a, constant(1.0 / cval(b)));
+            break;
+        case Op::Neg:
+            if (ca) return constant(-cval(a));
+            if (isneg(a)) return nodes_[a].a;
+            if (nodes_[a].op == Op::Sub) return make(Op::Sub, nodes_[a].b, nodes_[a].a);
+            break;
+        case Op::Sin:
+            if (ca) return constant(fold1(op, cval(a)));
+            if (isneg(a)) return make(Op::Neg, make(Op::Sin, nodes_[a].a));
+            if (nodes_[a].op == Op::Atan2) {  // sin(atan2(y,x)) = y / hypot
+                int y = nodes_[a].a, x = nodes_[a].b;
+                int h = make(Op::Sqrt, make(Op::Add, make(Op::Mul, y, y), make(Op::Mul, x, x)));
+                return make(Op::Div, y, h);
+            }
+            break;
+        case Op::Cos:
+            if (ca) return constant(fold1(op, cval(a)));
+            if (isneg(a)) return make(Op::Cos, nodes_[a].a);
+            if (nodes_[a].op == Op::Atan2) {
+                int y = nodes_[a].a, x = nodes_[a].b;
+                int h = make(Op::Sqrt, make(Op::Add, make(Op::Mul, y, y), make(Op::Mul, x, x)));
+                return make(Op::Div, x, h);
+            }
+            break;
+        case Op::Fabs:
+            if (ca) return constant(std::fabs(cval(a)));
+            if (isneg(a)) return make(Op::Fabs, nodes_[a].a);
+            if (nodes_[a].op == Op::Fabs || nodes_[a].op == Op::Sqrt || nodes_[a].op == Op::Exp ||
+                nodes_[a].op == Op::Cosh)
+                return a;
+            if (nodes_[a].op == Op::Mul && nodes_[a].a == nodes_[a].b) return a;  // |x*x|
+            break;
+        case Op::Tan: case Op::Asin: case Op::Acos: case Op::Atan: case Op::Log:
+        case Op::Exp: case Op::Sinh: case Op::Cosh: case Op::Tanh: case Op::Sign:
+            if (ca) return constant(fold1(op, cval(a)));
+            break;
+        case Op::Sqrt:
+            if (ca) return constant(std::sqrt(cval(a)));
+            break;
+        case Op::Pow:
+            if (ca && cb) return constant(std::pow(cval(a), cval(b)));
+            if (cb) {
+                double e = cval(b);
+                if (e == 0.0) return constant(1.0);
+                if (e == 1.0) return a;
+                if (e == 0.5) return make(Op::Sqrt, a);
+                if (e == -0.5) return make(Op::Div, constant(1.0), make(Op::Sqrt, a));
+                if (e == std::floor(e) && std::fabs(e) <= 16) {
+                    int n = (int)std::fabs(e);
+                    int result = -1, base = a;
+                    while (n) {  // square and multiply
+                        if (n & 1) result = result < 0 ? base : make(Op::Mul, result, base);
+                        n >>= 1;
+                        if (n) base = make(Op::Mul, base, base);
+                    }
+                    return e < 0 ? make(Op::Div, constant(1.0), result) : result;
+                }
+            }
+            if (is_const(a, 1.0)) return constant(1.0);
+            break;
+        case Op::Atan2: case Op::Fmod:
+            if (ca && cb) return constant(fold2(op, cval(a), cval(b)));
+            break;
+        case Op::Min: case Op::Max:
+            if (ca && cb) return constant(fold2(op, cval(a), cval(b)));
+            if (a == b) return a;
+            break;
+        case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte:
+            if (ca && cb) return constant(fold2(op, cval(a), cval(b)));
+            break;
+        case Op::Select:
+            if (ca) return cval(a) != 0.0 ? b : c;
+            if (b == c) return b;
+            break;
+        default: break;
+    }
+    done = false;
+    return -1;
+}
+
+int Graph::make(Op op, int a, int b, int c) {
+    bool done = false;
+    int r = simplify(op, a, b, c, done);
+    if (done) return r;
+    if (is_commutative(op) && a > b) std::swap(a, b);
+    Node n;
+    n.op = op;
+    n.a = a;
+    n.b = b;
+    n.c = c;
+    return intern(n);
+}
+
+int Graph::diff(int id, int wrt) {
+    auto key = std::make_pair(id, wrt);
+    auto it = diff_memo_.find(key);
+    if (it != diff_memo_.end()) return it->second;
+    const Node n = nodes_[id];  // copy: nodes_ may reallocate
+    int r;
+    auto D = [&](int x) { return diff(x, wrt); };
+    auto C = [&](double v) { return constant(v); };
+    auto M = [&](Op op, int x, int y = -1, int z = -1) { return make(op, x, y, z); };
+    switch (n.op) {
+        case Op::Const: case Op::Param: r = C(0.0); break;
+        case Op::Var: r = C(id == wrt ? 1.0 : 0.0); break;
+        case Op::Add: r = M(Op::Add, D(n.a), D(n.b)); break;
+        case Op::Sub: r = M(Op::Sub, D(n.a), D(n.b)); break;
+        case Op::Mul: r = M(Op::Add, M(Op::Mul, D(n.a), n.b), M(Op::Mul, n.a, D(n.b))); break;
+        case Op::Div: {
+            // (a'b - ab')/b^2
+            int da = D(n.a), db = D(n.b);
+            if (is_const(db, 0.0)) r = M(Op::Div, da, n.b);
+            else r = M(Op::Div, M(Op::Sub, M(Op::Mul, da, n.b), M(Op::Mul, n.a, db)), M(Op::Mul, n.b, n.b));
+            break;
+        }
+        case Op::Neg: r = M(Op::Neg, D(n.a)); break;
+        case Op::Sin: r = M(Op::Mul, M(Op::Cos, n.a), D(n.a)); break;
+        case Op::Cos: r = M(Op::Neg, M(Op::Mul, M(Op::Sin, n.a), D(n.a))); break;
+        case Op::Tan: { int cs = M(Op::Cos, n.a); r = M(Op::Div, D(n.a), M(Op::Mul, cs, cs)); break; }
+        case Op::Asin: r = M(Op::Div, D(n.a), M(Op::Sqrt, M(Op::Sub, C(1.0), M(Op::Mul, n.a, n.a)))); break;
+        case Op::Acos: r = M(Op::Neg, M(Op::Div, D(n.a), M(Op::Sqrt, M(Op::Sub, C(1.0), M(Op::Mul, n.a, n.a))))); break;
+        case Op::Atan: r = M(Op::Div, D(n.a), M(Op::Add, C(1.0), M(Op::Mul, n.a, n.a))); break;
+        case Op::Atan2: {
+            // d atan2(y,x) = (x dy - y dx)/(x^2+y^2)
+            int y = n.a, x = n.b;
+            r = M(Op::Div, M(Op::Sub, M(Op::Mul, x, D(y)), M(Op::Mul, y, D(x))),
+                  M(Op::Add, M(Op::Mul, x, x), M(Op::Mul, y, y)));
+            break;
+        }
+        case Op::Fabs: r = M(Op::Mul, M(Op::Sign, n.a), D(n.a)); break;
+        case Op::Log: r = M(Op::Div, D(n.a), n.a); break;
+        case Op::Sqrt: r = M(Op::Div, D(n.a), M(Op::Mul, C(2.0), id)); break;
+        case Op::Exp: r = M(Op::Mul, id, D(n.a)); break;
+        case Op::Sinh: r = M(Op::Mul, M(Op::Cosh, n.a), D(n.a)); break;
+        case Op::Cosh: r = M(Op::Mul, M(Op::Sinh, n.a), D(n.a)); break;
+        case Op::Tanh: r = M(Op::Mul, M(Op::Sub, C(1.0), M(Op::Mul, id, id)), D(n.a)); break;
+        case Op::Pow: {
+            int da = D(n.a), db = D(n.b);
+            if (is_const(n.b)) {
+                r = M(Op::Mul, M(Op::Mul, n.b, M(Op::Pow, n.a, C(cval(n.b) - 1.0))), da);
+            } else {
+                // a^b (b' ln a + b a'/a)
+                r = M(Op::Mul, id, M(Op::Add, M(Op::Mul, db, M(Op::Log, n.a)), M(Op::Div, M(Op::Mul, n.b, da), n.a)));
+            }
+            break;
+        }
+        case Op::Select: r = M(Op::Select, n.a, D(n.b), D(n.c)); break;
+        case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte: case Op::Sign:
+            r = C(0.0); break;
+        case Op::Fmod: r = D(n.a); break;
+        case Op::Min: r = M(Op::Select, M(Op::Lt, n.a, n.b), D(n.a), D(n.b)); break;
+        case Op::Max: r = M(Op::Select, M(Op::Gt, n.a, n.b), D(n.a), D(n.b)); break;
+        default: throw std::runtime_error("sym: diff bad op");
+    }
+    diff_memo_[key] = r;
+    return r;
+}
+
+int Graph::substitute(int id, const std::map<int, int>& repl) {
+    std::unordered_map<int, int> memo;
+    std::function<int(int)> go = [&](int x) -> int {
+        auto r = repl.find(x);
+        if (r != repl.end()) return r->second;
+        auto m = memo.find(x);
+        if (m != memo.end()) return m->second;
+        const Node n = nodes_[x];
+        int out;
+        if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param) out = x;
+        else {
+            int a = n.a >= 0 ? go(n.a) : -1, b = n.b >= 0 ? go(n.b) : -1, c = n.c >= 0 ? go(n.c) : -1;
+            out = (a == n.a && b == n.b && c == n.c) ? x : make(n.op, a, b, c);
+        }
+        memo[x] = out;
+        return out;
+    };
+    return go(id);
+}
+
+bool Graph::depends_on(int id, int leaf) const {
+    std::set<int> seen;
+    std::function<bool(int)> go = [&](int x) -> bool {
+        if (x == leaf) return true;
+        if (x < 0 || !seen.insert(x).second) return false;
+        const Node& n = nodes_[x];
+        return (n.a >= 0 && go(n.a)) || (n.b >= 0 && go(n.b)) || (n.c >= 0 && go(n.c));
+    };
+    return go(id);
+}
+
+size_t Graph::op_count(const std::vector<int>& outs) const {
+    std::set<int> seen;
+    size_t cnt = 0;
+    std::function<void(int)> go = [&](int x) {
+        if (x < 0 || !seen.insert(x).second) return;
+        const Node& n = nodes_[x];
+        if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param) return;
+        cnt++;
+        go(n.a); go(n.b); go(n.c);
+    };
+    for (int o : outs) go(o);
+    return cnt;
+}
+
+static const char* fn_name(Op op) {
+    switch (op) {
+        case Op::Sin: return "sin"; case Op::Cos: return "cos"; case Op::Tan: return "tan";
+        case Op::Asin: return "asin"; case Op::Acos: return "acos"; case Op::Atan: return "atan";
+        case Op::Atan2: return "atan2"; case Op::Fabs: return "fabs"; case Op::Log: return "log";
+        case Op::Sqrt: return "sqrt"; case Op::Exp: return "exp"; case Op::Sinh: return "sinh";
+        case Op::Cosh: return "cosh"; case Op::Tanh: return "tanh"; case Op::Pow: return "pow";
+        case Op::Fmod: return "fmod"; case Op::Sign: return "sign"; case Op::Min: return "min";
+        case Op::Max: return "max"; case Op::Select: return "select";
+        default: return "?";
+    }
+}
+
+std::string Graph::to_string(int id) const {
+    const Node& n = nodes_[id];
+    auto S = [&](int x) { return to_string(x); };
+    char buf[64];
+    switch (n.op) {
+        case Op::Const: snprintf(buf, sizeof buf, "%.9g", n.val); return buf;
+        case Op::Var: return n.name;
+        case Op::Param: return "cfg->" + n.name;
+        case Op::Add: return "(" + S(n.a) + "+" + S(n.b) + ")";
+        case Op::Sub: return "(" + S(n.a) + "-" + S(n.b) + ")";
+        case Op::Mul: return "(" + S(n.a) + "*" + S(n.b) + ")";
+        case Op::Div: return "(" + S(n.a) + "/" + S(n.b) + ")";
+        case Op::Neg: return "(-" + S(n.a) + ")";
+        case Op::Lt: return "(" + S(n.a) + "<" + S(n.b) + ")";
+        case Op::Lte: return "(" + S(n.a) + "<=" + S(n.b) + ")";
+        case Op::Eq: return "(" + S(n.a) + "==" + S(n.b) + ")";
+        case Op::Gt: return "(" + S(n.a) + ">" + S(n.b) + ")";
+        case Op::Gte: return "(" + S(n.a) + ">=" + S(n.b) + ")";
+        default: {
+            std::string s = std::string(fn_name(n.op)) + "(" + S(n.a);
+            if (n.b >= 0) s += "," + S(n.b);
+            if (n.c >= 0) s += "," + S(n.c);
+            return s + ")";
+        }
+    }
+}
+
+std::string float_literal(double v) {
+    if (std::isnan(v)) return "GRT_NAN";
+    if (std::isinf(v)) return v > 0 ? "GRT_INF" : "(-GRT_INF)";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.9g", (double)(float)v);
+    std::string s = buf;
+    if (s.find('.') == std::string::npos && s.find('e') == std::string::npos && s.find("inf") == std::string::npos)
+        s += ".0";
+    return s + "f";
+}
+
+std::string emit_block(const Graph& g, const std::vector<std::pair<std::string, int>>& outs,
+                       const EmitOptions& opt) {
+    // topological order of reachable op nodes (ids are already topological: children < parents)
+    std::set<int> reach;
+    std::function<void(int)> go = [&](int x) {
+        if (x < 0 || !reach.insert(x).second) return;
+        const Node& n = g.node(x);
+        go(n.a); go(n.b); go(n.c);
+    };
+    for (auto& o : outs) go(o.second);
+
+    auto ref = [&](int x) -> std::string {
+        const Node& n = g.node(x);
+        switch (n.op) {
+            case Op::Const: return float_literal(n.val);
+            case Op::Var: return n.name;
+            case Op::Param: {
+                auto it = opt.param_values.find(n.name);
+                if (it != opt.param_values.end()) return float_literal(it->second);
+                return opt.param_prefix + n.name;
+            }
+            default: return opt.tmp_prefix + std::to_string(x);
+        }
+    };
+
+    std::string out;
+    for (int x : reach) {  // std::set iterates ascending = topological
+        const Node& n = g.node(x);
+        if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param) continue;
+        std::string rhs;
+        auto A = [&]() { return ref(n.a); };
+        auto B = [&]() { return ref(n.b); };
+        auto Cc = [&]() { return ref(n.c); };
+        switch (n.op) {
+            case Op::Add: rhs = A() + " + " + B(); break;
+            case Op::Sub: rhs = A() + " - " + B(); break;
+            case Op::Mul: rhs = A() + " * " + B(); break;
+            case Op::Div: rhs = "GRT_DIV(" + A() + ", " + B() + ")"; break;
+            case Op::Neg: rhs = "-" + A(); break;
+            case Op::Sin: rhs = "GRT_SIN(" + A() + ")"; break;
+            case Op::Cos: rhs = "GRT_COS(" + A() + ")"; break;
+            case Op::Tan: rhs = "GRT_TAN(" + A() + ")"; break;
+            case Op::Asin: rhs = "asinf(" + A() + ")"; break;
+            case Op::Acos: rhs = "acosf(" + A() + ")"; break;
+            case Op::Atan: rhs = "atanf(" + A() + ")"; break;
+            case Op::Atan2: rhs = "atan2f(" + A() + ", " + B() + ")"; break;
+            case Op::Fabs: rhs = "fabsf(" + A() + ")"; break;
+            case Op::Log: rhs = "GRT_LOG(" + A() + ")"; break;
+            case Op::Sqrt: rhs = "GRT_SQRT(" + A() + ")"; break;
+            case Op::Exp: rhs = "GRT_EXP(" + A() + ")"; break;
+            case Op::Sinh: rhs = "sinhf(" + A() + ")"; break;
+            case Op::Cosh: rhs = "coshf(" + A() + ")"; break;
+            case Op::Tanh: rhs = "GRT_TANH(" + A() + ")"; break;
+            case Op::Pow: rhs = "GRT_POW(" + A() + ", " + B() + ")"; break;
+            case Op::Select: rhs = "((" + A() + " != 0.0f) ? " + B() + " : " + Cc() + ")"; break;
+            case Op::Lt: rhs = "((" + A() + " < " + B() + ") ? 1.0f : 0.0f)"; break;
+            case Op::Lte: rhs = "((" + A() + " <= " + B() + ") ? 1.0f : 0.0f)"; break;
+            case Op::Eq: rhs = "((" + A() + " == " + B() + ") ? 1.0f : 0.0f)"; break;
+            case Op::Gt: rhs = "((" + A() + " > " + B() + ") ? 1.0f : 0.0f)"; break;
+            case Op::Gte: rhs = "((" + A() + " >= " + B() + ") ? 1.0f : 0.0f)"; break;
+            case Op::Fmod: rhs = "fmodf(" + A() + ", " + B() + ")"; break;
+            case Op::Sign: rhs = "GRT_SIGN(" + A() + ")"; break;
+            case Op::Min: rhs = "fminf(" + A() + ", " + B() + ")"; break;
+            case Op::Max: rhs = "fmaxf(" + A() + ", " + B() + ")"; break;
+            default: throw std::runtime_error("sym: emit bad op");
+        }
+        out += opt.indent + "const float " + opt.tmp_prefix + std::to_string(x) + " = " + rhs + ";\n";
+    }
+    for (auto& o : outs) out += opt.indent + o.first + " = " + ref(o.second) + ";\n";
+    return out;
+}
+
+}  // namespace sym

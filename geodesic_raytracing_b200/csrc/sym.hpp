@@ -1,0 +1,150 @@
+// Symbolic expression DAG used by the metric plugin loader.
+//
+// Replaces the reference's missing `deps/vec` layer (20k/funvectormaths @ 7a8b639:
+// `value`, `dual`, `dual_complex`, `equivalent()`, `type_to_string()`), which
+// /root/reference/js_interop.cpp:219-297,481-616 and /root/reference/metric.hpp:38-274
+// drive.  Design differences (deliberate, B200-first):
+//   * hash-consed DAG: structurally equal sub-expressions are the same node, so
+//     `equivalent()` is an id compare and common sub-expression elimination is free
+//     (the reference needs script authors to call `$pin` for that,
+//     /root/reference/equation_context.hpp:16-43);
+//   * derivatives are taken symbolically on the DAG (memoised reverse walk) instead of
+//     re-running the script once per variable with forward-mode duals
+//     (/root/reference/metric.hpp:38-80) - same partials, one script run;
+//   * code is emitted as straight-line SSA `float` statements for a CUDA `__device__`
+//     function (and the identical text for the CPU oracle), not as `-D` macro strings.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace sym {
+
+enum class Op : uint8_t {
+    Const, Var, Param,
+    Add, Sub, Mul, Div, Neg,
+    Sin, Cos, Tan, Asin, Acos, Atan, Atan2,
+    Fabs, Log, Sqrt, Exp, Sinh, Cosh, Tanh, Pow,
+    Select, Lt, Lte, Eq, Gt, Gte,
+    Fmod, Sign, Min, Max
+};
+
+struct Node {
+    Op op = Op::Const;
+    int a = -1, b = -1, c = -1;
+    double val = 0.0;     // Const
+    std::string name;     // Var / Param
+};
+
+class Graph {
+public:
+    Graph();
+    // the graph new Expr constants are created in (one per metric load, single threaded)
+    static Graph* cur();
+    static void set_cur(Graph* g);
+
+    int constant(double v);
+    int var(const std::string& name);
+    int param(const std::string& name);
+    int make(Op op, int a, int b = -1, int c = -1);  // simplifying constructor
+
+    const Node& node(int id) const { return nodes_[id]; }
+    size_t size() const { return nodes_.size(); }
+    bool is_const(int id) const { return nodes_[id].op == Op::Const; }
+    bool is_const(int id, double v) const { return nodes_[id].op == Op::Const && nodes_[id].val == v; }
+    double cval(int id) const { return nodes_[id].val; }
+
+    // d(id)/d(variable node `wrt`)
+    int diff(int id, int wrt);
+    // replace nodes by other nodes (bottom-up rebuild with re-simplification)
+    int substitute(int id, const std::map<int, int>& repl);
+    // does `id` depend on node `leaf`?
+    bool depends_on(int id, int leaf) const;
+    // number of arithmetic nodes reachable from the outputs (flop-ish count, FMA not fused)
+    size_t op_count(const std::vector<int>& outs) const;
+    // human readable infix (tests, debugging, classification decisions)
+    std::string to_string(int id) const;
+
+private:
+    int intern(const Node& n);
+    int simplify(Op op, int a, int b, int c, bool& done);
+    std::vector<Node> nodes_;
+    std::unordered_map<std::string, int> table_;
+    std::map<std::pair<int, int>, int> diff_memo_;
+};
+
+// value-semantics handle
+struct Expr {
+    int id = 0;
+    Expr() : id(Graph::cur()->constant(0.0)) {}
+    Expr(double v) : id(Graph::cur()->constant(v)) {}
+    Expr(int v) : id(Graph::cur()->constant((double)v)) {}
+    static Expr from_id(int i) { Expr e(0.0); e.id = i; return e; }
+    static Expr var(const std::string& n) { return from_id(Graph::cur()->var(n)); }
+    static Expr param(const std::string& n) { return from_id(Graph::cur()->param(n)); }
+    bool is_const() const { return Graph::cur()->is_const(id); }
+    bool is_const(double v) const { return Graph::cur()->is_const(id, v); }
+    double cval() const { return Graph::cur()->cval(id); }
+    Expr diff(const Expr& wrt) const { return from_id(Graph::cur()->diff(id, wrt.id)); }
+    std::string str() const { return Graph::cur()->to_string(id); }
+    bool same(const Expr& o) const { return id == o.id; }
+};
+
+inline Expr mk(Op op, const Expr& a) { return Expr::from_id(Graph::cur()->make(op, a.id)); }
+inline Expr mk(Op op, const Expr& a, const Expr& b) { return Expr::from_id(Graph::cur()->make(op, a.id, b.id)); }
+inline Expr mk(Op op, const Expr& a, const Expr& b, const Expr& c) { return Expr::from_id(Graph::cur()->make(op, a.id, b.id, c.id)); }
+
+inline Expr operator+(const Expr& a, const Expr& b) { return mk(Op::Add, a, b); }
+inline Expr operator-(const Expr& a, const Expr& b) { return mk(Op::Sub, a, b); }
+inline Expr operator*(const Expr& a, const Expr& b) { return mk(Op::Mul, a, b); }
+inline Expr operator/(const Expr& a, const Expr& b) { return mk(Op::Div, a, b); }
+inline Expr operator-(const Expr& a) { return mk(Op::Neg, a); }
+inline Expr& operator+=(Expr& a, const Expr& b) { a = a + b; return a; }
+inline Expr& operator-=(Expr& a, const Expr& b) { a = a - b; return a; }
+
+inline Expr sin(const Expr& a) { return mk(Op::Sin, a); }
+inline Expr cos(const Expr& a) { return mk(Op::Cos, a); }
+inline Expr tan(const Expr& a) { return mk(Op::Tan, a); }
+inline Expr asin(const Expr& a) { return mk(Op::Asin, a); }
+inline Expr acos(const Expr& a) { return mk(Op::Acos, a); }
+inline Expr atan(const Expr& a) { return mk(Op::Atan, a); }
+inline Expr atan2(const Expr& y, const Expr& x) { return mk(Op::Atan2, y, x); }
+inline Expr fabs(const Expr& a) { return mk(Op::Fabs, a); }
+inline Expr log(const Expr& a) { return mk(Op::Log, a); }
+inline Expr sqrt(const Expr& a) { return mk(Op::Sqrt, a); }
+inline Expr exp(const Expr& a) { return mk(Op::Exp, a); }
+inline Expr sinh(const Expr& a) { return mk(Op::Sinh, a); }
+inline Expr cosh(const Expr& a) { return mk(Op::Cosh, a); }
+inline Expr tanh(const Expr& a) { return mk(Op::Tanh, a); }
+inline Expr pow(const Expr& a, const Expr& b) { return mk(Op::Pow, a, b); }
+inline Expr select(const Expr& c, const Expr& t, const Expr& f) { return mk(Op::Select, c, t, f); }
+inline Expr fmod(const Expr& a, const Expr& b) { return mk(Op::Fmod, a, b); }
+inline Expr sign(const Expr& a) { return mk(Op::Sign, a); }
+inline Expr min(const Expr& a, const Expr& b) { return mk(Op::Min, a, b); }
+inline Expr max(const Expr& a, const Expr& b) { return mk(Op::Max, a, b); }
+inline Expr lt(const Expr& a, const Expr& b) { return mk(Op::Lt, a, b); }
+inline Expr lte(const Expr& a, const Expr& b) { return mk(Op::Lte, a, b); }
+inline Expr eq(const Expr& a, const Expr& b) { return mk(Op::Eq, a, b); }
+inline Expr gt(const Expr& a, const Expr& b) { return mk(Op::Gt, a, b); }
+inline Expr gte(const Expr& a, const Expr& b) { return mk(Op::Gte, a, b); }
+
+// ---- code emission -------------------------------------------------------------------------
+struct EmitOptions {
+    // Param nodes are written as `<param_prefix><name>` (dynamic program) unless a literal is
+    // given in `param_values` (static program: /root/reference/metric.hpp:494-547 substitutes
+    // `cfg->x` by a literal).
+    std::string param_prefix = "cfg.";
+    std::map<std::string, double> param_values;
+    std::string tmp_prefix = "t";
+    std::string indent = "    ";
+};
+
+// Emit straight-line SSA statements computing every `outs[i].second` into the lvalue
+// `outs[i].first`.  Shared sub-expressions are computed once.
+std::string emit_block(const Graph& g, const std::vector<std::pair<std::string, int>>& outs,
+                       const EmitOptions& opt);
+std::string float_literal(double v);
+
+}  // namespace sym

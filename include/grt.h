@@ -1,0 +1,217 @@
+/* geodesic_raytracing_b200 - C ABI of libgrt.so
+ *
+ * The drop-in boundary for the reference's hot path.  Two halves:
+ *
+ *  (b1) plugin boundary - loads the reference's metric scripts unchanged.  Replaces, in
+ *       /root/reference: content_manager.{hpp,cpp} (content folders, config inheritance),
+ *       js_interop.{hpp,cpp} (script sandbox, CShim/CMath/$cfg/$pin), metric.hpp
+ *       (metric_descriptor::load, build_argument_string), metric_manager.hpp:19-170 (program build).
+ *  (b2) device boundary - replaces the OpenCL-by-name calls of the frame loop
+ *       (`cqueue.exec("<kernel>", args, global, local)`, main.cpp:139-205, 2244-2526, 2675-2760)
+ *       and render_state.hpp (device buffers) with one call per frame.
+ *
+ * Conventions: plain C, no exceptions cross the ABI; functions returning int return 0 on
+ * success and a negative GRT_E_* code on failure, pointer-returning functions return NULL on
+ * failure; the message is available from grt_last_error() (thread local).  All calls for one
+ * context come from one thread (the reference has a single issuing thread).
+ * There is NO CPU fallback: device functions fail with GRT_E_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef GRT_H_INCLUDED
+#define GRT_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRT_OK 0
+#define GRT_E_INVALID -1   /* bad argument */
+#define GRT_E_SCRIPT -2    /* script / JSON error (message carries the QuickJS-style text) */
+#define GRT_E_COMPILE -3   /* NVRTC failed; grt_last_error() holds the log */
+#define GRT_E_CUDA -4      /* CUDA runtime error, or no usable GPU */
+#define GRT_E_STATE -5     /* call order (no metric bound, no background, ...) */
+
+typedef struct grt_content grt_content;   /* content_manager */
+typedef struct grt_metric grt_metric;     /* metrics::metric {desc, metric_cfg, sand} */
+typedef struct grt_ctx grt_ctx;           /* one GPU: program + render_state + camera */
+
+const char* grt_last_error(void);
+const char* grt_version(void);
+
+/* ---- (b1) plugin boundary ------------------------------------------------------------- */
+
+/* content_manager::add_content_folder (content_manager.cpp:302-314): a folder with
+ * <m>.js + <m>.json, coordinates/*.js, origins/*.js and optionally sorting.json. */
+grt_content* grt_content_create(void);
+void grt_content_destroy(grt_content*);
+int grt_content_add_folder(grt_content*, const char* folder);
+/* metric friendly names (JSON "name") in UI order (sorting.json first, content_manager.cpp:193-253) */
+int grt_content_metric_count(const grt_content*);
+const char* grt_content_metric_name(const grt_content*, int index);
+
+/* load_metric_from_script (content_manager.cpp:9-53): runs the metric script, its coordinate,
+ * origin and periodicity scripts in one shared sandbox, derives g, dg, coordinate differentials,
+ * the acceleration and the classification flags.  `by_name` looks the script up through the
+ * JSON "name" as `-bench <name>` does (main.cpp:967-986, content_manager.cpp:316-379). */
+grt_metric* grt_metric_load(grt_content*, const char* js_path);
+grt_metric* grt_metric_load_by_name(grt_content*, const char* friendly_name);
+void grt_metric_destroy(grt_metric*);
+
+/* $cfg parameters in first-access order = field order of `struct dynamic_config`
+ * (js_interop.cpp:38-68, 795-815; cl.cl:940-945) */
+int grt_metric_param_count(const grt_metric*);
+const char* grt_metric_param_name(const grt_metric*, int index);
+float grt_metric_param_default(const grt_metric*, int index);
+float grt_metric_param_get(const grt_metric*, int index);
+int grt_metric_param_set(grt_metric*, int index, float value);
+
+typedef struct grt_metric_info {
+    int is_big;                 /* GENERIC_BIG_METRIC: off-diagonal terms (metric.hpp:665-708) */
+    int is_constant_theta;      /* GENERIC_CONSTANT_THETA (metric.hpp:557-622, 740) */
+    int use_prepass;
+    int singular;
+    int traversable_event_horizon;
+    int adaptive_precision;
+    int detect_singularities;
+    int coordinate_system;      /* 0 X_Y_THETA_PHI, 1 CARTESIAN, 2 CYLINDRICAL, 3 OTHER */
+    int has_periodicity;
+    int unconditionally_nonsingular;
+    float max_acceleration_change;
+    float singular_terminator;
+    float w_v[4];               /* step-error weights W_V1..4 (metric.hpp:849-869) */
+    int flops_expr;             /* ops in the emitted g + dg DAG (SURVEY.md 8(d) F_expr) */
+    int flops_accel;            /* ops in the emitted lowered-index acceleration */
+    int flops_accel_reference;  /* ops in the emitted reference-formulation acceleration (GEO_ACCEL0..3) */
+} grt_metric_info;
+int grt_metric_get_info(const grt_metric*, grt_metric_info* out);
+const char* grt_metric_name(const grt_metric*);
+const char* grt_metric_description(const grt_metric*);
+
+/* The generated-code ABI (replaces build_argument_string, metric.hpp:725-959): C source defining
+ * struct grt_params and grt_metric / grt_metric_partials / grt_to_polar / ... / grt_accel.
+ * is_static != 0 substitutes the current parameter values as literals (metric.hpp:494-547).
+ * The string stays valid until the next call for the same metric. */
+const char* grt_metric_source(grt_metric*, int is_static);
+
+/* ---- (b2) device boundary ------------------------------------------------------------- */
+
+/* dynamic_feature_config (main.cpp:1123-1158, dynamic_feature_config.cpp:182-237); the
+ * triangle-renderer features (use_triangle_rendering, ray_skip) are out of scope. */
+typedef struct grt_features {
+    float universe_size;                 /* 20 */
+    float max_acceleration_change;       /* overwritten per metric on grt_set_metric (metric_manager.hpp:50) */
+    float max_precision_radius;          /* 10 */
+    float min_step;                      /* 1e-6 */
+    float adaptive_sampling_threshold;   /* 32 (graphics_settings.hpp:40, main.cpp:1559) */
+    float field_of_view;                 /* 90 */
+    int redshift;                        /* 0 */
+    int reparameterisation;              /* 0 */
+    int use_old_redshift;                /* 0 */
+    int adaptive_sampling;               /* 1 */
+    int max_probes;                      /* anisotropy, 8 (graphics_settings.hpp:34) */
+    int use_prepass;                     /* -1: follow the metric's JSON */
+} grt_features;
+void grt_features_default(grt_features* out);
+
+typedef struct grt_stats {
+    uint64_t trial_steps;       /* Verlet bodies executed incl. rejected retries (SURVEY.md 8(d) unit of work) */
+    uint64_t accepted_steps;
+    uint64_t rays_integrated;   /* rays that entered the integration loop (prepass + first pass + refinement) */
+    uint64_t rays_finished;
+    uint64_t extra_rays;        /* refinement rays spawned by adaptive sampling */
+    float ms_camera, ms_prepass, ms_init, ms_integrate, ms_render_data, ms_adaptive, ms_render, ms_total;
+    int integrate_launches, total_launches;
+} grt_stats;
+
+grt_ctx* grt_create(int device);
+void grt_destroy(grt_ctx*);
+
+/* Builds (NVRTC -> sm_100a cubin, cached on disk by source hash) and binds the program for a
+ * metric (metric_manager::check_recompile, metric_manager.hpp:19-170).  is_static: parameters
+ * folded as literals; otherwise they are kernel arguments and grt_update_params() re-reads them
+ * without a rebuild.  Copies max_acceleration_change from the metric (metric_manager.hpp:50). */
+int grt_set_metric(grt_ctx*, grt_metric*, int is_static);
+int grt_update_params(grt_ctx*);
+/* compile only (no GPU needed): used by build checks to pre-populate the cubin cache */
+int grt_compile_metric(grt_metric*, int is_static, int fast_math, const char** log_out);
+
+int grt_set_features(grt_ctx*, const grt_features*);
+int grt_get_features(const grt_ctx*, grt_features* out);
+
+/* load_mipped_image (graphics_settings.cpp:152-212): RGBA8 pixels -> mip pyramid on the device.
+ * which = 0: the r >= 0 side (mip_background), 1: the r < 0 side (mip_background2);
+ * if side 1 is never set it shares side 0 (graphics_settings.cpp:214-243). */
+int grt_set_background(grt_ctx*, const uint8_t* rgba, int width, int height, int which);
+/* device-resident variant (pixels already in HBM) */
+int grt_set_background_device(grt_ctx*, const void* rgba_device, int width, int height, int which);
+
+/* camera (main.cpp:664-673, 2244-2262): position (t,x,y,z) cartesian, quaternion (x,y,z,w),
+ * flip_r = far side of a wormhole (cart_to_generic_kernel `flip`), observer 3-velocity in the
+ * camera tetrad frame (cartesian_basis_speed). */
+int grt_set_camera(grt_ctx*, const float pos_txyz[4], const float quat_xyzw[4], int flip_r);
+int grt_set_observer_speed(grt_ctx*, const float speed_xyz[3]);
+
+/* camera attached to a geodesic (main.cpp:2675-2760, 2264-2297): snapshot integrates the
+ * observer's timelike geodesic from the current camera and parallel transports the tetrad;
+ * returns the number of recorded points (<= 64000, main.cpp:1230).  set_camera_on_geodesic
+ * places the camera at proper time tau on it (handle_interpolating_geodesic). */
+int grt_snapshot_geodesic(grt_ctx*, float linear_basis_speed, int parallel_transport_observer);
+int grt_set_camera_on_geodesic(grt_ctx*, float proper_time);
+int grt_clear_camera_geodesic(grt_ctx*);
+
+#define GRT_FORMAT_RGBA32F 0
+#define GRT_FORMAT_RGBA8 1
+/* One frame (main.cpp:2244-2526): camera/tetrad -> [prepass] -> init_rays -> integrate ->
+ * render_data -> [adaptive sampling -> integrate -> render_data] -> render.
+ * out: width*height pixels in `format`, row-major; out_is_device selects a device pointer
+ * (no host copy) or a host pointer (one D2H copy inside the call).  stats may be NULL. */
+int grt_render(grt_ctx*, int width, int height, void* out, int format, int out_is_device, grt_stats* stats);
+/* Rows [y0, y1) of a width x height frame (row stripes for multi-GPU tiling);
+ * out receives (y1 - y0) * width pixels.  y0, y1 must be even when adaptive sampling is on. */
+int grt_render_rows(grt_ctx*, int width, int height, int y0, int y1, void* out, int format, int out_is_device, grt_stats* stats);
+
+/* ---- introspection for tests and tools --------------------------------------------------- */
+typedef struct grt_camera_state {
+    float pos_generic[4];
+    float tetrad[16];
+    int timelike_coordinate;
+} grt_camera_state;
+int grt_get_camera_state(grt_ctx*, grt_camera_state* out);   /* runs the camera kernel if needed */
+
+/* ray record as the reference's `struct lightray` (render_state.hpp:8-19), 96 bytes */
+typedef struct grt_lightray {
+    float position[4], velocity[4], initial_quat[4], acceleration[4];
+    float ku_uobsu, running_dlambda_dnew;
+    int terminated, sx, sy;
+    int pad[3];
+} grt_lightray;
+/* per-pixel shading record as `struct render_data` (cl.cl:5066-5074) */
+typedef struct grt_render_data {
+    float tex_coord[2];
+    float z_shift;
+    int sx, sy, terminated, side;
+    int pad;
+} grt_render_data;
+/* state of the last grt_render call: first-pass rays then refinement rays (in buffer order) */
+int grt_debug_ray_count(grt_ctx*, int* first_pass, int* extra);
+int grt_debug_read_rays(grt_ctx*, grt_lightray* out, int max_count);
+int grt_debug_read_render_data(grt_ctx*, grt_render_data* out, int max_count);
+int grt_debug_read_prepass_mask(grt_ctx*, int* out, int max_count, int* pw, int* ph);
+int grt_debug_read_mip_level(grt_ctx*, int which, int level, uint8_t* out, int* lw, int* lh, int* levels);
+int grt_debug_read_geodesic(grt_ctx*, float* positions, float* velocities, float* ds, float* transported, int max_points);
+/* evaluate generated functions on the device at `count` points (parity of g, dg, accel, maps) */
+int grt_debug_eval_metric(grt_ctx*, const float* positions, const float* velocities, int count, float* g16, float* dg64, float* accel4, float* polar4,
+                          float* radii2);
+int grt_debug_tetrad_at(grt_ctx*, const float* positions, int count, const float speed[3], int orient, float* tetrads16, int* timelike);
+
+/* register count / spill info of the bound program's kernels: "name regs local_bytes;..." */
+const char* grt_debug_kernel_info(grt_ctx*);
+/* device time (ms) of each kernel launch of the last frame: "name:ms;..." */
+const char* grt_debug_launch_log(grt_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRT_H_INCLUDED */
