@@ -1,0 +1,1243 @@
+// libgrt.so runtime: the C ABI of include/grt.h.
+//
+// (b1) plugin half: thin wrappers over metric_loader (content folders, script loading, generated
+//      source).  (b2) device half: per-metric program build (NVRTC -> sm_100a cubin, cached on
+//      disk), device buffers (replaces render_state.hpp), camera / geodesic-camera state and the
+//      per-frame kernel sequence of /root/reference/main.cpp:2244-2526 on one CUDA stream.
+// There is no CPU path in this file: every device entry point fails with GRT_E_CUDA when no
+// usable GPU is present.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/grt.h"
+#include "kernels/grt_device_structs.h"
+#include "kernels/grt_static_kernels.h"
+#include "metric_loader.hpp"
+
+extern "C" const char GRT_SRC_STRUCTS[];
+extern "C" const char GRT_SRC_COMMON[];
+extern "C" const char GRT_SRC_METRIC_KERNELS[];
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void ck(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw Error(GRT_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+// The driver API (module load + launch of the NVRTC-built cubins) is reached through
+// cudaGetDriverEntryPoint, so libgrt.so has no link-time dependency on libcuda.so.1 and still loads
+// (and exports every symbol) on a machine without a GPU driver.
+struct Driver {
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    bool loaded = false;
+} g_drv;
+
+void load_driver() {
+    if (g_drv.loaded) return;
+    auto get = [](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) throw Error(GRT_E_CUDA, std::string("CUDA driver entry point not available: ") + name);
+    };
+    get("cuGetErrorString", (void**)&g_drv.GetErrorString);
+    get("cuModuleLoadData", (void**)&g_drv.ModuleLoadData);
+    get("cuModuleUnload", (void**)&g_drv.ModuleUnload);
+    get("cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction);
+    get("cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute);
+    get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.OccupancyMaxActiveBlocksPerMultiprocessor);
+    get("cuLaunchKernel", (void**)&g_drv.LaunchKernel);
+    g_drv.loaded = true;
+}
+
+void cu(CUresult r, const char* what) {
+    if (r != CUDA_SUCCESS) {
+        const char* s = nullptr;
+        if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+        throw Error(GRT_E_CUDA, std::string(what) + ": " + (s ? s : "unknown CUDA driver error"));
+    }
+}
+#define CK(x) ck((x), #x)
+#define CU(x) cu((x), #x)
+
+template <class F>
+int guard(F&& f) {
+    try {
+        return f();
+    } catch (Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return GRT_E_INVALID;
+    }
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+
+std::string library_dir() {
+    Dl_info info;
+    if (dladdr((void*)&library_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        if (k != std::string::npos) return p.substr(0, k);
+    }
+    return ".";
+}
+std::string cache_dir() {
+    const char* e = getenv("GRT_CACHE_DIR");
+    std::string d = e && *e ? e : library_dir() + "/cubin_cache";
+    mkdir(d.c_str(), 0755);
+    return d;
+}
+
+// ---- per-metric program ---------------------------------------------------------------------------
+const char* kPrelude =
+    "#define GRT_FN static __device__ __forceinline__\n"
+    "#define GRT_DIV(a, b) ((a) / (b))\n"
+    "#define GRT_SIN(a) sinf(a)\n"
+    "#define GRT_COS(a) cosf(a)\n"
+    "#define GRT_TAN(a) tanf(a)\n"
+    "#define GRT_LOG(a) logf(a)\n"
+    "#define GRT_SQRT(a) sqrtf(a)\n"
+    "#define GRT_EXP(a) expf(a)\n"
+    "#define GRT_TANH(a) tanhf(a)\n"
+    "#define GRT_POW(a, b) powf(a, b)\n"
+    "#define GRT_SIGN(a) ((a) > 0.0f ? 1.0f : ((a) < 0.0f ? -1.0f : 0.0f))\n"
+    "#define GRT_INF __int_as_float(0x7f800000)\n"
+    "#define GRT_NAN __int_as_float(0x7fffffff)\n";
+
+std::string program_source(const grt::Metric& m, bool is_static) {
+    std::string s = kPrelude;
+    s += GRT_SRC_STRUCTS;
+    s += GRT_SRC_COMMON;
+    s += grt::emit_metric_source(m, is_static);
+    s += GRT_SRC_METRIC_KERNELS;
+    return s;
+}
+
+std::vector<std::string> nvrtc_options(bool fast_math) {
+    std::vector<std::string> o = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-DGRT_NVRTC=1", "-diag-suppress=177,550"};
+    if (fast_math) o.push_back("--use_fast_math");
+    return o;
+}
+
+// NVRTC -> cubin, with an on-disk cache keyed by hash(source + options + NVRTC version)
+// (the reference caches built programs through cl::build_program_with_cache, metric_manager.hpp:106)
+std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit) {
+    std::vector<std::string> opts = nvrtc_options(fast_math);
+    int major = 0, minor = 0;
+    nvrtcVersion(&major, &minor);
+    std::string key = src;
+    for (auto& o : opts) key += "\n" + o;
+    key += "\nnvrtc " + std::to_string(major) + "." + std::to_string(minor);
+    char hex[40];
+    snprintf(hex, sizeof hex, "%016llx%016llx", (unsigned long long)fnv1a(key, 14695981039346656037ull), (unsigned long long)fnv1a(key, 0x9e3779b97f4a7c15ull));
+    std::string path = cache_dir() + "/" + name + "_" + hex + ".cubin";
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (f) {
+            std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            if (!data.empty()) {
+                if (cache_hit) *cache_hit = true;
+                if (log_out) *log_out = "cubin cache hit: " + path;
+                return data;
+            }
+        }
+    }
+    if (cache_hit) *cache_hit = false;
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), (name + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) throw Error(GRT_E_COMPILE, "nvrtcCreateProgram failed");
+    std::vector<const char*> copts;
+    for (auto& o : opts) copts.push_back(o.c_str());
+    nvrtcResult res = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string log(log_size, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, log.data());
+    if (log_out) *log_out = log;
+    if (res != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        throw Error(GRT_E_COMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(res) + "\n" + log);
+    }
+    size_t size = 0;
+    if (nvrtcGetCUBINSize(prog, &size) != NVRTC_SUCCESS || size == 0) {
+        nvrtcDestroyProgram(&prog);
+        throw Error(GRT_E_COMPILE, "NVRTC produced no cubin");
+    }
+    std::vector<char> cubin(size);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        f.write(cubin.data(), (std::streamsize)cubin.size());
+    }
+    rename(tmp.c_str(), path.c_str());
+    return cubin;
+}
+
+struct Program {
+    CUmodule mod = nullptr;
+    CUfunction k_camera, k_tetrad_at, k_eval_metric, k_init_rays, k_prepass_mask, k_integrate, k_render_data, k_adaptive, k_geodesic_snapshot, k_geodesic_transport,
+        k_geodesic_interpolate;
+    int integrate_blocks_per_sm = 1;
+    std::string info;
+    std::string key;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Texture {
+    DevBuf data;
+    GrtTexture desc{};
+    bool set = false;
+};
+
+struct StripeGeom {
+    std::vector<GrtRenderStripe> stripes;
+};
+
+}  // namespace
+
+struct grt_content {
+    grt::ContentManager cm;
+    std::vector<std::string> names;
+};
+
+struct grt_metric {
+    std::unique_ptr<grt::Metric> m;
+    std::string source[2];
+    std::string compile_log;
+};
+
+struct grt_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool fast_math = true;
+    grt_features feat{};
+    grt_metric* metric = nullptr;
+    bool is_static = false;
+    std::map<std::string, std::unique_ptr<Program>> programs;
+    Program* prog = nullptr;
+    float params[64] = {0};
+
+    GrtCamera cam{};
+    bool camera_dirty = true, camera_on_geodesic = false;
+    GrtCamera* d_cam = nullptr;
+
+    Texture tex[2];
+    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, rdata, termination, tables, identity, out, scratch;
+    int identity_len = 0;
+    // counters: [0..3] work counters of the integrate launches, [4] extra ray count; then GrtStats
+    unsigned int* d_counters = nullptr;
+    GrtStats* d_stats = nullptr;
+
+    // geometry cache
+    std::vector<int> geom_key;
+    GrtFrame frame{};
+    std::vector<GrtRenderStripe> stripes;
+    size_t out_pixels = 0;
+
+    // geodesic camera
+    GrtGeodesic geo{};
+    DevBuf geo_pos, geo_vel, geo_ds, geo_tr, geo_misc;
+    int geo_count = 0;
+    float4 geo_speed = make_float4(0, 0, 0, 0);
+    int geo_parallel_transport = 1;
+
+    // last frame
+    int last_first_pass = 0, last_extra = 0, last_pw = 0, last_ph = 0;
+    bool last_prepass = false;
+    std::string launch_log, kernel_info;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+void features_default(grt_features* f) {
+    f->universe_size = 20.0f;
+    f->max_acceleration_change = 0.01f;
+    f->max_precision_radius = 10.0f;
+    f->min_step = 0.000001f;
+    f->adaptive_sampling_threshold = 32.0f;
+    f->field_of_view = 90.0f;
+    f->redshift = 0;
+    f->reparameterisation = 0;
+    f->use_old_redshift = 0;
+    f->adaptive_sampling = 1;
+    f->max_probes = 8;
+    f->use_prepass = -1;
+}
+
+void bind(grt_ctx* c) { CK(cudaSetDevice(c->device)); }
+
+Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
+    const grt::Metric& m = *gm->m;
+    std::string src = program_source(m, is_static);
+    std::string key = std::to_string(fnv1a(src, 14695981039346656037ull)) + (c->fast_math ? "f" : "p");
+    auto it = c->programs.find(key);
+    if (it != c->programs.end()) return it->second.get();
+    std::string stem = m.js_path;
+    size_t k = stem.find_last_of('/');
+    if (k != std::string::npos) stem = stem.substr(k + 1);
+    k = stem.find_last_of('.');
+    if (k != std::string::npos) stem = stem.substr(0, k);
+    std::vector<char> cubin = compile_cubin(src, c->fast_math, stem + (is_static ? "_static" : "_dynamic"), &gm->compile_log, nullptr);
+    auto p = std::make_unique<Program>();
+    p->key = key;
+    CU(g_drv.ModuleLoadData(&p->mod, cubin.data()));
+    struct { const char* name; CUfunction* f; } fns[] = {
+        {"k_camera", &p->k_camera}, {"k_tetrad_at", &p->k_tetrad_at}, {"k_eval_metric", &p->k_eval_metric}, {"k_init_rays", &p->k_init_rays},
+        {"k_prepass_mask", &p->k_prepass_mask}, {"k_integrate", &p->k_integrate}, {"k_render_data", &p->k_render_data}, {"k_adaptive", &p->k_adaptive},
+        {"k_geodesic_snapshot", &p->k_geodesic_snapshot}, {"k_geodesic_transport", &p->k_geodesic_transport}, {"k_geodesic_interpolate", &p->k_geodesic_interpolate}};
+    std::ostringstream info;
+    for (auto& f : fns) {
+        CU(g_drv.ModuleGetFunction(f.f, p->mod, f.name));
+        int regs = 0, local = 0;
+        g_drv.FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, *f.f);
+        g_drv.FuncGetAttribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, *f.f);
+        info << f.name << " " << regs << " " << local << ";";
+    }
+    int blocks = 1;
+    CU(g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&blocks, p->k_integrate, 128, 0));
+    p->integrate_blocks_per_sm = std::max(1, blocks);
+    info << "integrate_blocks_per_sm " << p->integrate_blocks_per_sm << ";";
+    p->info = info.str();
+    Program* raw = p.get();
+    c->programs[key] = std::move(p);
+    return raw;
+}
+
+struct Launcher {
+    grt_ctx* c;
+    int launches = 0, integrate_launches = 0;
+    void go(CUfunction f, unsigned grid, unsigned block, void** args) {
+        if (grid == 0) return;
+        CU(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)c->stream, args, nullptr));
+        launches++;
+    }
+};
+
+void fill_frame_features(grt_ctx* c, GrtFrame& fr) {
+    const grt_features& f = c->feat;
+    fr.universe_size = f.universe_size;
+    fr.max_acceleration_change = f.max_acceleration_change;
+    fr.max_precision_radius = f.max_precision_radius;
+    fr.min_step = f.min_step;
+    fr.adaptive_sampling_threshold = f.adaptive_sampling_threshold;
+    fr.field_of_view = f.field_of_view;
+    fr.redshift = f.redshift;
+    fr.reparameterisation = f.reparameterisation;
+    fr.use_old_redshift = f.use_old_redshift;
+    fr.adaptive_sampling = f.adaptive_sampling;
+    fr.max_probes = f.max_probes;
+    fr.flip_geodesic_direction = 0;
+}
+
+void set_grid(GrtFrame& fr) {
+    fr.grid_w = fr.full_w / fr.cell;
+    fr.grid_h = fr.n_rows / fr.cell;
+    fr.tiles_x = (fr.grid_w + 7) / 8;
+    int tiles_y = (fr.grid_h + 3) / 4;
+    fr.n_slots = fr.tiles_x * tiles_y * 32;
+}
+
+const int* identity_table(grt_ctx* c, int n) {
+    if (n > c->identity_len) {
+        int len = std::max(n, 4096);
+        std::vector<int> h(len);
+        for (int i = 0; i < len; i++) h[i] = i;
+        c->identity.ensure(sizeof(int) * (size_t)len);
+        CK(cudaMemcpyAsync(c->identity.p, h.data(), sizeof(int) * (size_t)len, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->identity_len = len;
+    }
+    return (const int*)c->identity.p;
+}
+
+// Row geometry of the stripes this GPU renders: each stripe [y0, y1) gets the
+// halo its stencils read - with adaptive sampling one 2x2-cell row above (neighbour of the first
+// refine decision) and two below (the Jacobian's row y1 needs cell row y1/2 decided, which reads
+// cell row y1/2 + 1); without it only the Jacobian's one row below.  Overlapping windows merge.
+void build_geometry(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n) {
+    const bool adaptive = c->feat.adaptive_sampling != 0;
+    std::vector<int> key = {w, h, adaptive ? 1 : 0, n};
+    for (int i = 0; i < n; i++) { key.push_back(y0s[i]); key.push_back(y1s[i]); }
+    if (key == c->geom_key) return;
+    if (adaptive && ((w & 1) || (h & 1))) throw Error(GRT_E_INVALID, "adaptive sampling needs even width and height");
+    int prev_end = 0;
+    for (int i = 0; i < n; i++) {
+        if (y0s[i] < prev_end || y1s[i] <= y0s[i] || y1s[i] > h) throw Error(GRT_E_INVALID, "row stripes must be sorted, disjoint, non-empty and inside the frame");
+        if (adaptive && ((y0s[i] & 1) || (y1s[i] & 1))) throw Error(GRT_E_INVALID, "row stripes must start and end on even rows when adaptive sampling is on");
+        prev_end = y1s[i];
+    }
+    std::vector<int> held(h, 0), refine(h, 0);   // per full-frame row
+    for (int i = 0; i < n; i++) {
+        int top = adaptive ? 2 : 0, bot = adaptive ? 4 : 1;
+        if (y1s[i] == h) top = std::max(top, adaptive ? 2 : 1);   // last frame row differences upwards (cl.cl:5509-5520)
+        for (int y = std::max(0, y0s[i] - top); y < std::min(h, y1s[i] + bot); y++) held[y] = 1;
+        // cell rows intersecting [y0, y1] decide refine-or-interpolate
+        for (int y = y0s[i]; y <= std::min(h - 1, y1s[i]); y++) refine[y] = 1;
+    }
+    std::vector<int> row_global, local_of_global(h, -1);
+    for (int y = 0; y < h; y++)
+        if (held[y]) { local_of_global[y] = (int)row_global.size(); row_global.push_back(y); }
+    GrtFrame fr{};
+    fr.full_w = w;
+    fr.full_h = h;
+    fr.n_rows = (int)row_global.size();
+    fr.cell = adaptive ? 2 : 1;
+    set_grid(fr);
+    std::vector<int> cellrow_refine(std::max(1, fr.grid_h), 0);
+    if (adaptive)
+        for (int gy = 0; gy < fr.grid_h; gy++) {
+            int y = row_global[gy * 2];
+            cellrow_refine[gy] = (refine[y] || refine[y + 1]) ? 1 : 0;
+        }
+    // tables: row_global | local_of_global | cellrow_refine
+    std::vector<int> all;
+    all.insert(all.end(), row_global.begin(), row_global.end());
+    all.insert(all.end(), local_of_global.begin(), local_of_global.end());
+    all.insert(all.end(), cellrow_refine.begin(), cellrow_refine.end());
+    c->tables.ensure(all.size() * sizeof(int));
+    CK(cudaMemcpyAsync(c->tables.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    fr.row_global = (const int*)c->tables.p;
+    fr.local_of_global = fr.row_global + row_global.size();
+    fr.cellrow_refine = fr.local_of_global + local_of_global.size();
+    c->frame = fr;
+    c->stripes.clear();
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        GrtRenderStripe st{};
+        st.out_global0 = y0s[i];
+        st.out_rows = y1s[i] - y0s[i];
+        st.out_local0 = local_of_global[y0s[i]];
+        int y = y1s[i];
+        while (y < h && held[y] && local_of_global[y] == st.out_local0 + (y - y0s[i])) y++;   // contiguous run
+        st.win_local_end = st.out_local0 + (y - y0s[i]);
+        st.out_offset_px = off;
+        off += (size_t)st.out_rows * w;
+        c->stripes.push_back(st);
+    }
+    c->out_pixels = off;
+    c->geom_key = key;
+}
+
+void upload_camera(grt_ctx* c, Launcher& L) {
+    if (c->camera_on_geodesic || !c->camera_dirty) return;
+    CK(cudaMemcpyAsync(c->d_cam, &c->cam, sizeof(GrtCamera), cudaMemcpyHostToDevice, c->stream));
+    void* args[] = {&c->d_cam, c->params};
+    L.go(c->prog->k_camera, 1, 32, args);
+    c->camera_dirty = false;
+}
+
+void need_program(grt_ctx* c) {
+    if (!c->prog || !c->metric) throw Error(GRT_E_STATE, "no metric bound: call grt_set_metric first");
+}
+
+GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
+    c->rays_pos.ensure(slots * 16);
+    c->rays_vel.ensure(slots * 16);
+    c->rays_acc.ensure(slots * 16);
+    c->rays_aux.ensure(slots * 16);
+    if (need_quat) c->rays_quat.ensure(slots * 16);
+    GrtRays r;
+    r.pos = (float4*)c->rays_pos.p;
+    r.vel = (float4*)c->rays_vel.p;
+    r.acc = (float4*)c->rays_acc.p;
+    r.quat = (float4*)c->rays_quat.p;
+    r.aux = (int4*)c->rays_aux.p;
+    return r;
+}
+
+cudaEvent_t event_at(grt_ctx* c, size_t i) {
+    while (c->events.size() <= i) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        c->events.push_back(e);
+    }
+    CK(cudaEventRecord(c->events[i], c->stream));
+    return c->events[i];
+}
+
+int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n, void* out, int format, int out_is_device, grt_stats* stats) {
+    bind(c);
+    need_program(c);
+    if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || n <= 0 || !out) throw Error(GRT_E_INVALID, "bad frame size, stripe list or output pointer");
+    if (format != GRT_FORMAT_RGBA32F && format != GRT_FORMAT_RGBA8) throw Error(GRT_E_INVALID, "unknown output format");
+    if (!c->tex[0].set) throw Error(GRT_E_STATE, "no background set: call grt_set_background first");
+    const grt::Metric& m = *c->metric->m;
+    Program* P = c->prog;
+    Launcher L{c};
+    build_geometry(c, w, h, y0s, y1s, n);
+    GrtFrame fr = c->frame;
+    fill_frame_features(c, fr);
+    const bool adaptive = fr.cell == 2;
+    const bool use_prepass = (c->feat.use_prepass < 0 ? m.cfg.use_prepass : c->feat.use_prepass != 0) && (w / 16) > 0 && (h / 16) > 0;
+    const int pw = w / 16, ph = h / 16;
+    fr.prepass_w = pw;
+    fr.prepass_h = ph;
+    fr.use_prepass_mask = use_prepass ? 1 : 0;
+
+    GrtFrame pf = fr;
+    if (use_prepass) {
+        pf.full_w = pw;
+        pf.full_h = ph;
+        pf.n_rows = ph;
+        pf.cell = 1;
+        set_grid(pf);
+        const int* ident = identity_table(c, ph);
+        pf.row_global = ident;
+        pf.local_of_global = ident;
+        pf.cellrow_refine = ident;
+        pf.use_prepass_mask = 0;
+        pf.adaptive_sampling = 0;
+    }
+    const size_t extra_cap = adaptive ? (size_t)3 * fr.grid_w * fr.grid_h : 0;
+    const size_t slots = std::max((size_t)fr.n_slots + extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)0);
+    const bool const_theta = m.constant_theta();
+    GrtRays rays = rays_of(c, slots, const_theta);
+    c->rdata.ensure((size_t)fr.n_rows * w * 16);
+    c->termination.ensure(sizeof(int) * (size_t)std::max(1, pw * ph));
+    int* d_term = (int*)c->termination.p;
+    const size_t px_bytes = format == GRT_FORMAT_RGBA32F ? 16 : 4;
+    void* d_out = out;
+    if (!out_is_device) {
+        c->out.ensure(c->out_pixels * px_bytes);
+        d_out = c->out.p;
+    }
+
+    size_t ev = 0;
+    cudaEvent_t e_start = event_at(c, ev++);
+    CK(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned int) + sizeof(GrtStats), c->stream));
+    upload_camera(c, L);
+    cudaEvent_t e_camera = event_at(c, ev++);
+
+    unsigned int* wc0 = c->d_counters + 0;
+    unsigned int* wc1 = c->d_counters + 1;
+    unsigned int* wc2 = c->d_counters + 2;
+    int* d_extra = (int*)(c->d_counters + 4);
+    const int* null_count = nullptr;
+    float max_accel = c->feat.max_acceleration_change;
+    const unsigned persistent_grid = (unsigned)(c->num_sms * P->integrate_blocks_per_sm);
+    auto integrate = [&](GrtFrame& f, int slot_begin, const int* count_ptr, int count_fixed, unsigned int* wc) {
+        unsigned grid = persistent_grid;
+        if (!count_ptr) grid = std::min(grid, (unsigned)((count_fixed + 127) / 128));
+        void* args[] = {&rays, &f, &slot_begin, &count_ptr, &count_fixed, &wc, &c->d_stats, &max_accel, c->params};
+        L.go(P->k_integrate, grid, 128, args);
+        L.integrate_launches++;
+    };
+
+    if (use_prepass) {
+        int one = 1;
+        void* a0[] = {&rays, &pf, &c->d_cam, &d_term, &one, c->params};
+        L.go(P->k_init_rays, (unsigned)((pf.n_slots + 127) / 128), 128, a0);
+        integrate(pf, 0, nullptr, pf.n_slots, wc0);
+        void* a1[] = {&rays, &pf, &d_term};
+        L.go(P->k_prepass_mask, (unsigned)((pf.n_slots + 127) / 128), 128, a1);
+    }
+    cudaEvent_t e_prepass = event_at(c, ev++);
+    {
+        int zero = 0;
+        void* a0[] = {&rays, &fr, &c->d_cam, &d_term, &zero, c->params};
+        L.go(P->k_init_rays, (unsigned)((fr.n_slots + 127) / 128), 128, a0);
+    }
+    cudaEvent_t e_init = event_at(c, ev++);
+    integrate(fr, 0, nullptr, fr.n_slots, wc1);
+    cudaEvent_t e_int1 = event_at(c, ev++);
+    GrtRenderData* d_rdata = (GrtRenderData*)c->rdata.p;
+    {
+        int begin = 0, fixed = fr.n_slots;
+        void* a[] = {&rays, &fr, &begin, &null_count, &fixed, &d_rdata, c->params};
+        L.go(P->k_render_data, (unsigned)std::min((fr.n_slots + 127) / 128, c->num_sms * 16), 128, a);
+    }
+    cudaEvent_t e_rd1 = event_at(c, ev++);
+    cudaEvent_t e_adapt = e_rd1, e_int2 = e_rd1, e_rd2 = e_rd1;
+    if (adaptive) {
+        void* a[] = {&rays, &fr, &c->d_cam, &d_rdata, &d_extra, c->params};
+        L.go(P->k_adaptive, (unsigned)((fr.n_slots + 127) / 128), 128, a);
+        e_adapt = event_at(c, ev++);
+        const int* cnt = d_extra;
+        integrate(fr, fr.n_slots, cnt, 0, wc2);
+        e_int2 = event_at(c, ev++);
+        int begin = fr.n_slots, fixed = 0;
+        void* a2[] = {&rays, &fr, &begin, &cnt, &fixed, &d_rdata, c->params};
+        L.go(P->k_render_data, (unsigned)(c->num_sms * 16), 128, a2);
+        e_rd2 = event_at(c, ev++);
+    }
+    const GrtTexture* t1 = &c->tex[0].desc;
+    const GrtTexture* t2 = c->tex[1].set ? &c->tex[1].desc : &c->tex[0].desc;
+    for (auto& st : c->stripes) {
+        grt_launch_render(d_rdata, &fr, &st, t1, t2, d_out, format, c->stream);
+        L.launches++;
+    }
+    CK(cudaGetLastError());
+    cudaEvent_t e_render = event_at(c, ev++);
+    if (!out_is_device) CK(cudaMemcpyAsync(out, d_out, c->out_pixels * px_bytes, cudaMemcpyDeviceToHost, c->stream));
+    cudaEvent_t e_end = event_at(c, ev++);
+
+    c->last_first_pass = fr.n_slots;
+    c->last_pw = pw;
+    c->last_ph = ph;
+    c->last_prepass = use_prepass;
+    if (stats || !out_is_device) {
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (stats) {
+        struct { unsigned int counters[8]; GrtStats s; } host;
+        CK(cudaMemcpy(&host, c->d_counters, sizeof host, cudaMemcpyDeviceToHost));
+        memset(stats, 0, sizeof *stats);
+        stats->trial_steps = host.s.trial_steps;
+        stats->accepted_steps = host.s.accepted_steps;
+        stats->rays_integrated = host.s.rays_integrated;
+        stats->rays_finished = host.s.rays_finished;
+        stats->extra_rays = host.counters[4];
+        c->last_extra = (int)host.counters[4];
+        auto ms = [](cudaEvent_t a, cudaEvent_t b) { float t = 0; cudaEventElapsedTime(&t, a, b); return t; };
+        stats->ms_camera = ms(e_start, e_camera);
+        stats->ms_prepass = ms(e_camera, e_prepass);
+        stats->ms_init = ms(e_prepass, e_init);
+        stats->ms_integrate = ms(e_init, e_int1) + (adaptive ? ms(e_adapt, e_int2) : 0.0f);
+        stats->ms_render_data = ms(e_int1, e_rd1) + (adaptive ? ms(e_int2, e_rd2) : 0.0f);
+        stats->ms_adaptive = adaptive ? ms(e_rd1, e_adapt) : 0.0f;
+        stats->ms_render = ms(e_rd2, e_render);
+        stats->ms_total = ms(e_start, e_end);
+        stats->integrate_launches = L.integrate_launches;
+        stats->total_launches = L.launches;
+        char buf[512];
+        snprintf(buf, sizeof buf, "camera:%.4f;prepass:%.4f;init_rays:%.4f;integrate:%.4f;render_data:%.4f;adaptive:%.4f;integrate_extra:%.4f;render_data_extra:%.4f;render:%.4f;copy_out:%.4f;",
+                 stats->ms_camera, stats->ms_prepass, stats->ms_init, ms(e_init, e_int1), ms(e_int1, e_rd1), stats->ms_adaptive, adaptive ? ms(e_adapt, e_int2) : 0.0f,
+                 adaptive ? ms(e_int2, e_rd2) : 0.0f, stats->ms_render, ms(e_render, e_end));
+        c->launch_log = buf;
+    } else {
+        c->last_extra = -1;   // unknown until read back
+    }
+    return GRT_OK;
+}
+
+void build_texture(grt_ctx* c, Texture& t, const void* src, bool src_is_device, int w, int h) {
+    if (w <= 0 || h <= 0 || !src) throw Error(GRT_E_INVALID, "bad background image");
+    int max_mips = (int)floorf(log2f((float)std::min(w, h))) + 1;
+    int levels = std::min(max_mips, GRT_MAX_MIP_LEVELS);
+    GrtTexture d{};
+    d.w = w;
+    d.h = h;
+    d.levels = levels;
+    size_t total = 0;
+    int lw = w, lh = h;
+    for (int l = 0; l < levels; l++) {
+        d.lw[l] = lw;
+        d.lh[l] = lh;
+        d.offset[l] = total;
+        total += (size_t)lw * lh;
+        lw = std::max(1, lw / 2);
+        lh = std::max(1, lh / 2);
+    }
+    // GL chain (box filter, round to nearest) in scratch, then the float-readback requantisation
+    c->scratch.ensure(total * 4);
+    t.data.ensure(total * 4);
+    uchar4* gl = (uchar4*)c->scratch.p;
+    CK(cudaMemcpyAsync(gl, src, (size_t)w * h * 4, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    for (int l = 1; l < levels; l++) grt_launch_mip_downsample(gl + d.offset[l - 1], d.lw[l - 1], d.lh[l - 1], gl + d.offset[l], d.lw[l], d.lh[l], c->stream);
+    grt_launch_mip_requantise(gl, t.data.p, total, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    d.data = (const uchar4*)t.data.p;
+    t.desc = d;
+    t.set = true;
+}
+
+void ensure_geodesic(grt_ctx* c) {
+    if (c->geo.positions) return;
+    const int max_len = 64000;   // main.cpp:1230
+    c->geo_pos.ensure((size_t)max_len * 16);
+    c->geo_vel.ensure((size_t)max_len * 16);
+    c->geo_ds.ensure((size_t)max_len * 4);
+    c->geo_tr.ensure((size_t)max_len * 16 * 4);
+    c->geo_misc.ensure(64);
+    c->geo.positions = (float4*)c->geo_pos.p;
+    c->geo.velocities = (float4*)c->geo_vel.p;
+    c->geo.ds = (float*)c->geo_ds.p;
+    c->geo.transported = (float4*)c->geo_tr.p;
+    c->geo.count = (int*)c->geo_misc.p;
+    c->geo.max_len = max_len;
+    CK(cudaMemsetAsync(c->geo_misc.p, 0, 64, c->stream));
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* grt_last_error(void) { return g_err.c_str(); }
+const char* grt_version(void) { return "geodesic_raytracing_b200 0.1 (sm_100a)"; }
+
+grt_content* grt_content_create(void) { return new grt_content(); }
+void grt_content_destroy(grt_content* c) { delete c; }
+int grt_content_add_folder(grt_content* c, const char* folder) {
+    return guard([&] {
+        if (!c || !folder) throw Error(GRT_E_INVALID, "null argument");
+        c->cm.add_content_folder(folder);
+        c->names = c->cm.metric_names();
+        return GRT_OK;
+    });
+}
+int grt_content_metric_count(const grt_content* c) { return c ? (int)c->names.size() : 0; }
+const char* grt_content_metric_name(const grt_content* c, int i) { return (c && i >= 0 && i < (int)c->names.size()) ? c->names[i].c_str() : nullptr; }
+
+grt_metric* grt_metric_load(grt_content* c, const char* js_path) {
+    grt_metric* out = nullptr;
+    int rc = guard([&] {
+        if (!c || !js_path) throw Error(GRT_E_INVALID, "null argument");
+        try {
+            auto m = grt::load_metric_from_script(c->cm, js_path);
+            out = new grt_metric();
+            out->m = std::move(m);
+        } catch (Error&) {
+            throw;
+        } catch (std::exception& e) {
+            throw Error(GRT_E_SCRIPT, e.what());
+        }
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? out : nullptr;
+}
+grt_metric* grt_metric_load_by_name(grt_content* c, const char* name) {
+    if (!c || !name) { g_err = "null argument"; return nullptr; }
+    std::string path;
+    if (!c->cm.lookup_metric_file(name, path)) { g_err = std::string("no metric named ") + name; return nullptr; }
+    return grt_metric_load(c, path.c_str());
+}
+void grt_metric_destroy(grt_metric* m) { delete m; }
+
+int grt_metric_param_count(const grt_metric* m) { return m ? (int)m->m->params.names.size() : 0; }
+const char* grt_metric_param_name(const grt_metric* m, int i) { return (m && i >= 0 && i < (int)m->m->params.names.size()) ? m->m->params.names[i].c_str() : nullptr; }
+float grt_metric_param_default(const grt_metric* m, int i) { return (m && i >= 0 && i < (int)m->m->params.names.size()) ? m->m->params.default_values[i] : 0.0f; }
+float grt_metric_param_get(const grt_metric* m, int i) { return (m && i >= 0 && i < (int)m->m->params.names.size()) ? m->m->params.current_values[i] : 0.0f; }
+int grt_metric_param_set(grt_metric* m, int i, float v) {
+    if (!m || i < 0 || i >= (int)m->m->params.names.size()) { g_err = "parameter index out of range"; return GRT_E_INVALID; }
+    m->m->params.current_values[i] = v;
+    return GRT_OK;
+}
+int grt_metric_get_info(const grt_metric* gm, grt_metric_info* o) {
+    if (!gm || !o) { g_err = "null argument"; return GRT_E_INVALID; }
+    const grt::Metric& m = *gm->m;
+    memset(o, 0, sizeof *o);
+    o->is_big = m.desc.big;
+    o->is_constant_theta = m.constant_theta();
+    o->use_prepass = m.cfg.use_prepass;
+    o->singular = m.cfg.singular;
+    o->traversable_event_horizon = m.cfg.traversable_event_horizon;
+    o->adaptive_precision = m.cfg.adaptive_precision;
+    o->detect_singularities = m.cfg.detect_singularities;
+    o->coordinate_system = (int)m.cfg.system;
+    o->has_periodicity = m.desc.has_period;
+    o->unconditionally_nonsingular = m.cfg.unconditionally_nonsingular;
+    o->max_acceleration_change = m.cfg.max_acceleration_change;
+    o->singular_terminator = m.cfg.singular_terminator;
+    o->w_v[0] = 1; o->w_v[1] = 1; o->w_v[2] = 1; o->w_v[3] = 1;
+    if (m.cfg.system == grt::CoordinateSystem::X_Y_THETA_PHI) { o->w_v[2] = 8; o->w_v[3] = m.constant_theta() ? 8.0f : 32.0f; }
+    else if (m.cfg.system == grt::CoordinateSystem::CYLINDRICAL) o->w_v[2] = 8;
+    o->flops_expr = (int)m.desc.flops_expr;
+    o->flops_accel = (int)m.desc.flops_accel;
+    o->flops_accel_reference = (int)m.desc.flops_accel_ref;
+    return GRT_OK;
+}
+const char* grt_metric_name(const grt_metric* m) { return m ? m->m->cfg.name.c_str() : nullptr; }
+const char* grt_metric_description(const grt_metric* m) { return m ? m->m->cfg.description.c_str() : nullptr; }
+const char* grt_metric_source(grt_metric* m, int is_static) {
+    if (!m) return nullptr;
+    int rc = guard([&] { m->source[is_static ? 1 : 0] = grt::emit_metric_source(*m->m, is_static != 0); return GRT_OK; });
+    return rc == GRT_OK ? m->source[is_static ? 1 : 0].c_str() : nullptr;
+}
+
+int grt_compile_metric(grt_metric* m, int is_static, int fast_math, const char** log_out) {
+    return guard([&] {
+        if (!m) throw Error(GRT_E_INVALID, "null metric");
+        std::string stem = m->m->js_path;
+        size_t k = stem.find_last_of('/');
+        if (k != std::string::npos) stem = stem.substr(k + 1);
+        k = stem.find_last_of('.');
+        if (k != std::string::npos) stem = stem.substr(0, k);
+        compile_cubin(program_source(*m->m, is_static != 0), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &m->compile_log, nullptr);
+        if (log_out) *log_out = m->compile_log.c_str();
+        return GRT_OK;
+    });
+}
+
+void grt_features_default(grt_features* f) { if (f) features_default(f); }
+
+grt_ctx* grt_create(int device) {
+    grt_ctx* c = nullptr;
+    int rc = guard([&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) throw Error(GRT_E_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+        if (device < 0 || device >= count) throw Error(GRT_E_INVALID, "device index out of range");
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) throw Error(GRT_E_CUDA, std::string("device is not sm_100 (Blackwell B200): ") + prop.name);
+        CK(cudaSetDevice(device));
+        CK(cudaFree(0));
+        load_driver();
+        c = new grt_ctx();
+        c->device = device;
+        c->num_sms = prop.multiProcessorCount;
+        features_default(&c->feat);
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaMalloc((void**)&c->d_cam, sizeof(GrtCamera)));
+        void* counters = nullptr;
+        CK(cudaMalloc(&counters, 8 * sizeof(unsigned int) + sizeof(GrtStats)));
+        c->d_counters = (unsigned int*)counters;
+        c->d_stats = (GrtStats*)(c->d_counters + 8);
+        // default camera (main.cpp:664-673)
+        c->cam.pos_cart = make_float4(0, 0, -4, 0);
+        c->cam.quat = make_float4(-0.70710678f, 0, 0, 0.70710678f);
+        c->cam.basis_speed = make_float4(0, 0, 0, 0);
+        return GRT_OK;
+    });
+    if (rc != GRT_OK) { delete c; return nullptr; }
+    return c;
+}
+
+void grt_destroy(grt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
+    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
+                      &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc})
+        b->release();
+    for (auto e : c->events) cudaEventDestroy(e);
+    cudaFree(c->d_cam);
+    cudaFree(c->d_counters);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int grt_set_fast_math(grt_ctx* c, int enabled) {
+    if (!c) { g_err = "null context"; return GRT_E_INVALID; }
+    c->fast_math = enabled != 0;
+    return GRT_OK;
+}
+
+int grt_update_params(grt_ctx* c) {
+    return guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        need_program(c);
+        const auto& p = c->metric->m->params;
+        if (p.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
+        for (size_t i = 0; i < p.names.size(); i++) c->params[i] = p.current_values[i];
+        if (c->is_static) c->prog = get_program(c, c->metric, true);   // literals changed: rebuild (metric_manager.hpp:153-167)
+        c->kernel_info = c->prog->info;
+        c->camera_dirty = true;
+        return GRT_OK;
+    });
+}
+
+int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
+    return guard([&] {
+        if (!c || !m) throw Error(GRT_E_INVALID, "null argument");
+        bind(c);
+        if (m->m->params.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
+        Program* p = get_program(c, m, is_static != 0);
+        c->metric = m;
+        c->is_static = is_static != 0;
+        c->prog = p;
+        c->kernel_info = p->info;
+        memset(c->params, 0, sizeof c->params);
+        for (size_t i = 0; i < m->m->params.names.size(); i++) c->params[i] = m->m->params.current_values[i];
+        c->feat.max_acceleration_change = m->m->cfg.max_acceleration_change;   // metric_manager.hpp:50
+        c->camera_dirty = true;
+        c->camera_on_geodesic = false;
+        c->geo_count = 0;
+        return GRT_OK;
+    });
+}
+
+int grt_set_features(grt_ctx* c, const grt_features* f) {
+    if (!c || !f) { g_err = "null argument"; return GRT_E_INVALID; }
+    c->feat = *f;
+    return GRT_OK;
+}
+int grt_get_features(const grt_ctx* c, grt_features* f) {
+    if (!c || !f) { g_err = "null argument"; return GRT_E_INVALID; }
+    *f = c->feat;
+    return GRT_OK;
+}
+
+int grt_set_background(grt_ctx* c, const uint8_t* rgba, int w, int h, int which) {
+    return guard([&] {
+        if (!c || which < 0 || which > 1) throw Error(GRT_E_INVALID, "bad argument");
+        bind(c);
+        build_texture(c, c->tex[which], rgba, false, w, h);
+        return GRT_OK;
+    });
+}
+int grt_set_background_device(grt_ctx* c, const void* rgba, int w, int h, int which) {
+    return guard([&] {
+        if (!c || which < 0 || which > 1) throw Error(GRT_E_INVALID, "bad argument");
+        bind(c);
+        build_texture(c, c->tex[which], rgba, true, w, h);
+        return GRT_OK;
+    });
+}
+
+int grt_set_camera(grt_ctx* c, const float pos[4], const float quat[4], int flip_r) {
+    if (!c || !pos || !quat) { g_err = "null argument"; return GRT_E_INVALID; }
+    c->cam.pos_cart = make_float4(pos[0], pos[1], pos[2], pos[3]);
+    c->cam.quat = make_float4(quat[0], quat[1], quat[2], quat[3]);
+    c->cam.flip = flip_r ? 1.0f : 0.0f;
+    c->camera_dirty = true;
+    return GRT_OK;
+}
+int grt_set_observer_speed(grt_ctx* c, const float s[3]) {
+    if (!c || !s) { g_err = "null argument"; return GRT_E_INVALID; }
+    c->cam.basis_speed = make_float4(s[0], s[1], s[2], 0);
+    c->camera_dirty = true;
+    return GRT_OK;
+}
+
+int grt_snapshot_geodesic(grt_ctx* c, float linear_basis_speed, int parallel_transport_observer) {
+    int count = 0;
+    int rc = guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        need_program(c);
+        Launcher L{c};
+        // the camera tetrad at the snapshot point (init_basis_vectors, main.cpp:2314-2331)
+        c->camera_on_geodesic = false;
+        c->camera_dirty = true;
+        upload_camera(c, L);
+        c->geo_parallel_transport = parallel_transport_observer != 0;
+        // observer 3-velocity = speed * camera forward (main.cpp:2253-2262): forward = rotate (0,0,1) by the camera quaternion
+        float4 q = c->cam.quat;
+        float qn = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+        q.x /= qn; q.y /= qn; q.z /= qn; q.w /= qn;
+        float3 fwd = make_float3(2 * (q.x * q.z + q.w * q.y), 2 * (q.y * q.z - q.w * q.x), 1 - 2 * (q.x * q.x + q.y * q.y));
+        float4 speed = make_float4(fwd.x * linear_basis_speed, fwd.y * linear_basis_speed, fwd.z * linear_basis_speed, 0);
+        c->geo_speed = speed;
+        CK(cudaMemcpyAsync((char*)c->d_cam + offsetof(GrtCamera, basis_speed), &c->geo_speed, sizeof speed, cudaMemcpyHostToDevice, c->stream));
+        ensure_geodesic(c);
+        GrtFrame fr{};
+        fill_frame_features(c, fr);
+        float max_accel = c->feat.max_acceleration_change;
+        void* a0[] = {&c->d_cam, &c->geo, &fr, &max_accel, c->params};
+        L.go(c->prog->k_geodesic_snapshot, 1, 32, a0);
+        void* a1[] = {&c->d_cam, &c->geo, c->params};
+        L.go(c->prog->k_geodesic_transport, 1, 32, a1);
+        CK(cudaMemcpyAsync(&count, c->geo.count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->geo_count = count;
+        c->camera_dirty = true;
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? count : rc;
+}
+
+int grt_set_camera_on_geodesic(grt_ctx* c, float proper_time) {
+    return guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        need_program(c);
+        if (c->geo_count <= 0) throw Error(GRT_E_STATE, "no geodesic snapshot: call grt_snapshot_geodesic first");
+        Launcher L{c};
+        // quat / speeds come from the host camera, position + tetrad from the path
+        CK(cudaMemcpyAsync((char*)c->d_cam + offsetof(GrtCamera, quat), &c->cam.quat, sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync((char*)c->d_cam + offsetof(GrtCamera, basis_speed), &c->geo_speed, sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        int pt = c->geo_parallel_transport;
+        float4* vel_out = nullptr;
+        void* a[] = {&c->d_cam, &c->geo, &proper_time, &pt, &vel_out, c->params};
+        L.go(c->prog->k_geodesic_interpolate, 1, 32, a);
+        c->camera_on_geodesic = true;
+        return GRT_OK;
+    });
+}
+int grt_clear_camera_geodesic(grt_ctx* c) {
+    if (!c) { g_err = "null context"; return GRT_E_INVALID; }
+    c->camera_on_geodesic = false;
+    c->camera_dirty = true;
+    return GRT_OK;
+}
+
+int grt_render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n, void* out, int format, int out_is_device, grt_stats* stats) {
+    return guard([&] {
+        if (!c || !y0s || !y1s) throw Error(GRT_E_INVALID, "null argument");
+        return render_stripes(c, w, h, y0s, y1s, n, out, format, out_is_device, stats);
+    });
+}
+int grt_render_rows(grt_ctx* c, int w, int h, int y0, int y1, void* out, int format, int out_is_device, grt_stats* stats) {
+    return grt_render_stripes(c, w, h, &y0, &y1, 1, out, format, out_is_device, stats);
+}
+int grt_render(grt_ctx* c, int w, int h, void* out, int format, int out_is_device, grt_stats* stats) {
+    int y0 = 0, y1 = h;
+    return grt_render_stripes(c, w, h, &y0, &y1, 1, out, format, out_is_device, stats);
+}
+int grt_synchronize(grt_ctx* c) {
+    return guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        CK(cudaStreamSynchronize(c->stream));
+        return GRT_OK;
+    });
+}
+void* grt_stream(grt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- introspection ------------------------------------------------------------------------------------
+int grt_get_camera_state(grt_ctx* c, grt_camera_state* o) {
+    return guard([&] {
+        if (!c || !o) throw Error(GRT_E_INVALID, "null argument");
+        bind(c);
+        need_program(c);
+        Launcher L{c};
+        upload_camera(c, L);
+        GrtCamera h;
+        CK(cudaMemcpyAsync(&h, c->d_cam, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(o->pos_generic, &h.pos_generic, 16);
+        memcpy(o->tetrad, h.e, 64);
+        o->timelike_coordinate = h.timelike_coordinate;
+        return GRT_OK;
+    });
+}
+
+int grt_debug_ray_count(grt_ctx* c, int* first, int* extra) {
+    return guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        if (c->last_extra < 0) {
+            CK(cudaStreamSynchronize(c->stream));
+            unsigned int v = 0;
+            CK(cudaMemcpy(&v, c->d_counters + 4, 4, cudaMemcpyDeviceToHost));
+            c->last_extra = (int)v;
+        }
+        if (first) *first = c->last_first_pass;
+        if (extra) *extra = c->last_extra;
+        return GRT_OK;
+    });
+}
+
+int grt_debug_read_rays(grt_ctx* c, grt_lightray* out, int max_count) {
+    int n = 0;
+    int rc = guard([&] {
+        if (!c || !out) throw Error(GRT_E_INVALID, "null argument");
+        int first = 0, extra = 0;
+        if (grt_debug_ray_count(c, &first, &extra) != GRT_OK) throw Error(GRT_E_CUDA, g_err);
+        n = std::min(max_count, first + extra);
+        if (n <= 0) return GRT_OK;
+        std::vector<float4> pos(n), vel(n), acc(n), quat(n, make_float4(0, 0, 0, 1));
+        std::vector<int4> aux(n);
+        CK(cudaMemcpy(pos.data(), c->rays_pos.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(vel.data(), c->rays_vel.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(acc.data(), c->rays_acc.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(aux.data(), c->rays_aux.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        if (c->metric->m->constant_theta() && c->rays_quat.p) CK(cudaMemcpy(quat.data(), c->rays_quat.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            grt_lightray& r = out[i];
+            memset(&r, 0, sizeof r);
+            memcpy(r.position, &pos[i], 16);
+            memcpy(r.velocity, &vel[i], 16);
+            memcpy(r.acceleration, &acc[i], 16);
+            memcpy(r.initial_quat, &quat[i], 16);
+            memcpy(&r.ku_uobsu, &aux[i].x, 4);
+            memcpy(&r.running_dlambda_dnew, &aux[i].y, 4);
+            r.terminated = aux[i].z;
+            r.sx = aux[i].w & 0xffff;
+            r.sy = (aux[i].w >> 16) & 0xffff;
+        }
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? n : rc;
+}
+
+int grt_debug_read_render_data(grt_ctx* c, grt_render_data* out, int max_count) {
+    int n = 0;
+    int rc = guard([&] {
+        if (!c || !out) throw Error(GRT_E_INVALID, "null argument");
+        bind(c);
+        CK(cudaStreamSynchronize(c->stream));
+        const GrtFrame& fr = c->frame;
+        n = std::min(max_count, fr.n_rows * fr.full_w);
+        if (n <= 0) return GRT_OK;
+        std::vector<float4> rd(n);
+        std::vector<int> row_global(fr.n_rows);
+        CK(cudaMemcpy(rd.data(), c->rdata.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(row_global.data(), fr.row_global, sizeof(int) * fr.n_rows, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            grt_render_data& r = out[i];
+            memset(&r, 0, sizeof r);
+            r.tex_coord[0] = rd[i].x;
+            r.tex_coord[1] = rd[i].y;
+            r.z_shift = rd[i].z;
+            int flags;
+            memcpy(&flags, &rd[i].w, 4);
+            r.terminated = flags & 0xff;
+            r.side = flags >> 8;
+            r.sx = i % fr.full_w;
+            r.sy = row_global[i / fr.full_w];
+        }
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? n : rc;
+}
+
+int grt_debug_read_prepass_mask(grt_ctx* c, int* out, int max_count, int* pw, int* ph) {
+    int n = 0;
+    int rc = guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        CK(cudaStreamSynchronize(c->stream));
+        if (pw) *pw = c->last_pw;
+        if (ph) *ph = c->last_ph;
+        if (!c->last_prepass) return GRT_OK;
+        n = std::min(max_count, c->last_pw * c->last_ph);
+        if (out && n > 0) CK(cudaMemcpy(out, c->termination.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? n : rc;
+}
+
+int grt_debug_read_mip_level(grt_ctx* c, int which, int level, uint8_t* out, int* lw, int* lh, int* levels) {
+    return guard([&] {
+        if (!c || which < 0 || which > 1) throw Error(GRT_E_INVALID, "bad argument");
+        bind(c);
+        Texture& t = c->tex[which].set ? c->tex[which] : c->tex[0];
+        if (!t.set) throw Error(GRT_E_STATE, "no background set");
+        if (levels) *levels = t.desc.levels;
+        if (level < 0 || level >= t.desc.levels) throw Error(GRT_E_INVALID, "mip level out of range");
+        if (lw) *lw = t.desc.lw[level];
+        if (lh) *lh = t.desc.lh[level];
+        if (out) CK(cudaMemcpy(out, (const uchar4*)t.data.p + t.desc.offset[level], (size_t)t.desc.lw[level] * t.desc.lh[level] * 4, cudaMemcpyDeviceToHost));
+        return GRT_OK;
+    });
+}
+
+int grt_debug_read_geodesic(grt_ctx* c, float* positions, float* velocities, float* ds, float* transported, int max_points) {
+    int n = 0;
+    int rc = guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        CK(cudaStreamSynchronize(c->stream));
+        n = std::min(max_points, c->geo_count);
+        if (n <= 0) return GRT_OK;
+        if (positions) CK(cudaMemcpy(positions, c->geo.positions, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        if (velocities) CK(cudaMemcpy(velocities, c->geo.velocities, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        if (ds) CK(cudaMemcpy(ds, c->geo.ds, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (transported)
+            for (int k = 0; k < 4; k++)
+                CK(cudaMemcpy(transported + (size_t)k * max_points * 4, c->geo.transported + (size_t)k * c->geo.max_len, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? n : rc;
+}
+
+int grt_debug_eval_metric(grt_ctx* c, const float* positions, const float* velocities, int count, float* g16, float* dg64, float* accel4, float* polar4, float* radii2) {
+    return guard([&] {
+        if (!c || !positions || !velocities || count <= 0) throw Error(GRT_E_INVALID, "bad argument");
+        bind(c);
+        need_program(c);
+        size_t n = (size_t)count;
+        size_t bytes = n * (16 + 16 + 64 + 256 + 16 + 16 + 8);
+        c->scratch.ensure(bytes);
+        char* base = (char*)c->scratch.p;
+        float4* d_pos = (float4*)base;
+        float4* d_vel = d_pos + n;
+        float* d_g = (float*)(d_vel + n);
+        float* d_dg = d_g + n * 16;
+        float4* d_acc = (float4*)(d_dg + n * 64);
+        float4* d_pol = d_acc + n;
+        float2* d_rad = (float2*)(d_pol + n);
+        CK(cudaMemcpyAsync(d_pos, positions, n * 16, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_vel, velocities, n * 16, cudaMemcpyHostToDevice, c->stream));
+        Launcher L{c};
+        void* a[] = {&d_pos, &d_vel, &count, &d_g, &d_dg, &d_acc, &d_pol, &d_rad, c->params};
+        L.go(c->prog->k_eval_metric, (unsigned)((count + 63) / 64), 64, a);
+        if (g16) CK(cudaMemcpyAsync(g16, d_g, n * 64, cudaMemcpyDeviceToHost, c->stream));
+        if (dg64) CK(cudaMemcpyAsync(dg64, d_dg, n * 256, cudaMemcpyDeviceToHost, c->stream));
+        if (accel4) CK(cudaMemcpyAsync(accel4, d_acc, n * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (polar4) CK(cudaMemcpyAsync(polar4, d_pol, n * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (radii2) CK(cudaMemcpyAsync(radii2, d_rad, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return GRT_OK;
+    });
+}
+
+int grt_debug_tetrad_at(grt_ctx* c, const float* positions, int count, const float speed[3], int orient, float* tetrads16, int* timelike) {
+    return guard([&] {
+        if (!c || !positions || count <= 0 || !tetrads16) throw Error(GRT_E_INVALID, "bad argument");
+        bind(c);
+        need_program(c);
+        size_t n = (size_t)count;
+        c->scratch.ensure(n * (16 + 64 + 4));
+        float4* d_pos = (float4*)c->scratch.p;
+        float4* d_tet = d_pos + n;
+        int* d_tl = (int*)(d_tet + n * 4);
+        CK(cudaMemcpyAsync(d_pos, positions, n * 16, cudaMemcpyHostToDevice, c->stream));
+        float3 sp = make_float3(speed ? speed[0] : 0.f, speed ? speed[1] : 0.f, speed ? speed[2] : 0.f);
+        Launcher L{c};
+        void* a[] = {&d_pos, &count, &sp, &orient, &d_tet, &d_tl, c->params};
+        L.go(c->prog->k_tetrad_at, (unsigned)((count + 63) / 64), 64, a);
+        CK(cudaMemcpyAsync(tetrads16, d_tet, n * 64, cudaMemcpyDeviceToHost, c->stream));
+        if (timelike) CK(cudaMemcpyAsync(timelike, d_tl, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return GRT_OK;
+    });
+}
+
+const char* grt_debug_kernel_info(grt_ctx* c) { return c ? c->kernel_info.c_str() : nullptr; }
+const char* grt_debug_launch_log(grt_ctx* c) { return c ? c->launch_log.c_str() : nullptr; }
+
+}  // extern "C"

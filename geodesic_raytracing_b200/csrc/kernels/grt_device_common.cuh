@@ -4,62 +4,7 @@
 // metric-independent kernels (grt_static_kernels.cu).  No host headers: NVRTC has none.
 #pragma once
 
-// ---- data layout in HBM -----------------------------------------------------------------------
-// Ray state is SoA in float4 planes so every access is one coalesced 128-bit load/store per lane
-// (the reference keeps a 96-byte AoS `struct lightray`, cl.cl:813-824 / render_state.hpp:8-19):
-//   pos[i], vel[i], acc[i]           position, velocity, acceleration
-//   quat[i]                          initial_quat, only allocated/touched for constant-theta metrics
-//   aux[i] = {ku_uobsu, running_dlambda_dnew, terminated, sy<<16|sx}
-// terminated: 0 live or dropped, 1 finished, 2 prepass-culled (as in the reference), 3 padding slot.
-struct GrtRays {
-    float4* pos;
-    float4* vel;
-    float4* acc;
-    float4* quat;
-    int4* aux;
-};
-
-// per-pixel shading record, 16 B (the reference's `struct render_data` is 32 B, cl.cl:5066-5074;
-// sx, sy are implied by the index): {u, v, z_shift, terminated | side << 8}
-typedef float4 GrtRenderData;
-
-// runtime features (dynamic_feature_config, main.cpp:1123-1158) + frame/window geometry
-struct GrtFrame {
-    int full_w, full_h;     // full frame size: pixel directions and border rules use these
-    int y0, y1;             // rows [y0, y1) of the full frame held by the local buffers (stripe + halo)
-    int cell;               // 1: one first-pass ray per pixel, 2: one per 2x2 cell (adaptive sampling)
-    int grid_w, grid_h;     // first-pass grid (cells) covering the window
-    int grid_y0;            // first cell row of the window in full-frame cell coordinates
-    int tiles_x;            // 8x4-cell tiles per grid row
-    int n_slots;            // tiles_x * tiles_y * 32 first-pass ray slots (padding slots are terminated=3)
-    int prepass_w, prepass_h;
-    int use_prepass_mask;   // main pass consults the prepass termination mask
-    int flip_geodesic_direction;
-    int max_probes;
-    int out_y0, out_y1;     // rows actually written to the output image (stripe without halo)
-    float universe_size, max_acceleration_change, max_precision_radius, min_step;
-    float adaptive_sampling_threshold, field_of_view;
-    int redshift, reparameterisation, use_old_redshift, adaptive_sampling;
-};
-
-struct GrtCamera {
-    float4 pos_generic;     // camera position in the metric's native coordinates
-    float4 e[4];            // tetrad, contravariant
-    float4 quat;            // camera orientation (x, y, z, w)
-    float4 basis_speed;     // observer 3-velocity in the tetrad frame
-    float4 pos_cart;        // (t, x, y, z)
-    float flip;
-    int timelike_coordinate;
-    int pad0, pad1;
-};
-
-// statistics accumulated by the integration kernel
-struct GrtStats {
-    unsigned long long trial_steps;     // Verlet bodies executed, rejected retries included
-    unsigned long long accepted_steps;
-    unsigned long long rays_integrated; // rays that entered the loop
-    unsigned long long rays_finished;   // terminated == 1
-};
+#include "grt_device_structs.h"
 
 #define GRT_PI_F 3.14159265358979323846f
 

@@ -357,7 +357,7 @@ extern "C" __global__ void __launch_bounds__(128) k_init_rays(GrtRays rays, GrtF
         return;
     }
     const GrtCamera& cam = *camp;
-    int cx = gx * fr.cell, cy = (gy + fr.grid_y0) * fr.cell;
+    int cx = gx * fr.cell, cy = fr.row_global[gy * fr.cell];
     RayInit r = pixel_ray(cx, cy, fr, cam, cfg, true);
     int terminated = 0;
     if (!is_prepass && fr.use_prepass_mask) {
@@ -623,7 +623,7 @@ extern "C" __global__ void __launch_bounds__(128) k_render_data(GrtRays rays, Gr
         int4 aux = rays.aux[slot];
         if (aux.z == 3) continue;
         int sx = aux.w & 0xffff, sy = aux.w >> 16;
-        int id = (sy - fr.y0) * fr.full_w + sx;
+        int id = fr.local_of_global[sy] * fr.full_w + sx;
         if (aux.z != 1) { rdata[id] = pack_render_data(0, 0, 0, aux.z, 1); continue; }
         float4 rpos = rays.pos[slot], rvel = rays.vel[slot];
 #if GRT_CONSTANT_THETA
@@ -672,14 +672,10 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
         grt_cell_of(slot, fr.tiles_x, gx, gy);
         valid = gx < fr.grid_w && gy < fr.grid_h;
     }
-    // cells whose refinement result is not needed by this window's output rows are skipped
-    const int cell_y = gy + fr.grid_y0;                 // full-frame cell row
+    // halo cell rows only supply first-pass neighbours: no refine-or-interpolate decision for them
+    if (valid) valid = fr.cellrow_refine[gy] != 0;
+    const int cell_y = valid ? fr.row_global[gy * 2] / 2 : 0;   // full-frame cell row
     const int half_w = fr.full_w / 2, half_h = fr.full_h / 2;
-    if (valid) {
-        int row0 = cell_y * 2;
-        // output rows [out_y0, out_y1) plus the row below (render Jacobian, cl.cl:5509-5520)
-        valid = row0 + 1 >= fr.out_y0 && row0 <= fr.out_y1;
-    }
     bool should_sample = true;
     if (valid) {
         if (gx != 0 && gx != half_w - 1 && cell_y != 0 && cell_y != half_h - 1) {
@@ -728,7 +724,7 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
             store_ray(rays, out + i, r, 0, px + ox[i], py + oy[i]);
         }
     } else {
-        const int w = fr.full_w, ly = py - fr.y0;
+        const int w = fr.full_w, ly = gy * 2;
         GrtRenderData c = rdata[ly * w + px], rr = rdata[ly * w + px + 2], dd = rdata[(ly + 2) * w + px], dr = rdata[(ly + 2) * w + px + 2];
         rdata[ly * w + px + 1] = interpolate_rdata(c, rr);
         rdata[(ly + 1) * w + px] = interpolate_rdata(c, dd);
@@ -737,14 +733,6 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
 }
 
 // ---- camera on a geodesic (single-thread latency kernels, main.cpp:2675-2760) -----------------------------
-struct GrtGeodesic {
-    float4* positions;     // max_len
-    float4* velocities;
-    float* ds;
-    float4* transported;   // 4 * max_len: transported tetrad legs
-    int* count;
-    int max_len;
-};
 
 static __device__ float4 transport_rhs(float4 X, float4 gpos, float4 gvel, const grt_params& cfg) {
     // dX^a = -Gamma^a_bs X^b Y^s, in lowered form: -g^{-1}[ 1/2 (d_s g_mb + d_b g_ms - d_m g_bs) X^b Y^s ]

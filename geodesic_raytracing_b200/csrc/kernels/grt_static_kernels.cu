@@ -108,21 +108,23 @@ static __device__ float3 redshift_colour(float3 v, float z, int use_old) {  // c
 
 // One thread per output pixel. The (u,v) records of the 32x8 tile plus a one-pixel apron on the
 // right/bottom are staged through shared memory (each record is read by up to three pixels).
-__global__ void __launch_bounds__(RT_W * RT_H) k_render(const GrtRenderData* __restrict__ rdata, GrtFrame fr, GrtTexture tex1, GrtTexture tex2, void* out, int out_format) {
+__global__ void __launch_bounds__(RT_W * RT_H) k_render(const GrtRenderData* __restrict__ rdata, GrtFrame fr, GrtRenderStripe st, GrtTexture tex1, GrtTexture tex2, void* out, int out_format) {
     __shared__ float4 tile[RT_H + 1][RT_W + 1];
     const int w = fr.full_w, h = fr.full_h;
-    const int bx = blockIdx.x * RT_W, by = fr.out_y0 + blockIdx.y * RT_H;
+    const int bx = blockIdx.x * RT_W, by = blockIdx.y * RT_H;   // by: row inside the stripe
     const int tid = threadIdx.y * RT_W + threadIdx.x;
     for (int i = tid; i < (RT_W + 1) * (RT_H + 1); i += RT_W * RT_H) {
         int tx = i % (RT_W + 1), ty = i / (RT_W + 1);
-        int gx = bx + tx, gy = by + ty;
+        int gx = bx + tx, lrow = st.out_local0 + by + ty;
         float4 v = make_float4(0, 0, 0, 0);
-        if (gx < w && gy < h && gy < fr.y1) v = rdata[(size_t)(gy - fr.y0) * w + gx];
+        if (gx < w && lrow < st.win_local_end) v = rdata[(size_t)lrow * w + gx];
         tile[ty][tx] = v;
     }
     __syncthreads();
-    const int sx = bx + threadIdx.x, sy = by + threadIdx.y;
-    if (sx >= w || sy >= fr.out_y1) return;
+    const int sx = bx + threadIdx.x, srow = by + threadIdx.y;
+    if (sx >= w || srow >= st.out_rows) return;
+    const int sy = st.out_global0 + srow;          // full-frame row
+    const int lrow = st.out_local0 + srow;         // local row in rdata
     const float4 rd = tile[threadIdx.y][threadIdx.x];
     const int flags = __float_as_int(rd.w);
     const int terminated = flags & 0xff, side = flags >> 8;
@@ -134,9 +136,9 @@ __global__ void __launch_bounds__(RT_W * RT_H) k_render(const GrtRenderData* __r
         float2 tr, bl;
         const bool flipx = sx == w - 1, flipy = sy == h - 1;
         if (!flipx) { float4 n = tile[threadIdx.y][threadIdx.x + 1]; tr = make_float2(n.x, n.y); }
-        else { float4 n = rdata[(size_t)(sy - fr.y0) * w + sx - 1]; tr = make_float2(n.x, n.y); }
+        else { float4 n = rdata[(size_t)lrow * w + sx - 1]; tr = make_float2(n.x, n.y); }
         if (!flipy) { float4 n = tile[threadIdx.y + 1][threadIdx.x]; bl = make_float2(n.x, n.y); }
-        else { float4 n = rdata[(size_t)(sy - 1 - fr.y0) * w + sx]; bl = make_float2(n.x, n.y); }
+        else { float4 n = rdata[(size_t)(lrow - 1) * w + sx]; bl = make_float2(n.x, n.y); }
         const float bias_frac = 1.3f;
         float du_dx = circular_diff1(sxf, tr.x) / bias_frac, dv_dx = circular_diff1(syf, tr.y) / bias_frac;
         float du_dy = circular_diff1(sxf, bl.x) / bias_frac, dv_dy = circular_diff1(syf, bl.y) / bias_frac;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(RT_W * RT_H) k_render(const GrtRenderData* __r
         } else rgb = f3(srgb_to_lin1(rgb.x), srgb_to_lin1(rgb.y), srgb_to_lin1(rgb.z));
         result = make_float4(rgb.x, rgb.y, rgb.z, result.w);
     }
-    const size_t o = (size_t)(sy - fr.out_y0) * w + sx;
+    const size_t o = (size_t)st.out_offset_px + (size_t)srow * w + sx;
     if (out_format == GRT_FORMAT_RGBA32F) ((float4*)out)[o] = result;
     else {
         // screenshot path: clamp, lin_to_srgb, clamp, * 255 truncated (main.cpp:2788-2797)
@@ -225,8 +227,8 @@ extern "C" void grt_launch_mip_downsample(const void* src, int sw, int sh, void*
 extern "C" void grt_launch_mip_requantise(const void* src, void* dst, size_t n, cudaStream_t s) {
     k_mip_requantise<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const uchar4*)src, (uchar4*)dst, n);
 }
-extern "C" void grt_launch_render(const void* rdata, const GrtFrame* fr, const GrtTexture* t1, const GrtTexture* t2, void* out, int out_format, cudaStream_t s) {
-    int rows = fr->out_y1 - fr->out_y0;
-    dim3 block(RT_W, RT_H), grid((fr->full_w + RT_W - 1) / RT_W, (rows + RT_H - 1) / RT_H);
-    k_render<<<grid, block, 0, s>>>((const GrtRenderData*)rdata, *fr, *t1, *t2, out, out_format);
+extern "C" void grt_launch_render(const void* rdata, const GrtFrame* fr, const GrtRenderStripe* st, const GrtTexture* t1, const GrtTexture* t2, void* out, int out_format,
+                                  cudaStream_t s) {
+    dim3 block(RT_W, RT_H), grid((fr->full_w + RT_W - 1) / RT_W, (st->out_rows + RT_H - 1) / RT_H);
+    k_render<<<grid, block, 0, s>>>((const GrtRenderData*)rdata, *fr, *st, *t1, *t2, out, out_format);
 }

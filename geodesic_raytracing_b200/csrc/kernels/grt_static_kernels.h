@@ -19,9 +19,11 @@ struct GrtTexture {
 extern "C" {
 #endif
 struct GrtFrame;
+struct GrtRenderStripe;
 void grt_launch_mip_downsample(const void* src, int sw, int sh, void* dst, int dw, int dh, cudaStream_t s);
 void grt_launch_mip_requantise(const void* src, void* dst, size_t n, cudaStream_t s);
-void grt_launch_render(const void* rdata, const struct GrtFrame* fr, const struct GrtTexture* t1, const struct GrtTexture* t2, void* out, int out_format, cudaStream_t s);
+void grt_launch_render(const void* rdata, const struct GrtFrame* fr, const struct GrtRenderStripe* st, const struct GrtTexture* t1, const struct GrtTexture* t2, void* out,
+                       int out_format, cudaStream_t s);
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,7 @@ const char* grt_version(void);
 /* ---- (b1) plugin boundary ------------------------------------------------------------- */
 
 /* content_manager::add_content_folder (content_manager.cpp:302-314): a folder with
- * <m>.js + <m>.json, coordinates/*.js, origins/*.js and optionally sorting.json. */
+ * <m>.js + <m>.json, coordinates/<c>.js, origins/<o>.js and optionally sorting.json. */
 grt_content* grt_content_create(void);
 void grt_content_destroy(grt_content*);
 int grt_content_add_folder(grt_content*, const char* folder);
@@ -137,6 +137,10 @@ int grt_update_params(grt_ctx*);
 /* compile only (no GPU needed): used by build checks to pre-populate the cubin cache */
 int grt_compile_metric(grt_metric*, int is_static, int fast_math, const char** log_out);
 
+/* NVRTC `--use_fast_math` for programs built after this call (default on: the reference builds
+ * with -cl-unsafe-math-optimizations and native_* functions, metric_manager.hpp:70, cl.cl:115-117) */
+int grt_set_fast_math(grt_ctx*, int enabled);
+
 int grt_set_features(grt_ctx*, const grt_features*);
 int grt_get_features(const grt_ctx*, grt_features* out);
 
@@ -171,6 +175,14 @@ int grt_render(grt_ctx*, int width, int height, void* out, int format, int out_i
 /* Rows [y0, y1) of a width x height frame (row stripes for multi-GPU tiling);
  * out receives (y1 - y0) * width pixels.  y0, y1 must be even when adaptive sampling is on. */
 int grt_render_rows(grt_ctx*, int width, int height, int y0, int y1, void* out, int format, int out_is_device, grt_stats* stats);
+/* Several row stripes [y0s[i], y1s[i]) in one pass (sorted, disjoint): the interleaved stripes one
+ * GPU owns when a frame is tiled over several GPUs.  All stripes share one integration launch so
+ * the divergent tail of the slowest rays is paid once.  out receives the stripes back to back. */
+int grt_render_stripes(grt_ctx*, int width, int height, const int* y0s, const int* y1s, int n_stripes, void* out, int format, int out_is_device, grt_stats* stats);
+/* Frames are queued on the context's CUDA stream; with out_is_device and stats == NULL the call
+ * returns without waiting.  grt_synchronize waits; grt_stream returns the cudaStream_t. */
+int grt_synchronize(grt_ctx*);
+void* grt_stream(grt_ctx*);
 
 /* ---- introspection for tests and tools --------------------------------------------------- */
 typedef struct grt_camera_state {

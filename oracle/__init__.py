@@ -1,0 +1,263 @@
+"""CPU ORACLE - TEST INFRASTRUCTURE ONLY (see geodesic_oracle.hpp). PARITY UNPINNED.
+
+Builds and binds the C++ restatement of the reference's OpenCL kernels for one metric. Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD_DIR = os.path.join(_HERE, "_build")
+
+
+class OracleFeatures(C.Structure):
+    _fields_ = [
+        ("universe_size", C.c_float), ("max_acceleration_change", C.c_float), ("max_precision_radius", C.c_float),
+        ("min_step", C.c_float), ("adaptive_sampling_threshold", C.c_float), ("field_of_view", C.c_float),
+        ("redshift", C.c_int), ("reparameterisation", C.c_int), ("use_old_redshift", C.c_int), ("adaptive_sampling", C.c_int),
+    ]
+
+
+class OracleFrameArgs(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("camera_pos", C.c_float * 4), ("camera_quat", C.c_float * 4),
+        ("basis_speed", C.c_float * 3), ("flip", C.c_int), ("use_given_camera", C.c_int), ("camera_generic", C.c_float * 4),
+        ("tetrad", C.c_float * 16), ("features", OracleFeatures), ("params", C.c_float * 32), ("max_probes", C.c_int),
+        ("use_prepass", C.c_int), ("bg1", C.c_void_p), ("bg1_w", C.c_int), ("bg1_h", C.c_int), ("bg2", C.c_void_p),
+        ("bg2_w", C.c_int), ("bg2_h", C.c_int),
+    ]
+
+
+class OracleFrameOut(C.Structure):
+    _fields_ = [
+        ("image", C.c_void_p), ("rays", C.c_void_p), ("rdata", C.c_void_p), ("termination", C.c_void_p),
+        ("trial_steps", C.c_longlong), ("accepted_steps", C.c_longlong), ("rays_traced", C.c_longlong), ("extra_rays", C.c_longlong),
+        ("t_init_s", C.c_double), ("t_integrate_s", C.c_double), ("t_render_data_s", C.c_double), ("t_adaptive_s", C.c_double),
+        ("t_render_s", C.c_double), ("t_total_s", C.c_double), ("camera_generic", C.c_float * 4), ("tetrad", C.c_float * 16),
+    ]
+
+
+ORACLE_LIGHTRAY_DTYPE = np.dtype([
+    ("position", "<f4", 4), ("velocity", "<f4", 4), ("initial_quat", "<f4", 4), ("acceleration", "<f4", 4),
+    ("ku_uobsu", "<f4"), ("running_dlambda_dnew", "<f4"), ("terminated", "<i4"), ("sx", "<i4"), ("sy", "<i4"),
+])
+ORACLE_RENDER_DATA_DTYPE = np.dtype([
+    ("tex_coord", "<f4", 2), ("z_shift", "<f4"), ("sx", "<i4"), ("sy", "<i4"), ("terminated", "<i4"), ("side", "<i4"),
+])
+
+
+def build(metric_source: str, name: str, native: bool = False) -> str:
+    """Compile the oracle against one generated metric header. Returns the .so path (cached by hash)."""
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "geodesic_oracle.hpp")]
+    h = hashlib.sha1(metric_source.encode())
+    for s in srcs:
+        h.update(open(s, "rb").read())
+    if native:
+        # -march=native objects must not travel between different host CPUs
+        try:
+            flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0]
+        except Exception:
+            flags = "unknown"
+        h.update(b"native" + flags.encode())
+    else:
+        h.update(b"generic")
+    tag = h.hexdigest()[:16]
+    so = os.path.join(BUILD_DIR, f"liboracle_{name}_{tag}.so")
+    if os.path.exists(so):
+        return so
+    hdr = os.path.join(BUILD_DIR, f"metric_{name}_{tag}.h")
+    with open(hdr, "w") as f:
+        f.write(metric_source)
+    cmd = ["g++", "-std=c++17", "-O2", "-fopenmp", "-shared", "-fPIC", f'-DGRT_METRIC_HEADER="{hdr}"', srcs[0], "-o", so + ".tmp"]
+    if native:
+        cmd[3:3] = ["-O3", "-march=native"]
+    subprocess.run(cmd, check=True)
+    os.replace(so + ".tmp", so)
+    return so
+
+
+class Oracle:
+    def __init__(self, metric_source: str, name: str, params: Sequence[float] = (), native: bool = False):
+        self.path = build(metric_source, name, native)
+        L = C.CDLL(self.path)
+        self.lib = L
+        info = (C.c_int * 16)()
+        L.oracle_info(info)
+        self.info = dict(zip(["big", "constant_theta", "singular", "adaptive_precision", "singularity_detection", "use_prepass", "num_params", "static_params",
+                              "sizeof_lightray", "sizeof_render_data", "threads"], list(info)))
+        assert self.info["sizeof_lightray"] == ORACLE_LIGHTRAY_DTYPE.itemsize, self.info
+        assert self.info["sizeof_render_data"] == ORACLE_RENDER_DATA_DTYPE.itemsize, self.info
+        self.params = np.zeros(32, np.float32)
+        self.params[:len(params)] = params
+        L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
+        L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                              C.POINTER(C.c_double), C.c_void_p]
+
+    # -- helpers ---------------------------------------------------------------------------------
+    @staticmethod
+    def features(**kw) -> OracleFeatures:
+        f = OracleFeatures(20.0, 0.01, 10.0, 1e-6, 32.0, 90.0, 0, 0, 0, 1)
+        for k, v in kw.items():
+            if not hasattr(f, k):
+                raise AttributeError(k)
+            setattr(f, k, v)
+        return f
+
+    def _args(self, width, height, features, camera_pos, camera_quat, basis_speed=(0, 0, 0), flip=False, max_probes=8, use_prepass=-1, bg1=None, bg2=None,
+              given_camera=None) -> OracleFrameArgs:
+        a = OracleFrameArgs()
+        a.width, a.height = width, height
+        a.camera_pos[:] = list(camera_pos)
+        a.camera_quat[:] = list(camera_quat)
+        a.basis_speed[:] = list(basis_speed)
+        a.flip = int(flip)
+        a.features = features
+        a.params[:] = list(self.params)
+        a.max_probes = max_probes
+        a.use_prepass = use_prepass
+        if given_camera is not None:
+            a.use_given_camera = 1
+            a.camera_generic[:] = list(given_camera[0])
+            a.tetrad[:] = list(np.asarray(given_camera[1], np.float32).reshape(-1))
+        self._keep = []
+        if bg1 is not None:
+            bg1 = np.ascontiguousarray(bg1, np.uint8)
+            self._keep.append(bg1)
+            a.bg1, a.bg1_w, a.bg1_h = bg1.ctypes.data, bg1.shape[1], bg1.shape[0]
+        if bg2 is not None:
+            bg2 = np.ascontiguousarray(bg2, np.uint8)
+            self._keep.append(bg2)
+            a.bg2, a.bg2_w, a.bg2_h = bg2.ctypes.data, bg2.shape[1], bg2.shape[0]
+        return a
+
+    def frame(self, width, height, features, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678), background=None, background2=None,
+              want_rays=False, **kw):
+        a = self._args(width, height, features, camera_pos, camera_quat, bg1=background, bg2=background2, **kw)
+        o = OracleFrameOut()
+        image = np.zeros((height, width, 4), np.float32) if background is not None else None
+        rdata = np.zeros(width * height, ORACLE_RENDER_DATA_DTYPE)
+        rays = np.zeros(width * height, ORACLE_LIGHTRAY_DTYPE) if want_rays else None
+        pw, ph = width // 16, height // 16
+        term = np.zeros(max(1, pw * ph), np.int32)
+        o.image = image.ctypes.data if image is not None else None
+        o.rdata = rdata.ctypes.data
+        o.rays = rays.ctypes.data if rays is not None else None
+        o.termination = term.ctypes.data
+        rc = self.lib.oracle_frame(C.byref(a), C.byref(o))
+        assert rc == 0
+        return {
+            "image": image, "rdata": rdata.reshape(height, width), "rays": rays, "termination": term[:pw * ph].reshape(ph, pw) if pw * ph else None,
+            "trial_steps": o.trial_steps, "accepted_steps": o.accepted_steps, "rays_traced": o.rays_traced, "extra_rays": o.extra_rays,
+            "t_integrate_s": o.t_integrate_s, "t_total_s": o.t_total_s, "t_render_s": o.t_render_s,
+            "camera_generic": np.array(list(o.camera_generic), np.float32), "tetrad": np.array(list(o.tetrad), np.float32).reshape(4, 4),
+        }
+
+    def integrate_sample(self, width, height, features, x0, y0, cw, ch, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678)):
+        a = self._args(width, height, features, camera_pos, camera_quat)
+        trial, acc, sec = C.c_longlong(), C.c_longlong(), C.c_double()
+        term = np.zeros(cw * ch, np.int32)
+        self.lib.oracle_integrate_sample(C.byref(a), x0, y0, cw, ch, C.byref(trial), C.byref(acc), C.byref(sec), term.ctypes.data)
+        return {"trial_steps": trial.value, "accepted_steps": acc.value, "seconds": sec.value, "terminated": term.reshape(ch, cw)}
+
+    def metric_eval(self, pos):
+        g = np.zeros(16, np.float32)
+        dg = np.zeros(64, np.float32)
+        p = np.ascontiguousarray(pos, np.float32)
+        self.lib.oracle_metric_eval(p.ctypes.data_as(C.c_void_p), self.params.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), dg.ctypes.data_as(C.c_void_p))
+        return g, dg
+
+    def accel(self, pos, vel):
+        p, v = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(vel, np.float32)
+        out = [np.zeros(4, np.float32) for _ in range(3)]
+        self.lib.oracle_accel(p.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), self.params.ctypes.data_as(C.c_void_p),
+                              *[o.ctypes.data_as(C.c_void_p) for o in out])
+        return {"ref": out[0], "numeric": out[1], "lowered": out[2]}
+
+    def coords(self, pos, vel):
+        p, v = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(vel, np.float32)
+        outs = [np.zeros(4, np.float32) for _ in range(4)]
+        dist = C.c_float()
+        period = np.zeros(4, np.float32)
+        self.lib.oracle_coords(p.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), self.params.ctypes.data_as(C.c_void_p),
+                               *[o.ctypes.data_as(C.c_void_p) for o in outs], C.byref(dist), period.ctypes.data_as(C.c_void_p))
+        return {"to_polar": outs[0], "to_polar_vel": outs[1], "from_polar": outs[2], "from_polar_vel": outs[3], "distance": dist.value, "period": period}
+
+    def camera(self, cam_pos, flip=False, basis_speed=(0, 0, 0)):
+        p = np.ascontiguousarray(cam_pos, np.float32)
+        s = np.ascontiguousarray(basis_speed, np.float32)
+        gen = np.zeros(4, np.float32)
+        tet = np.zeros(16, np.float32)
+        self.lib.oracle_camera(p.ctypes.data_as(C.c_void_p), int(flip), s.ctypes.data_as(C.c_void_p), self.params.ctypes.data_as(C.c_void_p),
+                               gen.ctypes.data_as(C.c_void_p), tet.ctypes.data_as(C.c_void_p))
+        return gen, tet.reshape(4, 4)
+
+    def tetrad_at(self, generic_pos, basis_speed=(0, 0, 0), orient=False):
+        p = np.ascontiguousarray(generic_pos, np.float32)
+        s = np.ascontiguousarray(basis_speed, np.float32)
+        tet = np.zeros(16, np.float32)
+        self.lib.oracle_tetrad_at(p.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), int(orient), self.params.ctypes.data_as(C.c_void_p),
+                                  tet.ctypes.data_as(C.c_void_p))
+        return tet.reshape(4, 4)
+
+    def mip_level(self, rgba, level):
+        a = np.ascontiguousarray(rgba, np.uint8)
+        lw, lh, levels = C.c_int(), C.c_int(), C.c_int()
+        self.lib.oracle_mip_level(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], level, None, C.byref(lw), C.byref(lh), C.byref(levels))
+        out = np.zeros((lh.value, lw.value, 4), np.uint8)
+        self.lib.oracle_mip_level(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], level, out.ctypes.data_as(C.c_void_p), C.byref(lw), C.byref(lh), C.byref(levels))
+        return out, levels.value
+
+    def trace_path(self, pos, vel, features, max_points=20000):
+        p, v = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(vel, np.float32)
+        P = np.zeros((max_points, 4), np.float32)
+        V = np.zeros((max_points, 4), np.float32)
+        term = C.c_int()
+        self.lib.oracle_trace_path.restype = C.c_int
+        n = self.lib.oracle_trace_path(p.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.byref(features), self.params.ctypes.data_as(C.c_void_p), max_points,
+                                       P.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), C.byref(term))
+        return P[:n], V[:n], term.value
+
+    def geodesic_snapshot(self, camera_generic, tetrad, basis_speed, features, max_len=64000):
+        cg = np.ascontiguousarray(camera_generic, np.float32)
+        te = np.ascontiguousarray(tetrad, np.float32).reshape(-1)
+        sp = np.ascontiguousarray(basis_speed, np.float32)
+        pos = np.zeros((max_len, 4), np.float32)
+        vel = np.zeros((max_len, 4), np.float32)
+        ds = np.zeros(max_len, np.float32)
+        tr = np.zeros((4, max_len, 4), np.float32)
+        boosted = np.zeros(16, np.float32)
+        self.lib.oracle_geodesic_snapshot.restype = C.c_int
+        n = self.lib.oracle_geodesic_snapshot(cg.ctypes.data_as(C.c_void_p), te.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p), C.byref(features),
+                                              self.params.ctypes.data_as(C.c_void_p), max_len, pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p),
+                                              ds.ctypes.data_as(C.c_void_p), tr.ctypes.data_as(C.c_void_p), boosted.ctypes.data_as(C.c_void_p))
+        return pos[:n], vel[:n], ds[:n], tr[:, :n], boosted.reshape(4, 4)
+
+    def geodesic_interpolate(self, pos, vel, ds, tr, target_time, parallel_transport, basis_speed=(0, 0, 0)):
+        n = len(pos)
+        max_len = n
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        ds = np.ascontiguousarray(ds, np.float32)
+        tr = np.ascontiguousarray(tr, np.float32)
+        sp = np.ascontiguousarray(basis_speed, np.float32)
+        cam = np.zeros(4, np.float32)
+        tet = np.zeros(16, np.float32)
+        v = np.zeros(4, np.float32)
+        self.lib.oracle_geodesic_interpolate(pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p), ds.ctypes.data_as(C.c_void_p), tr.ctypes.data_as(C.c_void_p),
+                                             max_len, n, C.c_float(target_time), int(parallel_transport), sp.ctypes.data_as(C.c_void_p),
+                                             self.params.ctypes.data_as(C.c_void_p), cam.ctypes.data_as(C.c_void_p), tet.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p))
+        return cam, tet.reshape(4, 4), v
+
+
+def for_metric(metric, is_static: bool = False, native: bool = False) -> Oracle:
+    """Oracle for a geodesic_raytracing_b200.Metric (same generated functions as the CUDA program)."""
+    stem = os.path.splitext(os.path.basename(metric.name.replace(" ", "_").replace("(", "").replace(")", "")))[0]
+    return Oracle(metric.source(is_static), stem + ("_static" if is_static else ""), metric.params, native)
