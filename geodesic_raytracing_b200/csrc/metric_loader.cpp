@@ -226,17 +226,9 @@ static CVal c_conj(const CVal& a) { return a.cx ? CVal(a.re, -a.im) : a; }
 static Expr c_abs2(const CVal& a) { return a.cx ? a.re * a.re + a.im * a.im : a.re * a.re; }
 static CVal c_sqrt(const CVal& a) {
     if (!a.cx) return CVal(sym::sqrt(a.re));
-    if (a.im.is_const(0.0)) {
-        // real argument carried in a complex: principal root of a possibly negative real
-        if (a.re.is_const()) return a.re.cval() >= 0 ? CVal(sym::sqrt(a.re), Expr(0.0)) : CVal(Expr(0.0), sym::sqrt(-a.re));
-        return CVal(sym::sqrt(sym::max(a.re, Expr(0.0))), sym::sqrt(sym::max(-a.re, Expr(0.0))));
-    }
-    // principal square root: sqrt((|z|+re)/2) + i sign(im) sqrt((|z|-re)/2)
-    Expr mod = sym::sqrt(c_abs2(a));
-    Expr r = sym::sqrt(sym::max((mod + a.re) * Expr(0.5), Expr(0.0)));
-    Expr i = sym::sqrt(sym::max((mod - a.re) * Expr(0.5), Expr(0.0)));
-    Expr sgn = sym::select(sym::lt(a.im, Expr(0.0)), Expr(-1.0), Expr(1.0));
-    return CVal(r, sgn * i);
+    // principal complex square root as one differentiable primitive pair: ds = dz / (2 s) stays finite
+    // on the real axis, where the (|z| +- re)/2 formulas have 0/0 derivatives
+    return CVal(sym::csqrt_re(a.re, a.im), sym::csqrt_im(a.re, a.im));
 }
 static CVal c_pow_int(const CVal& a, int n) {
     if (n == 0) return CVal(Expr(1.0), Expr(0.0));
@@ -738,6 +730,11 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
     defflag("GRT_USE_PREPASS", m.cfg.use_prepass);
     defflag("GRT_STATIC_PARAMS", is_static);
     o << "#define GRT_NUM_PARAMS " << m.params.names.size() << "\n";
+    // principal complex square root (stable on both half planes): re >= 0 -> (t, im / 2t), else (|im| / 2t, +-t)
+    o << "GRT_FN float grt_csqrt_re(float re, float im) { float t = GRT_SQRT(0.5f * (GRT_SQRT(re * re + im * im) + fabsf(re))); "
+         "return re >= 0.0f ? t : (t > 0.0f ? GRT_DIV(fabsf(im), 2.0f * t) : 0.0f); }\n";
+    o << "GRT_FN float grt_csqrt_im(float re, float im) { float t = GRT_SQRT(0.5f * (GRT_SQRT(re * re + im * im) + fabsf(re))); "
+         "return re >= 0.0f ? (t > 0.0f ? GRT_DIV(im, 2.0f * t) : 0.0f) : (im < 0.0f ? -t : t); }\n";
     // struct dynamic_config { float DYNVARS; } (cl.cl:940-945): first-access order
     o << "struct grt_params {\n";
     if (m.params.names.empty()) o << "    float _unused;\n";

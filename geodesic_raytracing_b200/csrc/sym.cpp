@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -224,6 +225,12 @@ int Graph::simplify(Op op, int a, int b, int c, bool& done) {
             if (ca && cb) return constant(fold2(op, cval(a), cval(b)));
             if (a == b) return a;
             break;
+        case Op::CsqrtRe: case Op::CsqrtIm:
+            if (ca && cb) {
+                std::complex<double> r = std::sqrt(std::complex<double>(cval(a), cval(b) == 0.0 ? 0.0 : cval(b)));
+                return constant(op == Op::CsqrtRe ? r.real() : r.imag());
+            }
+            break;
         case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte:
             if (ca && cb) return constant(fold2(op, cval(a), cval(b)));
             break;
@@ -309,6 +316,15 @@ int Graph::diff(int id, int wrt) {
         case Op::Fmod: r = D(n.a); break;
         case Op::Min: r = M(Op::Select, M(Op::Lt, n.a, n.b), D(n.a), D(n.b)); break;
         case Op::Max: r = M(Op::Select, M(Op::Gt, n.a, n.b), D(n.a), D(n.b)); break;
+        case Op::CsqrtRe: case Op::CsqrtIm: {
+            // s = sqrt(z): ds = dz / (2 s) = dz conj(s) / (2 |s|^2)
+            int sr = M(Op::CsqrtRe, n.a, n.b), si = M(Op::CsqrtIm, n.a, n.b);
+            int da = D(n.a), db = D(n.b);
+            int den = M(Op::Mul, C(2.0), M(Op::Add, M(Op::Mul, sr, sr), M(Op::Mul, si, si)));
+            if (n.op == Op::CsqrtRe) r = M(Op::Div, M(Op::Add, M(Op::Mul, da, sr), M(Op::Mul, db, si)), den);
+            else r = M(Op::Div, M(Op::Sub, M(Op::Mul, db, sr), M(Op::Mul, da, si)), den);
+            break;
+        }
         default: throw std::runtime_error("sym: diff bad op");
     }
     diff_memo_[key] = r;
@@ -369,6 +385,7 @@ static const char* fn_name(Op op) {
         case Op::Cosh: return "cosh"; case Op::Tanh: return "tanh"; case Op::Pow: return "pow";
         case Op::Fmod: return "fmod"; case Op::Sign: return "sign"; case Op::Min: return "min";
         case Op::Max: return "max"; case Op::Select: return "select";
+        case Op::CsqrtRe: return "csqrt_re"; case Op::CsqrtIm: return "csqrt_im";
         default: return "?";
     }
 }
@@ -475,6 +492,8 @@ std::string emit_block(const Graph& g, const std::vector<std::pair<std::string, 
             case Op::Sign: rhs = "GRT_SIGN(" + A() + ")"; break;
             case Op::Min: rhs = "fminf(" + A() + ", " + B() + ")"; break;
             case Op::Max: rhs = "fmaxf(" + A() + ", " + B() + ")"; break;
+            case Op::CsqrtRe: rhs = "grt_csqrt_re(" + A() + ", " + B() + ")"; break;
+            case Op::CsqrtIm: rhs = "grt_csqrt_im(" + A() + ", " + B() + ")"; break;
             default: throw std::runtime_error("sym: emit bad op");
         }
         out += opt.indent + "const float " + opt.tmp_prefix + std::to_string(x) + " = " + rhs + ";\n";

@@ -28,7 +28,8 @@ enum class Op : uint8_t {
     Sin, Cos, Tan, Asin, Acos, Atan, Atan2,
     Fabs, Log, Sqrt, Exp, Sinh, Cosh, Tanh, Pow,
     Select, Lt, Lte, Eq, Gt, Gte,
-    Fmod, Sign, Min, Max
+    Fmod, Sign, Min, Max,
+    CsqrtRe, CsqrtIm   // real / imaginary part of the principal complex square root of (a + i b)
 };
 
 struct Node {
@@ -124,6 +125,8 @@ inline Expr fmod(const Expr& a, const Expr& b) { return mk(Op::Fmod, a, b); }
 inline Expr sign(const Expr& a) { return mk(Op::Sign, a); }
 inline Expr min(const Expr& a, const Expr& b) { return mk(Op::Min, a, b); }
 inline Expr max(const Expr& a, const Expr& b) { return mk(Op::Max, a, b); }
+inline Expr csqrt_re(const Expr& re, const Expr& im) { return mk(Op::CsqrtRe, re, im); }
+inline Expr csqrt_im(const Expr& re, const Expr& im) { return mk(Op::CsqrtIm, re, im); }
 inline Expr lt(const Expr& a, const Expr& b) { return mk(Op::Lt, a, b); }
 inline Expr lte(const Expr& a, const Expr& b) { return mk(Op::Lte, a, b); }
 inline Expr eq(const Expr& a, const Expr& b) { return mk(Op::Eq, a, b); }

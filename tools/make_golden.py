@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/reference_metric_vectors.json from the reference's own metric scripts.
+
+Run in a container where /root/reference is mounted. For each listed script the reference file is loaded
+unchanged through the plugin boundary, the CPU oracle is built on the generated functions, and g, dg, the
+reference-formulation acceleration (GEO_ACCEL) and the coordinate maps are evaluated at seeded points.
+The bundled content (geodesic_raytracing_b200/content) is tested against these vectors on machines that do
+not have the reference (tests/test_reference_scripts.py)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import geodesic_raytracing_b200 as grt  # noqa: E402
+import oracle  # noqa: E402
+
+REFERENCE = "/root/reference/scripts"
+NAMES = ["minkowski", "schwarzschild_fast", "kerr_schild", "alcubierre", "double_unequal_kerr", "kerr_boyer", "schwarzschild_ingoing_ef_hawking", "configurable_wormhole",
+         "krasnikov_tube", "misner_4d"]
+
+
+def points(name, n=4):
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+    pos = rng.uniform(0.6, 2.5, (n, 4))
+    vel = rng.uniform(-1, 1, (n, 4))
+    vel[:, 0] = -1
+    return pos.astype(np.float32), vel.astype(np.float32)
+
+
+def main():
+    content = grt.Content(REFERENCE)
+    out = {}
+    for name in NAMES:
+        m = content.load_by_name(name)
+        o = oracle.for_metric(m)
+        pos, vel = points(name)
+        rec = {"params": m.param_names, "defaults": m.param_defaults, "info": {k: getattr(m.info, k) for k in
+               ["is_big", "is_constant_theta", "use_prepass", "singular", "adaptive_precision", "detect_singularities", "coordinate_system", "has_periodicity"]},
+               "w_v": list(m.info.w_v), "points": []}
+        for p, v in zip(pos, vel):
+            if m.info.is_constant_theta:
+                p = p.copy(); v = v.copy()
+                p[2] = np.float32(np.pi / 2)
+                v[2] = 0
+            g, dg = o.metric_eval(p)
+            a = o.accel(p, v)
+            c = o.coords(p, v)
+            rec["points"].append({"pos": p.tolist(), "vel": v.tolist(), "g": g.tolist(), "dg": dg.tolist(), "accel_ref": a["ref"].tolist(),
+                                  "to_polar": c["to_polar"].tolist(), "from_polar": c["from_polar"].tolist(), "distance": c["distance"], "period": c["period"].tolist()})
+        out[name] = rec
+        print(name, "ok")
+    path = os.path.join(ROOT, "tests", "golden", "reference_metric_vectors.json")
+    json.dump(out, open(path, "w"), indent=1)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()
