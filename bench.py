@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""Headline benchmark: kerr_schild at 3840x2160 (BASELINE.json configs[2]) through the C ABI.
+
+A "step" is one frame of the hot path: camera/tetrad -> prepass -> init_rays -> integrate -> render_data ->
+adaptive sampling -> integrate -> render_data -> render, in the reference's default operating mode (prepass as the
+metric's JSON asks, adaptive sampling on at threshold 32 - main.cpp:1123-1158, graphics_settings.hpp:39-40).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* value   Mray-steps/s: trial Verlet steps of the frame (SURVEY.md 8(d) unit of work) / device frame time, output and
+          all inputs resident in HBM, CUDA events on the launching stream, L2 flushed between frames.
+* e2e     the same metric with the frame delivered into pinned HOST memory through grt_render_stripes
+          (camera upload H2D, RGBA8 frame D2H, and for N > 1 the NCCL gather to rank 0, all inside the timed region).
+* N > 1   the frame is tiled in interleaved 54-row stripes over N ranks (one process per GPU, torchrun), every rank
+          traces its stripes (+ halo, + the redundant 1/16 prepass) and the finished tiles are gathered on rank 0 over
+          NCCL/NVLink; strong scaling: the work of ONE frame is fixed, value = its single-GPU step count / max-over-ranks time.
+* --impl reference   the CPU oracle (a restatement of the reference's OpenCL kernels; the reference itself cannot be
+          built or run here - DESIGN.md) on all host cores, on a bounded pixel subsample of the same frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import geodesic_raytracing_b200 as grt  # noqa: E402
+
+WIDTH, HEIGHT = 3840, 2160
+METRIC_NAME = "kerr_schild"
+STRIPE_ROWS = 54
+BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"{METRIC_NAME}.js {WIDTH}x{HEIGHT}, camera (0,0,-4,0) quat (-sin(pi/4),0,0,cos(pi/4)), fov 90, universe 20, a=-0.5 rs=1",
+        "mode": "reference defaults: prepass on (kerr_schild.json), adaptive sampling on (threshold 32), redshift off, anisotropy 8",
+        "background": "synthetic 4096x2048 RGBA8 (the reference's nasa.png is not redistributable)",
+        "out_format": "rgba8 (sRGB, the reference's screenshot encoding)",
+        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, interleaved {STRIPE_ROWS}-row stripes + halo, redundant prepass, NCCL gather to rank 0",
+        "l2": "256 MiB write between timed frames, outside the per-frame event pairs",
+        "fast_math": True,
+    }
+
+
+def gather_frame(local, height, width, rank, world, stripe_rows, device):
+    """Gather every rank's stripes on rank 0 and reassemble the frame (rows, width, C). Returns the frame on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    rows = [sum(b - a for a, b in grt.interleaved_stripes(height, r, world, stripe_rows)) for r in range(world)]
+    max_rows = max(rows)
+    if local.shape[0] < max_rows:
+        pad = torch.zeros((max_rows - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=device)
+        local = torch.cat([local, pad], 0)
+    bucket = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, bucket, dst=0)
+    if rank != 0:
+        return None
+    frame = torch.empty((height, width) + tuple(local.shape[2:]), dtype=local.dtype, device=device)
+    for r in range(world):
+        row = 0
+        for (y0, y1) in grt.interleaved_stripes(height, r, world, stripe_rows):
+            frame[y0:y1] = bucket[r][row:row + (y1 - y0)]
+            row += y1 - y0
+    return frame
+
+
+class ClockSampler:
+    """nvidia-smi clocks + event reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                out["sm_max_mhz"] = float(p[2])
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_baseline_sample(stride, threads_note=True):
+    """The CPU oracle on a bounded subsample of the frame's rays: every `stride`-th pixel in x and y of the 4K pixel grid,
+    integration stage only (the stage that is > 90 % of a frame), all host cores (OpenMP, dynamic schedule)."""
+    import oracle
+
+    content = grt.Content(grt.CONTENT_DIR)
+    metric = content.load_by_name(METRIC_NAME)
+    orc = oracle.for_metric(metric, native=True)
+    feat = orc.features(max_acceleration_change=metric.info.max_acceleration_change)
+    cw, ch = WIDTH // stride, HEIGHT // stride
+    return orc, feat, cw, ch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    stride = 4 if total <= 4 else (8 if total <= 30 else 16)
+    orc, feat, cw, ch = cpu_baseline_sample(stride)
+    times, steps = [], 0
+    for i in range(total):
+        r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
+        if i >= args.warmup:
+            times.append(r["seconds"])
+            steps += r["trial_steps"]
+    t = sum(times)
+    value = steps / t / 1e6
+    sample = f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw}x{ch} = {cw * ch} rays, {steps // max(1, args.steps)} ray-steps per step), integration stage, no prepass cull"
+    line = {
+        "impl": "reference", "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle = C++ restatement of the reference's OpenCL kernels (the reference host and cl.cl cannot be built or run in this image: DESIGN.md)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world != 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    content = grt.Content(grt.CONTENT_DIR)
+    metric = content.load_by_name(METRIC_NAME)
+    ctx = grt.Context(local_rank)           # raises when libgrt.so or a B200 is missing: no fallback
+    ctx.set_fast_math(True)
+    ctx.set_metric(metric)
+    bg = grt.synthetic_background(4096, 2048)
+    bg_dev = torch.from_numpy(bg).to(device)
+    torch.cuda.synchronize()
+    ctx.set_background(bg_dev, 0, 4096, 2048)
+    cam_pos, cam_quat = (0.0, 0.0, -4.0, 0.0), (-0.70710678, 0.0, 0.0, 0.70710678)
+    ctx.set_camera(cam_pos, cam_quat)
+    stripes = grt.interleaved_stripes(HEIGHT, rank, world, STRIPE_ROWS)
+    rows = sum(b - a for a, b in stripes)
+    fmt = grt.GRT_FORMAT_RGBA8
+    local = torch.empty((rows, WIDTH, 4), dtype=torch.uint8, device=device)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    # canonical work count of the frame (single-GPU trace of the whole frame), untimed
+    if rank == 0:
+        full = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, device=device)
+        _, st_full = ctx.render(WIDTH, HEIGHT, fmt, out=full)
+        frame_steps = int(st_full.trial_steps)
+        del full
+    else:
+        frame_steps = 0
+
+    def one_frame(collect=False):
+        """Device-resident frame. Returns (ms on this rank's stream incl. gather, Stats or None)."""
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _, st = ctx.render(WIDTH, HEIGHT, fmt, out=local, stats=collect, stripes=stripes)
+            if world > 1:
+                gather_frame(local, HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+            e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        one_frame()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms, last_stats, launches = [], None, 0
+    for _ in range(args.steps):
+        t, st = one_frame(collect=True)
+        ms.append(t)
+        last_stats = st
+        launches += st.total_launches
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+    steps_all = torch.tensor([float(last_stats.trial_steps)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps_all, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+
+    # end to end: pinned host frame on rank 0, host clock, copies inside
+    host_out = torch.empty((HEIGHT if world == 1 else rows, WIDTH, 4), dtype=torch.uint8).pin_memory()
+    host_frame = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
+
+    def one_frame_e2e():
+        ctx.set_camera(cam_pos, cam_quat)                      # per-frame camera upload (48 B H2D), as main.cpp:2244-2262
+        if world == 1:
+            ctx.render(WIDTH, HEIGHT, fmt, out=host_out.numpy(), stats=False)     # D2H inside the call, synchronous
+        else:
+            with torch.cuda.stream(stream):
+                ctx.render(WIDTH, HEIGHT, fmt, out=local, stats=False, stripes=stripes)
+                frame = gather_frame(local, HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+                if rank == 0:
+                    host_frame.copy_(frame, non_blocking=True)
+            stream.synchronize()
+
+    one_frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_frame_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        value = frame_steps * args.steps / (total_ms * 1e-3) / 1e6
+        st = last_stats
+        rays_per_launch = (int(st.rays_integrated)) / max(1, st.integrate_launches)
+        integrate_ms = st.ms_integrate + st.ms_prepass          # prepass time is its integrate launch to within microseconds
+        algo_bytes = int(st.rays_integrated) * BYTES_PER_RAY
+        achieved_gbs = algo_bytes / (integrate_ms * 1e-3) / 1e9
+        info = metric.info
+        flops_ref_step = info.flops_expr + 2090          # reference-formulation count, 16-component metric
+        flops_own_step = info.flops_accel + 110          # emitted lowered acceleration + Verlet update + step control + radii
+        gsteps = int(st.trial_steps) / (integrate_ms * 1e-3)
+        line = {
+            "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
+                      "rank0_stage_ms": ctx.launch_log(), "sum_ranks_ray_steps": float(steps_all.item())},
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
+                         "peak_kind": peak_kind, "kernel": "k_integrate (all integrate launches of one frame on rank 0)",
+                         "algorithmic_bytes": algo_bytes, "launch_ms": integrate_ms / max(1, st.integrate_launches), "rays_per_launch": rays_per_launch,
+                         "note": "register-resident loop: 96 B per ray and 0 B per ray-step, so the HBM fraction is tiny by construction; the kernel is FP32-issue bound - see fp32"},
+            "fp32": {"gsteps_per_s_in_kernel": gsteps / 1e9, "flops_per_step_emitted": flops_own_step, "flops_per_step_reference_formulation": flops_ref_step,
+                     "achieved_tflops_emitted": gsteps * flops_own_step / 1e12, "achieved_tflops_reference_formulation": gsteps * flops_ref_step / 1e12,
+                     "peak_tflops_derived": FP32_PEAK_TFLOPS, "frac_emitted": gsteps * flops_own_step / 1e12 / FP32_PEAK_TFLOPS},
+            "e2e": {"value": frame_steps * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s", "fps": args.steps / e2e_s, "h2d_bytes_per_step": 48,
+                    "d2h_bytes_per_step": HEIGHT * WIDTH * 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "kernel_info": {k: v for k, v in ctx.kernel_info().items() if k in ("k_integrate", "integrate_blocks_per_sm")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            stride = 8
+            orc, feat, cw, ch = cpu_baseline_sample(stride)
+            r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
+            line["cpu_baseline"] = {
+                "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": "port",
+                "sample": f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw * ch} rays, {r['trial_steps']} ray-steps, {r['seconds']:.1f} s), integration stage, no prepass cull"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

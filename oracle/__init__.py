@@ -98,7 +98,7 @@ class Oracle:
         self.params = np.zeros(32, np.float32)
         self.params[:len(params)] = params
         L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
-        L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+        L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double), C.c_void_p]
 
     # -- helpers ---------------------------------------------------------------------------------
@@ -160,11 +160,11 @@ class Oracle:
             "camera_generic": np.array(list(o.camera_generic), np.float32), "tetrad": np.array(list(o.tetrad), np.float32).reshape(4, 4),
         }
 
-    def integrate_sample(self, width, height, features, x0, y0, cw, ch, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678)):
+    def integrate_sample(self, width, height, features, x0, y0, cw, ch, stride=1, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678)):
         a = self._args(width, height, features, camera_pos, camera_quat)
         trial, acc, sec = C.c_longlong(), C.c_longlong(), C.c_double()
         term = np.zeros(cw * ch, np.int32)
-        self.lib.oracle_integrate_sample(C.byref(a), x0, y0, cw, ch, C.byref(trial), C.byref(acc), C.byref(sec), term.ctypes.data)
+        self.lib.oracle_integrate_sample(C.byref(a), x0, y0, cw, ch, stride, C.byref(trial), C.byref(acc), C.byref(sec), term.ctypes.data)
         return {"trial_steps": trial.value, "accepted_steps": acc.value, "seconds": sec.value, "terminated": term.reshape(ch, cw)}
 
     def metric_eval(self, pos):

@@ -242,9 +242,9 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
     return 0;
 }
 
-// Bounded CPU-baseline sample: trace the rays of a window [x0,x0+cw) x [y0,y0+ch) of the full
+// Bounded CPU-baseline sample: trace cw x ch rays at pixels (x0 + i*stride, y0 + j*stride) of the full
 // width x height pixel grid (same pixel directions as the full frame), integration stage only.
-int oracle_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int ch, long long* trial_steps, long long* accepted_steps, double* seconds,
+int oracle_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int ch, int stride, long long* trial_steps, long long* accepted_steps, double* seconds,
                             int* terminated_out /* cw*ch or null */) {
     Features dfg = to_features(a->features);
     grt_params cfg = to_params(a->params);
@@ -255,7 +255,7 @@ int oracle_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, in
     std::vector<lightray> rays((size_t)cw * ch);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int i = 0; i < cw * ch; i++) {
-        int cx = x0 + i % cw, cy = y0 + i / cw;
+        int cx = x0 + (i % cw) * stride, cy = y0 + (i / cw) * stride;
         rays[i] = make_pixel_ray(cx, cy, a->width, a->height, camera_generic, camera_quat, e, 0, cfg, dfg, true);
     }
     Counters cnt;
