@@ -37,6 +37,7 @@ extern "C" const char GRT_SRC_METRIC_KERNELS[];
 namespace {
 
 thread_local std::string g_err;
+constexpr int kCounterWords = 8 + 3 * 64;
 
 struct Error : std::runtime_error {
     int code;
@@ -275,10 +276,14 @@ struct grt_ctx {
     GrtCamera* d_cam = nullptr;
 
     Texture tex[2];
-    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, rdata, termination, tables, identity, out, scratch;
+    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, rays_cont, queue[2], rdata, termination, tables, identity, out, scratch;
     int identity_len = 0;
-    // counters: [0..3] work counters of the integrate launches, [4] extra ray count; then GrtStats
+    // counters (zeroed every frame): [4] extra ray count; [8 + phase * 64 + pass] work counter and
+    // [8 + phase * 64 + 32 + pass] parked-ray count of integration pass `pass` of phase 0 (prepass),
+    // 1 (first pass), 2 (refinement); then GrtStats
     unsigned int* d_counters = nullptr;
+    int passes = 12;          // compaction passes per integration phase (GRT_PASSES)
+    int park_threshold = 20;  // a warp parks its rays when this many lanes or fewer are live (GRT_PARK_THRESHOLD)
     GrtStats* d_stats = nullptr;
 
     // geometry cache
@@ -490,6 +495,9 @@ GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
     c->rays_vel.ensure(slots * 16);
     c->rays_acc.ensure(slots * 16);
     c->rays_aux.ensure(slots * 16);
+    c->rays_cont.ensure(slots * 16);
+    c->queue[0].ensure(slots * 4);
+    c->queue[1].ensure(slots * 4);
     if (need_quat) c->rays_quat.ensure(slots * 16);
     GrtRays r;
     r.pos = (float4*)c->rays_pos.p;
@@ -497,6 +505,7 @@ GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
     r.acc = (float4*)c->rays_acc.p;
     r.quat = (float4*)c->rays_quat.p;
     r.aux = (int4*)c->rays_aux.p;
+    r.cont = (float4*)c->rays_cont.p;
     return r;
 }
 
@@ -559,30 +568,41 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
 
     size_t ev = 0;
     cudaEvent_t e_start = event_at(c, ev++);
-    CK(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned int) + sizeof(GrtStats), c->stream));
+    CK(cudaMemsetAsync(c->d_counters, 0, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats), c->stream));
     upload_camera(c, L);
     cudaEvent_t e_camera = event_at(c, ev++);
 
-    unsigned int* wc0 = c->d_counters + 0;
-    unsigned int* wc1 = c->d_counters + 1;
-    unsigned int* wc2 = c->d_counters + 2;
     int* d_extra = (int*)(c->d_counters + 4);
     const int* null_count = nullptr;
     float max_accel = c->feat.max_acceleration_change;
     const unsigned persistent_grid = (unsigned)(c->num_sms * P->integrate_blocks_per_sm);
-    auto integrate = [&](GrtFrame& f, int slot_begin, const int* count_ptr, int count_fixed, unsigned int* wc) {
-        unsigned grid = persistent_grid;
-        if (!count_ptr) grid = std::min(grid, (unsigned)((count_fixed + 127) / 128));
-        void* args[] = {&rays, &f, &slot_begin, &count_ptr, &count_fixed, &wc, &c->d_stats, &max_accel, c->params};
-        L.go(P->k_integrate, grid, 128, args);
-        L.integrate_launches++;
+    // One integration phase = `passes` launches of k_integrate: pass 0 takes the fresh rays, every
+    // later pass the rays the previous one parked (re-packed 32 to a warp); the last never parks.
+    auto integrate = [&](GrtFrame& f, int slot_begin, const int* count_ptr, int count_fixed, int phase) {
+        const int passes = std::max(1, std::min(c->passes, 32));
+        unsigned int* base = c->d_counters + 8 + phase * 64;
+        for (int k = 0; k < passes; k++) {
+            unsigned grid = persistent_grid;
+            if (k == 0 && !count_ptr) grid = std::min(grid, (unsigned)((count_fixed + 127) / 128));
+            const int* fresh_ptr = k == 0 ? count_ptr : nullptr;
+            int fresh_fixed = k == 0 ? count_fixed : 0;
+            const int* in_queue = k == 0 ? nullptr : (const int*)c->queue[k & 1].p;
+            const unsigned int* in_count = k == 0 ? nullptr : base + 32 + (k - 1);
+            int* out_queue = k == passes - 1 ? nullptr : (int*)c->queue[(k + 1) & 1].p;
+            unsigned int* out_count = base + 32 + k;
+            unsigned int* wc = base + k;
+            int threshold = c->park_threshold;
+            void* args[] = {&rays, &f, &slot_begin, &fresh_ptr, &fresh_fixed, &in_queue, &in_count, &out_queue, &out_count, &threshold, &wc, &c->d_stats, &max_accel, c->params};
+            L.go(P->k_integrate, grid, 128, args);
+            L.integrate_launches++;
+        }
     };
 
     if (use_prepass) {
         int one = 1;
         void* a0[] = {&rays, &pf, &c->d_cam, &d_term, &one, c->params};
         L.go(P->k_init_rays, (unsigned)((pf.n_slots + 127) / 128), 128, a0);
-        integrate(pf, 0, nullptr, pf.n_slots, wc0);
+        integrate(pf, 0, nullptr, pf.n_slots, 0);
         void* a1[] = {&rays, &pf, &d_term};
         L.go(P->k_prepass_mask, (unsigned)((pf.n_slots + 127) / 128), 128, a1);
     }
@@ -593,7 +613,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         L.go(P->k_init_rays, (unsigned)((fr.n_slots + 127) / 128), 128, a0);
     }
     cudaEvent_t e_init = event_at(c, ev++);
-    integrate(fr, 0, nullptr, fr.n_slots, wc1);
+    integrate(fr, 0, nullptr, fr.n_slots, 1);
     cudaEvent_t e_int1 = event_at(c, ev++);
     GrtRenderData* d_rdata = (GrtRenderData*)c->rdata.p;
     {
@@ -608,7 +628,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         L.go(P->k_adaptive, (unsigned)((fr.n_slots + 127) / 128), 128, a);
         e_adapt = event_at(c, ev++);
         const int* cnt = d_extra;
-        integrate(fr, fr.n_slots, cnt, 0, wc2);
+        integrate(fr, fr.n_slots, cnt, 0, 2);
         e_int2 = event_at(c, ev++);
         int begin = fr.n_slots, fixed = 0;
         void* a2[] = {&rays, &fr, &begin, &cnt, &fixed, &d_rdata, c->params};
@@ -634,7 +654,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         CK(cudaStreamSynchronize(c->stream));
     }
     if (stats) {
-        struct { unsigned int counters[8]; GrtStats s; } host;
+        struct { unsigned int counters[kCounterWords]; GrtStats s; } host;
         CK(cudaMemcpy(&host, c->d_counters, sizeof host, cudaMemcpyDeviceToHost));
         memset(stats, 0, sizeof *stats);
         stats->trial_steps = host.s.trial_steps;
@@ -839,9 +859,11 @@ grt_ctx* grt_create(int device) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaMalloc((void**)&c->d_cam, sizeof(GrtCamera)));
         void* counters = nullptr;
-        CK(cudaMalloc(&counters, 8 * sizeof(unsigned int) + sizeof(GrtStats)));
+        CK(cudaMalloc(&counters, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats)));
         c->d_counters = (unsigned int*)counters;
-        c->d_stats = (GrtStats*)(c->d_counters + 8);
+        c->d_stats = (GrtStats*)(c->d_counters + kCounterWords);
+        if (const char* e = getenv("GRT_PASSES")) c->passes = atoi(e);
+        if (const char* e = getenv("GRT_PARK_THRESHOLD")) c->park_threshold = atoi(e);
         // default camera (main.cpp:664-673)
         c->cam.pos_cart = make_float4(0, 0, -4, 0);
         c->cam.quat = make_float4(-0.70710678f, 0, 0, 0.70710678f);
@@ -857,7 +879,7 @@ void grt_destroy(grt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
-    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
+    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->rays_cont, &c->queue[0], &c->queue[1], &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
                       &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc})
         b->release();
     for (auto e : c->events) cudaEventDestroy(e);
@@ -870,6 +892,13 @@ void grt_destroy(grt_ctx* c) {
 int grt_set_fast_math(grt_ctx* c, int enabled) {
     if (!c) { g_err = "null context"; return GRT_E_INVALID; }
     c->fast_math = enabled != 0;
+    return GRT_OK;
+}
+
+int grt_set_tuning(grt_ctx* c, int passes, int park_threshold) {
+    if (!c || passes < 1 || passes > 32 || park_threshold < 0 || park_threshold > 31) { g_err = "tuning out of range (passes 1..32, park_threshold 0..31)"; return GRT_E_INVALID; }
+    c->passes = passes;
+    c->park_threshold = park_threshold;
     return GRT_OK;
 }
 

@@ -8,13 +8,17 @@
 //   pos[i], vel[i], acc[i]           position, velocity, acceleration
 //   quat[i]                          initial_quat, only allocated/touched for constant-theta metrics
 //   aux[i] = {ku_uobsu, running_dlambda_dnew, terminated, sy<<16|sx}
-// terminated: 0 live or dropped, 1 finished, 2 prepass-culled (as in the reference), 3 padding slot.
+//   cont[i] = {next_ds, accepted-step count (int bits), |v.t| at launch, -}: the rest of the loop state
+//             of a ray parked between compaction passes of the integration kernel
+// terminated: 0 live or dropped, 1 finished, 2 prepass-culled (as in the reference), 3 padding slot,
+//             4 parked mid-flight (never visible outside the integration passes).
 struct GrtRays {
     float4* pos;
     float4* vel;
     float4* acc;
     float4* quat;
     int4* aux;
+    float4* cont;
 };
 
 // per-pixel shading record, 16 B (the reference's `struct render_data` is 32 B, cl.cl:5066-5074;

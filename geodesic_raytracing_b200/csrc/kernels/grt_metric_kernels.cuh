@@ -399,14 +399,25 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
 }
 
 // The integration loop.  Each lane owns one ray; a lane whose ray ends stores it and immediately
-// pulls the next slot from `work_counter` (warp-aggregated atomicAdd), so lanes never idle waiting
-// for the slowest ray of their warp.  Ray state lives in registers; HBM traffic is one 64-byte load
-// and (for finished rays) one 48-byte store per ray, zero bytes per step.
-extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtFrame fr, int slot_begin, const int* __restrict__ slot_count_ptr, int slot_count_fixed,
-                                                              unsigned int* work_counter, GrtStats* stats, float max_acceleration, grt_params cfg) {
+// pulls the next work item from `work_counter` (warp-aggregated atomicAdd), so lanes never idle
+// waiting for the slowest ray of their warp.  Ray state lives in registers; HBM traffic is one
+// 64-byte load and (for finished rays) one 48-byte store per ray, zero bytes per step.
+//
+// Compaction passes: step counts range from ~50 to the 16384 cap, so once the work queue is empty
+// the surviving long rays are scattered a few per warp.  When a warp is down to `park_threshold`
+// live lanes it parks them (80 B of loop state per ray, slot index appended to `out_queue` through
+// a ballot-ranked, warp-aggregated reservation) and exits; the next launch of this kernel consumes
+// that queue, so the survivors are re-packed 32 to a warp.  Work items of a pass are the fresh
+// slots [slot_begin, slot_begin + n_fresh) followed by the parked slots of the previous pass.
+extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtFrame fr, int slot_begin, const int* __restrict__ fresh_count_ptr, int fresh_count_fixed,
+                                                              const int* __restrict__ in_queue, const unsigned int* __restrict__ in_count_ptr, int* out_queue,
+                                                              unsigned int* out_count, int park_threshold, unsigned int* work_counter, GrtStats* stats,
+                                                              float max_acceleration, grt_params cfg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned int count = slot_count_ptr ? (unsigned int)*slot_count_ptr : (unsigned int)slot_count_fixed;
+    const unsigned lanes_below = (1u << lane) - 1u;
+    const unsigned int n_fresh = fresh_count_ptr ? (unsigned int)*fresh_count_ptr : (unsigned int)fresh_count_fixed;
+    const unsigned int count = n_fresh + (in_count_ptr ? *in_count_ptr : 0u);
 
     bool alive = false, exhausted = false;
     int slot = 0, iter = 0;
@@ -426,37 +437,67 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                 base = __shfl_sync(FULL, base, leader);
                 exhausted = base + ndead >= count;
                 if (!alive) {
-                    unsigned int mine = base + __popc(dead & ((1u << lane) - 1u));
+                    unsigned int mine = base + __popc(dead & lanes_below);
                     if (mine < count) {
-                        slot = slot_begin + (int)mine;
+                        const bool fresh = mine < n_fresh;
+                        slot = fresh ? slot_begin + (int)mine : in_queue[mine - n_fresh];
                         int4 aux = rays.aux[slot];
-                        if (aux.z == 0) {
+                        if (!fresh || aux.z == 0) {
                             pos = rays.pos[slot];
                             vel = rays.vel[slot];
                             acc = rays.acc[slot];
                             ku = __int_as_float(aux.x);
                             sxsy = aux.w;
+                            if (fresh) {
 #if GRT_CONSTANT_THETA
-                            pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
+                                pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
 #endif
-                            f_in_x = fabsf(vel.x);
-                            next_ds = 0.00001f;
+                                f_in_x = fabsf(vel.x);
+                                next_ds = 0.00001f;
 #if GRT_ADAPTIVE_PRECISION
-                            (void)accel_to_precision(acc, max_acceleration, &next_ds);
+                                (void)accel_to_precision(acc, max_acceleration, &next_ds);
 #endif
-                            dlambda = 1.0f;
-                            iter = 0;
+                                dlambda = 1.0f;
+                                iter = 0;
+                                nrays++;
+                            } else {
+                                float4 c = rays.cont[slot];
+                                next_ds = c.x;
+                                iter = __float_as_int(c.y);
+                                f_in_x = c.z;
+                                dlambda = __int_as_float(aux.y);
+                            }
                             float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
                             grt_radii(p, cfg, rr);
                             polar_r_abs = fabsf(rr[0]);
                             r_abs = fabsf(rr[1]);
                             alive = true;
-                            nrays++;
                         }
                     }
                 }
             }
-            if (!__any_sync(FULL, alive)) {
+            unsigned live = __ballot_sync(FULL, alive);
+            if (exhausted && out_queue && live) {
+                int nlive = __popc(live);
+                if (nlive <= park_threshold) {
+                    // park the survivors for the next pass and retire this warp
+                    int leader = __ffs(live) - 1;
+                    unsigned int base = 0;
+                    if (lane == leader) base = atomicAdd(out_count, (unsigned int)nlive);
+                    base = __shfl_sync(FULL, base, leader);
+                    if (alive) {
+                        rays.pos[slot] = pos;
+                        rays.vel[slot] = vel;
+                        rays.acc[slot] = acc;
+                        rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 4, sxsy);
+                        rays.cont[slot] = f4(next_ds, __int_as_float(iter), f_in_x, 0.0f);
+                        out_queue[base + __popc(live & lanes_below)] = slot;
+                        alive = false;
+                    }
+                    live = 0;
+                }
+            }
+            if (!live) {
                 if (exhausted) break;
                 continue;
             }
@@ -476,6 +517,7 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
 #endif
             if (drop) {
                 alive = false;
+                finish = false;
             } else if (finish) {
                 rays.pos[slot] = pos;
                 rays.vel[slot] = vel;
@@ -541,6 +583,8 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                     }
                 }
             }
+            // a dropped ray reads terminated = 0; a ray that had been parked carries 4 in memory
+            if (!alive && !finish) rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 0, sxsy);
         }
     }
     // statistics: warp reduce, one atomic per warp
