@@ -276,14 +276,14 @@ struct grt_ctx {
     GrtCamera* d_cam = nullptr;
 
     Texture tex[2];
-    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, rays_cont, queue[2], rdata, termination, tables, identity, out, scratch;
+    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, pool_buf, worklist, rdata, termination, tables, identity, out, scratch;
     int identity_len = 0;
     // counters (zeroed every frame): [4] extra ray count; [8 + phase * 64 + pass] work counter and
     // [8 + phase * 64 + 32 + pass] parked-ray count of integration pass `pass` of phase 0 (prepass),
     // 1 (first pass), 2 (refinement); then GrtStats
     unsigned int* d_counters = nullptr;
-    int passes = 12;          // compaction passes per integration phase (GRT_PASSES)
-    int park_threshold = 20;  // a warp parks its rays when this many lanes or fewer are live (GRT_PARK_THRESHOLD)
+    int passes = 0;           // 128-thread blocks of the integration kernel per SM; 0 = as many as fit (GRT_PASSES)
+    int park_threshold = 16;  // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_PARK_THRESHOLD)
     GrtStats* d_stats = nullptr;
 
     // geometry cache
@@ -495,9 +495,6 @@ GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
     c->rays_vel.ensure(slots * 16);
     c->rays_acc.ensure(slots * 16);
     c->rays_aux.ensure(slots * 16);
-    c->rays_cont.ensure(slots * 16);
-    c->queue[0].ensure(slots * 4);
-    c->queue[1].ensure(slots * 4);
     if (need_quat) c->rays_quat.ensure(slots * 16);
     GrtRays r;
     r.pos = (float4*)c->rays_pos.p;
@@ -505,7 +502,6 @@ GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
     r.acc = (float4*)c->rays_acc.p;
     r.quat = (float4*)c->rays_quat.p;
     r.aux = (int4*)c->rays_aux.p;
-    r.cont = (float4*)c->rays_cont.p;
     return r;
 }
 
@@ -575,45 +571,63 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     int* d_extra = (int*)(c->d_counters + 4);
     const int* null_count = nullptr;
     float max_accel = c->feat.max_acceleration_change;
-    const unsigned persistent_grid = (unsigned)(c->num_sms * P->integrate_blocks_per_sm);
-    // One integration phase = `passes` launches of k_integrate: pass 0 takes the fresh rays, every
-    // later pass the rays the previous one parked (re-packed 32 to a warp); the last never parks.
-    auto integrate = [&](GrtFrame& f, int slot_begin, const int* count_ptr, int count_fixed, int phase) {
-        const int passes = std::max(1, std::min(c->passes, 32));
-        unsigned int* base = c->d_counters + 8 + phase * 64;
-        for (int k = 0; k < passes; k++) {
-            unsigned grid = persistent_grid;
-            if (k == 0 && !count_ptr) grid = std::min(grid, (unsigned)((count_fixed + 127) / 128));
-            const int* fresh_ptr = k == 0 ? count_ptr : nullptr;
-            int fresh_fixed = k == 0 ? count_fixed : 0;
-            const int* in_queue = k == 0 ? nullptr : (const int*)c->queue[k & 1].p;
-            const unsigned int* in_count = k == 0 ? nullptr : base + 32 + (k - 1);
-            int* out_queue = k == passes - 1 ? nullptr : (int*)c->queue[(k + 1) & 1].p;
-            unsigned int* out_count = base + 32 + k;
-            unsigned int* wc = base + k;
-            int threshold = c->park_threshold;
-            void* args[] = {&rays, &f, &slot_begin, &fresh_ptr, &fresh_fixed, &in_queue, &in_count, &out_queue, &out_count, &threshold, &wc, &c->d_stats, &max_accel, c->params};
-            L.go(P->k_integrate, grid, 128, args);
-            L.integrate_launches++;
-        }
+    const unsigned persistent_grid = (unsigned)(c->num_sms * (c->passes > 0 ? std::min(c->passes, P->integrate_blocks_per_sm) : P->integrate_blocks_per_sm));
+    // exchange pool of the integration kernel (see GrtPool): capacity = 4x the threads of the persistent grid
+    GrtPool pool{};
+    {
+        unsigned cap = 1;
+        while (cap < persistent_grid * 128u * 4u) cap <<= 1;
+        const size_t bytes = (size_t)cap * 84 + 64;
+        const bool fresh = c->pool_buf.cap < bytes;
+        c->pool_buf.ensure(bytes);
+        if (fresh) CK(cudaMemsetAsync(c->pool_buf.p, 0, c->pool_buf.cap, c->stream));   // tickets run on across launches; ready flags start at 0
+        char* p = (char*)c->pool_buf.p;
+        pool.counters = (unsigned int*)p;
+        p += 64;
+        pool.pos = (float4*)p;
+        pool.vel = (float4*)(p + (size_t)cap * 16);
+        pool.acc = (float4*)(p + (size_t)cap * 32);
+        pool.misc = (float4*)(p + (size_t)cap * 48);
+        pool.ids = (int4*)(p + (size_t)cap * 64);
+        pool.ready = c->park_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 80) : nullptr;
+        pool.mask = cap - 1;
+        pool.donate_threshold = c->park_threshold;
+    }
+    // work lists (see GrtWorkList): one int buffer reused by the three phases, which run back to back
+    c->worklist.ensure(sizeof(int) * std::max<size_t>({(size_t)fr.n_slots, extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)1}));
+    auto worklist = [&](int phase, size_t capacity) {
+        GrtWorkList wl;
+        wl.slots = (int*)c->worklist.p;
+        wl.n_hot = c->d_counters + 16 + 2 * phase;
+        wl.n_cold = c->d_counters + 17 + 2 * phase;
+        wl.capacity = (int)capacity;
+        return wl;
+    };
+    GrtWorkList wl_p = worklist(0, use_prepass ? pf.n_slots : 1), wl_f = worklist(1, fr.n_slots), wl_x = worklist(2, std::max<size_t>(extra_cap, 1));
+    auto integrate = [&](GrtFrame& f, GrtWorkList& wl, int phase, size_t max_items) {
+        unsigned grid = std::min(persistent_grid, (unsigned)((max_items + 127) / 128));
+        unsigned int* wc = c->d_counters + 8 + phase;
+        void* args[] = {&rays, &f, &wl, &pool, &wc, &c->d_stats, &max_accel, c->params};
+        L.go(P->k_integrate, grid, 128, args);
+        L.integrate_launches++;
     };
 
     if (use_prepass) {
         int one = 1;
-        void* a0[] = {&rays, &pf, &c->d_cam, &d_term, &one, c->params};
+        void* a0[] = {&rays, &pf, &c->d_cam, &d_term, &one, &wl_p, c->params};
         L.go(P->k_init_rays, (unsigned)((pf.n_slots + 127) / 128), 128, a0);
-        integrate(pf, 0, nullptr, pf.n_slots, 0);
+        integrate(pf, wl_p, 0, pf.n_slots);
         void* a1[] = {&rays, &pf, &d_term};
         L.go(P->k_prepass_mask, (unsigned)((pf.n_slots + 127) / 128), 128, a1);
     }
     cudaEvent_t e_prepass = event_at(c, ev++);
     {
         int zero = 0;
-        void* a0[] = {&rays, &fr, &c->d_cam, &d_term, &zero, c->params};
+        void* a0[] = {&rays, &fr, &c->d_cam, &d_term, &zero, &wl_f, c->params};
         L.go(P->k_init_rays, (unsigned)((fr.n_slots + 127) / 128), 128, a0);
     }
     cudaEvent_t e_init = event_at(c, ev++);
-    integrate(fr, 0, nullptr, fr.n_slots, 1);
+    integrate(fr, wl_f, 1, fr.n_slots);
     cudaEvent_t e_int1 = event_at(c, ev++);
     GrtRenderData* d_rdata = (GrtRenderData*)c->rdata.p;
     {
@@ -624,11 +638,11 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     cudaEvent_t e_rd1 = event_at(c, ev++);
     cudaEvent_t e_adapt = e_rd1, e_int2 = e_rd1, e_rd2 = e_rd1;
     if (adaptive) {
-        void* a[] = {&rays, &fr, &c->d_cam, &d_rdata, &d_extra, c->params};
+        void* a[] = {&rays, &fr, &c->d_cam, &d_rdata, &d_extra, &wl_x, c->params};
         L.go(P->k_adaptive, (unsigned)((fr.n_slots + 127) / 128), 128, a);
         e_adapt = event_at(c, ev++);
         const int* cnt = d_extra;
-        integrate(fr, fr.n_slots, cnt, 0, 2);
+        integrate(fr, wl_x, 2, extra_cap);
         e_int2 = event_at(c, ev++);
         int begin = fr.n_slots, fixed = 0;
         void* a2[] = {&rays, &fr, &begin, &cnt, &fixed, &d_rdata, c->params};
@@ -879,7 +893,7 @@ void grt_destroy(grt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
-    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->rays_cont, &c->queue[0], &c->queue[1], &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
+    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->pool_buf, &c->worklist, &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
                       &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc})
         b->release();
     for (auto e : c->events) cudaEventDestroy(e);
@@ -896,7 +910,7 @@ int grt_set_fast_math(grt_ctx* c, int enabled) {
 }
 
 int grt_set_tuning(grt_ctx* c, int passes, int park_threshold) {
-    if (!c || passes < 1 || passes > 32 || park_threshold < 0 || park_threshold > 31) { g_err = "tuning out of range (passes 1..32, park_threshold 0..31)"; return GRT_E_INVALID; }
+    if (!c || passes < 0 || passes > 32 || park_threshold < 0 || park_threshold > 31) { g_err = "tuning out of range (blocks_per_sm 0..32, donate_threshold 0..31)"; return GRT_E_INVALID; }
     c->passes = passes;
     c->park_threshold = park_threshold;
     return GRT_OK;

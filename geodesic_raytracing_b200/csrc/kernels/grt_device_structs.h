@@ -8,17 +8,44 @@
 //   pos[i], vel[i], acc[i]           position, velocity, acceleration
 //   quat[i]                          initial_quat, only allocated/touched for constant-theta metrics
 //   aux[i] = {ku_uobsu, running_dlambda_dnew, terminated, sy<<16|sx}
-//   cont[i] = {next_ds, accepted-step count (int bits), |v.t| at launch, -}: the rest of the loop state
-//             of a ray parked between compaction passes of the integration kernel
-// terminated: 0 live or dropped, 1 finished, 2 prepass-culled (as in the reference), 3 padding slot,
-//             4 parked mid-flight (never visible outside the integration passes).
+// terminated: 0 live or dropped, 1 finished, 2 prepass-culled (as in the reference), 3 padding slot.
+// A dropped ray's slot keeps its *initial* state, as in the reference (do_generic_rays only writes
+// cleanly terminated rays, cl.cl:4088-4130): the adaptive-sampling stencil reads it (cl.cl:5244-5256).
 struct GrtRays {
     float4* pos;
     float4* vel;
     float4* acc;
     float4* quat;
     int4* aux;
-    float4* cont;
+};
+
+// Exchange pool of the integration kernel: a ring of in-flight ray records (80 B of loop state per
+// ray, SoA) through which sparse warps hand their surviving rays to warps with free lanes, so warps
+// stay converged under divergent step counts.  Tickets are reserved with atomicAdd on counters[0]
+// (push) and claimed with atomicCAS on counters[1] (pop); ready[ticket & mask] == ticket + 1 once
+// the record is visible.  Capacity (mask + 1) exceeds the threads of the persistent grid several
+// times over: only rays in flight are ever outstanding.
+struct GrtPool {
+    float4* pos;
+    float4* vel;
+    float4* acc;
+    float4* misc;   // {next_ds, accepted-step count (int bits), |v.t| at launch, running_dlambda_dnew}
+    int4* ids;      // {slot, ku_uobsu (float bits), sy<<16|sx, -}
+    unsigned int* ready;
+    unsigned int* counters;
+    unsigned int mask;
+    int donate_threshold;   // a warp with this many live lanes or fewer (after the queue ran dry) gives its rays away
+};
+
+// Work list of one integration phase: the slots of the rays that really have to be traced (culled
+// and padding slots never enter it), "hot" rays - the ones expected to run longest, next to the
+// shadow - filled in from the front and the rest from the back, so the kernel starts the long rays
+// first.  Item i is slots[i] for i < *n_hot, else slots[capacity - 1 - (i - *n_hot)].
+struct GrtWorkList {
+    int* slots;
+    unsigned int* n_hot;
+    unsigned int* n_cold;
+    int capacity;
 };
 
 // per-pixel shading record, 16 B (the reference's `struct render_data` is 32 B, cl.cl:5066-5074;

@@ -306,6 +306,26 @@ static __device__ __forceinline__ void store_ray(const GrtRays& rays, int slot, 
     rays.aux[slot] = make_int4(__float_as_int(r.ku), __float_as_int(1.0f), terminated, (sy << 16) | sx);
 }
 
+// Append this lane's slot to the work list (all 32 lanes call; `add` selects the lanes that have a ray
+// to trace, `hot` the end of the list): one atomicAdd per warp and list end.
+static __device__ __forceinline__ void worklist_append(const GrtWorkList& wl, int slot, bool add, bool hot) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    unsigned mh = __ballot_sync(FULL, add && hot), mc = __ballot_sync(FULL, add && !hot);
+    unsigned int bh = 0, bc = 0;
+    if (lane == 0) {
+        if (mh) bh = atomicAdd(wl.n_hot, (unsigned int)__popc(mh));
+        if (mc) bc = atomicAdd(wl.n_cold, (unsigned int)__popc(mc));
+    }
+    bh = __shfl_sync(FULL, bh, 0);
+    bc = __shfl_sync(FULL, bc, 0);
+    if (add) {
+        if (hot) wl.slots[bh + __popc(mh & below)] = slot;
+        else wl.slots[wl.capacity - 1 - (int)(bc + __popc(mc & below))] = slot;
+    }
+}
+
 // ---- kernels ----------------------------------------------------------------------------------------
 extern "C" __global__ void k_camera(GrtCamera* cam, grt_params cfg) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -347,28 +367,32 @@ extern "C" __global__ void k_eval_metric(const float4* positions, const float4* 
 
 // One thread per first-pass slot. is_prepass: the 1/16 grid traced before the frame (main.cpp:2387-2436).
 extern "C" __global__ void __launch_bounds__(128) k_init_rays(GrtRays rays, GrtFrame fr, const GrtCamera* __restrict__ camp, const int* __restrict__ termination,
-                                                            int is_prepass, grt_params cfg) {
-    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+                                                            int is_prepass, GrtWorkList wl, grt_params cfg) {
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;   // n_slots is a multiple of 32: whole warps stay or leave
     if (slot >= fr.n_slots) return;
     int gx, gy;
     grt_cell_of(slot, fr.tiles_x, gx, gy);
-    if (gx >= fr.grid_w || gy >= fr.grid_h) {
-        rays.aux[slot] = make_int4(0, 0, 3, 0);
-        return;
-    }
-    const GrtCamera& cam = *camp;
-    int cx = gx * fr.cell, cy = fr.row_global[gy * fr.cell];
-    RayInit r = pixel_ray(cx, cy, fr, cam, cfg, true);
-    int terminated = 0;
-    if (!is_prepass && fr.use_prepass_mask) {
-        // cull when the 5-point prepass neighbourhood all failed (cl.cl:3213-3232)
-        float fx = (float)cx / fr.full_w, fy = (float)cy / fr.full_h;
-        int lx = (int)roundf(fx * fr.prepass_w), ly = (int)roundf(fy * fr.prepass_h);
-        const int pw = fr.prepass_w, ph = fr.prepass_h;
-        auto dead = [&](int x, int y) { return x >= 0 && y >= 0 && x <= pw - 1 && y <= ph - 1 && termination[y * pw + x] == 1; };
-        if (dead(lx - 1, ly) && dead(lx, ly) && dead(lx + 1, ly) && dead(lx, ly - 1) && dead(lx, ly + 1)) terminated = 2;
-    }
-    store_ray(rays, slot, r, terminated, cx, cy);
+    const bool real = gx < fr.grid_w && gy < fr.grid_h;
+    int terminated = 3;
+    bool hot = false;
+    if (real) {
+        const GrtCamera& cam = *camp;
+        int cx = gx * fr.cell, cy = fr.row_global[gy * fr.cell];
+        RayInit r = pixel_ray(cx, cy, fr, cam, cfg, true);
+        terminated = 0;
+        if (!is_prepass && fr.use_prepass_mask) {
+            // cull when the 5-point prepass neighbourhood all failed (cl.cl:3213-3232)
+            float fx = (float)cx / fr.full_w, fy = (float)cy / fr.full_h;
+            int lx = (int)roundf(fx * fr.prepass_w), ly = (int)roundf(fy * fr.prepass_h);
+            const int pw = fr.prepass_w, ph = fr.prepass_h;
+            auto dead = [&](int x, int y) { return x >= 0 && y >= 0 && x <= pw - 1 && y <= ph - 1 && termination[y * pw + x] == 1; };
+            const bool d0 = dead(lx - 1, ly), d1 = dead(lx, ly), d2 = dead(lx + 1, ly), d3 = dead(lx, ly - 1), d4 = dead(lx, ly + 1);
+            if (d0 && d1 && d2 && d3 && d4) terminated = 2;
+            hot = d0 || d1 || d2 || d3 || d4;   // next to the shadow: the longest rays, start them first
+        }
+        store_ray(rays, slot, r, terminated, cx, cy);
+    } else rays.aux[slot] = make_int4(0, 0, 3, 0);
+    worklist_append(wl, slot, terminated == 0, hot);
 }
 
 // termination mask: 1 = the prepass ray did not finish cleanly (cl.cl:4997-5020)
@@ -399,25 +423,24 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
 }
 
 // The integration loop.  Each lane owns one ray; a lane whose ray ends stores it and immediately
-// pulls the next work item from `work_counter` (warp-aggregated atomicAdd), so lanes never idle
+// pulls the next fresh slot from `work_counter` (warp-aggregated atomicAdd), so lanes never idle
 // waiting for the slowest ray of their warp.  Ray state lives in registers; HBM traffic is one
 // 64-byte load and (for finished rays) one 48-byte store per ray, zero bytes per step.
 //
-// Compaction passes: step counts range from ~50 to the 16384 cap, so once the work queue is empty
-// the surviving long rays are scattered a few per warp.  When a warp is down to `park_threshold`
-// live lanes it parks them (80 B of loop state per ray, slot index appended to `out_queue` through
-// a ballot-ranked, warp-aggregated reservation) and exits; the next launch of this kernel consumes
-// that queue, so the survivors are re-packed 32 to a warp.  Work items of a pass are the fresh
-// slots [slot_begin, slot_begin + n_fresh) followed by the parked slots of the previous pass.
-extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtFrame fr, int slot_begin, const int* __restrict__ fresh_count_ptr, int fresh_count_fixed,
-                                                              const int* __restrict__ in_queue, const unsigned int* __restrict__ in_count_ptr, int* out_queue,
-                                                              unsigned int* out_count, int park_threshold, unsigned int* work_counter, GrtStats* stats,
+// Live-ray compaction: step counts range from ~50 to the 16384 cap, so once the work queue is dry
+// the surviving long rays are scattered a few per warp.  A warp that is down to
+// `pool.donate_threshold` live lanes pushes their loop state into the exchange pool (ballot-ranked,
+// one atomicAdd per warp) and any warp with free lanes claims records from it, so the survivors
+// are re-packed into full warps without leaving the kernel.  A donor always tries to claim after
+// it pushed, so a record is never orphaned; results do not depend on which lane runs a ray.
+static __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+
+extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtFrame fr, GrtWorkList wl, GrtPool pool, unsigned int* work_counter, GrtStats* stats,
                                                               float max_acceleration, grt_params cfg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lanes_below = (1u << lane) - 1u;
-    const unsigned int n_fresh = fresh_count_ptr ? (unsigned int)*fresh_count_ptr : (unsigned int)fresh_count_fixed;
-    const unsigned int count = n_fresh + (in_count_ptr ? *in_count_ptr : 0u);
+    const unsigned int n_hot = *wl.n_hot, count = n_hot + *wl.n_cold;
 
     bool alive = false, exhausted = false;
     int slot = 0, iter = 0;
@@ -426,6 +449,8 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
     int sxsy = 0;
     unsigned long long trial = 0, accepted = 0, nrays = 0, nfinished = 0;
     const float new_max = fr.max_precision_radius;
+    unsigned int tail_tick = 0;
+    int cooldown = 0;
 
     for (;;) {
         unsigned dead = __ballot_sync(FULL, !alive);
@@ -439,34 +464,25 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                 if (!alive) {
                     unsigned int mine = base + __popc(dead & lanes_below);
                     if (mine < count) {
-                        const bool fresh = mine < n_fresh;
-                        slot = fresh ? slot_begin + (int)mine : in_queue[mine - n_fresh];
+                        slot = wl.slots[mine < n_hot ? (int)mine : wl.capacity - 1 - (int)(mine - n_hot)];
                         int4 aux = rays.aux[slot];
-                        if (!fresh || aux.z == 0) {
+                        {
                             pos = rays.pos[slot];
                             vel = rays.vel[slot];
                             acc = rays.acc[slot];
                             ku = __int_as_float(aux.x);
                             sxsy = aux.w;
-                            if (fresh) {
 #if GRT_CONSTANT_THETA
-                                pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
+                            pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
 #endif
-                                f_in_x = fabsf(vel.x);
-                                next_ds = 0.00001f;
+                            f_in_x = fabsf(vel.x);
+                            next_ds = 0.00001f;
 #if GRT_ADAPTIVE_PRECISION
-                                (void)accel_to_precision(acc, max_acceleration, &next_ds);
+                            (void)accel_to_precision(acc, max_acceleration, &next_ds);
 #endif
-                                dlambda = 1.0f;
-                                iter = 0;
-                                nrays++;
-                            } else {
-                                float4 c = rays.cont[slot];
-                                next_ds = c.x;
-                                iter = __float_as_int(c.y);
-                                f_in_x = c.z;
-                                dlambda = __int_as_float(aux.y);
-                            }
+                            dlambda = 1.0f;
+                            iter = 0;
+                            nrays++;
                             float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
                             grt_radii(p, cfg, rr);
                             polar_r_abs = fabsf(rr[0]);
@@ -475,29 +491,76 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                         }
                     }
                 }
-            }
-            unsigned live = __ballot_sync(FULL, alive);
-            if (exhausted && out_queue && live) {
+            } else if (pool.ready && (dead == FULL || (tail_tick++ & 7u) == 0u)) {
+                // ---- queue is dry: exchange rays through the pool (rate limited to every 8th step) ----
+                unsigned live = ~dead;
                 int nlive = __popc(live);
-                if (nlive <= park_threshold) {
-                    // park the survivors for the next pass and retire this warp
+                bool donated = false;
+                if (nlive > 0 && nlive <= pool.donate_threshold && cooldown == 0) {
                     int leader = __ffs(live) - 1;
                     unsigned int base = 0;
-                    if (lane == leader) base = atomicAdd(out_count, (unsigned int)nlive);
+                    if (lane == leader) base = atomicAdd(&pool.counters[0], (unsigned int)nlive);
                     base = __shfl_sync(FULL, base, leader);
                     if (alive) {
-                        rays.pos[slot] = pos;
-                        rays.vel[slot] = vel;
-                        rays.acc[slot] = acc;
-                        rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 4, sxsy);
-                        rays.cont[slot] = f4(next_ds, __int_as_float(iter), f_in_x, 0.0f);
-                        out_queue[base + __popc(live & lanes_below)] = slot;
+                        const unsigned int ticket = base + __popc(live & lanes_below), rec = ticket & pool.mask;
+                        pool.pos[rec] = pos;
+                        pool.vel[rec] = vel;
+                        pool.acc[rec] = acc;
+                        pool.misc[rec] = f4(next_ds, __int_as_float(iter), f_in_x, dlambda);
+                        pool.ids[rec] = make_int4(slot, __float_as_int(ku), sxsy, 0);
+                        __threadfence();
+                        *(volatile unsigned int*)&pool.ready[rec] = ticket + 1u;
                         alive = false;
                     }
-                    live = 0;
+                    donated = true;
+                    dead = FULL;
+                    __nanosleep(2000);   // let other sparse warps add theirs before anyone claims
+                } else if (cooldown > 0) cooldown--;
+                // claim up to one record per free lane
+                const int want = __popc(dead);
+                unsigned int base = 0, n = 0;
+                if (lane == 0) {
+                    unsigned int pop = ld_volatile_u32(&pool.counters[1]);
+                    for (;;) {
+                        unsigned int push = ld_volatile_u32(&pool.counters[0]);
+                        n = min((unsigned int)want, push - pop);
+                        if (n == 0) break;
+                        unsigned int old = atomicCAS(&pool.counters[1], pop, pop + n);
+                        if (old == pop) break;
+                        pop = old;
+                    }
+                    base = pop;
                 }
+                base = __shfl_sync(FULL, base, 0);
+                n = __shfl_sync(FULL, n, 0);
+                if (!alive) {
+                    const unsigned int rank = __popc(dead & lanes_below);
+                    if (rank < n) {
+                        const unsigned int ticket = base + rank, rec = ticket & pool.mask;
+                        while (ld_volatile_u32(&pool.ready[rec]) != ticket + 1u) {}
+                        __threadfence();
+                        pos = __ldcg(&pool.pos[rec]);
+                        vel = __ldcg(&pool.vel[rec]);
+                        acc = __ldcg(&pool.acc[rec]);
+                        float4 m = __ldcg(&pool.misc[rec]);
+                        int4 ids = __ldcg(&pool.ids[rec]);
+                        next_ds = m.x;
+                        iter = __float_as_int(m.y);
+                        f_in_x = m.z;
+                        dlambda = m.w;
+                        slot = ids.x;
+                        ku = __int_as_float(ids.y);
+                        sxsy = ids.z;
+                        float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
+                        grt_radii(p, cfg, rr);
+                        polar_r_abs = fabsf(rr[0]);
+                        r_abs = fabsf(rr[1]);
+                        alive = true;
+                    }
+                }
+                if (donated && (int)n <= nlive) cooldown = 8;   // nobody to merge with: do not churn
             }
-            if (!live) {
+            if (!__any_sync(FULL, alive)) {
                 if (exhausted) break;
                 continue;
             }
@@ -517,7 +580,6 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
 #endif
             if (drop) {
                 alive = false;
-                finish = false;
             } else if (finish) {
                 rays.pos[slot] = pos;
                 rays.vel[slot] = vel;
@@ -583,8 +645,6 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                     }
                 }
             }
-            // a dropped ray reads terminated = 0; a ray that had been parked carries 4 in memory
-            if (!alive && !finish) rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 0, sxsy);
         }
     }
     // statistics: warp reduce, one atomic per warp
@@ -708,7 +768,7 @@ static __device__ GrtRenderData interpolate_rdata(GrtRenderData a, GrtRenderData
 }
 
 extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFrame fr, const GrtCamera* __restrict__ camp, GrtRenderData* rdata, int* extra_count,
-                                                           grt_params cfg) {
+                                                           GrtWorkList wl, grt_params cfg) {
     int slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = slot < fr.n_slots;
     int gx = 0, gy = 0;
@@ -720,7 +780,7 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
     if (valid) valid = fr.cellrow_refine[gy] != 0;
     const int cell_y = valid ? fr.row_global[gy * 2] / 2 : 0;   // full-frame cell row
     const int half_w = fr.full_w / 2, half_h = fr.full_h / 2;
-    bool should_sample = true;
+    bool should_sample = true, hot = false;
     if (valid) {
         if (gx != 0 && gx != half_w - 1 && cell_y != 0 && cell_y != half_h - 1) {
             auto term_of = [&](int x, int y) { return rays.aux[grt_slot_of(x, y, fr.tiles_x)].z; };
@@ -742,8 +802,11 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
             float rough_change_per_pixel = (fr.field_of_view * 2.0f * GRT_PI_F / 360.0f) / fr.full_w;
             should_sample = relative_angular_error >= rough_change_per_pixel * fr.adaptive_sampling_threshold;
             int c = term_of(gx, gy);
-            if (c != term_of(gx - 1, gy) || c != term_of(gx + 1, gy) || c != term_of(gx, gy - 1) || c != term_of(gx, gy + 1) || c != term_of(gx + 1, gy + 1))
+            if (c != term_of(gx - 1, gy) || c != term_of(gx + 1, gy) || c != term_of(gx, gy - 1) || c != term_of(gx, gy + 1) || c != term_of(gx + 1, gy + 1)) {
                 should_sample = true;
+                hot = true;   // the shadow edge crosses this cell: its rays are the long ones
+            }
+            hot = hot || c != 1;
         }
     }
     // append 3 rays per refined cell: warp-aggregated reservation
@@ -757,10 +820,11 @@ extern "C" __global__ void __launch_bounds__(128) k_adaptive(GrtRays rays, GrtFr
         if (lane == leader) base = atomicAdd(extra_count, 3 * __popc(mask));
         base = __shfl_sync(FULL, base, leader);
     }
-    if (!valid) return;
     const int px = gx * 2, py = cell_y * 2;
+    const int out = fr.n_slots + base + 3 * __popc(mask & ((1u << lane) - 1u));
+    for (int i = 0; i < 3; i++) worklist_append(wl, out + i, refine, hot);
+    if (!valid) return;
     if (refine) {
-        int out = fr.n_slots + base + 3 * __popc(mask & ((1u << lane) - 1u));
         const GrtCamera& cam = *camp;
         const int ox[3] = {1, 0, 1}, oy[3] = {0, 1, 1};
         for (int i = 0; i < 3; i++) {

@@ -141,10 +141,11 @@ int grt_compile_metric(grt_metric*, int is_static, int fast_math, const char** l
  * with -cl-unsafe-math-optimizations and native_* functions, metric_manager.hpp:70, cl.cl:115-117) */
 int grt_set_fast_math(grt_ctx*, int enabled);
 
-/* Scheduling of the integration kernel (results do not depend on it): each integration phase runs
- * `passes` launches; a warp whose live rays drop to `park_threshold` after the work queue is empty
- * parks them for the next launch, which re-packs the survivors 32 to a warp.  Defaults 12 / 20. */
-int grt_set_tuning(grt_ctx*, int passes, int park_threshold);
+/* Scheduling of the integration kernel (results do not depend on it): `blocks_per_sm` 128-thread
+ * blocks of the persistent grid per SM (0 = as many as fit: throughput; fewer = lower per-step
+ * latency for the longest rays); once the work queue is dry, a warp with `donate_threshold` live rays
+ * or fewer hands them to warps with free lanes through the exchange pool (0 disables the exchange). */
+int grt_set_tuning(grt_ctx*, int blocks_per_sm, int donate_threshold);
 
 int grt_set_features(grt_ctx*, const grt_features*);
 int grt_get_features(const grt_ctx*, grt_features* out);

@@ -99,7 +99,7 @@ class Oracle:
         self.params[:len(params)] = params
         L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
         L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
-                                              C.POINTER(C.c_double), C.c_void_p]
+                                              C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
 
     # -- helpers ---------------------------------------------------------------------------------
     @staticmethod
@@ -164,8 +164,9 @@ class Oracle:
         a = self._args(width, height, features, camera_pos, camera_quat)
         trial, acc, sec = C.c_longlong(), C.c_longlong(), C.c_double()
         term = np.zeros(cw * ch, np.int32)
-        self.lib.oracle_integrate_sample(C.byref(a), x0, y0, cw, ch, stride, C.byref(trial), C.byref(acc), C.byref(sec), term.ctypes.data)
-        return {"trial_steps": trial.value, "accepted_steps": acc.value, "seconds": sec.value, "terminated": term.reshape(ch, cw)}
+        steps = np.zeros(cw * ch, np.int32)
+        self.lib.oracle_integrate_sample(C.byref(a), x0, y0, cw, ch, stride, C.byref(trial), C.byref(acc), C.byref(sec), term.ctypes.data, steps.ctypes.data)
+        return {"trial_steps": trial.value, "accepted_steps": acc.value, "seconds": sec.value, "terminated": term.reshape(ch, cw), "steps": steps.reshape(ch, cw)}
 
     def metric_eval(self, pos):
         g = np.zeros(16, np.float32)

@@ -855,7 +855,7 @@ static inline void do_generic_ray(lightray* ray, const grt_params& cfg, const Fe
     }
 }
 
-static inline void do_generic_rays(lightray* rays, int count, const grt_params& cfg, const Features& dfg, Counters* total) {
+static inline void do_generic_rays(lightray* rays, int count, const grt_params& cfg, const Features& dfg, Counters* total, int* per_ray_steps = nullptr) {
     long long trial = 0, accepted = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : trial, accepted)
     for (int id = 0; id < count; id++) {
@@ -863,6 +863,7 @@ static inline void do_generic_rays(lightray* rays, int count, const grt_params& 
         do_generic_ray(&rays[id], cfg, dfg, &c);
         trial += c.trial_steps;
         accepted += c.accepted_steps;
+        if (per_ray_steps) per_ray_steps[id] = (int)c.trial_steps;
     }
     if (total) { total->trial_steps += trial; total->accepted_steps += accepted; }
 }

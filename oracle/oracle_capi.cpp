@@ -245,7 +245,7 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
 // Bounded CPU-baseline sample: trace cw x ch rays at pixels (x0 + i*stride, y0 + j*stride) of the full
 // width x height pixel grid (same pixel directions as the full frame), integration stage only.
 int oracle_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int ch, int stride, long long* trial_steps, long long* accepted_steps, double* seconds,
-                            int* terminated_out /* cw*ch or null */) {
+                            int* terminated_out /* cw*ch or null */, int* steps_out /* cw*ch or null */) {
     Features dfg = to_features(a->features);
     grt_params cfg = to_params(a->params);
     float4 camera_quat = from_arr(a->camera_quat);
@@ -260,7 +260,7 @@ int oracle_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, in
     }
     Counters cnt;
     double t0 = now_s();
-    do_generic_rays(rays.data(), cw * ch, cfg, dfg, &cnt);
+    do_generic_rays(rays.data(), cw * ch, cfg, dfg, &cnt, steps_out);
     *seconds = now_s() - t0;
     *trial_steps = cnt.trial_steps;
     *accepted_steps = cnt.accepted_steps;
