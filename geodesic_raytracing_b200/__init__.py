@@ -346,17 +346,20 @@ class Context:
     def render(self, width: int, height: int, fmt: int = GRT_FORMAT_RGBA32F, out=None, stats: bool = True, stripes: Optional[Sequence[Tuple[int, int]]] = None):
         """Render one frame (or the given row stripes). Returns (image, Stats|None).
 
-        out None -> a new host numpy array; a numpy array -> host output (one D2H copy inside the call);
-        a CUDA torch tensor -> device output, no copy."""
+        out None -> a new host numpy array; a numpy array -> host output (one D2H copy inside the call, synchronous);
+        a CUDA torch tensor -> device output, no copy, asynchronous unless stats are requested;
+        a pinned CPU torch tensor -> host output, D2H copy queued behind the frame, asynchronous likewise.
+        Two frames can be in flight: consecutive asynchronous calls alternate between two streams."""
         if stripes is None:
             stripes = [(0, height)]
         rows = sum(b - a for a, b in stripes)
         dtype, ch = (np.float32, 4) if fmt == GRT_FORMAT_RGBA32F else (np.uint8, 4)
-        is_device = False
+        is_device = 0
         if out is None:
             out = np.empty((rows, width, ch), dtype=dtype)
         elif not isinstance(out, np.ndarray):
-            is_device = True
+            # torch tensor: CUDA -> device output; pinned CPU -> asynchronous host output (call synchronize() before reading)
+            is_device = 1 if getattr(out, "is_cuda", True) else 2
         st = Stats() if stats else None
         y0 = (C.c_int * len(stripes))(*[a for a, _ in stripes])
         y1 = (C.c_int * len(stripes))(*[b for _, b in stripes])

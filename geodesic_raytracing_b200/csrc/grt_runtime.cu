@@ -138,8 +138,12 @@ const char* kPrelude =
     "#define GRT_INF __int_as_float(0x7f800000)\n"
     "#define GRT_NAN __int_as_float(0x7fffffff)\n";
 
-std::string program_source(const grt::Metric& m, bool is_static) {
+// `reparameterisation` is the one runtime feature the integration loop branches on every step; like the
+// reference's static program (-DFEATURE_name=value, dynamic_feature_config.cpp:122-180) it is baked in.
+std::string program_source(const grt::Metric& m, bool is_static, bool reparameterisation) {
     std::string s = kPrelude;
+    s += reparameterisation ? "#define GRT_FEATURE_REPARAMETERISATION 1\n" : "#define GRT_FEATURE_REPARAMETERISATION 0\n";
+    if (const char* e = getenv("GRT_INTEGRATE_MIN_BLOCKS")) s += std::string("#define GRT_INTEGRATE_MIN_BLOCKS ") + std::to_string(atoi(e)) + "\n";
     s += GRT_SRC_STRUCTS;
     s += GRT_SRC_COMMON;
     s += grt::emit_metric_source(m, is_static);
@@ -259,10 +263,33 @@ struct grt_metric {
     std::string compile_log;
 };
 
+// Everything one frame in flight owns.  Two slots alternate (the reference keeps two render_state
+// objects in flight, main.cpp:1463-1469): consecutive asynchronous frames run on different streams,
+// so the latency-bound stretches of one frame (the 1/16 prepass, the tails of the integration
+// launches) are filled with the next frame's rays.
+struct FrameSlot {
+    cudaStream_t stream = nullptr;
+    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, pool_buf, worklist, rdata, termination, out;
+    // counters (zeroed every frame): [4] extra ray count; [8 + phase] work counter and [16 + 2 * phase], [17 + 2 * phase]
+    // hot / cold work-list lengths of phase 0 (prepass), 1 (first pass), 2 (refinement); then GrtStats
+    unsigned int* d_counters = nullptr;
+    GrtStats* d_stats = nullptr;
+    GrtCamera* d_cam = nullptr;
+    std::vector<cudaEvent_t> events;
+    GrtFrame frame{};
+    int last_first_pass = 0, last_extra = 0, last_pw = 0, last_ph = 0;
+    bool last_prepass = false;
+    bool used = false;
+};
+
 struct grt_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // cold-path work: textures, tables, geodesic snapshot, introspection
+    FrameSlot slots[4];
+    int n_slots = 2;             // frames in flight (GRT_FRAME_SLOTS, 1..4)
+    unsigned frame_index = 0;
+    FrameSlot* last = nullptr;       // slot of the most recently submitted frame
     bool fast_math = true;
     grt_features feat{};
     grt_metric* metric = nullptr;
@@ -276,15 +303,10 @@ struct grt_ctx {
     GrtCamera* d_cam = nullptr;
 
     Texture tex[2];
-    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, pool_buf, worklist, rdata, termination, tables, identity, out, scratch;
+    DevBuf tables, identity, scratch;
     int identity_len = 0;
-    // counters (zeroed every frame): [4] extra ray count; [8 + phase * 64 + pass] work counter and
-    // [8 + phase * 64 + 32 + pass] parked-ray count of integration pass `pass` of phase 0 (prepass),
-    // 1 (first pass), 2 (refinement); then GrtStats
-    unsigned int* d_counters = nullptr;
-    int passes = 0;           // 128-thread blocks of the integration kernel per SM; 0 = as many as fit (GRT_PASSES)
-    int park_threshold = 16;  // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_PARK_THRESHOLD)
-    GrtStats* d_stats = nullptr;
+    int passes = 3;           // 128-thread blocks of the integration kernel per SM and frame slot; 0 = as many as fit (GRT_BLOCKS_PER_SM)
+    int park_threshold = 0;   // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_DONATE_THRESHOLD)
 
     // geometry cache
     std::vector<int> geom_key;
@@ -299,11 +321,7 @@ struct grt_ctx {
     float4 geo_speed = make_float4(0, 0, 0, 0);
     int geo_parallel_transport = 1;
 
-    // last frame
-    int last_first_pass = 0, last_extra = 0, last_pw = 0, last_ph = 0;
-    bool last_prepass = false;
     std::string launch_log, kernel_info;
-    std::vector<cudaEvent_t> events;
 };
 
 namespace {
@@ -327,7 +345,7 @@ void bind(grt_ctx* c) { CK(cudaSetDevice(c->device)); }
 
 Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
     const grt::Metric& m = *gm->m;
-    std::string src = program_source(m, is_static);
+    std::string src = program_source(m, is_static, c->feat.reparameterisation != 0);
     std::string key = std::to_string(fnv1a(src, 14695981039346656037ull)) + (c->fast_math ? "f" : "p");
     auto it = c->programs.find(key);
     if (it != c->programs.end()) return it->second.get();
@@ -363,14 +381,19 @@ Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
 }
 
 struct Launcher {
-    grt_ctx* c;
+    cudaStream_t stream;
     int launches = 0, integrate_launches = 0;
     void go(CUfunction f, unsigned grid, unsigned block, void** args) {
         if (grid == 0) return;
-        CU(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)c->stream, args, nullptr));
+        CU(g_drv.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, (CUstream)stream, args, nullptr));
         launches++;
     }
 };
+
+void sync_all(grt_ctx* c) {
+    for (auto& S : c->slots) if (S.stream) CK(cudaStreamSynchronize(S.stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
 
 void fill_frame_features(grt_ctx* c, GrtFrame& fr) {
     const grt_features& f = c->feat;
@@ -401,6 +424,7 @@ const int* identity_table(grt_ctx* c, int n) {
         int len = std::max(n, 4096);
         std::vector<int> h(len);
         for (int i = 0; i < len; i++) h[i] = i;
+        sync_all(c);
         c->identity.ensure(sizeof(int) * (size_t)len);
         CK(cudaMemcpyAsync(c->identity.p, h.data(), sizeof(int) * (size_t)len, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream));
@@ -448,6 +472,7 @@ void build_geometry(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, in
             int y = row_global[gy * 2];
             cellrow_refine[gy] = (refine[y] || refine[y + 1]) ? 1 : 0;
         }
+    sync_all(c);   // frames in flight still read the old tables
     // tables: row_global | local_of_global | cellrow_refine
     std::vector<int> all;
     all.insert(all.end(), row_global.begin(), row_global.end());
@@ -478,6 +503,7 @@ void build_geometry(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, in
     c->geom_key = key;
 }
 
+// master camera (geodesic snapshot, introspection) on the cold-path stream
 void upload_camera(grt_ctx* c, Launcher& L) {
     if (c->camera_on_geodesic || !c->camera_dirty) return;
     CK(cudaMemcpyAsync(c->d_cam, &c->cam, sizeof(GrtCamera), cudaMemcpyHostToDevice, c->stream));
@@ -485,34 +511,45 @@ void upload_camera(grt_ctx* c, Launcher& L) {
     L.go(c->prog->k_camera, 1, 32, args);
     c->camera_dirty = false;
 }
+// per-frame camera: uploaded and converted on the frame's own stream (main.cpp:2244-2331); a camera
+// attached to a geodesic is copied from the master, which handle_interpolating_geodesic wrote
+void frame_camera(grt_ctx* c, FrameSlot& S, Launcher& L) {
+    if (c->camera_on_geodesic) {
+        CK(cudaMemcpyAsync(S.d_cam, c->d_cam, sizeof(GrtCamera), cudaMemcpyDeviceToDevice, S.stream));
+        return;
+    }
+    CK(cudaMemcpyAsync(S.d_cam, &c->cam, sizeof(GrtCamera), cudaMemcpyHostToDevice, S.stream));
+    void* args[] = {&S.d_cam, c->params};
+    L.go(c->prog->k_camera, 1, 32, args);
+}
 
 void need_program(grt_ctx* c) {
     if (!c->prog || !c->metric) throw Error(GRT_E_STATE, "no metric bound: call grt_set_metric first");
 }
 
-GrtRays rays_of(grt_ctx* c, size_t slots, bool need_quat) {
-    c->rays_pos.ensure(slots * 16);
-    c->rays_vel.ensure(slots * 16);
-    c->rays_acc.ensure(slots * 16);
-    c->rays_aux.ensure(slots * 16);
-    if (need_quat) c->rays_quat.ensure(slots * 16);
+GrtRays rays_of(FrameSlot& S, size_t slots, bool need_quat) {
+    S.rays_pos.ensure(slots * 16);
+    S.rays_vel.ensure(slots * 16);
+    S.rays_acc.ensure(slots * 16);
+    S.rays_aux.ensure(slots * 16);
+    if (need_quat) S.rays_quat.ensure(slots * 16);
     GrtRays r;
-    r.pos = (float4*)c->rays_pos.p;
-    r.vel = (float4*)c->rays_vel.p;
-    r.acc = (float4*)c->rays_acc.p;
-    r.quat = (float4*)c->rays_quat.p;
-    r.aux = (int4*)c->rays_aux.p;
+    r.pos = (float4*)S.rays_pos.p;
+    r.vel = (float4*)S.rays_vel.p;
+    r.acc = (float4*)S.rays_acc.p;
+    r.quat = (float4*)S.rays_quat.p;
+    r.aux = (int4*)S.rays_aux.p;
     return r;
 }
 
-cudaEvent_t event_at(grt_ctx* c, size_t i) {
-    while (c->events.size() <= i) {
+cudaEvent_t event_at(FrameSlot& S, size_t i) {
+    while (S.events.size() <= i) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
-        c->events.push_back(e);
+        S.events.push_back(e);
     }
-    CK(cudaEventRecord(c->events[i], c->stream));
-    return c->events[i];
+    CK(cudaEventRecord(S.events[i], S.stream));
+    return S.events[i];
 }
 
 int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n, void* out, int format, int out_is_device, grt_stats* stats) {
@@ -523,8 +560,11 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     if (!c->tex[0].set) throw Error(GRT_E_STATE, "no background set: call grt_set_background first");
     const grt::Metric& m = *c->metric->m;
     Program* P = c->prog;
-    Launcher L{c};
     build_geometry(c, w, h, y0s, y1s, n);
+    FrameSlot& S = c->slots[c->frame_index++ % (unsigned)c->n_slots];
+    c->last = &S;
+    S.used = true;
+    Launcher L{S.stream};
     GrtFrame fr = c->frame;
     fill_frame_features(c, fr);
     const bool adaptive = fr.cell == 2;
@@ -551,24 +591,24 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     const size_t extra_cap = adaptive ? (size_t)3 * fr.grid_w * fr.grid_h : 0;
     const size_t slots = std::max((size_t)fr.n_slots + extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)0);
     const bool const_theta = m.constant_theta();
-    GrtRays rays = rays_of(c, slots, const_theta);
-    c->rdata.ensure((size_t)fr.n_rows * w * 16);
-    c->termination.ensure(sizeof(int) * (size_t)std::max(1, pw * ph));
-    int* d_term = (int*)c->termination.p;
+    GrtRays rays = rays_of(S, slots, const_theta);
+    S.rdata.ensure((size_t)fr.n_rows * w * 16);
+    S.termination.ensure(sizeof(int) * (size_t)std::max(1, pw * ph));
+    int* d_term = (int*)S.termination.p;
     const size_t px_bytes = format == GRT_FORMAT_RGBA32F ? 16 : 4;
     void* d_out = out;
-    if (!out_is_device) {
-        c->out.ensure(c->out_pixels * px_bytes);
-        d_out = c->out.p;
+    if (out_is_device != 1) {
+        S.out.ensure(c->out_pixels * px_bytes);
+        d_out = S.out.p;
     }
 
     size_t ev = 0;
-    cudaEvent_t e_start = event_at(c, ev++);
-    CK(cudaMemsetAsync(c->d_counters, 0, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats), c->stream));
-    upload_camera(c, L);
-    cudaEvent_t e_camera = event_at(c, ev++);
+    cudaEvent_t e_start = event_at(S, ev++);
+    CK(cudaMemsetAsync(S.d_counters, 0, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats), S.stream));
+    frame_camera(c, S, L);
+    cudaEvent_t e_camera = event_at(S, ev++);
 
-    int* d_extra = (int*)(c->d_counters + 4);
+    int* d_extra = (int*)(S.d_counters + 4);
     const int* null_count = nullptr;
     float max_accel = c->feat.max_acceleration_change;
     const unsigned persistent_grid = (unsigned)(c->num_sms * (c->passes > 0 ? std::min(c->passes, P->integrate_blocks_per_sm) : P->integrate_blocks_per_sm));
@@ -578,10 +618,10 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         unsigned cap = 1;
         while (cap < persistent_grid * 128u * 4u) cap <<= 1;
         const size_t bytes = (size_t)cap * 84 + 64;
-        const bool fresh = c->pool_buf.cap < bytes;
-        c->pool_buf.ensure(bytes);
-        if (fresh) CK(cudaMemsetAsync(c->pool_buf.p, 0, c->pool_buf.cap, c->stream));   // tickets run on across launches; ready flags start at 0
-        char* p = (char*)c->pool_buf.p;
+        const bool fresh = S.pool_buf.cap < bytes;
+        S.pool_buf.ensure(bytes);
+        if (fresh) CK(cudaMemsetAsync(S.pool_buf.p, 0, S.pool_buf.cap, S.stream));   // tickets run on across launches; ready flags start at 0
+        char* p = (char*)S.pool_buf.p;
         pool.counters = (unsigned int*)p;
         p += 64;
         pool.pos = (float4*)p;
@@ -594,89 +634,88 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         pool.donate_threshold = c->park_threshold;
     }
     // work lists (see GrtWorkList): one int buffer reused by the three phases, which run back to back
-    c->worklist.ensure(sizeof(int) * std::max<size_t>({(size_t)fr.n_slots, extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)1}));
+    S.worklist.ensure(sizeof(int) * std::max<size_t>({(size_t)fr.n_slots, extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)1}));
     auto worklist = [&](int phase, size_t capacity) {
         GrtWorkList wl;
-        wl.slots = (int*)c->worklist.p;
-        wl.n_hot = c->d_counters + 16 + 2 * phase;
-        wl.n_cold = c->d_counters + 17 + 2 * phase;
+        wl.slots = (int*)S.worklist.p;
+        wl.n_hot = S.d_counters + 16 + 2 * phase;
+        wl.n_cold = S.d_counters + 17 + 2 * phase;
         wl.capacity = (int)capacity;
         return wl;
     };
     GrtWorkList wl_p = worklist(0, use_prepass ? pf.n_slots : 1), wl_f = worklist(1, fr.n_slots), wl_x = worklist(2, std::max<size_t>(extra_cap, 1));
     auto integrate = [&](GrtFrame& f, GrtWorkList& wl, int phase, size_t max_items) {
         unsigned grid = std::min(persistent_grid, (unsigned)((max_items + 127) / 128));
-        unsigned int* wc = c->d_counters + 8 + phase;
-        void* args[] = {&rays, &f, &wl, &pool, &wc, &c->d_stats, &max_accel, c->params};
+        unsigned int* wc = S.d_counters + 8 + phase;
+        void* args[] = {&rays, &f, &wl, &pool, &wc, &S.d_stats, &max_accel, c->params};
         L.go(P->k_integrate, grid, 128, args);
         L.integrate_launches++;
     };
 
     if (use_prepass) {
         int one = 1;
-        void* a0[] = {&rays, &pf, &c->d_cam, &d_term, &one, &wl_p, c->params};
+        void* a0[] = {&rays, &pf, &S.d_cam, &d_term, &one, &wl_p, c->params};
         L.go(P->k_init_rays, (unsigned)((pf.n_slots + 127) / 128), 128, a0);
         integrate(pf, wl_p, 0, pf.n_slots);
         void* a1[] = {&rays, &pf, &d_term};
         L.go(P->k_prepass_mask, (unsigned)((pf.n_slots + 127) / 128), 128, a1);
     }
-    cudaEvent_t e_prepass = event_at(c, ev++);
+    cudaEvent_t e_prepass = event_at(S, ev++);
     {
         int zero = 0;
-        void* a0[] = {&rays, &fr, &c->d_cam, &d_term, &zero, &wl_f, c->params};
+        void* a0[] = {&rays, &fr, &S.d_cam, &d_term, &zero, &wl_f, c->params};
         L.go(P->k_init_rays, (unsigned)((fr.n_slots + 127) / 128), 128, a0);
     }
-    cudaEvent_t e_init = event_at(c, ev++);
+    cudaEvent_t e_init = event_at(S, ev++);
     integrate(fr, wl_f, 1, fr.n_slots);
-    cudaEvent_t e_int1 = event_at(c, ev++);
-    GrtRenderData* d_rdata = (GrtRenderData*)c->rdata.p;
+    cudaEvent_t e_int1 = event_at(S, ev++);
+    GrtRenderData* d_rdata = (GrtRenderData*)S.rdata.p;
     {
         int begin = 0, fixed = fr.n_slots;
         void* a[] = {&rays, &fr, &begin, &null_count, &fixed, &d_rdata, c->params};
         L.go(P->k_render_data, (unsigned)std::min((fr.n_slots + 127) / 128, c->num_sms * 16), 128, a);
     }
-    cudaEvent_t e_rd1 = event_at(c, ev++);
+    cudaEvent_t e_rd1 = event_at(S, ev++);
     cudaEvent_t e_adapt = e_rd1, e_int2 = e_rd1, e_rd2 = e_rd1;
     if (adaptive) {
-        void* a[] = {&rays, &fr, &c->d_cam, &d_rdata, &d_extra, &wl_x, c->params};
+        void* a[] = {&rays, &fr, &S.d_cam, &d_rdata, &d_extra, &wl_x, c->params};
         L.go(P->k_adaptive, (unsigned)((fr.n_slots + 127) / 128), 128, a);
-        e_adapt = event_at(c, ev++);
+        e_adapt = event_at(S, ev++);
         const int* cnt = d_extra;
         integrate(fr, wl_x, 2, extra_cap);
-        e_int2 = event_at(c, ev++);
+        e_int2 = event_at(S, ev++);
         int begin = fr.n_slots, fixed = 0;
         void* a2[] = {&rays, &fr, &begin, &cnt, &fixed, &d_rdata, c->params};
         L.go(P->k_render_data, (unsigned)(c->num_sms * 16), 128, a2);
-        e_rd2 = event_at(c, ev++);
+        e_rd2 = event_at(S, ev++);
     }
     const GrtTexture* t1 = &c->tex[0].desc;
     const GrtTexture* t2 = c->tex[1].set ? &c->tex[1].desc : &c->tex[0].desc;
     for (auto& st : c->stripes) {
-        grt_launch_render(d_rdata, &fr, &st, t1, t2, d_out, format, c->stream);
+        grt_launch_render(d_rdata, &fr, &st, t1, t2, d_out, format, S.stream);
         L.launches++;
     }
     CK(cudaGetLastError());
-    cudaEvent_t e_render = event_at(c, ev++);
-    if (!out_is_device) CK(cudaMemcpyAsync(out, d_out, c->out_pixels * px_bytes, cudaMemcpyDeviceToHost, c->stream));
-    cudaEvent_t e_end = event_at(c, ev++);
+    cudaEvent_t e_render = event_at(S, ev++);
+    if (out_is_device != 1) CK(cudaMemcpyAsync(out, d_out, c->out_pixels * px_bytes, cudaMemcpyDeviceToHost, S.stream));
+    cudaEvent_t e_end = event_at(S, ev++);
 
-    c->last_first_pass = fr.n_slots;
-    c->last_pw = pw;
-    c->last_ph = ph;
-    c->last_prepass = use_prepass;
-    if (stats || !out_is_device) {
-        CK(cudaStreamSynchronize(c->stream));
-    }
+    S.last_first_pass = fr.n_slots;
+    S.last_pw = pw;
+    S.last_ph = ph;
+    S.last_prepass = use_prepass;
+    S.frame = fr;
+    if (stats || out_is_device == 0) CK(cudaStreamSynchronize(S.stream));
     if (stats) {
         struct { unsigned int counters[kCounterWords]; GrtStats s; } host;
-        CK(cudaMemcpy(&host, c->d_counters, sizeof host, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&host, S.d_counters, sizeof host, cudaMemcpyDeviceToHost));
         memset(stats, 0, sizeof *stats);
         stats->trial_steps = host.s.trial_steps;
         stats->accepted_steps = host.s.accepted_steps;
         stats->rays_integrated = host.s.rays_integrated;
         stats->rays_finished = host.s.rays_finished;
         stats->extra_rays = host.counters[4];
-        c->last_extra = (int)host.counters[4];
+        S.last_extra = (int)host.counters[4];
         auto ms = [](cudaEvent_t a, cudaEvent_t b) { float t = 0; cudaEventElapsedTime(&t, a, b); return t; };
         stats->ms_camera = ms(e_start, e_camera);
         stats->ms_prepass = ms(e_camera, e_prepass);
@@ -694,7 +733,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
                  adaptive ? ms(e_int2, e_rd2) : 0.0f, stats->ms_render, ms(e_render, e_end));
         c->launch_log = buf;
     } else {
-        c->last_extra = -1;   // unknown until read back
+        S.last_extra = -1;   // unknown until read back
     }
     return GRT_OK;
 }
@@ -717,6 +756,7 @@ void build_texture(grt_ctx* c, Texture& t, const void* src, bool src_is_device, 
         lw = std::max(1, lw / 2);
         lh = std::max(1, lh / 2);
     }
+    sync_all(c);   // frames in flight still sample the old pyramid
     // GL chain (box filter, round to nearest) in scratch, then the float-readback requantisation
     c->scratch.ensure(total * 4);
     t.data.ensure(total * 4);
@@ -845,7 +885,7 @@ int grt_compile_metric(grt_metric* m, int is_static, int fast_math, const char**
         if (k != std::string::npos) stem = stem.substr(k + 1);
         k = stem.find_last_of('.');
         if (k != std::string::npos) stem = stem.substr(0, k);
-        compile_cubin(program_source(*m->m, is_static != 0), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &m->compile_log, nullptr);
+        compile_cubin(program_source(*m->m, is_static != 0, false), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &m->compile_log, nullptr);
         if (log_out) *log_out = m->compile_log.c_str();
         return GRT_OK;
     });
@@ -872,12 +912,18 @@ grt_ctx* grt_create(int device) {
         features_default(&c->feat);
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaMalloc((void**)&c->d_cam, sizeof(GrtCamera)));
-        void* counters = nullptr;
-        CK(cudaMalloc(&counters, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats)));
-        c->d_counters = (unsigned int*)counters;
-        c->d_stats = (GrtStats*)(c->d_counters + kCounterWords);
-        if (const char* e = getenv("GRT_PASSES")) c->passes = atoi(e);
-        if (const char* e = getenv("GRT_PARK_THRESHOLD")) c->park_threshold = atoi(e);
+        if (const char* e = getenv("GRT_FRAME_SLOTS")) c->n_slots = std::max(1, std::min(4, atoi(e)));
+        for (auto& S : c->slots) {
+            CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+            CK(cudaMalloc((void**)&S.d_cam, sizeof(GrtCamera)));
+            void* counters = nullptr;
+            CK(cudaMalloc(&counters, kCounterWords * sizeof(unsigned int) + sizeof(GrtStats)));
+            S.d_counters = (unsigned int*)counters;
+            S.d_stats = (GrtStats*)(S.d_counters + kCounterWords);
+        }
+        c->last = &c->slots[0];
+        if (const char* e = getenv("GRT_BLOCKS_PER_SM")) c->passes = atoi(e);
+        if (const char* e = getenv("GRT_DONATE_THRESHOLD")) c->park_threshold = atoi(e);
         // default camera (main.cpp:664-673)
         c->cam.pos_cart = make_float4(0, 0, -4, 0);
         c->cam.quat = make_float4(-0.70710678f, 0, 0, 0.70710678f);
@@ -891,14 +937,18 @@ grt_ctx* grt_create(int device) {
 void grt_destroy(grt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (auto& S : c->slots) if (S.stream) cudaStreamSynchronize(S.stream);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
-    for (DevBuf* b : {&c->rays_pos, &c->rays_vel, &c->rays_acc, &c->rays_quat, &c->rays_aux, &c->pool_buf, &c->worklist, &c->rdata, &c->termination, &c->tables, &c->identity, &c->out, &c->scratch,
-                      &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc})
-        b->release();
-    for (auto e : c->events) cudaEventDestroy(e);
+    for (auto& S : c->slots) {
+        for (DevBuf* b : {&S.rays_pos, &S.rays_vel, &S.rays_acc, &S.rays_quat, &S.rays_aux, &S.pool_buf, &S.worklist, &S.rdata, &S.termination, &S.out}) b->release();
+        for (auto e : S.events) cudaEventDestroy(e);
+        cudaFree(S.d_cam);
+        cudaFree(S.d_counters);
+        if (S.stream) cudaStreamDestroy(S.stream);
+    }
+    for (DevBuf* b : {&c->tables, &c->identity, &c->scratch, &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc}) b->release();
     cudaFree(c->d_cam);
-    cudaFree(c->d_counters);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -952,9 +1002,17 @@ int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
 }
 
 int grt_set_features(grt_ctx* c, const grt_features* f) {
-    if (!c || !f) { g_err = "null argument"; return GRT_E_INVALID; }
-    c->feat = *f;
-    return GRT_OK;
+    return guard([&] {
+        if (!c || !f) throw Error(GRT_E_INVALID, "null argument");
+        const bool rebuild = c->prog && (c->feat.reparameterisation != 0) != (f->reparameterisation != 0);
+        c->feat = *f;
+        if (rebuild) {   // a feature the program is specialised on changed (soft recompile, metric_manager.hpp:153-167)
+            bind(c);
+            c->prog = get_program(c, c->metric, c->is_static);
+            c->kernel_info = c->prog->info;
+        }
+        return GRT_OK;
+    });
 }
 int grt_get_features(const grt_ctx* c, grt_features* f) {
     if (!c || !f) { g_err = "null argument"; return GRT_E_INVALID; }
@@ -1000,7 +1058,7 @@ int grt_snapshot_geodesic(grt_ctx* c, float linear_basis_speed, int parallel_tra
         if (!c) throw Error(GRT_E_INVALID, "null context");
         bind(c);
         need_program(c);
-        Launcher L{c};
+        Launcher L{c->stream};
         // the camera tetrad at the snapshot point (init_basis_vectors, main.cpp:2314-2331)
         c->camera_on_geodesic = false;
         c->camera_dirty = true;
@@ -1037,7 +1095,7 @@ int grt_set_camera_on_geodesic(grt_ctx* c, float proper_time) {
         bind(c);
         need_program(c);
         if (c->geo_count <= 0) throw Error(GRT_E_STATE, "no geodesic snapshot: call grt_snapshot_geodesic first");
-        Launcher L{c};
+        Launcher L{c->stream};
         // quat / speeds come from the host camera, position + tetrad from the path
         CK(cudaMemcpyAsync((char*)c->d_cam + offsetof(GrtCamera, quat), &c->cam.quat, sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync((char*)c->d_cam + offsetof(GrtCamera, basis_speed), &c->geo_speed, sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -1045,6 +1103,7 @@ int grt_set_camera_on_geodesic(grt_ctx* c, float proper_time) {
         float4* vel_out = nullptr;
         void* a[] = {&c->d_cam, &c->geo, &proper_time, &pt, &vel_out, c->params};
         L.go(c->prog->k_geodesic_interpolate, 1, 32, a);
+        CK(cudaStreamSynchronize(c->stream));   // frames copy the master camera on their own streams
         c->camera_on_geodesic = true;
         return GRT_OK;
     });
@@ -1073,11 +1132,11 @@ int grt_synchronize(grt_ctx* c) {
     return guard([&] {
         if (!c) throw Error(GRT_E_INVALID, "null context");
         bind(c);
-        CK(cudaStreamSynchronize(c->stream));
+        sync_all(c);
         return GRT_OK;
     });
 }
-void* grt_stream(grt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+void* grt_stream(grt_ctx* c) { return c ? (void*)c->last->stream : nullptr; }
 
 // ---- introspection ------------------------------------------------------------------------------------
 int grt_get_camera_state(grt_ctx* c, grt_camera_state* o) {
@@ -1085,7 +1144,7 @@ int grt_get_camera_state(grt_ctx* c, grt_camera_state* o) {
         if (!c || !o) throw Error(GRT_E_INVALID, "null argument");
         bind(c);
         need_program(c);
-        Launcher L{c};
+        Launcher L{c->stream};
         upload_camera(c, L);
         GrtCamera h;
         CK(cudaMemcpyAsync(&h, c->d_cam, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -1101,14 +1160,14 @@ int grt_debug_ray_count(grt_ctx* c, int* first, int* extra) {
     return guard([&] {
         if (!c) throw Error(GRT_E_INVALID, "null context");
         bind(c);
-        if (c->last_extra < 0) {
-            CK(cudaStreamSynchronize(c->stream));
+        if (c->last->last_extra < 0) {
+            sync_all(c);
             unsigned int v = 0;
-            CK(cudaMemcpy(&v, c->d_counters + 4, 4, cudaMemcpyDeviceToHost));
-            c->last_extra = (int)v;
+            CK(cudaMemcpy(&v, c->last->d_counters + 4, 4, cudaMemcpyDeviceToHost));
+            c->last->last_extra = (int)v;
         }
-        if (first) *first = c->last_first_pass;
-        if (extra) *extra = c->last_extra;
+        if (first) *first = c->last->last_first_pass;
+        if (extra) *extra = c->last->last_extra;
         return GRT_OK;
     });
 }
@@ -1119,15 +1178,16 @@ int grt_debug_read_rays(grt_ctx* c, grt_lightray* out, int max_count) {
         if (!c || !out) throw Error(GRT_E_INVALID, "null argument");
         int first = 0, extra = 0;
         if (grt_debug_ray_count(c, &first, &extra) != GRT_OK) throw Error(GRT_E_CUDA, g_err);
+        sync_all(c);
         n = std::min(max_count, first + extra);
         if (n <= 0) return GRT_OK;
         std::vector<float4> pos(n), vel(n), acc(n), quat(n, make_float4(0, 0, 0, 1));
         std::vector<int4> aux(n);
-        CK(cudaMemcpy(pos.data(), c->rays_pos.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(vel.data(), c->rays_vel.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(acc.data(), c->rays_acc.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(aux.data(), c->rays_aux.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        if (c->metric->m->constant_theta() && c->rays_quat.p) CK(cudaMemcpy(quat.data(), c->rays_quat.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pos.data(), c->last->rays_pos.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(vel.data(), c->last->rays_vel.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(acc.data(), c->last->rays_acc.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(aux.data(), c->last->rays_aux.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        if (c->metric->m->constant_theta() && c->last->rays_quat.p) CK(cudaMemcpy(quat.data(), c->last->rays_quat.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; i++) {
             grt_lightray& r = out[i];
             memset(&r, 0, sizeof r);
@@ -1151,13 +1211,13 @@ int grt_debug_read_render_data(grt_ctx* c, grt_render_data* out, int max_count) 
     int rc = guard([&] {
         if (!c || !out) throw Error(GRT_E_INVALID, "null argument");
         bind(c);
-        CK(cudaStreamSynchronize(c->stream));
-        const GrtFrame& fr = c->frame;
+        sync_all(c);
+        const GrtFrame& fr = c->last->frame;
         n = std::min(max_count, fr.n_rows * fr.full_w);
         if (n <= 0) return GRT_OK;
         std::vector<float4> rd(n);
         std::vector<int> row_global(fr.n_rows);
-        CK(cudaMemcpy(rd.data(), c->rdata.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rd.data(), c->last->rdata.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(row_global.data(), fr.row_global, sizeof(int) * fr.n_rows, cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; i++) {
             grt_render_data& r = out[i];
@@ -1182,12 +1242,12 @@ int grt_debug_read_prepass_mask(grt_ctx* c, int* out, int max_count, int* pw, in
     int rc = guard([&] {
         if (!c) throw Error(GRT_E_INVALID, "null context");
         bind(c);
-        CK(cudaStreamSynchronize(c->stream));
-        if (pw) *pw = c->last_pw;
-        if (ph) *ph = c->last_ph;
-        if (!c->last_prepass) return GRT_OK;
-        n = std::min(max_count, c->last_pw * c->last_ph);
-        if (out && n > 0) CK(cudaMemcpy(out, c->termination.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+        sync_all(c);
+        if (pw) *pw = c->last->last_pw;
+        if (ph) *ph = c->last->last_ph;
+        if (!c->last->last_prepass) return GRT_OK;
+        n = std::min(max_count, c->last->last_pw * c->last->last_ph);
+        if (out && n > 0) CK(cudaMemcpy(out, c->last->termination.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
         return GRT_OK;
     });
     return rc == GRT_OK ? n : rc;
@@ -1245,7 +1305,7 @@ int grt_debug_eval_metric(grt_ctx* c, const float* positions, const float* veloc
         float2* d_rad = (float2*)(d_pol + n);
         CK(cudaMemcpyAsync(d_pos, positions, n * 16, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d_vel, velocities, n * 16, cudaMemcpyHostToDevice, c->stream));
-        Launcher L{c};
+        Launcher L{c->stream};
         void* a[] = {&d_pos, &d_vel, &count, &d_g, &d_dg, &d_acc, &d_pol, &d_rad, c->params};
         L.go(c->prog->k_eval_metric, (unsigned)((count + 63) / 64), 64, a);
         if (g16) CK(cudaMemcpyAsync(g16, d_g, n * 64, cudaMemcpyDeviceToHost, c->stream));
@@ -1270,7 +1330,7 @@ int grt_debug_tetrad_at(grt_ctx* c, const float* positions, int count, const flo
         int* d_tl = (int*)(d_tet + n * 4);
         CK(cudaMemcpyAsync(d_pos, positions, n * 16, cudaMemcpyHostToDevice, c->stream));
         float3 sp = make_float3(speed ? speed[0] : 0.f, speed ? speed[1] : 0.f, speed ? speed[2] : 0.f);
-        Launcher L{c};
+        Launcher L{c->stream};
         void* a[] = {&d_pos, &count, &sp, &orient, &d_tet, &d_tl, c->params};
         L.go(c->prog->k_tetrad_at, (unsigned)((count + 63) / 64), 64, a);
         CK(cudaMemcpyAsync(tetrads16, d_tet, n * 64, cudaMemcpyDeviceToHost, c->stream));

@@ -435,7 +435,10 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
 // it pushed, so a record is never orphaned; results do not depend on which lane runs a ray.
 static __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
 
-extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtFrame fr, GrtWorkList wl, GrtPool pool, unsigned int* work_counter, GrtStats* stats,
+#ifndef GRT_INTEGRATE_MIN_BLOCKS
+#define GRT_INTEGRATE_MIN_BLOCKS 1
+#endif
+extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_integrate(GrtRays rays, GrtFrame fr, GrtWorkList wl, GrtPool pool, unsigned int* work_counter, GrtStats* stats,
                                                               float max_acceleration, grt_params cfg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -576,7 +579,11 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
             drop = pos.y < GRT_CYLINDRICAL_TERMINATOR;
 #endif
 #if !GRT_UNCONDITIONALLY_NONSINGULAR
+#if GRT_FEATURE_REPARAMETERISATION
             drop = drop || (fabsf(vel.x / dlambda) > 1000.0f + f_in_x && fabsf(acc.x / dlambda) > 100.0f);
+#else
+            drop = drop || (fabsf(vel.x) > 1000.0f + f_in_x && fabsf(acc.x) > 100.0f);   // running_dlambda_dnew stays 1
+#endif
 #endif
             if (drop) {
                 alive = false;
@@ -605,12 +612,14 @@ extern "C" __global__ void __launch_bounds__(128) k_integrate(GrtRays rays, GrtF
                 const float hds = 0.5f * ds;
                 float4 nvel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds,
                                  vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
-                if (fr.reparameterisation) {
+#if GRT_FEATURE_REPARAMETERISATION
+                {
                     float K = 1.0f / fmaxf(fmaxf(fabsf(nvel.x), fabsf(nvel.y)), fmaxf(fabsf(nvel.z), fabsf(nvel.w)));
                     nvel = nvel * K;
                     nacc = nacc * (K * K);
                     dlambda *= K;
                 }
+#endif
                 trial++;
                 bool accept = true;
 #if GRT_ADAPTIVE_PRECISION

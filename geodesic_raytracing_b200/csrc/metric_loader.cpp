@@ -635,6 +635,41 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         Expr a[4];
         symbolic_solve_sym4(g, w, a);
         for (int i = 0; i < 4; i++) d.accel[i] = a[i].id;
+        // Second arrangement of the same w_m: with the covector P_m = g_ml v^l and the scalar
+        // S = g_kl v^k v^l (v held constant), w_m = (v . grad) P_m - 1/2 d_m S.  P and S are cleaned up
+        // (common factors pulled out) *before* they are differentiated, so metrics with product
+        // structure - Kerr-Schild forms g = eta + H l l, conformally flat ones - never expand the
+        // 40 separate partials.  The cheaper of the two arrangements is emitted.
+        size_t best_n = G.op_count(std::vector<int>(d.accel, d.accel + 4));
+        auto consider = [&](const int cand[4]) {
+            size_t n = G.op_count(std::vector<int>(cand, cand + 4));
+            if (n < best_n) { best_n = n; for (int i = 0; i < 4; i++) d.accel[i] = cand[i]; }
+        };
+        const int base[4] = {d.accel[0], d.accel[1], d.accel[2], d.accel[3]};
+        for (int dist = 0; dist < 2; dist++) {
+            int cur[4];
+            for (int i = 0; i < 4; i++) cur[i] = G.factor(base[i], dist != 0);
+            consider(cur);
+            Expr P[4], S(0.0);
+            for (int mm = 0; mm < 4; mm++) {
+                Expr s(0.0);
+                for (int l = 0; l < 4; l++) s += g[mm * 4 + l] * iv[l];
+                P[mm] = Expr::from_id(G.factor(s.id, dist != 0));
+            }
+            for (int mm = 0; mm < 4; mm++) S += P[mm] * iv[mm];
+            S = Expr::from_id(G.factor(S.id, dist != 0));
+            Expr w2[4], a2[4];
+            for (int mm = 0; mm < 4; mm++) {
+                Expr first(0.0);
+                for (int k = 0; k < 4; k++) first += P[mm].diff(v[k]) * iv[k];
+                w2[mm] = Expr::from_id(G.factor((first - Expr(0.5) * S.diff(v[mm])).id, dist != 0));
+            }
+            symbolic_solve_sym4(g, w2, a2);
+            int alt[4], alt_raw[4];
+            for (int i = 0; i < 4; i++) { alt_raw[i] = a2[i].id; alt[i] = G.factor(a2[i].id, dist != 0); }
+            consider(alt_raw);
+            consider(alt);
+        }
     }
     // constant-theta specialisation (cl.cl:3294-3306): v3 = (float)(pi/2), iv3 = 0, a.z = 0
     if (m.constant_theta()) {

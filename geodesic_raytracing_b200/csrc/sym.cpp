@@ -273,10 +273,10 @@ int Graph::diff(int id, int wrt) {
         case Op::Sub: r = M(Op::Sub, D(n.a), D(n.b)); break;
         case Op::Mul: r = M(Op::Add, M(Op::Mul, D(n.a), n.b), M(Op::Mul, n.a, D(n.b))); break;
         case Op::Div: {
-            // (a'b - ab')/b^2
+            // q = a/b: q' = (a' - q b')/b reuses the quotient (three ops instead of five)
             int da = D(n.a), db = D(n.b);
             if (is_const(db, 0.0)) r = M(Op::Div, da, n.b);
-            else r = M(Op::Div, M(Op::Sub, M(Op::Mul, da, n.b), M(Op::Mul, n.a, db)), M(Op::Mul, n.b, n.b));
+            else r = M(Op::Div, M(Op::Sub, da, M(Op::Mul, id, db)), n.b);
             break;
         }
         case Op::Neg: r = M(Op::Neg, D(n.a)); break;
@@ -349,6 +349,151 @@ int Graph::substitute(int id, const std::map<int, int>& repl) {
         return out;
     };
     return go(id);
+}
+
+namespace {
+struct Term {
+    double coef = 1.0;
+    std::vector<int> factors;   // sorted node ids, repeats allowed
+};
+}  // namespace
+
+int Graph::factor(int id, bool distribute) {
+    auto& memo_table = factor_memo_[distribute ? 1 : 0];
+    auto memo = memo_table.find(id);
+    if (memo != memo_table.end()) return memo->second;
+    const Node n = nodes_[id];
+    int result;
+    auto is_sum = [&](Op op) { return op == Op::Add || op == Op::Sub; };
+    if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param) {
+        result = id;
+    } else if (is_sum(n.op) || n.op == Op::Neg || n.op == Op::Mul) {
+        // flatten the sum rooted here into signed products of (recursively cleaned) atomic factors
+        std::vector<Term> terms;
+        std::function<void(int, Term&)> flatten_mul = [&](int x, Term& t) {
+            const Node m = nodes_[x];
+            if (m.op == Op::Mul) { flatten_mul(m.a, t); flatten_mul(m.b, t); }
+            else if (m.op == Op::Neg) { t.coef = -t.coef; flatten_mul(m.a, t); }
+            else if (m.op == Op::Const) t.coef *= m.val;
+            else t.factors.push_back(factor(x, distribute));
+        };
+        std::function<void(int, double)> collect = [&](int x, double sign) {
+            const Node m = nodes_[x];
+            if (m.op == Op::Add) { collect(m.a, sign); collect(m.b, sign); }
+            else if (m.op == Op::Sub) { collect(m.a, sign); collect(m.b, -sign); }
+            else if (m.op == Op::Neg) collect(m.a, -sign);
+            else {
+                Term t;
+                t.coef = sign;
+                flatten_mul(x, t);
+                // a cleaned factor may itself have become a product or a constant: absorb it
+                std::vector<int> flat;
+                for (size_t i = 0; i < t.factors.size(); i++) {
+                    const Node f = nodes_[t.factors[i]];
+                    if (f.op == Op::Const) t.coef *= f.val;
+                    else if (f.op == Op::Neg) { t.coef = -t.coef; t.factors.push_back(f.a); }
+                    else if (f.op == Op::Mul) { t.factors.push_back(f.a); t.factors.push_back(f.b); }
+                    else flat.push_back(t.factors[i]);
+                }
+                std::sort(flat.begin(), flat.end());
+                t.factors = flat;
+                if (t.coef == 0.0) return;
+                if (distribute) {
+                    // multiply out short sums sitting inside the product (bounded, so nothing blows up)
+                    std::vector<Term> work{t}, done;
+                    bool gave_up = false;
+                    while (!work.empty() && !gave_up) {
+                        Term cur = work.back();
+                        work.pop_back();
+                        size_t at = cur.factors.size();
+                        for (size_t i = 0; i < cur.factors.size(); i++)
+                            if (is_sum(nodes_[cur.factors[i]].op)) { at = i; break; }
+                        if (at == cur.factors.size()) { done.push_back(cur); continue; }
+                        int sum_node = cur.factors[at];
+                        cur.factors.erase(cur.factors.begin() + at);
+                        std::vector<std::pair<double, int>> parts;
+                        std::function<void(int, double)> split = [&](int y, double sg) {
+                            const Node q = nodes_[y];
+                            if (q.op == Op::Add) { split(q.a, sg); split(q.b, sg); }
+                            else if (q.op == Op::Sub) { split(q.a, sg); split(q.b, -sg); }
+                            else if (q.op == Op::Neg) split(q.a, -sg);
+                            else parts.push_back({sg, y});
+                        };
+                        split(sum_node, 1.0);
+                        if (parts.size() > 4 || work.size() + done.size() + parts.size() > 12) { gave_up = true; break; }
+                        for (auto& pr : parts) {
+                            Term nt = cur;
+                            nt.coef *= pr.first;
+                            std::vector<int> stack{pr.second};
+                            while (!stack.empty()) {
+                                int y = stack.back();
+                                stack.pop_back();
+                                const Node q = nodes_[y];
+                                if (q.op == Op::Mul) { stack.push_back(q.a); stack.push_back(q.b); }
+                                else if (q.op == Op::Neg) { nt.coef = -nt.coef; stack.push_back(q.a); }
+                                else if (q.op == Op::Const) nt.coef *= q.val;
+                                else nt.factors.push_back(y);
+                            }
+                            std::sort(nt.factors.begin(), nt.factors.end());
+                            if (nt.coef != 0.0) work.push_back(nt);
+                        }
+                    }
+                    if (!gave_up) { for (auto& d : done) terms.push_back(d); return; }
+                }
+                terms.push_back(t);
+            }
+        };
+        collect(id, 1.0);
+        std::function<int(std::vector<Term>&)> build = [&](std::vector<Term>& ts) -> int {
+            if (ts.empty()) return constant(0.0);
+            // most frequent factor (counted once per term)
+            std::map<int, int> freq;
+            for (auto& t : ts) {
+                int prev = -1;
+                for (int f : t.factors) { if (f != prev) freq[f]++; prev = f; }
+            }
+            int best = -1, best_n = 1;
+            for (auto& kv : freq) if (kv.second > best_n) { best = kv.first; best_n = kv.second; }
+            auto product = [&](const Term& t) {
+                int acc = -1;
+                for (int f : t.factors) acc = acc < 0 ? f : make(Op::Mul, acc, f);
+                if (acc < 0) return constant(t.coef);
+                if (t.coef != 1.0) acc = make(Op::Mul, constant(t.coef), acc);
+                return acc;
+            };
+            if (best < 0 || ts.size() == 1) {
+                // no shared factor: plain sum, positive terms first so that it emits as a + b - c
+                std::stable_sort(ts.begin(), ts.end(), [](const Term& a, const Term& b) { return (a.coef > 0) > (b.coef > 0); });
+                int acc = -1;
+                for (auto& t : ts) {
+                    Term p = t;
+                    bool neg = p.coef < 0 && acc >= 0;
+                    if (neg) p.coef = -p.coef;
+                    int v = product(p);
+                    acc = acc < 0 ? v : make(neg ? Op::Sub : Op::Add, acc, v);
+                }
+                return acc;
+            }
+            std::vector<Term> with, without;
+            for (auto& t : ts) {
+                auto it = std::find(t.factors.begin(), t.factors.end(), best);
+                if (it == t.factors.end()) without.push_back(t);
+                else { Term r = t; r.factors.erase(r.factors.begin() + (it - t.factors.begin())); with.push_back(r); }
+            }
+            int inner = build(with);
+            int lhs = make(Op::Mul, best, inner);
+            if (without.empty()) return lhs;
+            int rest = build(without);
+            return make(Op::Add, lhs, rest);
+        };
+        result = build(terms);
+    } else {
+        int a = n.a >= 0 ? factor(n.a, distribute) : -1, b = n.b >= 0 ? factor(n.b, distribute) : -1, c = n.c >= 0 ? factor(n.c, distribute) : -1;
+        result = (a == n.a && b == n.b && c == n.c) ? id : make(n.op, a, b, c);
+    }
+    memo_table[id] = result;
+    memo_table[result] = result;
+    return result;
 }
 
 bool Graph::depends_on(int id, int leaf) const {

@@ -65,6 +65,12 @@ public:
     bool depends_on(int id, int leaf) const;
     // number of arithmetic nodes reachable from the outputs (flop-ish count, FMA not fused)
     size_t op_count(const std::vector<int>& outs) const;
+    // Algebraic clean-up of an expression: every maximal sum is flattened into signed product terms and
+    // common factors are pulled out greedily (a*b*x + a*c*x -> a*x*(b + c)), recursively, bottom-up and
+    // memoised so shared sub-expressions stay shared.  Same value up to floating-point reassociation.
+    // With `distribute`, a product that contains a short sum is multiplied out first ((c + H l l) v ->
+    // c v + H l l v) so that factors hidden inside it can be shared with the neighbouring terms.
+    int factor(int id, bool distribute = false);
     // human readable infix (tests, debugging, classification decisions)
     std::string to_string(int id) const;
 
@@ -74,6 +80,7 @@ private:
     std::vector<Node> nodes_;
     std::unordered_map<std::string, int> table_;
     std::map<std::pair<int, int>, int> diff_memo_;
+    std::unordered_map<int, int> factor_memo_[2];
 };
 
 // value-semantics handle

@@ -144,7 +144,8 @@ int grt_set_fast_math(grt_ctx*, int enabled);
 /* Scheduling of the integration kernel (results do not depend on it): `blocks_per_sm` 128-thread
  * blocks of the persistent grid per SM (0 = as many as fit: throughput; fewer = lower per-step
  * latency for the longest rays); once the work queue is dry, a warp with `donate_threshold` live rays
- * or fewer hands them to warps with free lanes through the exchange pool (0 disables the exchange). */
+ * or fewer hands them to warps with free lanes through the exchange pool (0 disables the exchange).
+ * Defaults 3 and 0: measured best on the 4K kerr_schild frame (profiles/round1_tuning.md). */
 int grt_set_tuning(grt_ctx*, int blocks_per_sm, int donate_threshold);
 
 int grt_set_features(grt_ctx*, const grt_features*);
@@ -173,10 +174,16 @@ int grt_clear_camera_geodesic(grt_ctx*);
 
 #define GRT_FORMAT_RGBA32F 0
 #define GRT_FORMAT_RGBA8 1
+#define GRT_OUT_HOST 0         /* host pointer, one D2H copy inside the call, returns when the frame is there */
+#define GRT_OUT_DEVICE 1       /* device pointer, no copy, asynchronous */
+#define GRT_OUT_HOST_ASYNC 2   /* pinned host pointer, D2H copy queued behind the frame, asynchronous */
 /* One frame (main.cpp:2244-2526): camera/tetrad -> [prepass] -> init_rays -> integrate ->
  * render_data -> [adaptive sampling -> integrate -> render_data] -> render.
- * out: width*height pixels in `format`, row-major; out_is_device selects a device pointer
- * (no host copy) or a host pointer (one D2H copy inside the call).  stats may be NULL. */
+ * out: width*height pixels in `format`, row-major; out_is_device is one of GRT_OUT_*.  stats may be
+ * NULL; asking for stats makes the call wait for the frame.  Asynchronous frames alternate between
+ * two frame slots with their own stream and buffers (the reference keeps two render_state objects
+ * in flight, main.cpp:1463-1469), so two consecutive frames overlap on the GPU; grt_synchronize
+ * waits for all of them. */
 int grt_render(grt_ctx*, int width, int height, void* out, int format, int out_is_device, grt_stats* stats);
 /* Rows [y0, y1) of a width x height frame (row stripes for multi-GPU tiling);
  * out receives (y1 - y0) * width pixels.  y0, y1 must be even when adaptive sampling is on. */
@@ -185,8 +192,8 @@ int grt_render_rows(grt_ctx*, int width, int height, int y0, int y1, void* out, 
  * GPU owns when a frame is tiled over several GPUs.  All stripes share one integration launch so
  * the divergent tail of the slowest rays is paid once.  out receives the stripes back to back. */
 int grt_render_stripes(grt_ctx*, int width, int height, const int* y0s, const int* y1s, int n_stripes, void* out, int format, int out_is_device, grt_stats* stats);
-/* Frames are queued on the context's CUDA stream; with out_is_device and stats == NULL the call
- * returns without waiting.  grt_synchronize waits; grt_stream returns the cudaStream_t. */
+/* grt_synchronize waits for every frame in flight; grt_stream returns the cudaStream_t of the most
+ * recently submitted frame (for ordering a consumer, e.g. the NCCL gather, behind it). */
 int grt_synchronize(grt_ctx*);
 void* grt_stream(grt_ctx*);
 
