@@ -181,8 +181,15 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
         }
     }
     if (cache_hit) *cache_hit = false;
+    // the program text is kept next to the cubin under the name NVRTC records in the line info,
+    // so `ncu --import-source on` and cuobjdump can map SASS back to the generated code
+    const std::string src_path = path.substr(0, path.size() - 6) + ".cu";
+    {
+        std::ofstream f(src_path, std::ios::binary);
+        f.write(src.data(), (std::streamsize)src.size());
+    }
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, src.c_str(), (name + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) throw Error(GRT_E_COMPILE, "nvrtcCreateProgram failed");
+    if (nvrtcCreateProgram(&prog, src.c_str(), src_path.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) throw Error(GRT_E_COMPILE, "nvrtcCreateProgram failed");
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
     nvrtcResult res = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());

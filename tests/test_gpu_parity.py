@@ -292,4 +292,5 @@ def test_frame_properties_at_headline_size(gpu_ctx, oracles, grt):
     gpu_ctx.render(w // 16, h // 16)
     small = gpu_ctx.read_render_data(w // 16, h // 16).reshape(h // 16, w // 16)
     assert ((small["terminated"] == 1) == fin[::16, ::16]).mean() >= 0.99
-    assert int(st.trial_steps) > 1e9 and int(st.rays_finished) == int(fin.sum())
+    # the statistics also count the 1/16 prepass rays (240 x 135 of them)
+    assert int(st.trial_steps) > 1e9 and 0 <= int(st.rays_finished) - int(fin.sum()) <= (w // 16) * (h // 16)
