@@ -36,6 +36,8 @@ import geodesic_raytracing_b200 as grt  # noqa: E402
 WIDTH, HEIGHT = 3840, 2160
 METRIC_NAME = "kerr_schild"
 STRIPE_ROWS = 54
+FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", "4"))   # frame slots the benchmark keeps busy (grt_set_frames_in_flight)
+BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", "2"))
 BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)
 
@@ -55,7 +57,8 @@ def workload_config(n_gpus):
         "out_format": "rgba8 (sRGB, the reference's screenshot encoding)",
         "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, interleaved {STRIPE_ROWS}-row stripes + halo, redundant prepass, NCCL gather to rank 0",
         "l2": "256 MiB flush write queued before every frame; the per-frame working set (ray planes + shading records, > 260 MB) also exceeds the 126 MB L2",
-        "pipelining": "frames are queued back to back, two in flight on the context's two frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469)",
+        "pipelining": f"frames are queued back to back, {FRAMES_IN_FLIGHT} in flight on the context's frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469); frame_latency_ms is the time of one frame alone",
+        "integrate_blocks_per_sm_per_slot": BLOCKS_PER_SM,
         "fast_math": True,
     }
 
@@ -193,6 +196,8 @@ def run_ours(args):
     metric = content.load_by_name(METRIC_NAME)
     ctx = grt.Context(local_rank)           # raises when libgrt.so or a B200 is missing: no fallback
     ctx.set_fast_math(True)
+    ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
+    ctx.set_tuning(BLOCKS_PER_SM, 0)
     ctx.set_metric(metric)
     bg = grt.synthetic_background(4096, 2048)
     bg_dev = torch.from_numpy(bg).to(device)
@@ -217,7 +222,7 @@ def run_ours(args):
         frame_steps = 0
 
     # two output buffers: frames alternate between the context's two frame slots
-    locals_ = [local, torch.empty_like(local)]
+    locals_ = [local] + [torch.empty_like(local) for _ in range(FRAMES_IN_FLIGHT - 1)]
 
     def barrier():
         ctx.synchronize()
@@ -229,11 +234,11 @@ def run_ours(args):
     def submit(k):
         """Queue frame k (device-resident output; with N > 1 the NCCL gather to rank 0 is queued behind it). Returns its stream."""
         flush.fill_(k & 1)                                        # evict L2 (256 MiB write) - see config.l2
-        ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k & 1], stats=False, stripes=stripes)
+        ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
         st = torch.cuda.ExternalStream(ctx.stream, device=device)
         if world > 1:
             with torch.cuda.stream(st):
-                gather_frame(locals_[k & 1], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+                gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
         return st
 
     def timed_batch(n_frames):
@@ -245,7 +250,7 @@ def run_ours(args):
         ends = []
         for k in range(n_frames):
             st = submit(k)
-            if k >= n_frames - 2:
+            if k >= n_frames - FRAMES_IN_FLIGHT:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(st)
                 ends.append(e)
@@ -279,22 +284,22 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
 
     # end to end: every frame delivered into pinned HOST memory on rank 0 (two buffers, two frames in flight), host clock
-    host_out = [torch.empty((HEIGHT if world == 1 else rows, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    host_frame = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(2)] if (world > 1 and rank == 0) else None
+    host_out = [torch.empty((HEIGHT if world == 1 else rows, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(FRAMES_IN_FLIGHT)]
+    host_frame = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(FRAMES_IN_FLIGHT)] if (world > 1 and rank == 0) else None
 
     def submit_e2e(k):
         ctx.set_camera(cam_pos, cam_quat)                      # per-frame camera upload (48 B H2D on the frame's stream), as main.cpp:2244-2262
         if world == 1:
-            ctx.render(WIDTH, HEIGHT, fmt, out=host_out[k & 1], stats=False)      # D2H queued behind the frame
+            ctx.render(WIDTH, HEIGHT, fmt, out=host_out[k % FRAMES_IN_FLIGHT], stats=False)      # D2H queued behind the frame
         else:
-            ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k & 1], stats=False, stripes=stripes)
+            ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
             st = torch.cuda.ExternalStream(ctx.stream, device=device)
             with torch.cuda.stream(st):
-                frame = gather_frame(locals_[k & 1], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+                frame = gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
                 if rank == 0:
-                    host_frame[k & 1].copy_(frame, non_blocking=True)
+                    host_frame[k % FRAMES_IN_FLIGHT].copy_(frame, non_blocking=True)
 
-    for k in range(2):
+    for k in range(FRAMES_IN_FLIGHT):
         submit_e2e(k)
     barrier()
     t0 = time.perf_counter()
@@ -320,7 +325,7 @@ def run_ours(args):
         gsteps = int(st.trial_steps) / (integrate_ms * 1e-3)
         line = {
             "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "frame_latency_ms": float(np.median(lat)), "frames_in_flight": 2, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "frame_latency_ms": float(np.median(lat)), "frames_in_flight": FRAMES_IN_FLIGHT, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
                       "rank0_stage_ms": ctx.launch_log(), "sum_ranks_ray_steps": float(steps_all.item())},

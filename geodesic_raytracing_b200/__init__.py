@@ -115,7 +115,7 @@ def lib() -> C.CDLL:
         "grt_metric_source": (cp, [vp, ci]), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
         "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]),
-        "grt_set_fast_math": (ci, [vp, ci]), "grt_set_tuning": (ci, [vp, ci, ci]), "grt_set_features": (ci, [vp, C.POINTER(Features)]), "grt_get_features": (ci, [vp, C.POINTER(Features)]),
+        "grt_set_fast_math": (ci, [vp, ci]), "grt_set_tuning": (ci, [vp, ci, ci]), "grt_set_frames_in_flight": (ci, [vp, ci]), "grt_set_features": (ci, [vp, C.POINTER(Features)]), "grt_get_features": (ci, [vp, C.POINTER(Features)]),
         "grt_set_background": (ci, [vp, vp, ci, ci, ci]), "grt_set_background_device": (ci, [vp, vp, ci, ci, ci]),
         "grt_set_camera": (ci, [vp, pf, pf, ci]), "grt_set_observer_speed": (ci, [vp, pf]),
         "grt_snapshot_geodesic": (ci, [vp, cf, ci]), "grt_set_camera_on_geodesic": (ci, [vp, cf]), "grt_clear_camera_geodesic": (ci, [vp]),
@@ -287,6 +287,9 @@ class Context:
 
     def set_tuning(self, passes: int, park_threshold: int) -> None:
         _check(lib().grt_set_tuning(self._h, int(passes), int(park_threshold)))
+
+    def set_frames_in_flight(self, n: int) -> None:
+        _check(lib().grt_set_frames_in_flight(self._h, int(n)))
 
     def set_metric(self, metric: Metric, is_static: bool = False) -> None:
         _check(lib().grt_set_metric(self._h, metric._h, int(is_static)))

@@ -973,6 +973,17 @@ int grt_set_tuning(grt_ctx* c, int passes, int park_threshold) {
     return GRT_OK;
 }
 
+int grt_set_frames_in_flight(grt_ctx* c, int n) {
+    return guard([&] {
+        if (!c || n < 1 || n > 4) throw Error(GRT_E_INVALID, "frames in flight must be 1..4");
+        bind(c);
+        sync_all(c);
+        c->n_slots = n;
+        c->frame_index = 0;
+        return GRT_OK;
+    });
+}
+
 int grt_update_params(grt_ctx* c) {
     return guard([&] {
         if (!c) throw Error(GRT_E_INVALID, "null context");
