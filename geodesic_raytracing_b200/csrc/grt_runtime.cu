@@ -622,8 +622,10 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     // exchange pool of the integration kernel (see GrtPool): capacity = 4x the threads of the persistent grid
     GrtPool pool{};
     {
+        // sized for the largest persistent grid any tuning can ask for, so the ring layout (and the ready
+        // flags, which must never hold stale data) stays put when the tuning changes
         unsigned cap = 1;
-        while (cap < persistent_grid * 128u * 4u) cap <<= 1;
+        while (cap < (unsigned)(c->num_sms * P->integrate_blocks_per_sm) * 128u * 4u) cap <<= 1;
         const size_t bytes = (size_t)cap * 84 + 64;
         const bool fresh = S.pool_buf.cap < bytes;
         S.pool_buf.ensure(bytes);

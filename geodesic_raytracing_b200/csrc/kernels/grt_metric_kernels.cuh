@@ -448,7 +448,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
     bool alive = false, exhausted = false;
     int slot = 0, iter = 0;
     float4 pos = f4(0, 0, 0, 0), vel = pos, acc = pos;
-    float next_ds = 0.00001f, dlambda = 1.0f, f_in_x = 0.0f, r_abs = 0.0f, polar_r_abs = 0.0f, ku = 0.0f;
+    float next_ds = 0.00001f, dlambda = 1.0f, f_in_x = 0.0f, r_abs, polar_r_abs, ku = 0.0f;
     int sxsy = 0;
     unsigned long long trial = 0, accepted = 0, nrays = 0, nfinished = 0;
     const float new_max = fr.max_precision_radius;
@@ -486,10 +486,6 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                             dlambda = 1.0f;
                             iter = 0;
                             nrays++;
-                            float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
-                            grt_radii(p, cfg, rr);
-                            polar_r_abs = fabsf(rr[0]);
-                            r_abs = fabsf(rr[1]);
                             alive = true;
                         }
                     }
@@ -554,10 +550,6 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                         slot = ids.x;
                         ku = __int_as_float(ids.y);
                         sxsy = ids.z;
-                        float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
-                        grt_radii(p, cfg, rr);
-                        polar_r_abs = fabsf(rr[0]);
-                        r_abs = fabsf(rr[1]);
                         alive = true;
                     }
                 }
@@ -569,6 +561,15 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
             }
         }
         if (alive) {
+            // polar r and distance to the object of the current state (cl.cl:4062-4068).  Evaluated at this one
+            // place only: a second inlined copy may be contracted into FMAs differently, and a ray must not
+            // depend on which path (fresh load, exchange pool, previous step) brought it here.
+            {
+                float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
+                grt_radii(p, cfg, rr);
+                polar_r_abs = fabsf(rr[0]);
+                r_abs = fabsf(rr[1]);
+            }
             // ---- top-of-iteration checks on the current state (cl.cl:4088-4130) ----
             bool finish = polar_r_abs >= fr.universe_size;
 #if GRT_SINGULAR
@@ -646,12 +647,6 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                     accepted++;
                     iter++;
                     if (bad4(pos) || bad4(vel) || bad4(acc) || iter >= GRT_LOOP_LIMIT) alive = false;
-                    else {
-                        float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
-                        grt_radii(p, cfg, rr);
-                        polar_r_abs = fabsf(rr[0]);
-                        r_abs = fabsf(rr[1]);
-                    }
                 }
             }
         }

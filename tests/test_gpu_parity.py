@@ -294,3 +294,110 @@ def test_frame_properties_at_headline_size(gpu_ctx, oracles, grt):
     assert ((small["terminated"] == 1) == fin[::16, ::16]).mean() >= 0.99
     # the statistics also count the 1/16 prepass rays (240 x 135 of them)
     assert int(st.trial_steps) > 1e9 and 0 <= int(st.rays_finished) - int(fin.sum()) <= (w // 16) * (h // 16)
+
+
+def test_odd_sizes_and_tiny_frames(gpu_ctx, oracles, background):
+    """Ragged inputs: sizes that are not multiples of the 8x4 ray tile, of 16 (prepass grid) or of 2; a frame smaller than one prepass cell."""
+    metric, orc = oracles("kerr_schild")
+    for (w, h), adaptive in [((101, 67), 0), ((50, 34), 1), ((8, 8), 0), ((16, 16), 1), ((33, 17), 0)]:
+        base = bind(gpu_ctx, metric, background, adaptive_sampling=adaptive)
+        img, st = gpu_ctx.render(w, h)
+        ref = orc.frame(w, h, oracle_features(orc, base), background=background)
+        rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
+        assert img.shape == (h, w, 4)
+        assert (rd["terminated"] == ref["rdata"]["terminated"]).mean() >= 0.98, (w, h)
+        assert abs(int(st.extra_rays) - ref["extra_rays"]) <= 0.05 * ref["extra_rays"] + 12
+
+
+def test_invalid_arguments_are_refused(gpu_ctx, oracles, background, grt):
+    metric, _ = oracles("minkowski")
+    bind(gpu_ctx, metric, background, adaptive_sampling=1)
+    with pytest.raises(grt.GrtError) as e:
+        gpu_ctx.render(65, 64)                       # adaptive sampling needs even sizes
+    assert e.value.code == -1
+    with pytest.raises(grt.GrtError):
+        gpu_ctx.render(64, 64, stripes=[(0, 31)])    # odd stripe edge with adaptive sampling
+    with pytest.raises(grt.GrtError):
+        gpu_ctx.render(64, 64, stripes=[(32, 64), (0, 32)])   # unsorted
+    with pytest.raises(grt.GrtError):
+        gpu_ctx.render(64, 64, stripes=[(0, 80)])    # outside the frame
+    with pytest.raises(grt.GrtError):
+        gpu_ctx.render(0, 64)
+    fresh = grt.Context(0)
+    try:
+        with pytest.raises(grt.GrtError) as e:
+            fresh.render(64, 64)                     # no metric bound
+        assert e.value.code == -5
+        fresh.set_metric(metric)
+        with pytest.raises(grt.GrtError) as e:
+            fresh.render(64, 64)                     # no background
+        assert e.value.code == -5
+        with pytest.raises(grt.GrtError):
+            fresh.set_camera_on_geodesic(1.0)        # no snapshot
+    finally:
+        fresh.close()
+    gpu_ctx.set_features(adaptive_sampling=0)
+    img, _ = gpu_ctx.render(65, 63)                  # fine without adaptive sampling
+    assert img.shape == (63, 65, 4)
+
+
+def test_frames_in_flight_do_not_interfere(gpu_ctx, oracles, background):
+    """Asynchronous frames rotate through the frame slots; each must equal the same frame rendered alone."""
+    import torch
+
+    metric, _ = oracles("kerr_schild")
+    bind(gpu_ctx, metric, background)
+    cams = [(0.0, 0.0, -4.0 - 0.5 * i, 0.3 * i) for i in range(6)]
+    w, h = 192, 128
+    alone = []
+    for c in cams:
+        gpu_ctx.set_camera(c)
+        img, _ = gpu_ctx.render(w, h)
+        alone.append(img.copy())
+    for n in (1, 2, 3, 4):
+        gpu_ctx.set_frames_in_flight(n)
+        outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda:0") for _ in cams]
+        for c, o in zip(cams, outs):
+            gpu_ctx.set_camera(c)
+            gpu_ctx.render(w, h, out=o, stats=False)      # returns at once
+        gpu_ctx.synchronize()
+        for a, o in zip(alone, outs):
+            assert np.array_equal(a, o.cpu().numpy()), n
+    # pinned host output, asynchronous
+    host = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in cams]
+    for c, o in zip(cams, host):
+        gpu_ctx.set_camera(c)
+        gpu_ctx.render(w, h, out=o, stats=False)
+    gpu_ctx.synchronize()
+    for a, o in zip(alone, host):
+        assert np.array_equal(a, o.numpy())
+    gpu_ctx.set_frames_in_flight(2)
+    gpu_ctx.set_camera()
+
+
+def test_scheduling_knobs_do_not_change_results(gpu_ctx, oracles, background):
+    """Occupancy and the in-kernel live-ray exchange only move rays between lanes: images are bit-identical."""
+    metric, _ = oracles("kerr_schild")
+    bind(gpu_ctx, metric, background)
+    w, h = 256, 160
+    gpu_ctx.set_tuning(3, 0)
+    ref, st0 = gpu_ctx.render(w, h)
+    for blocks, donate in [(0, 0), (1, 0), (2, 4), (3, 16), (4, 31)]:
+        gpu_ctx.set_tuning(blocks, donate)
+        img, st = gpu_ctx.render(w, h)
+        assert np.array_equal(img, ref), (blocks, donate)
+        assert int(st.trial_steps) == int(st0.trial_steps) and int(st.rays_finished) == int(st0.rays_finished)
+    gpu_ctx.set_tuning(3, 0)
+
+
+def test_feature_changes_take_effect(gpu_ctx, oracles, background):
+    metric, orc = oracles("schwarzschild_fast")
+    for feats in [dict(universe_size=12.0), dict(field_of_view=60.0), dict(max_precision_radius=6.0), dict(reparameterisation=1), dict(max_probes=2),
+                  dict(adaptive_sampling_threshold=4.0)]:
+        base = bind(gpu_ctx, metric, background, **feats)
+        img, _ = gpu_ctx.render(160, 96)
+        ref = orc.frame(160, 96, oracle_features(orc, base), background=background, max_probes=base["max_probes"])
+        rd = gpu_ctx.read_render_data(160, 96).reshape(96, 160)
+        assert (rd["terminated"] == ref["rdata"]["terminated"]).mean() >= 0.995, feats
+        assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean() >= 0.97, feats
+    bind(gpu_ctx, metric, background)

@@ -11,13 +11,13 @@ ctx.set_camera()
 ctx.set_features(adaptive_sampling=0, use_prepass=0)
 w, h = 256, 144
 res = {}
-for passes, thr in [(1, 0), (2, 31), (4, 31), (4, 8)]:
+for passes, thr in [(3, 0), (3, 16), (3, 31), (0, 31)]:
     ctx.set_tuning(passes, thr)
     img, st = ctx.render(w, h)
     rays = ctx.read_rays().copy()
     res[(passes, thr)] = (rays, st.trial_steps, st.accepted_steps, st.rays_integrated, st.rays_finished)
     print(passes, thr, 'steps', st.trial_steps, st.accepted_steps, 'rays', st.rays_integrated, st.rays_finished, 'term hist', np.bincount(rays['terminated'], minlength=5))
-a = res[(1, 0)][0]
+a = res[(3, 0)][0]
 for k, v in res.items():
     b = v[0]
     diff = (a['terminated'] != b['terminated'])
@@ -27,3 +27,7 @@ for k, v in res.items():
     idx = np.where(diff)[0][:5]
     for i in idx:
         print('   slot', i, 'a', a[i]['terminated'], a[i]['position'], 'b', b[i]['terminated'], b[i]['position'])
+    pdiff = np.abs(a['position'] - b['position']).max(axis=1)
+    j = np.where((pdiff > 0) & fin)[0][:5]
+    for i in j:
+        print('   pos diff slot', i, a[i]['position'], b[i]['position'], a[i]['velocity'], b[i]['velocity'])
