@@ -114,7 +114,7 @@ def lib() -> C.CDLL:
         "grt_metric_get_info": (ci, [vp, C.POINTER(MetricInfo)]), "grt_metric_name": (cp, [vp]), "grt_metric_description": (cp, [vp]),
         "grt_metric_source": (cp, [vp, ci]), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
-        "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]),
+        "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]), "grt_set_metric_async": (ci, [vp, vp, ci]), "grt_build_poll": (ci, [vp]),
         "grt_set_fast_math": (ci, [vp, ci]), "grt_set_tuning": (ci, [vp, ci, ci]), "grt_set_frames_in_flight": (ci, [vp, ci]), "grt_set_features": (ci, [vp, C.POINTER(Features)]), "grt_get_features": (ci, [vp, C.POINTER(Features)]),
         "grt_set_background": (ci, [vp, vp, ci, ci, ci]), "grt_set_background_device": (ci, [vp, vp, ci, ci, ci]),
         "grt_set_camera": (ci, [vp, pf, pf, ci]), "grt_set_observer_speed": (ci, [vp, pf]),
@@ -294,6 +294,17 @@ class Context:
     def set_metric(self, metric: Metric, is_static: bool = False) -> None:
         _check(lib().grt_set_metric(self._h, metric._h, int(is_static)))
         self._metric = metric
+
+    def set_metric_async(self, metric: Metric, is_static: bool = False) -> None:
+        """Build in the background; keep rendering with the bound program and call build_poll() until it returns True."""
+        _check(lib().grt_set_metric_async(self._h, metric._h, int(is_static)))
+        self._pending_metric = metric
+
+    def build_poll(self) -> bool:
+        done = _check(lib().grt_build_poll(self._h)) == 1
+        if done and getattr(self, "_pending_metric", None) is not None:
+            self._metric, self._pending_metric = self._pending_metric, None
+        return done
 
     def update_params(self) -> None:
         _check(lib().grt_update_params(self._h))

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -329,6 +330,16 @@ struct grt_ctx {
     int geo_parallel_transport = 1;
 
     std::string launch_log, kernel_info;
+
+    // background build (metric_manager's soft recompile, metric_manager.hpp:153-219)
+    struct PendingBuild {
+        std::future<std::vector<char>> cubin;
+        std::shared_ptr<std::string> log;
+        std::string key;
+        grt_metric* metric = nullptr;
+        bool is_static = false;
+        bool active = false;
+    } build;
 };
 
 namespace {
@@ -350,18 +361,30 @@ void features_default(grt_features* f) {
 
 void bind(grt_ctx* c) { CK(cudaSetDevice(c->device)); }
 
-Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
-    const grt::Metric& m = *gm->m;
-    std::string src = program_source(m, is_static, c->feat.reparameterisation != 0);
-    std::string key = std::to_string(fnv1a(src, 14695981039346656037ull)) + (c->fast_math ? "f" : "p");
-    auto it = c->programs.find(key);
-    if (it != c->programs.end()) return it->second.get();
+std::string program_key(grt_ctx* c, const std::string& src) { return std::to_string(fnv1a(src, 14695981039346656037ull)) + (c->fast_math ? "f" : "p"); }
+std::string program_stem(const grt::Metric& m, bool is_static) {
     std::string stem = m.js_path;
     size_t k = stem.find_last_of('/');
     if (k != std::string::npos) stem = stem.substr(k + 1);
     k = stem.find_last_of('.');
     if (k != std::string::npos) stem = stem.substr(0, k);
-    std::vector<char> cubin = compile_cubin(src, c->fast_math, stem + (is_static ? "_static" : "_dynamic"), &gm->compile_log, nullptr);
+    return stem + (is_static ? "_static" : "_dynamic");
+}
+
+Program* load_program(grt_ctx* c, const std::string& key, const std::vector<char>& cubin);
+
+Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
+    const grt::Metric& m = *gm->m;
+    std::string src = program_source(m, is_static, c->feat.reparameterisation != 0);
+    std::string key = program_key(c, src);
+    auto it = c->programs.find(key);
+    if (it != c->programs.end()) return it->second.get();
+    std::vector<char> cubin = compile_cubin(src, c->fast_math, program_stem(m, is_static), &gm->compile_log, nullptr);
+    return load_program(c, key, cubin);
+}
+
+// cubin -> module + kernel handles (needs the device; the NVRTC step above does not)
+Program* load_program(grt_ctx* c, const std::string& key, const std::vector<char>& cubin) {
     auto p = std::make_unique<Program>();
     p->key = key;
     CU(g_drv.ModuleLoadData(&p->mod, cubin.data()));
@@ -945,6 +968,7 @@ grt_ctx* grt_create(int device) {
 
 void grt_destroy(grt_ctx* c) {
     if (!c) return;
+    if (c->build.active) c->build.cubin.wait();
     cudaSetDevice(c->device);
     for (auto& S : c->slots) if (S.stream) cudaStreamSynchronize(S.stream);
     cudaStreamSynchronize(c->stream);
@@ -983,6 +1007,53 @@ int grt_set_frames_in_flight(grt_ctx* c, int n) {
         c->n_slots = n;
         c->frame_index = 0;
         return GRT_OK;
+    });
+}
+
+int grt_set_metric_async(grt_ctx* c, grt_metric* m, int is_static) {
+    return guard([&] {
+        if (!c || !m) throw Error(GRT_E_INVALID, "null argument");
+        if (m->m->params.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
+        if (c->build.active) {   // a newer request supersedes the one in flight (metric_manager.hpp:172-219 cancels it)
+            c->build.cubin.wait();
+            c->build.active = false;
+        }
+        std::string src = program_source(*m->m, is_static != 0, c->feat.reparameterisation != 0);
+        c->build.key = program_key(c, src);
+        c->build.metric = m;
+        c->build.is_static = is_static != 0;
+        c->build.log = std::make_shared<std::string>();
+        const bool fast = c->fast_math;
+        const std::string stem = program_stem(*m->m, is_static != 0);
+        auto log = c->build.log;
+        c->build.cubin = std::async(std::launch::async, [src, fast, stem, log]() { return compile_cubin(src, fast, stem, log.get(), nullptr); });
+        c->build.active = true;
+        return GRT_OK;
+    });
+}
+
+int grt_build_poll(grt_ctx* c) {
+    return guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        if (!c->build.active) return 1;
+        if (c->build.cubin.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return 0;
+        c->build.active = false;
+        std::vector<char> cubin = c->build.cubin.get();   // rethrows a compile error as GRT_E_COMPILE
+        bind(c);
+        grt_metric* m = c->build.metric;
+        m->compile_log = *c->build.log;
+        auto it = c->programs.find(c->build.key);
+        Program* p = it != c->programs.end() ? it->second.get() : load_program(c, c->build.key, cubin);
+        // swap: frames already queued keep the module they were launched with
+        c->metric = m;
+        c->is_static = c->build.is_static;
+        c->prog = p;
+        c->kernel_info = p->info;
+        memset(c->params, 0, sizeof c->params);
+        for (size_t i = 0; i < m->m->params.names.size(); i++) c->params[i] = m->m->params.current_values[i];
+        c->feat.max_acceleration_change = m->m->cfg.max_acceleration_change;
+        c->camera_dirty = true;
+        return 1;
     });
 }
 

@@ -134,6 +134,12 @@ void grt_destroy(grt_ctx*);
  * without a rebuild.  Copies max_acceleration_change from the metric (metric_manager.hpp:50). */
 int grt_set_metric(grt_ctx*, grt_metric*, int is_static);
 int grt_update_params(grt_ctx*);
+/* Soft recompile (metric_manager.hpp:153-219): NVRTC runs on a background thread while the bound program
+ * keeps rendering; grt_build_poll returns 0 while the build runs, 1 once the new program has been swapped
+ * in (or when nothing is pending), a negative code if the build failed (the old program stays bound).
+ * A new request supersedes one still in flight.  The metric must stay alive until the poll returns != 0. */
+int grt_set_metric_async(grt_ctx*, grt_metric*, int is_static);
+int grt_build_poll(grt_ctx*);
 /* compile only (no GPU needed): used by build checks to pre-populate the cubin cache */
 int grt_compile_metric(grt_metric*, int is_static, int fast_math, const char** log_out);
 

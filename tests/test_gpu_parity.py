@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CAM_POS = (0.0, 0.0, -4.0, 0.0)
-METRICS = ["minkowski", "schwarzschild_fast", "kerr_schild", "alcubierre", "double_schwarzschild"]
+METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild"]
 
 
 def bind(gpu_ctx, metric, background, **features):
@@ -401,3 +401,47 @@ def test_feature_changes_take_effect(gpu_ctx, oracles, background):
         assert (rd["terminated"] == ref["rdata"]["terminated"]).mean() >= 0.995, feats
         assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean() >= 0.97, feats
     bind(gpu_ctx, metric, background)
+
+
+def test_wormhole_far_side_uses_the_second_background(gpu_ctx, oracles, background, grt):
+    """Rays that cross the throat end at r < 0: `side` 0, sampled from the second background (cl.cl:5176, 5445-5448)."""
+    metric, orc = oracles("wormhole (morris-thorne)")
+    base = bind(gpu_ctx, metric, background, adaptive_sampling=0)
+    other = grt.synthetic_background(512, 256, seed=99)[..., [2, 0, 1, 3]].copy()
+    gpu_ctx.set_background(other, which=1)
+    w, h = 192, 128
+    img, _ = gpu_ctx.render(w, h)
+    ref = orc.frame(w, h, oracle_features(orc, base), background=background, background2=other)
+    rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
+    assert (rd["side"] == 0).sum() > 50 and (rd["side"] == 1).sum() > 50
+    both = (rd["terminated"] == 1) & (ref["rdata"]["terminated"] == 1)
+    assert np.array_equal(rd["side"][both], ref["rdata"]["side"][both])
+    assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean() >= 0.99
+    gpu_ctx.set_background(background, which=1)
+
+
+def test_background_build_swaps_program_in(gpu_ctx, content, background, tmp_path, monkeypatch):
+    """metric_manager's soft recompile: the static program is built off-thread while frames keep coming, then swapped in."""
+    import time
+
+    monkeypatch.setenv("GRT_CACHE_DIR", str(tmp_path))      # force a real NVRTC build
+    metric = content.load_by_name("kerr_schild")
+    bind(gpu_ctx, metric, background, adaptive_sampling=0)   # dynamic program (from the regular cache or built here)
+    dyn, _ = gpu_ctx.render(128, 96)
+    metric.set_param("a", -0.25)
+    gpu_ctx.update_params()
+    before, _ = gpu_ctx.render(128, 96)
+    gpu_ctx.set_metric_async(metric, is_static=True)
+    frames = 0
+    t0 = time.time()
+    while not gpu_ctx.build_poll():
+        img, _ = gpu_ctx.render(128, 96)                     # the old program keeps rendering
+        assert np.array_equal(img, before)
+        frames += 1
+        assert time.time() - t0 < 120
+    gpu_ctx.set_features(max_acceleration_change=metric.info.max_acceleration_change, adaptive_sampling=0)
+    after, _ = gpu_ctx.render(128, 96)
+    assert frames >= 1
+    assert not np.array_equal(dyn, before)
+    assert (np.abs(after - before).max(axis=-1) <= 2 / 255).mean() >= 0.99   # same parameters, now folded as literals
+    assert "-0.25f" in metric.source(True)
