@@ -49,6 +49,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per k_integrate launch from the committed `ncu --set full` capture of this same command (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "round1_ncu_traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("mean_dram_bytes_per_launch")
+    return None
+
+
 def workload_config(n_gpus):
     return {
         "workload": f"{METRIC_NAME}.js {WIDTH}x{HEIGHT}, camera (0,0,-4,0) quat (-sin(pi/4),0,0,cos(pi/4)), fov 90, universe 20, a=-0.5 rs=1",
@@ -317,8 +325,8 @@ def run_ours(args):
         st = last_stats
         rays_per_launch = (int(st.rays_integrated)) / max(1, st.integrate_launches)
         integrate_ms = st.ms_integrate + st.ms_prepass          # prepass time is its integrate launch to within microseconds
-        algo_bytes = int(st.rays_integrated) * BYTES_PER_RAY
-        achieved_gbs = algo_bytes / (integrate_ms * 1e-3) / 1e9
+        algo_bytes = int(st.rays_integrated) * BYTES_PER_RAY            # all integrate launches of the frame
+        achieved_gbs = algo_bytes / (integrate_ms * 1e-3) / 1e9        # = per-launch bytes / mean launch duration
         info = metric.info
         flops_ref_step = info.flops_expr + 2090          # reference-formulation count, 16-component metric
         flops_own_step = info.flops_accel + 110          # emitted lowered acceleration + Verlet update + step control + radii
@@ -329,9 +337,9 @@ def run_ours(args):
             "config": workload_config(world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
                       "rank0_stage_ms": ctx.launch_log(), "sum_ranks_ray_steps": float(steps_all.item())},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic(),
                          "peak_kind": peak_kind, "kernel": "k_integrate (all integrate launches of one frame on rank 0)",
-                         "algorithmic_bytes": algo_bytes, "launch_ms": integrate_ms / max(1, st.integrate_launches), "rays_per_launch": rays_per_launch,
+                         "algorithmic_bytes_per_launch": algo_bytes / max(1, st.integrate_launches), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the 3 integrate launches of a frame)", "launch_ms": integrate_ms / max(1, st.integrate_launches), "rays_per_launch": rays_per_launch,
                          "note": "register-resident loop: 96 B per ray and 0 B per ray-step, so the HBM fraction is tiny by construction; the kernel is FP32-issue bound - see fp32"},
             "fp32": {"gsteps_per_s_in_kernel": gsteps / 1e9, "flops_per_step_emitted": flops_own_step, "flops_per_step_reference_formulation": flops_ref_step,
                      "achieved_tflops_emitted": gsteps * flops_own_step / 1e12, "achieved_tflops_reference_formulation": gsteps * flops_ref_step / 1e12,
