@@ -285,8 +285,9 @@ class Context:
     def set_fast_math(self, enabled: bool) -> None:
         _check(lib().grt_set_fast_math(self._h, int(enabled)))
 
-    def set_tuning(self, passes: int, park_threshold: int) -> None:
-        _check(lib().grt_set_tuning(self._h, int(passes), int(park_threshold)))
+    def set_tuning(self, blocks_per_sm: int, donate_threshold: int) -> None:
+        """Scheduling knobs of the integration kernel (never change results): see grt_set_tuning in include/grt.h."""
+        _check(lib().grt_set_tuning(self._h, int(blocks_per_sm), int(donate_threshold)))
 
     def set_frames_in_flight(self, n: int) -> None:
         _check(lib().grt_set_frames_in_flight(self._h, int(n)))

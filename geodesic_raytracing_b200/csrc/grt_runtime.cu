@@ -254,10 +254,6 @@ struct Texture {
     bool set = false;
 };
 
-struct StripeGeom {
-    std::vector<GrtRenderStripe> stripes;
-};
-
 }  // namespace
 
 struct grt_content {
@@ -313,8 +309,8 @@ struct grt_ctx {
     Texture tex[2];
     DevBuf tables, identity, scratch;
     int identity_len = 0;
-    int passes = 3;           // 128-thread blocks of the integration kernel per SM and frame slot; 0 = as many as fit (GRT_BLOCKS_PER_SM)
-    int park_threshold = 0;   // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_DONATE_THRESHOLD)
+    int blocks_per_sm = 3;           // 128-thread blocks of the integration kernel per SM and frame slot; 0 = as many as fit (GRT_BLOCKS_PER_SM)
+    int donate_threshold = 0;   // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_DONATE_THRESHOLD)
 
     // geometry cache
     std::vector<int> geom_key;
@@ -641,7 +637,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     int* d_extra = (int*)(S.d_counters + 4);
     const int* null_count = nullptr;
     float max_accel = c->feat.max_acceleration_change;
-    const unsigned persistent_grid = (unsigned)(c->num_sms * (c->passes > 0 ? std::min(c->passes, P->integrate_blocks_per_sm) : P->integrate_blocks_per_sm));
+    const unsigned persistent_grid = (unsigned)(c->num_sms * (c->blocks_per_sm > 0 ? std::min(c->blocks_per_sm, P->integrate_blocks_per_sm) : P->integrate_blocks_per_sm));
     // exchange pool of the integration kernel (see GrtPool): capacity = 4x the threads of the persistent grid
     GrtPool pool{};
     {
@@ -661,9 +657,9 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         pool.acc = (float4*)(p + (size_t)cap * 32);
         pool.misc = (float4*)(p + (size_t)cap * 48);
         pool.ids = (int4*)(p + (size_t)cap * 64);
-        pool.ready = c->park_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 80) : nullptr;
+        pool.ready = c->donate_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 80) : nullptr;
         pool.mask = cap - 1;
-        pool.donate_threshold = c->park_threshold;
+        pool.donate_threshold = c->donate_threshold;
     }
     // work lists (see GrtWorkList): one int buffer reused by the three phases, which run back to back
     S.worklist.ensure(sizeof(int) * std::max<size_t>({(size_t)fr.n_slots, extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)1}));
@@ -954,8 +950,8 @@ grt_ctx* grt_create(int device) {
             S.d_stats = (GrtStats*)(S.d_counters + kCounterWords);
         }
         c->last = &c->slots[0];
-        if (const char* e = getenv("GRT_BLOCKS_PER_SM")) c->passes = atoi(e);
-        if (const char* e = getenv("GRT_DONATE_THRESHOLD")) c->park_threshold = atoi(e);
+        if (const char* e = getenv("GRT_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
+        if (const char* e = getenv("GRT_DONATE_THRESHOLD")) c->donate_threshold = atoi(e);
         // default camera (main.cpp:664-673)
         c->cam.pos_cart = make_float4(0, 0, -4, 0);
         c->cam.quat = make_float4(-0.70710678f, 0, 0, 0.70710678f);
@@ -992,10 +988,10 @@ int grt_set_fast_math(grt_ctx* c, int enabled) {
     return GRT_OK;
 }
 
-int grt_set_tuning(grt_ctx* c, int passes, int park_threshold) {
-    if (!c || passes < 0 || passes > 32 || park_threshold < 0 || park_threshold > 31) { g_err = "tuning out of range (blocks_per_sm 0..32, donate_threshold 0..31)"; return GRT_E_INVALID; }
-    c->passes = passes;
-    c->park_threshold = park_threshold;
+int grt_set_tuning(grt_ctx* c, int blocks_per_sm, int donate_threshold) {
+    if (!c || blocks_per_sm < 0 || blocks_per_sm > 32 || donate_threshold < 0 || donate_threshold > 31) { g_err = "tuning out of range (blocks_per_sm 0..32, donate_threshold 0..31)"; return GRT_E_INVALID; }
+    c->blocks_per_sm = blocks_per_sm;
+    c->donate_threshold = donate_threshold;
     return GRT_OK;
 }
 

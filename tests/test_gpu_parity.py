@@ -449,3 +449,52 @@ def test_background_build_swaps_program_in(gpu_ctx, content, background, tmp_pat
     assert not np.array_equal(dyn, before)
     assert (np.abs(after - before).max(axis=-1) <= 2 / 255).mean() >= 0.99   # same parameters, now folded as literals
     assert "-0.25f" in metric.source(True)
+
+
+def test_baseline_config_shapes_at_full_size(gpu_ctx, oracles, grt):
+    """BASELINE.json configs 2, 4 and 5 at their full sizes, through size-independent properties (an oracle frame at these
+    sizes takes minutes): (2) schwarzschild 1920x1080 - the shadow is a disc of the analytic radius, centred, and the frame is
+    left-right mirror symmetric in `terminated`; (4) alcubierre 1920x1080 with redshift on and the camera on a geodesic -
+    finite colours, idempotent; (5) a 3840x2160 frame of the heaviest bundled cylindrical metric tiled for 8 ranks - the
+    stripes of every rank reassemble the single-GPU frame bit for bit."""
+    bg = grt.synthetic_background(2048, 1024)
+    # (2)
+    metric, _ = oracles("schwarzschild_fast")
+    bind(gpu_ctx, metric, bg, adaptive_sampling=0)
+    w, h = 1920, 1080
+    gpu_ctx.render(w, h)
+    rays = gpu_ctx.read_rays()
+    cap = np.zeros((h, w), bool)
+    captured = (rays["terminated"] == 1) & (np.abs(rays["position"][:, 1]) < 2.0)
+    cap[rays["sy"][captured], rays["sx"][captured]] = True
+    fstop = (w / 2) / np.tan(np.pi / 4)
+    expect = fstop * np.tan(np.arcsin(1.5 * np.sqrt(3.0) * np.sqrt(1 - 1 / 4.0) / 4.0))
+    xs = np.where(cap[h // 2])[0]
+    assert abs((xs.max() - xs.min() + 1) / 2 - expect) < 3.0
+    assert abs((xs.max() + xs.min()) / 2 - w / 2) <= 1.5
+    assert (cap[:, 1:] == cap[:, :0:-1]).mean() > 0.9995      # mirror about the column w/2 (no half-pixel offset, cl.cl:2044-2059)
+    # (4)
+    metric, _ = oracles("alcubierre")
+    bind(gpu_ctx, metric, bg, redshift=1)
+    n = gpu_ctx.snapshot_geodesic(0.3, True)
+    assert n > 10
+    gpu_ctx.set_camera_on_geodesic(2.0)
+    a, st = gpu_ctx.render(w, h)
+    b, _ = gpu_ctx.render(w, h)
+    assert np.isfinite(a).all() and np.array_equal(a, b) and int(st.rays_finished) > 0.9 * (w // 2) * (h // 2)
+    gpu_ctx.clear_camera_geodesic()
+    # (5)
+    import torch
+
+    metric, _ = oracles("double_schwarzschild")
+    bind(gpu_ctx, metric, bg)
+    w, h = 3840, 2160
+    full = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda:0")
+    gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8, out=full)
+    for rank in (0, 3, 7):
+        stripes = grt.interleaved_stripes(h, rank, 8, 54)
+        rows = sum(b - a for a, b in stripes)
+        part = torch.empty((rows, w, 4), dtype=torch.uint8, device="cuda:0")
+        gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8, out=part, stripes=stripes)
+        want = torch.cat([full[a:b] for a, b in stripes], 0)
+        assert torch.equal(part, want), rank
