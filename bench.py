@@ -49,12 +49,29 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def ncu_traffic():
-    """DRAM bytes per k_integrate launch from the committed `ncu --set full` capture of this same command (profiles/)."""
+def ncu_facts():
+    """Per-launch DRAM bytes and per-step SASS instruction counts of k_integrate from the committed `ncu --set full`
+    capture of this same command (profiles/round1_ncu_traffic.json)."""
     path = os.path.join(ROOT, "profiles", "round1_ncu_traffic.json")
-    if os.path.exists(path):
-        return json.load(open(path)).get("mean_dram_bytes_per_launch")
-    return None
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+def fp32_microbench():
+    """FP32 pipe rate this GPU sustains on independent FFMA/FMUL chains (tools/microbench/fp32_pipes.cu, < 1 s): the
+    practical ceiling for an FP32-issue-bound kernel; MEASURED_PEAKS.json has no FP32 figure."""
+    exe = os.path.join(ROOT, "tools", "microbench", "fp32_pipes")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+    except Exception:
+        return None
+    best = {}
+    for line in out.splitlines():
+        p = line.split()
+        if len(p) >= 9 and p[1] == "blocks/SM":
+            best[p[0]] = max(best.get(p[0], 0.0), float(p[6]) / 1e3)     # T lane-ops/s
+    return best or None
 
 
 def workload_config(n_gpus):
@@ -331,19 +348,28 @@ def run_ours(args):
         flops_ref_step = info.flops_expr + 2090          # reference-formulation count, 16-component metric
         flops_own_step = info.flops_accel + 110          # emitted lowered acceleration + Verlet update + step control + radii
         gsteps = int(st.trial_steps) / (integrate_ms * 1e-3)
+        facts = ncu_facts()
+        micro = fp32_microbench() if world == 1 else None
+        fp_instr = facts.get("sass_fp_instr_per_step")
         line = {
             "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "frame_latency_ms": float(np.median(lat)), "frames_in_flight": FRAMES_IN_FLIGHT, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
                       "rank0_stage_ms": ctx.launch_log(), "sum_ranks_ray_steps": float(steps_all.item())},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": ncu_traffic(),
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": facts.get("mean_dram_bytes_per_launch"),
                          "peak_kind": peak_kind, "kernel": "k_integrate (all integrate launches of one frame on rank 0)",
                          "algorithmic_bytes_per_launch": algo_bytes / max(1, st.integrate_launches), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the 3 integrate launches of a frame)", "launch_ms": integrate_ms / max(1, st.integrate_launches), "rays_per_launch": rays_per_launch,
                          "note": "register-resident loop: 96 B per ray and 0 B per ray-step, so the HBM fraction is tiny by construction; the kernel is FP32-issue bound - see fp32"},
             "fp32": {"gsteps_per_s_in_kernel": gsteps / 1e9, "flops_per_step_emitted": flops_own_step, "flops_per_step_reference_formulation": flops_ref_step,
                      "achieved_tflops_emitted": gsteps * flops_own_step / 1e12, "achieved_tflops_reference_formulation": gsteps * flops_ref_step / 1e12,
-                     "peak_tflops_derived": FP32_PEAK_TFLOPS, "frac_emitted": gsteps * flops_own_step / 1e12 / FP32_PEAK_TFLOPS},
+                     "peak_tflops_derived": FP32_PEAK_TFLOPS, "frac_emitted": gsteps * flops_own_step / 1e12 / FP32_PEAK_TFLOPS,
+                     "sass_fp_instr_per_step": fp_instr, "sass_instr_per_step": facts.get("sass_instr_per_step"),
+                     "sustained_gsteps_per_s": frame_steps * args.steps / (total_ms * 1e-3) / 1e9,
+                     "sustained_fp_tlaneops": (frame_steps * args.steps / (total_ms * 1e-3)) * fp_instr / 1e12 if fp_instr else None,
+                     "microbench_tlaneops": micro,
+                     "frac_of_microbench_ffma_fmul_mix": ((frame_steps * args.steps / (total_ms * 1e-3)) * fp_instr / 1e12 / micro["mix_fma_mul"]) if (fp_instr and micro and micro.get("mix_fma_mul")) else None,
+                     "note": "FP lane-op rate = ray-steps/s x FFMA+FMUL+FADD instructions per step (ncu); the microbenchmark is what independent FFMA/FMUL chains sustain on this GPU"},
             "e2e": {"value": frame_steps * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s", "fps": args.steps / e2e_s, "h2d_bytes_per_step": 48,
                     "d2h_bytes_per_step": HEIGHT * WIDTH * 4},
             "gpu_launches": launches,
