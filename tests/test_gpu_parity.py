@@ -498,3 +498,32 @@ def test_baseline_config_shapes_at_full_size(gpu_ctx, oracles, grt):
         gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8, out=part, stripes=stripes)
         want = torch.cat([full[a:b] for a, b in stripes], 0)
         assert torch.equal(part, want), rank
+
+
+@pytest.mark.parametrize("name, speed", [("schwarzschild", 0.0), ("schwarzschild", 0.35), ("kerr_boyer", 0.2), ("kerr_schild", -0.3)])
+def test_geodesic_camera_paths(gpu_ctx, oracles, background, name, speed):
+    """get_geodesic_path + parallel_transport_quantity on more metrics: a constant-theta one (the path is rotated back out of the
+    theta = pi/2 plane and unwrapped by the coordinate periods, cl.cl:4878-4909), a polar big metric and a cartesian one."""
+    metric, orc = oracles(name)
+    base = bind(gpu_ctx, metric, background, adaptive_sampling=0)
+    gpu_ctx.set_camera((0.0, 0.5, -6.0, 1.0))
+    cs = gpu_ctx.camera_state()
+    n = gpu_ctx.snapshot_geodesic(speed, True)
+    pos, vel, ds, tr = gpu_ctx.read_geodesic(n)
+    q = np.array([-0.70710678, 0, 0, 0.70710678])
+    fwd = np.array([2 * (q[0] * q[2] + q[3] * q[1]), 2 * (q[1] * q[2] - q[3] * q[0]), 1 - 2 * (q[0] ** 2 + q[1] ** 2)])
+    opos, ovel, ods, otr, _ = orc.geodesic_snapshot(np.array(list(cs.pos_generic)), np.array(list(cs.tetrad)).reshape(4, 4), fwd * speed, oracle_features(orc, base))
+    assert n > 20 and abs(n - len(opos)) <= max(3, 0.03 * n), (n, len(opos))
+    k = min(n, len(opos)) // 3          # compare the first third: the two integrations separate slowly afterwards
+    assert np.allclose(pos[:k], opos[:k], rtol=3e-3, atol=3e-3)
+    assert np.allclose(vel[:k], ovel[:k], rtol=1e-2, atol=1e-2)
+    assert np.allclose(ds[:k], ods[:k], rtol=2e-2, atol=1e-6)
+    assert np.allclose(tr[:, :k], otr[:, :k], rtol=2e-2, atol=2e-2)
+    # the transported tetrad stays orthonormal along the path (a property the oracle shares, checked on the GPU result)
+    for i in (0, k // 2, k - 1):
+        g, _ = orc.metric_eval(pos[i])
+        G = g.reshape(4, 4).astype(np.float64)
+        E = tr[:, i].astype(np.float64)
+        assert np.allclose(E @ G @ E.T, np.diag([-1, 1, 1, 1]), atol=5e-2), (name, i)
+    gpu_ctx.clear_camera_geodesic()
+    gpu_ctx.set_camera()
