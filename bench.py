@@ -36,7 +36,11 @@ import geodesic_raytracing_b200 as grt  # noqa: E402
 WIDTH, HEIGHT = 3840, 2160
 METRIC_NAME = "kerr_schild"
 STRIPE_ROWS = 54
-FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", "4"))   # frame slots the benchmark keeps busy (grt_set_frames_in_flight)
+# Frame slots the benchmark keeps busy (grt_set_frames_in_flight): enough frames to cover the latency-bound critical path of a
+# frame (prepass -> first pass -> refinement, each as long as its slowest ray) with bulk work. One frame alone takes ~45 ms on 1 GPU
+# for ~30 ms of bulk work, and ~24 ms on 8 GPUs for ~4 ms of bulk work per GPU, so the count grows with the number of GPUs.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(4 if _WORLD == 1 else min(8, 2 * _WORLD + 2))))
 BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", "2"))
 BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)

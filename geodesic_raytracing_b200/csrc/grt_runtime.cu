@@ -290,8 +290,8 @@ struct grt_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;   // cold-path work: textures, tables, geodesic snapshot, introspection
-    FrameSlot slots[4];
-    int n_slots = 2;             // frames in flight (GRT_FRAME_SLOTS, 1..4)
+    FrameSlot slots[8];
+    int n_slots = 2;             // frames in flight (GRT_FRAME_SLOTS, 1..8)
     unsigned frame_index = 0;
     FrameSlot* last = nullptr;       // slot of the most recently submitted frame
     bool fast_math = true;
@@ -940,7 +940,7 @@ grt_ctx* grt_create(int device) {
         features_default(&c->feat);
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaMalloc((void**)&c->d_cam, sizeof(GrtCamera)));
-        if (const char* e = getenv("GRT_FRAME_SLOTS")) c->n_slots = std::max(1, std::min(4, atoi(e)));
+        if (const char* e = getenv("GRT_FRAME_SLOTS")) c->n_slots = std::max(1, std::min(8, atoi(e)));
         for (auto& S : c->slots) {
             CK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
             CK(cudaMalloc((void**)&S.d_cam, sizeof(GrtCamera)));
@@ -997,7 +997,7 @@ int grt_set_tuning(grt_ctx* c, int blocks_per_sm, int donate_threshold) {
 
 int grt_set_frames_in_flight(grt_ctx* c, int n) {
     return guard([&] {
-        if (!c || n < 1 || n > 4) throw Error(GRT_E_INVALID, "frames in flight must be 1..4");
+        if (!c || n < 1 || n > 8) throw Error(GRT_E_INVALID, "frames in flight must be 1..8");
         bind(c);
         sync_all(c);
         c->n_slots = n;

@@ -154,7 +154,7 @@ int grt_set_fast_math(grt_ctx*, int enabled);
  * Defaults 3 and 0: measured best on the 4K kerr_schild frame (profiles/round1_tuning.md). */
 int grt_set_tuning(grt_ctx*, int blocks_per_sm, int donate_threshold);
 
-/* Frame slots that asynchronous frames rotate through (1..4, default 2 as the reference's two
+/* Frame slots that asynchronous frames rotate through (1..8, default 2 as the reference's two
  * render_state objects, main.cpp:1463-1469).  More slots fill the latency-bound stretches of a frame
  * (prepass, tails of the integration launches) with other frames' rays: throughput up, latency up. */
 int grt_set_frames_in_flight(grt_ctx*, int n);

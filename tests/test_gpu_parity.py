@@ -358,7 +358,7 @@ def test_frames_in_flight_do_not_interfere(gpu_ctx, oracles, background):
         gpu_ctx.set_camera(c)
         img, _ = gpu_ctx.render(w, h)
         alone.append(img.copy())
-    for n in (1, 2, 3, 4):
+    for n in (1, 2, 3, 4, 8):
         gpu_ctx.set_frames_in_flight(n)
         outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda:0") for _ in cams]
         for c, o in zip(cams, outs):
