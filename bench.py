@@ -92,8 +92,9 @@ def workload_config(n_gpus):
     }
 
 
-def gather_frame(local, height, width, rank, world, stripe_rows, device):
-    """Gather every rank's stripes on rank 0 and reassemble the frame (rows, width, C). Returns the frame on rank 0, None elsewhere."""
+def gather_frame(local, height, width, rank, world, stripe_rows, device, buffers=None):
+    """Gather every rank's stripes on rank 0 and reassemble the frame (rows, width, C). Returns the frame on rank 0, None elsewhere.
+    `buffers` (a dict the caller keeps per frame slot) makes the receive bucket and the frame persistent."""
     import torch
     import torch.distributed as dist
 
@@ -104,16 +105,27 @@ def gather_frame(local, height, width, rank, world, stripe_rows, device):
     if local.shape[0] < max_rows:
         pad = torch.zeros((max_rows - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=device)
         local = torch.cat([local, pad], 0)
-    bucket = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+    buffers = buffers if buffers is not None else {}
+    if rank == 0 and "bucket" not in buffers:
+        buffers["bucket"] = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=device)
+        buffers["frame"] = torch.empty((height, width) + tuple(local.shape[2:]), dtype=local.dtype, device=device)
+    bucket = list(buffers["bucket"].unbind(0)) if rank == 0 else None
     dist.gather(local, bucket, dst=0)
     if rank != 0:
         return None
-    frame = torch.empty((height, width) + tuple(local.shape[2:]), dtype=local.dtype, device=device)
-    for r in range(world):
-        row = 0
-        for (y0, y1) in grt.interleaved_stripes(height, r, world, stripe_rows):
-            frame[y0:y1] = bucket[r][row:row + (y1 - y0)]
-            row += y1 - y0
+    frame = buffers["frame"]
+    n_stripes = -(-height // stripe_rows)
+    if height % stripe_rows == 0 and n_stripes % world == 0:
+        # regular interleave: stripe s = group * world + rank  ->  one strided copy
+        groups = n_stripes // world
+        src = buffers["bucket"].view(world, groups, stripe_rows, width, -1).permute(1, 0, 2, 3, 4)
+        frame.view(groups, world, stripe_rows, width, -1).copy_(src)
+    else:
+        for r in range(world):
+            row = 0
+            for (y0, y1) in grt.interleaved_stripes(height, r, world, stripe_rows):
+                frame[y0:y1] = bucket[r][row:row + (y1 - y0)]
+                row += y1 - y0
     return frame
 
 
@@ -252,6 +264,7 @@ def run_ours(args):
 
     # two output buffers: frames alternate between the context's two frame slots
     locals_ = [local] + [torch.empty_like(local) for _ in range(FRAMES_IN_FLIGHT - 1)]
+    gather_bufs = [dict() for _ in range(FRAMES_IN_FLIGHT)]
 
     def barrier():
         ctx.synchronize()
@@ -267,7 +280,7 @@ def run_ours(args):
         st = torch.cuda.ExternalStream(ctx.stream, device=device)
         if world > 1:
             with torch.cuda.stream(st):
-                gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+                gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device, gather_bufs[k % FRAMES_IN_FLIGHT])
         return st
 
     def timed_batch(n_frames):
@@ -324,7 +337,7 @@ def run_ours(args):
             ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
             st = torch.cuda.ExternalStream(ctx.stream, device=device)
             with torch.cuda.stream(st):
-                frame = gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device)
+                frame = gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device, gather_bufs[k % FRAMES_IN_FLIGHT])
                 if rank == 0:
                     host_frame[k % FRAMES_IN_FLIGHT].copy_(frame, non_blocking=True)
 

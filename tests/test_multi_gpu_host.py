@@ -28,7 +28,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, h, w, q):
+def _worker(rank, world, port, h, w, rows, q):
     import torch
     import torch.distributed as dist
 
@@ -38,21 +38,24 @@ def _worker(rank, world, port, h, w, q):
     import bench
 
     full = torch.arange(h * w * 4, dtype=torch.float32).reshape(h, w, 4)       # the frame every rank would agree on
-    stripes = bench.grt.interleaved_stripes(h, rank, world, 16)
+    stripes = bench.grt.interleaved_stripes(h, rank, world, rows)
     local = torch.cat([full[a:b] for a, b in stripes], 0)
-    frame = bench.gather_frame(local, h, w, rank, world, 16, torch.device("cpu"))
+    bufs = {}
+    for _ in range(2):      # twice: the second call reuses the persistent buffers
+        frame = bench.gather_frame(local, h, w, rank, world, rows, torch.device("cpu"), bufs)
     if rank == 0:
         q.put(bool(torch.equal(frame, full)))
     dist.destroy_process_group()
 
 
-def test_gather_reassembles_the_frame_world_size_2():
+@pytest.mark.parametrize("h, rows", [(100, 16), (128, 16)])   # ragged last stripe / regular interleave (single strided copy)
+def test_gather_reassembles_the_frame_world_size_2(h, rows):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 100, 24, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, h, 24, rows, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
