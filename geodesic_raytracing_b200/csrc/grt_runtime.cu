@@ -296,8 +296,9 @@ struct grt_ctx {
     FrameSlot* last = nullptr;       // slot of the most recently submitted frame
     bool fast_math = true;
     grt_features feat{};
-    grt_metric* metric = nullptr;
+    grt_metric* metric = nullptr;          // only dereferenced by grt_update_params / feature-driven rebuilds
     bool is_static = false;
+    bool bound_use_prepass = false, bound_constant_theta = false;   // what the frame path needs of the bound metric
     std::map<std::string, std::unique_ptr<Program>> programs;
     Program* prog = nullptr;
     float params[64] = {0};
@@ -584,7 +585,6 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || n <= 0 || !out) throw Error(GRT_E_INVALID, "bad frame size, stripe list or output pointer");
     if (format != GRT_FORMAT_RGBA32F && format != GRT_FORMAT_RGBA8) throw Error(GRT_E_INVALID, "unknown output format");
     if (!c->tex[0].set) throw Error(GRT_E_STATE, "no background set: call grt_set_background first");
-    const grt::Metric& m = *c->metric->m;
     Program* P = c->prog;
     build_geometry(c, w, h, y0s, y1s, n);
     FrameSlot& S = c->slots[c->frame_index++ % (unsigned)c->n_slots];
@@ -594,7 +594,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     GrtFrame fr = c->frame;
     fill_frame_features(c, fr);
     const bool adaptive = fr.cell == 2;
-    const bool use_prepass = (c->feat.use_prepass < 0 ? m.cfg.use_prepass : c->feat.use_prepass != 0) && (w / 16) > 0 && (h / 16) > 0;
+    const bool use_prepass = (c->feat.use_prepass < 0 ? c->bound_use_prepass : c->feat.use_prepass != 0) && (w / 16) > 0 && (h / 16) > 0;
     const int pw = w / 16, ph = h / 16;
     fr.prepass_w = pw;
     fr.prepass_h = ph;
@@ -616,7 +616,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     }
     const size_t extra_cap = adaptive ? (size_t)3 * fr.grid_w * fr.grid_h : 0;
     const size_t slots = std::max((size_t)fr.n_slots + extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)0);
-    const bool const_theta = m.constant_theta();
+    const bool const_theta = c->bound_constant_theta;
     GrtRays rays = rays_of(S, slots, const_theta);
     S.rdata.ensure((size_t)fr.n_rows * w * 16);
     S.termination.ensure(sizeof(int) * (size_t)std::max(1, pw * ph));
@@ -1043,6 +1043,8 @@ int grt_build_poll(grt_ctx* c) {
         // swap: frames already queued keep the module they were launched with
         c->metric = m;
         c->is_static = c->build.is_static;
+        c->bound_use_prepass = m->m->cfg.use_prepass;
+        c->bound_constant_theta = m->m->constant_theta();
         c->prog = p;
         c->kernel_info = p->info;
         memset(c->params, 0, sizeof c->params);
@@ -1076,6 +1078,8 @@ int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
         Program* p = get_program(c, m, is_static != 0);
         c->metric = m;
         c->is_static = is_static != 0;
+        c->bound_use_prepass = m->m->cfg.use_prepass;
+        c->bound_constant_theta = m->m->constant_theta();
         c->prog = p;
         c->kernel_info = p->info;
         memset(c->params, 0, sizeof c->params);
@@ -1274,7 +1278,7 @@ int grt_debug_read_rays(grt_ctx* c, grt_lightray* out, int max_count) {
         CK(cudaMemcpy(vel.data(), c->last->rays_vel.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(acc.data(), c->last->rays_acc.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(aux.data(), c->last->rays_aux.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
-        if (c->metric->m->constant_theta() && c->last->rays_quat.p) CK(cudaMemcpy(quat.data(), c->last->rays_quat.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        if (c->bound_constant_theta && c->last->rays_quat.p) CK(cudaMemcpy(quat.data(), c->last->rays_quat.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; i++) {
             grt_lightray& r = out[i];
             memset(&r, 0, sizeof r);
