@@ -148,7 +148,8 @@ def test_coordinate_maps_round_trip(oracles):
 
 
 def test_camera_tetrad_is_orthonormal(oracles):
-    for name in ("minkowski", "schwarzschild_fast", "kerr_schild", "alcubierre", "double_schwarzschild"):
+    # schwarzschild_skewed keeps time in coordinate slot 1: the frame construction has to find and swap the timelike leg (cl.cl:1761-1861)
+    for name in ("minkowski", "schwarzschild_fast", "schwarzschild_skewed", "kerr_schild", "kerr_boyer", "alcubierre", "double_schwarzschild"):
         _, o = oracles(name)
         cam, tet = o.camera(CAM_POS)
         g, _ = o.metric_eval(cam)
