@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CAM_POS = (0.0, 0.0, -4.0, 0.0)
-METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild"]
+METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild"]
 
 
 def bind(gpu_ctx, metric, background, **features):

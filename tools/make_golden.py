@@ -18,7 +18,7 @@ import geodesic_raytracing_b200 as grt  # noqa: E402
 import oracle  # noqa: E402
 
 REFERENCE = "/root/reference/scripts"
-NAMES = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "wormhole (morris-thorne)", "kerr_schild", "alcubierre", "double_unequal_kerr", "kerr_boyer", "schwarzschild_ingoing_ef_hawking", "configurable_wormhole",
+NAMES = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "wormhole (morris-thorne)", "kerr_schild", "alcubierre", "double_unequal_kerr", "kerr_boyer", "schwarzschild_ingoing_ef_hawking", "configurable_wormhole",
          "krasnikov_tube", "misner_4d"]
 
 
