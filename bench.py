@@ -366,7 +366,7 @@ def run_ours(args):
         flops_own_step = info.flops_accel + 110          # emitted lowered acceleration + Verlet update + step control + radii
         gsteps = int(st.trial_steps) / (integrate_ms * 1e-3)
         facts = ncu_facts()
-        micro = fp32_microbench() if world == 1 else None
+        micro = fp32_microbench() if (world == 1 and not args.no_cpu_baseline) else None   # side measurement, like the CPU baseline
         fp_instr = facts.get("sass_fp_instr_per_step")
         line = {
             "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
