@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/reference_metric_vectors.json from the reference's own metric scripts.
+"""Generate tests/golden/reference_metric_vectors.json from the reference's own metric scripts (test infrastructure).
 
 Run in a container where /root/reference is mounted. For each listed script the reference file is loaded
 unchanged through the plugin boundary, the CPU oracle is built on the generated functions, and g, dg, the
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 import geodesic_raytracing_b200 as grt  # noqa: E402
 import oracle  # noqa: E402

@@ -1,4 +1,4 @@
-"""The bundled content against golden vectors produced from the reference's own scripts (tools/make_golden.py),
+"""The bundled content against golden vectors produced from the reference's own scripts (tests/golden/make_golden.py),
 and - where /root/reference is mounted - the reference scripts themselves through the unchanged plugin boundary."""
 import json
 import os
