@@ -85,21 +85,32 @@ def build(metric_source: str, name: str, native: bool = False) -> str:
 
 
 class Oracle:
+    _prefix = "oracle_"
+    _rdata_dtype = ORACLE_RENDER_DATA_DTYPE
+    _lightray_dtype = ORACLE_LIGHTRAY_DTYPE
+
     def __init__(self, metric_source: str, name: str, params: Sequence[float] = (), native: bool = False):
-        self.path = build(metric_source, name, native)
+        self.path = self._build(metric_source, name, native)
         L = C.CDLL(self.path)
         self.lib = L
+        for fn in ("info", "frame", "integrate_sample", "metric_eval", "tetrad_at"):   # one binding for both libraries
+            setattr(L, "oracle_" + fn, getattr(L, self._prefix + fn))
         info = (C.c_int * 16)()
         L.oracle_info(info)
+        self._info_raw = list(info)
         self.info = dict(zip(["big", "constant_theta", "singular", "adaptive_precision", "singularity_detection", "use_prepass", "num_params", "static_params",
                               "sizeof_lightray", "sizeof_render_data", "threads"], list(info)))
-        assert self.info["sizeof_lightray"] == ORACLE_LIGHTRAY_DTYPE.itemsize, self.info
-        assert self.info["sizeof_render_data"] == ORACLE_RENDER_DATA_DTYPE.itemsize, self.info
+        assert self.info["sizeof_lightray"] == self._lightray_dtype.itemsize, self.info
+        assert self.info["sizeof_render_data"] == self._rdata_dtype.itemsize, self.info
         self.params = np.zeros(32, np.float32)
         self.params[:len(params)] = params
         L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
         L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+
+    @staticmethod
+    def _build(metric_source, name, native):
+        return build(metric_source, name, native)
 
     # -- helpers ---------------------------------------------------------------------------------
     @staticmethod
@@ -143,8 +154,8 @@ class Oracle:
         a = self._args(width, height, features, camera_pos, camera_quat, bg1=background, bg2=background2, **kw)
         o = OracleFrameOut()
         image = np.zeros((height, width, 4), np.float32) if background is not None else None
-        rdata = np.zeros(width * height, ORACLE_RENDER_DATA_DTYPE)
-        rays = np.zeros(width * height, ORACLE_LIGHTRAY_DTYPE) if want_rays else None
+        rdata = np.zeros(width * height, self._rdata_dtype)
+        rays = np.zeros(width * height, self._lightray_dtype) if want_rays else None
         pw, ph = width // 16, height // 16
         term = np.zeros(max(1, pw * ph), np.int32)
         o.image = image.ctypes.data if image is not None else None
@@ -258,7 +269,52 @@ class Oracle:
         return cam, tet.reshape(4, 4), v
 
 
+class ClReference(Oracle):
+    """The reference's OWN kernels: /root/reference/cl.cl compiled as C++ for the host into oracle/_ref/
+    (ref_build.py, ref_shim/).  Same calls as Oracle where the reference has the kernel: frame,
+    integrate_sample, metric_eval, tetrad_at, plus step_verlet.  `accepted_steps` is -1 (the reference
+    does not count them); `trial_steps` counts evaluations of its GEO_ACCEL0 macro."""
+    _prefix = "clref_"
+    # struct render_data of cl.cl:5066-5074 under OpenCL layout rules (float2 is 8-byte aligned): 32 bytes
+    _rdata_dtype = np.dtype({"names": ["tex_coord", "z_shift", "sx", "sy", "terminated", "side"], "formats": [("<f4", 2), "<f4", "<i4", "<i4", "<i4", "<i4"],
+                             "offsets": [0, 8, 12, 16, 20, 24], "itemsize": 32})
+    # struct lightray of cl.cl:813-824: 84 bytes of fields, 16-byte aligned -> 96
+    _lightray_dtype = np.dtype({"names": list(ORACLE_LIGHTRAY_DTYPE.names), "formats": [ORACLE_LIGHTRAY_DTYPE.fields[n][0] for n in ORACLE_LIGHTRAY_DTYPE.names],
+                                "offsets": [ORACLE_LIGHTRAY_DTYPE.fields[n][1] for n in ORACLE_LIGHTRAY_DTYPE.names], "itemsize": 96})
+
+    @staticmethod
+    def _build(metric_source, name, native):
+        from . import ref_build
+        so = ref_build.build_clref(metric_source, name, native)
+        if so is None:
+            raise FileNotFoundError(f"no prebuilt oracle/_ref/libclref_{name}_*.so for this metric source and /root/reference is not mounted")
+        return so
+
+    def __init__(self, metric_source, name, params=(), native=False):
+        super().__init__(metric_source, name, params, native)
+        assert self._info_raw[11] == 1, "feature block layout mismatch"
+
+    def step_verlet(self, pos, vel, acc, ds, features):
+        """One trial step of the reference's step_verlet (cl.cl:3273-3346) -> (position, velocity, acceleration)."""
+        p, v, a = (np.array(x, np.float32) for x in (pos, vel, acc))
+        block = np.zeros(12, np.float32)      # struct dynamic_feature_config of the dynamic program: 7 floats, 5 ints
+        block[:7] = [features.adaptive_sampling_threshold, features.field_of_view, features.max_acceleration_change, features.max_precision_radius,
+                     features.min_step, 4.0, features.universe_size]
+        block[7:].view(np.int32)[:] = [features.adaptive_sampling, features.redshift, features.reparameterisation, features.use_old_redshift, 0]
+        self.lib.clref_step_verlet(p.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p), C.c_float(ds),
+                                   self.params.ctypes.data_as(C.c_void_p), block.ctypes.data_as(C.c_void_p))
+        return p, v, a
+
+
+def _stem(metric) -> str:
+    return os.path.splitext(os.path.basename(metric.name.replace(" ", "_").replace("(", "").replace(")", "")))[0]
+
+
 def for_metric(metric, is_static: bool = False, native: bool = False) -> Oracle:
     """Oracle for a geodesic_raytracing_b200.Metric (same generated functions as the CUDA program)."""
-    stem = os.path.splitext(os.path.basename(metric.name.replace(" ", "_").replace("(", "").replace(")", "")))[0]
-    return Oracle(metric.source(is_static), stem + ("_static" if is_static else ""), metric.params, native)
+    return Oracle(metric.source(is_static), _stem(metric) + ("_static" if is_static else ""), metric.params, native)
+
+
+def reference_for_metric(metric, native: bool = False) -> ClReference:
+    """The reference's own cl.cl kernels (oracle/_ref) for a geodesic_raytracing_b200.Metric."""
+    return ClReference(metric.source(False), _stem(metric), metric.params, native)

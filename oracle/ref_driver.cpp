@@ -1,0 +1,341 @@
+// =============================================================================================
+// TEST INFRASTRUCTURE ONLY.  Host driver for oracle/_ref/libclref_<metric>.so: runs the
+// reference's OWN kernels - /root/reference/cl.cl compiled as C++ where it lies (ref_build.py,
+// ref_shim/) - on host cores, one OpenMP iteration per OpenCL work-item, in the order the
+// reference's frame loop enqueues them (/root/reference/main.cpp:2299-2331 camera,
+// :2356-2526 frame, :139-205 execute_kernel).  Same C structs as oracle_capi.cpp so the Python
+// side shares one binding.  Nothing here is part of the product path.
+// =============================================================================================
+#include <chrono>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+// the host-side texture build (graphics_settings.cpp:152-212) has no device source to compile:
+// the restatement in geodesic_oracle.hpp supplies the mip chain; it is expanded below into the
+// reference's padded full-size array layers, which the reference's own read_mipmap then samples.
+#include "geodesic_oracle.hpp"
+
+#include "ref_shim/opencl_as_cxx.hpp"
+#undef printf
+
+// trial ray-steps: GEO_ACCEL0 is evaluated exactly once per step_verlet call (cl.cl:3299); the
+// counter lives in the cl.cl translation unit (ref_shim/cl_macro_abi.hpp, cl_trailer.inc)
+extern "C" long long clref_take_trial_steps();
+
+// kernel prototypes (cl.cl line of each __kernel in the comment); struct bodies live in cl.cl
+struct lightray;
+struct render_data;
+struct dynamic_config;
+struct dynamic_feature_config;
+extern "C" {
+void cart_to_generic_kernel(const float4*, float4*, int, float, const dynamic_config*);                                              // cl.cl:6018
+void init_basis_vectors(const float4*, int, float3, float4*, float4*, float4*, float4*, const dynamic_config*);                      // cl.cl:2483
+void clear_termination_buffer(int*, int, int);                                                                                       // cl.cl:4997
+void calculate_singularities(const lightray*, const int*, int*, int, int);                                                           // cl.cl:5008
+void init_rays_generic(const float4*, const float4*, lightray*, int*, int, int, const int*, int, int, int, const float4*, const float4*, const float4*,
+                       const float4*, const dynamic_config*, const dynamic_feature_config*, int);                                    // cl.cl:3143
+void do_generic_rays(lightray*, const int*, int*, int*, const dynamic_config*, const dynamic_feature_config*, int, int, int, int, float4*, int*, int);  // cl.cl:3954
+void calculate_render_data(const lightray*, const int*, render_data*, int*, int, int, const dynamic_config*, const dynamic_feature_config*);            // cl.cl:5135
+void handle_adaptive_sampling(const lightray*, const int*, render_data*, int*, lightray*, int*, float4*, float4*, const float4*, const float4*, const float4*,
+                              const float4*, int, int, const dynamic_config*, const dynamic_feature_config*);                        // cl.cl:5223
+void render(const render_data*, const int*, image2d_t, image2d_array_t, image2d_array_t, int, int, int, const dynamic_config*, const dynamic_feature_config*);  // cl.cl:5453
+int clref_sizeof_lightray();
+int clref_sizeof_render_data();
+int clref_sizeof_features();
+}
+
+namespace {
+
+// struct dynamic_feature_config of the dynamic program (cl_macro_abi.hpp: floats then ints, alphabetical)
+struct FeatureBlock {
+    float adaptive_sampling_threshold, field_of_view, max_acceleration_change, max_precision_radius, min_step, ray_skip, universe_size;
+    int adaptive_sampling, redshift, reparameterisation, use_old_redshift, use_triangle_rendering;
+};
+
+template <typename T> struct Buf {  // 64-byte aligned, zero-filled device-buffer stand-in
+    T* p = nullptr;
+    explicit Buf(size_t n) { size_t bytes = ((n ? n : 1) * sizeof(T) + 63) / 64 * 64; p = (T*)aligned_alloc(64, bytes); memset((void*)p, 0, bytes); }
+    ~Buf() { free((void*)p); }
+    Buf(const Buf&) = delete;
+};
+struct RawBuf {
+    char* p;
+    RawBuf(size_t n, size_t elem) { size_t bytes = ((n ? n : 1) * elem + 63) / 64 * 64; p = (char*)aligned_alloc(64, bytes); memset(p, 0, bytes); }
+    ~RawBuf() { free(p); }
+    RawBuf(const RawBuf&) = delete;
+};
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// clEnqueueNDRangeKernel over a 1-D range: global size rounded up to the work-group size, as an
+// OpenCL 1.2 launch needs; every kernel bounds-checks its id.
+template <typename F> void launch_1d(size_t gsize, size_t wgs, long long* steps, F&& body) {
+    size_t n = (gsize + wgs - 1) / wgs * wgs;
+    long long total = 0;
+#pragma omp parallel reduction(+ : total)
+    {
+#pragma omp for schedule(dynamic, 16)
+        for (long long id = 0; id < (long long)n; id++) {
+            clshim::work_item.gid[0] = (size_t)id; clshim::work_item.gid[1] = 0;
+            clshim::work_item.lid[0] = (size_t)id % wgs; clshim::work_item.grp[0] = (size_t)id / wgs;
+            clshim::work_item.gsz[0] = n; clshim::work_item.lsz[0] = wgs;
+            body();
+        }
+        total += clref_take_trial_steps();
+    }
+    if (steps) *steps += total;
+}
+template <typename F> void launch_2d(size_t gx, size_t gy, size_t lx, size_t ly, F&& body) {
+    size_t nx = (gx + lx - 1) / lx * lx, ny = (gy + ly - 1) / ly * ly;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long y = 0; y < (long long)ny; y++)
+        for (size_t x = 0; x < nx; x++) {
+            clshim::work_item.gid[0] = x; clshim::work_item.gid[1] = (size_t)y;
+            clshim::work_item.lid[0] = x % lx; clshim::work_item.lid[1] = (size_t)y % ly;
+            clshim::work_item.grp[0] = x / lx; clshim::work_item.grp[1] = (size_t)y / ly;
+            clshim::work_item.gsz[0] = nx; clshim::work_item.gsz[1] = ny; clshim::work_item.lsz[0] = lx; clshim::work_item.lsz[1] = ly;
+            body();
+        }
+}
+
+// the padded array image of load_mipped_image (graphics_settings.cpp:164-211)
+std::vector<uint8_t> padded_layers(const oracle::MipImage& m) {
+    std::vector<uint8_t> out((size_t)m.levels * m.width * m.height * 4);
+    for (int l = 0; l < m.levels; l++) {
+        const uint8_t* src = m.level[l].data();
+        uint8_t* dst = out.data() + (size_t)l * m.width * m.height * 4;
+        for (int y = 0; y < m.height; y++)
+            for (int x = 0; x < m.width; x++) {
+                int lx = std::min(x, m.lw[l] - 1), ly = std::min(y, m.lh[l] - 1);
+                memcpy(dst + ((size_t)y * m.width + x) * 4, src + ((size_t)ly * m.lw[l] + lx) * 4, 4);
+            }
+    }
+    return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+// identical to oracle_capi.cpp
+struct OracleFeatures {
+    float universe_size, max_acceleration_change, max_precision_radius, min_step, adaptive_sampling_threshold, field_of_view;
+    int redshift, reparameterisation, use_old_redshift, adaptive_sampling;
+};
+struct OracleFrameArgs {
+    int width, height;
+    float camera_pos[4];
+    float camera_quat[4];
+    float basis_speed[3];
+    int flip;
+    int use_given_camera;
+    float camera_generic[4];
+    float tetrad[16];
+    OracleFeatures features;
+    float params[32];
+    int max_probes;
+    int use_prepass;
+    const uint8_t* bg1; int bg1_w, bg1_h;
+    const uint8_t* bg2; int bg2_w, bg2_h;
+};
+struct OracleFrameOut {
+    float* image;
+    void* rays;
+    void* rdata;
+    int* termination;
+    long long trial_steps, accepted_steps;
+    long long rays_traced, extra_rays;
+    double t_init_s, t_integrate_s, t_render_data_s, t_adaptive_s, t_render_s, t_total_s;
+    float camera_generic[4];
+    float tetrad[16];
+};
+
+static FeatureBlock to_block(const OracleFeatures& f) {
+    FeatureBlock b;
+    b.adaptive_sampling_threshold = f.adaptive_sampling_threshold; b.field_of_view = f.field_of_view;
+    b.max_acceleration_change = f.max_acceleration_change; b.max_precision_radius = f.max_precision_radius;
+    b.min_step = f.min_step; b.ray_skip = 4.f; b.universe_size = f.universe_size;
+    b.adaptive_sampling = f.adaptive_sampling; b.redshift = f.redshift; b.reparameterisation = f.reparameterisation;
+    b.use_old_redshift = f.use_old_redshift; b.use_triangle_rendering = 0;
+    return b;
+}
+
+void clref_info(int* out) {
+    out[0] = GRT_BIG_METRIC; out[1] = GRT_CONSTANT_THETA; out[2] = GRT_SINGULAR; out[3] = GRT_ADAPTIVE_PRECISION;
+    out[4] = GRT_SINGULARITY_DETECTION; out[5] = GRT_USE_PREPASS; out[6] = GRT_NUM_PARAMS; out[7] = GRT_STATIC_PARAMS;
+    out[8] = clref_sizeof_lightray(); out[9] = clref_sizeof_render_data();
+#ifdef _OPENMP
+    out[10] = omp_get_max_threads();
+#else
+    out[10] = 1;
+#endif
+    out[11] = clref_sizeof_features() == (int)sizeof(FeatureBlock);
+}
+
+struct CameraState { Buf<float4> generic{1}, quat{1}, e0{1}, e1{1}, e2{1}, e3{1}; };
+
+static void setup_camera(const OracleFrameArgs* a, const dynamic_config* cfg, CameraState& c) {
+    *c.quat.p = float4(a->camera_quat[0], a->camera_quat[1], a->camera_quat[2], a->camera_quat[3]);
+    if (a->use_given_camera) {
+        *c.generic.p = float4(a->camera_generic[0], a->camera_generic[1], a->camera_generic[2], a->camera_generic[3]);
+        float4* e[4] = {c.e0.p, c.e1.p, c.e2.p, c.e3.p};
+        for (int i = 0; i < 4; i++) *e[i] = float4(a->tetrad[i * 4], a->tetrad[i * 4 + 1], a->tetrad[i * 4 + 2], a->tetrad[i * 4 + 3]);
+        return;
+    }
+    // main.cpp:2299-2331
+    Buf<float4> cart(1);
+    *cart.p = float4(a->camera_pos[0], a->camera_pos[1], a->camera_pos[2], a->camera_pos[3]);
+    float clflip = a->flip ? 1.f : 0.f;
+    launch_1d(1, 1, nullptr, [&] { cart_to_generic_kernel(cart.p, c.generic.p, 1, clflip, cfg); });
+    float3 speed(a->basis_speed[0], a->basis_speed[1], a->basis_speed[2]);
+    launch_1d(1, 1, nullptr, [&] { init_basis_vectors(c.generic.p, 1, speed, c.e0.p, c.e1.p, c.e2.p, c.e3.p, cfg); });
+}
+
+// One frame, main.cpp:2356-2526 (triangle rendering off).
+int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
+    const int width = a->width, height = a->height;
+    const size_t LR = (size_t)clref_sizeof_lightray(), RD = (size_t)clref_sizeof_render_data();
+    double t_start = now_s();
+    Buf<float> cfg_buf(32);
+    memcpy(cfg_buf.p, a->params, sizeof(float) * 32);
+    const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
+    Buf<FeatureBlock> dfg_buf(1);
+    *dfg_buf.p = to_block(a->features);
+    const dynamic_feature_config* dfg = (const dynamic_feature_config*)dfg_buf.p;
+
+    CameraState cam;
+    setup_camera(a, cfg, cam);
+    memcpy(o->camera_generic, cam.generic.p, 16);
+    memcpy(o->tetrad + 0, cam.e0.p, 16); memcpy(o->tetrad + 4, cam.e1.p, 16); memcpy(o->tetrad + 8, cam.e2.p, 16); memcpy(o->tetrad + 12, cam.e3.p, 16);
+
+    const int prepass_width = width / 16, prepass_height = height / 16;   // main.cpp:2378-2379
+    const size_t npx = (size_t)width * height;
+    RawBuf rays_in(npx, LR), rays_adaptive(npx, LR), rdata(npx, RD);
+    Buf<int> rays_count_in(1), rays_adaptive_count(1), render_data_count(1), termination_buffer(npx), stored_ray_counts(npx), tmin(npx), tmax(npx);
+    const int isnap = 0;
+    long long steps = 0;
+    o->rays_traced = 0; o->t_integrate_s = 0; o->extra_rays = 0; o->t_adaptive_s = 0; o->t_render_s = 0;
+    const size_t wg = 64;   // workgroup_size 8x8 (graphics_settings.hpp:42)
+
+    auto execute_kernel = [&](char* rays, int* count) {   // main.cpp:139-205; global size {width*height}
+        memset(stored_ray_counts.p, 0, sizeof(int) * npx);
+        double t = now_s();
+        launch_1d(npx, wg, &steps, [&] { do_generic_rays((lightray*)rays, count, tmin.p, tmax.p, cfg, dfg, width, height, 0, 0, nullptr, stored_ray_counts.p, 0); });
+        o->t_integrate_s += now_s() - t;
+        o->rays_traced += *count;
+    };
+
+    double t0 = now_s();
+    int use_prepass = a->use_prepass < 0 ? GRT_USE_PREPASS : a->use_prepass;
+    if (use_prepass && prepass_width > 0 && prepass_height > 0) {   // main.cpp:2387-2436
+        size_t np = (size_t)prepass_width * prepass_height;
+        launch_1d(np, 256, nullptr, [&] { clear_termination_buffer(termination_buffer.p, prepass_width, prepass_height); });
+        *rays_count_in.p = 0;
+        launch_1d(np, 256, nullptr, [&] {
+            init_rays_generic(cam.generic.p, cam.quat.p, (lightray*)rays_in.p, rays_count_in.p, prepass_width, prepass_height, termination_buffer.p, prepass_width,
+                              prepass_height, isnap, cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, cfg, dfg, 1);
+        });
+        execute_kernel(rays_in.p, rays_count_in.p);
+        launch_1d(np, 256, nullptr, [&] { calculate_singularities((const lightray*)rays_in.p, rays_count_in.p, termination_buffer.p, prepass_width, prepass_height); });
+    }
+    if (o->termination) memcpy(o->termination, termination_buffer.p, sizeof(int) * (size_t)prepass_width * prepass_height);
+
+    launch_1d(npx, 256, nullptr, [&] {   // main.cpp:2438-2461
+        init_rays_generic(cam.generic.p, cam.quat.p, (lightray*)rays_in.p, rays_count_in.p, width, height, termination_buffer.p, prepass_width, prepass_height, isnap,
+                          cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, cfg, dfg, 0);
+    });
+    o->t_init_s = now_s() - t0 - o->t_integrate_s;
+    execute_kernel(rays_in.p, rays_count_in.p);
+
+    *render_data_count.p = 0;
+    double t1 = now_s();
+    launch_1d(npx, 256, nullptr, [&] { calculate_render_data((const lightray*)rays_in.p, rays_count_in.p, (render_data*)rdata.p, render_data_count.p, width, height, cfg, dfg); });
+    o->t_render_data_s = now_s() - t1;
+
+    if (a->features.adaptive_sampling) {   // main.cpp:2478-2511
+        *rays_adaptive_count.p = 0;
+        double t2 = now_s();
+        launch_2d((size_t)width / 2, (size_t)height / 2, 8, 8, [&] {
+            handle_adaptive_sampling((const lightray*)rays_in.p, rays_count_in.p, (render_data*)rdata.p, render_data_count.p, (lightray*)rays_adaptive.p,
+                                     rays_adaptive_count.p, cam.generic.p, cam.quat.p, cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, width, height, cfg, dfg);
+        });
+        o->t_adaptive_s = now_s() - t2;
+        execute_kernel(rays_adaptive.p, rays_adaptive_count.p);
+        double t4 = now_s();
+        launch_1d(npx, 256, nullptr, [&] {
+            calculate_render_data((const lightray*)rays_adaptive.p, rays_adaptive_count.p, (render_data*)rdata.p, render_data_count.p, width, height, cfg, dfg);
+        });
+        o->t_render_data_s += now_s() - t4;
+        o->extra_rays = *rays_adaptive_count.p;
+    }
+    if (o->rays) memcpy(o->rays, rays_in.p, LR * (size_t)*rays_count_in.p);
+    if (o->rdata) memcpy(o->rdata, rdata.p, RD * npx);
+
+    if (o->image && a->bg1) {   // main.cpp:2513-2525
+        oracle::MipImage m1 = oracle::build_mip_image(a->bg1, a->bg1_w, a->bg1_h);
+        std::vector<uint8_t> l1 = padded_layers(m1), l2;
+        image2d_array_t i1{l1.data(), m1.width, m1.height, m1.levels}, i2 = i1;
+        if (a->bg2) {
+            oracle::MipImage m2 = oracle::build_mip_image(a->bg2, a->bg2_w, a->bg2_h);
+            l2 = padded_layers(m2);
+            i2 = image2d_array_t{l2.data(), m2.width, m2.height, m2.levels};
+        }
+        image2d_t out{o->image, width, height};
+        double t6 = now_s();
+        launch_1d(npx, 256, nullptr, [&] { render((const render_data*)rdata.p, render_data_count.p, out, i1, i2, width, height, a->max_probes, cfg, dfg); });
+        o->t_render_s = now_s() - t6;
+    }
+    o->trial_steps = steps;
+    o->accepted_steps = -1;   // the reference does not count them
+    o->t_total_s = now_s() - t_start;
+    return 0;
+}
+
+// Bounded CPU-baseline sample for bench.py: rays of the pixels (x0 + i*stride, y0 + j*stride) of the
+// full width x height grid, produced by the reference's init_rays_generic (full grid, adaptive
+// sampling and prepass off so that every pixel's ray exists), gathered, then integrated by the
+// reference's do_generic_rays; `seconds` covers the integration launch only.
+int clref_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int ch, int stride, long long* trial_steps, long long* accepted_steps, double* seconds,
+                           int* terminated_out, int* steps_out) {
+    const int width = a->width, height = a->height;
+    const size_t LR = (size_t)clref_sizeof_lightray();
+    Buf<float> cfg_buf(32);
+    memcpy(cfg_buf.p, a->params, sizeof(float) * 32);
+    const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
+    Buf<FeatureBlock> dfg_buf(1);
+    *dfg_buf.p = to_block(a->features);
+    dfg_buf.p->adaptive_sampling = 0;
+    const dynamic_feature_config* dfg = (const dynamic_feature_config*)dfg_buf.p;
+    CameraState cam;
+    setup_camera(a, cfg, cam);
+    const size_t npx = (size_t)width * height, n = (size_t)cw * ch;
+    RawBuf all(npx, LR), sample(n, LR);
+    Buf<int> count(1), termination_buffer(npx), stored(n), tmin(n), tmax(n);
+    launch_1d(npx, 256, nullptr, [&] {
+        init_rays_generic(cam.generic.p, cam.quat.p, (lightray*)all.p, count.p, width, height, termination_buffer.p, width / 16, height / 16, 0, cam.e0.p, cam.e1.p,
+                          cam.e2.p, cam.e3.p, cfg, dfg, 0);
+    });
+    for (size_t i = 0; i < n; i++) {
+        int cx = x0 + (int)(i % cw) * stride, cy = y0 + (int)(i / cw) * stride;
+        memcpy(sample.p + i * LR, all.p + ((size_t)cy * width + cx) * LR, LR);
+    }
+    *count.p = (int)n;
+    long long steps = 0;
+    double t = now_s();
+    launch_1d(n, 64, &steps, [&] { do_generic_rays((lightray*)sample.p, count.p, tmin.p, tmax.p, cfg, dfg, cw, ch, 0, 0, nullptr, stored.p, 0); });
+    *seconds = now_s() - t;
+    *trial_steps = steps;
+    if (accepted_steps) *accepted_steps = -1;
+    if (terminated_out)
+        for (size_t i = 0; i < n; i++) terminated_out[i] = *(const int*)(sample.p + i * LR + 72);   // lightray::terminated (cl.cl:813-824)
+    if (steps_out) memset(steps_out, 0, sizeof(int) * n);
+    return 0;
+}
+
+}  // extern "C"
