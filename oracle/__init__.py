@@ -93,7 +93,7 @@ class Oracle:
         self.path = self._build(metric_source, name, native)
         L = C.CDLL(self.path)
         self.lib = L
-        for fn in ("info", "frame", "integrate_sample", "metric_eval", "tetrad_at"):   # one binding for both libraries
+        for fn in ("info", "frame", "integrate_sample", "metric_eval", "tetrad_at", "geodesic_snapshot", "geodesic_interpolate"):   # one binding for both libraries
             setattr(L, "oracle_" + fn, getattr(L, self._prefix + fn))
         info = (C.c_int * 16)()
         L.oracle_info(info)

@@ -45,6 +45,12 @@ void calculate_render_data(const lightray*, const int*, render_data*, int*, int,
 void handle_adaptive_sampling(const lightray*, const int*, render_data*, int*, lightray*, int*, float4*, float4*, const float4*, const float4*, const float4*,
                               const float4*, int, int, const dynamic_config*, const dynamic_feature_config*);                        // cl.cl:5223
 void render(const render_data*, const int*, image2d_t, image2d_array_t, image2d_array_t, int, int, int, const dynamic_config*, const dynamic_feature_config*);  // cl.cl:5453
+void boost_tetrad(float4*, int, float3*, float4*, float4*, float4*, float4*, const dynamic_config*);                                   // cl.cl:2441
+void init_inertial_ray(float4*, int, lightray*, int*, float4*, float4*, float4*, float4*, float3*, const dynamic_config*);            // cl.cl:3117
+void get_geodesic_path(lightray*, float4*, float4*, float*, int*, int, const dynamic_config*, const dynamic_feature_config*, int*);   // cl.cl:4735
+void parallel_transport_quantity(float4*, float4*, float*, float4*, int*, int, float4*, const dynamic_config*);                       // cl.cl:2569
+void handle_interpolating_geodesic(const float4*, const float4*, const float*, float4*, const float4*, const float4*, const float4*, const float4*, float4*, float4*,
+                                   float4*, float4*, float, const int*, int, const float3*, float4*, const dynamic_config*);          // cl.cl:2738
 int clref_sizeof_lightray();
 int clref_sizeof_render_data();
 int clref_sizeof_features();
@@ -336,6 +342,69 @@ int clref_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int
         for (size_t i = 0; i < n; i++) terminated_out[i] = *(const int*)(sample.p + i * LR + 72);   // lightray::terminated (cl.cl:813-824)
     if (steps_out) memset(steps_out, 0, sizeof(int) * n);
     return 0;
+}
+
+// main.cpp:2675-2760: boost_tetrad -> init_inertial_ray -> get_geodesic_path -> 4x parallel_transport_quantity
+int clref_geodesic_snapshot(const float* camera_generic, const float* tetrad_in, const float* basis_speed, const OracleFeatures* f, const float* params,
+                            int max_path_length, float* positions, float* velocities, float* ds, float* transported /* 4 * max * 4 */, float* boosted_tetrad) {
+    Buf<float> cfg_buf(32);
+    memcpy(cfg_buf.p, params, sizeof(float) * 32);
+    const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
+    Buf<FeatureBlock> dfg_buf(1);
+    *dfg_buf.p = to_block(*f);
+    const dynamic_feature_config* dfg = (const dynamic_feature_config*)dfg_buf.p;
+    Buf<float4> cam(1), e0(1), e1(1), e2(1), e3(1);
+    Buf<float3> speed(1);
+    *cam.p = float4(camera_generic[0], camera_generic[1], camera_generic[2], camera_generic[3]);
+    float4* e[4] = {e0.p, e1.p, e2.p, e3.p};
+    for (int i = 0; i < 4; i++) *e[i] = float4(tetrad_in[i * 4], tetrad_in[i * 4 + 1], tetrad_in[i * 4 + 2], tetrad_in[i * 4 + 3]);
+    *speed.p = float3(basis_speed[0], basis_speed[1], basis_speed[2]);
+    launch_1d(1, 1, nullptr, [&] { boost_tetrad(cam.p, 1, speed.p, e0.p, e1.p, e2.p, e3.p, cfg); });
+    for (int i = 0; i < 4; i++) memcpy(boosted_tetrad + i * 4, e[i], 16);
+    RawBuf ray(1, (size_t)clref_sizeof_lightray());
+    Buf<int> ray_count(1), count_out(1);
+    launch_1d(1, 1, nullptr, [&] { init_inertial_ray(cam.p, 1, (lightray*)ray.p, ray_count.p, e0.p, e1.p, e2.p, e3.p, speed.p, cfg); });
+    Buf<float4> pos((size_t)max_path_length), vel((size_t)max_path_length), q((size_t)max_path_length);
+    Buf<float> dsv((size_t)max_path_length);
+    launch_1d(1, 1, nullptr, [&] { get_geodesic_path((lightray*)ray.p, pos.p, vel.p, dsv.p, ray_count.p, max_path_length, cfg, dfg, count_out.p); });
+    int cnt = *count_out.p;
+    memcpy(positions, pos.p, sizeof(float) * 4 * (size_t)cnt);
+    memcpy(velocities, vel.p, sizeof(float) * 4 * (size_t)cnt);
+    memcpy(ds, dsv.p, sizeof(float) * (size_t)cnt);
+    for (int k = 0; k < 4; k++) {
+        launch_1d(1, 1, nullptr, [&] { parallel_transport_quantity(pos.p, vel.p, dsv.p, e[k], count_out.p, 1, q.p, cfg); });
+        memcpy(transported + (size_t)k * max_path_length * 4, q.p, sizeof(float) * 4 * (size_t)cnt);
+    }
+    return cnt;
+}
+
+// main.cpp:2264-2296
+void clref_geodesic_interpolate(const float* positions, const float* velocities, const float* ds, const float* transported, int max_path_length, int cnt,
+                                float target_time, int parallel_transport_observer, const float* basis_speed, const float* params, float* camera_generic_out,
+                                float* tetrad_out, float* velocity_out) {
+    Buf<float> cfg_buf(32);
+    memcpy(cfg_buf.p, params, sizeof(float) * 32);
+    const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
+    size_t n = (size_t)std::max(cnt, 1);
+    Buf<float4> pos(n), vel(n), t0(n), t1(n), t2(n), t3(n), cam(1), e0(1), e1(1), e2(1), e3(1), v(1);
+    Buf<float> dsv(n);
+    Buf<int> count(1);
+    Buf<float3> speed(1);
+    *count.p = cnt;
+    *speed.p = float3(basis_speed[0], basis_speed[1], basis_speed[2]);
+    float4* te[4] = {t0.p, t1.p, t2.p, t3.p};
+    memcpy(pos.p, positions, sizeof(float) * 4 * (size_t)cnt);
+    memcpy(vel.p, velocities, sizeof(float) * 4 * (size_t)cnt);
+    memcpy(dsv.p, ds, sizeof(float) * (size_t)cnt);
+    for (int k = 0; k < 4; k++) memcpy(te[k], transported + (size_t)k * max_path_length * 4, sizeof(float) * 4 * (size_t)cnt);
+    *e0.p = float4(1, 0, 0, 0); *e1.p = float4(0, 1, 0, 0); *e2.p = float4(0, 0, 1, 0); *e3.p = float4(0, 0, 0, 1);
+    launch_1d(1, 1, nullptr, [&] {
+        handle_interpolating_geodesic(pos.p, vel.p, dsv.p, cam.p, t0.p, t1.p, t2.p, t3.p, e0.p, e1.p, e2.p, e3.p, target_time, count.p, parallel_transport_observer,
+                                      speed.p, v.p, cfg);
+    });
+    memcpy(camera_generic_out, cam.p, 16);
+    memcpy(velocity_out, v.p, 16);
+    memcpy(tetrad_out + 0, e0.p, 16); memcpy(tetrad_out + 4, e1.p, 16); memcpy(tetrad_out + 8, e2.p, 16); memcpy(tetrad_out + 12, e3.p, 16);
 }
 
 }  // extern "C"

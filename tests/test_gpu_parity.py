@@ -527,3 +527,48 @@ def test_geodesic_camera_paths(gpu_ctx, oracles, background, name, speed):
         assert np.allclose(E @ G @ E.T, np.diag([-1, 1, 1, 1]), atol=5e-2), (name, i)
     gpu_ctx.clear_camera_geodesic()
     gpu_ctx.set_camera()
+
+
+# ---- against the REFERENCE'S OWN KERNELS ----------------------------------------------------------------------------------
+# tests/golden/clref_frames.npz holds frames produced by /root/reference/cl.cl itself (compiled as C++ for the host,
+# oracle/ref_build.py; generated by tests/golden/make_clref_golden.py).  Same fp32 tolerances as above.
+def _clref_cases():
+    from test_reference_kernels import ALL
+    return ALL
+
+
+@pytest.mark.parametrize("name,case", _clref_cases(), ids=[f"{n}-{c[0]}" for n, c in _clref_cases()])
+def test_frame_matches_reference_kernel_output(gpu_ctx, content, grt, name, case):
+    import os
+    tag, feat_kw, kw = case
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clref_frames.npz"))
+    key = f"{name}|{tag}|"
+    metric = content.load_by_name(name)
+    bg = grt.synthetic_background(512, 256)
+    base = bind(gpu_ctx, metric, bg, **feat_kw)
+    gpu_ctx.set_background(bg[::-1].copy(), which=1)
+    gpu_ctx.set_camera(kw.get("camera_pos", CAM_POS), kw.get("camera_quat", (-0.70710678, 0, 0, 0.70710678)), flip_r=kw.get("flip", False))
+    gpu_ctx.set_observer_speed(kw.get("basis_speed", (0, 0, 0)))
+    try:
+        w, h = 64, 48
+        img, st = gpu_ctx.render(w, h)
+        rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
+    finally:
+        gpu_ctx.set_observer_speed((0, 0, 0))
+        gpu_ctx.set_camera()
+        gpu_ctx.set_background(bg, which=1)
+    term = gold[key + "terminated"]
+    assert (rd["terminated"] == term).mean() >= 0.99, (rd["terminated"] == term).mean()
+    both = (rd["terminated"] == 1) & (term == 1)
+    duv = np.abs(rd["tex_coord"] - gold[key + "tex_coord"])
+    duv = np.minimum(duv, 1 - duv)[both]
+    if duv.size:
+        assert (duv.max(axis=-1) < 1e-3).mean() >= 0.99, np.percentile(duv, 99)
+        assert np.array_equal(rd["side"][both], gold[key + "side"][both])
+        dz = np.abs(rd["z_shift"][both] - gold[key + "z_shift"][both])
+        assert (dz < 2e-3).mean() >= 0.99
+    px = (np.abs(img[..., :3] - gold[key + "image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean()
+    assert px >= (0.96 if base["adaptive_sampling"] else 0.985), px
+    steps, rays, extra = gold[key + "counts"].tolist()
+    assert abs(int(st.trial_steps) - steps) <= 0.03 * steps + 64
+    assert abs(int(st.extra_rays) - extra) <= 0.10 * extra + 12
