@@ -14,8 +14,8 @@ metric's JSON asks, adaptive sampling on at threshold 32 - main.cpp:1123-1158, g
 * N > 1   the frame is tiled in interleaved 54-row stripes over N ranks (one process per GPU, torchrun), every rank
           traces its stripes (+ halo, + the redundant 1/16 prepass) and the finished tiles are gathered on rank 0 over
           NCCL/NVLink; strong scaling: the work of ONE frame is fixed, value = its single-GPU step count / max-over-ranks time.
-* --impl reference   the CPU oracle (a restatement of the reference's OpenCL kernels; the reference itself cannot be
-          built or run here - DESIGN.md) on all host cores, on a bounded pixel subsample of the same frame.
+* --impl reference   the reference's own integration kernel (oracle/_ref: /root/reference/cl.cl compiled as C++ for the host,
+          DESIGN.md) on all host cores, on a bounded pixel subsample of the same frame.
 """
 import argparse
 import json
@@ -179,13 +179,20 @@ class ClockSampler:
 
 
 def cpu_baseline_sample(stride, threads_note=True):
-    """The CPU oracle on a bounded subsample of the frame's rays: every `stride`-th pixel in x and y of the 4K pixel grid,
-    integration stage only (the stage that is > 90 % of a frame), all host cores (OpenMP, dynamic schedule)."""
+    """The reference's own integration kernel (oracle/_ref: cl.cl's do_generic_rays compiled as C++ for the host, one OpenMP
+    iteration per work-item, all host cores) on a bounded subsample of the frame's rays: every `stride`-th pixel in x and y
+    of the 4K pixel grid, integration stage only (the stage that is > 90 % of a frame).  Falls back to the C++ restatement
+    (kind "port") when no oracle/_ref library was prebuilt."""
     import oracle
 
     content = grt.Content(grt.CONTENT_DIR)
     metric = content.load_by_name(METRIC_NAME)
-    orc = oracle.for_metric(metric, native=True)
+    try:
+        orc = oracle.reference_for_metric(metric, native=True)     # oracle/_ref: the reference's own cl.cl kernels, compiled for the host
+        orc.kind = "reference"
+    except FileNotFoundError:
+        orc = oracle.for_metric(metric, native=True)               # the C++ restatement (bit-exact against oracle/_ref, tests/test_reference_kernels.py)
+        orc.kind = "port"
     feat = orc.features(max_acceleration_change=metric.info.max_acceleration_change)
     cw, ch = WIDTH // stride, HEIGHT // stride
     return orc, feat, cw, ch
@@ -211,9 +218,10 @@ def run_reference(args):
         "impl": "reference", "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": orc.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU oracle = C++ restatement of the reference's OpenCL kernels (the reference host and cl.cl cannot be built or run in this image: DESIGN.md)",
+        "note": ("oracle/_ref = the reference's cl.cl compiled as C++ for the host cores (g++ -O3 -march=x86-64-v3, OpenMP over work-items); no OpenCL runtime exists in this image"
+                 if orc.kind == "reference" else "C++ restatement of the reference's OpenCL kernels (no prebuilt oracle/_ref library found)"),
     }
     print(json.dumps(line), flush=True)
 
@@ -398,7 +406,7 @@ def run_ours(args):
             orc, feat, cw, ch = cpu_baseline_sample(stride)
             r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
             line["cpu_baseline"] = {
-                "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": "port",
+                "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": orc.kind,
                 "sample": f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw * ch} rays, {r['trial_steps']} ray-steps, {r['seconds']:.1f} s), integration stage, no prepass cull"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,7 +1,9 @@
-"""CPU ORACLE - TEST INFRASTRUCTURE ONLY (see geodesic_oracle.hpp). PARITY UNPINNED.
+"""CPU ORACLE - TEST INFRASTRUCTURE ONLY (see geodesic_oracle.hpp).
 
-Builds and binds the C++ restatement of the reference's OpenCL kernels for one metric. Only
-tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+Builds and binds (i) `Oracle`: the C++ restatement of the reference's OpenCL kernels for one metric, and
+(ii) `ClReference`: the reference's OWN kernels, /root/reference/cl.cl compiled as C++ for the host into
+oracle/_ref/ (ref_build.py).  (i) is pinned bit for bit against (ii) (tests/test_reference_kernels.py).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
 """
 from __future__ import annotations
 

@@ -6,12 +6,18 @@
 // cl.cl lines it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
 // / --impl reference legs may build or call this.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for
-// this path and neither its host (missing deps/vec, deps/toolkit) nor
-// cl.cl (needs an OpenCL C compiler + the generated -D macro set) can be built here, so this
-// restatement is pinned only by analytic identities (tests/test_oracle_physics.py): straight
-// rays in Minkowski, the Schwarzschild shadow radius, null-norm and conserved-quantity checks
-// in Kerr-Schild, AD-vs-finite-difference partials, and symbolic-vs-numeric accelerations.
+// PARITY: PINNED AGAINST THE REFERENCE'S OWN DEVICE CODE.  The reference ships no golden vectors or
+// known-answer tests for this path, but its kernels can be run here: oracle/ref_build.py
+// compiles /root/reference/cl.cl itself as C++ for the host (oracle/ref_shim/: an OpenCL-C-as-C++
+// environment plus the -D macro ABI over the generated metric functions) into oracle/_ref/, and
+// ref_driver.cpp runs the reference's kernel sequence.  This restatement reproduces those kernels BIT
+// FOR BIT - frames (render_data, image, prepass mask, ray / step counts), tetrads, the geodesic camera
+// path - on every bundled metric (tests/test_reference_kernels.py, live and against the committed
+// fixtures tests/golden/clref_frames.npz).  What stays unpinned is upstream of cl.cl: the symbolic
+// layer deps/vec (empty submodule; our emitter supplies the expressions, cross-checked numerically) and
+// the GL driver's mip generation (graphics_settings.cpp:161-186).  Analytic anchors as well
+// (tests/test_oracle_physics.py): straight rays in Minkowski, the Schwarzschild shadow radius,
+// null-norm and conserved quantities in Kerr-Schild, AD-vs-finite-difference partials.
 //
 // The metric itself comes from the generated header (GRT_METRIC_HEADER): the same emitted
 // functions the CUDA kernels compile, with this file using the *reference formulation*

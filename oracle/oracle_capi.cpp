@@ -1,7 +1,7 @@
 // =============================================================================================
 // CPU ORACLE - TEST INFRASTRUCTURE ONLY (see geodesic_oracle.hpp).  C entry points for ctypes.
 // Frame orchestration follows /root/reference/main.cpp:2244-2526 (per-frame kernel sequence) and
-// main.cpp:2675-2760 (geodesic snapshot).  PARITY UNPINNED - see geodesic_oracle.hpp.
+// main.cpp:2675-2760 (geodesic snapshot).  Pinned against the reference's own kernels - see geodesic_oracle.hpp.
 // =============================================================================================
 #include <chrono>
 #include <cstdio>

@@ -42,11 +42,22 @@ def _source_tag(metric_source: str) -> str:
     return h.hexdigest()[:16]
 
 
+def _cpu_has_v3() -> bool:
+    try:
+        flags = set([ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0].split())
+    except Exception:
+        return False
+    return {"avx2", "fma", "bmi2", "f16c", "movbe"} <= flags
+
+
 def build_clref(metric_source: str, name: str, native: bool = False) -> str | None:
     """Returns the path of libclref for this metric, building it if the reference is mounted; None if neither
-    a prebuilt library nor the reference exists."""
+    a prebuilt library nor the reference exists.  `native` = the CPU-baseline build: -O3 for x86-64-v3 (AVX2 + FMA;
+    not -march=native, because the library is built in one container and timed on another host)."""
     os.makedirs(REF_DIR, exist_ok=True)
-    tag = _source_tag(metric_source) + ("_native" if native else "")
+    if native and not _cpu_has_v3():
+        native = False
+    tag = _source_tag(metric_source) + ("_v3u" if native else "")
     so = os.path.join(REF_DIR, f"libclref_{name}_{tag}.so")
     if os.path.exists(so):
         return so
@@ -57,7 +68,9 @@ def build_clref(metric_source: str, name: str, native: bool = False) -> str | No
     hdr = os.path.join(REF_DIR, f"metric_{name}_{tag}.h")   # OUR generated metric functions (not reference text)
     with open(hdr, "w") as f:
         f.write(metric_source)
-    opt = ["-O3", "-march=native"] if native else ["-O2"]
+    # the timed build mirrors the reference's own compile options, "-cl-unsafe-math-optimizations" (metric_manager.hpp:70);
+    # the pinning build stays strict IEEE so that it can be compared bit for bit with the restatement
+    opt = ["-O3", "-march=x86-64-v3", "-funsafe-math-optimizations", "-fno-math-errno"] if native else ["-O2"]
     common = ["-std=c++20", "-fopenmp", "-fPIC", "-fpermissive", "-w", "-fvisibility=hidden", f'-DGRT_METRIC_HEADER="{hdr}"', "-I", _HERE] + opt
     obj_cl, obj_drv = so + ".cl.o", so + ".drv.o"
     pipeline = (f"(sed -E '{SED_REWRITE}' '{CL_SOURCE}'; cat '{_SHIM[2]}') | g++ -x c++ " + " ".join(f"'{c}'" for c in common) +
