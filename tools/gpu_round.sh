@@ -12,6 +12,7 @@ if [ "$2" != "skip-tests" ]; then
 fi
 timeout 600 python bench.py --steps 10 --warmup 3 2> gpurun_out/bench_$tag.err | tee gpurun_out/bench_$tag.json | cut -c1-1500
 tail -3 gpurun_out/bench_$tag.err
+timeout 600 python bench.py --impl reference --steps 10 --warmup 3 2> gpurun_out/bench_ref_$tag.err | tee gpurun_out/bench_ref_$tag.json | cut -c1-900
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 3 -c 3 -o gpurun_out/prof_integrate_$tag python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out | tail -12
