@@ -86,3 +86,34 @@ def build_clref(metric_source: str, name: str, native: bool = False) -> str | No
 
 def prebuilt(name: str) -> list[str]:
     return sorted(glob.glob(os.path.join(REF_DIR, f"libclref_{name}_*.so")))
+
+
+# ---- the reference's JavaScript engine (vendored QuickJS 2020-04-12 + bignum extension) -----------------------------------
+QUICKJS_DIR = os.path.join(REFERENCE_ROOT, "deps", "quickjs")
+NUMBER_JS = os.path.join(REFERENCE_ROOT, "number.js")
+_QJS_SOURCES = ["cutils.c", "libbf.c", "libregexp.c", "libunicode.c", "quickjs.c"]
+
+
+def build_qjsref() -> str | None:
+    """oracle/_ref/libqjsref.so: QuickJS compiled from /root/reference/deps/quickjs where it lies (same defines as the
+    reference's xmake.lua:45-46: CONFIG_BIGNUM, CONFIG_VERSION) + oracle/ref_quickjs.cpp (our numeric CShim/CMath binding).
+    None when neither the library nor the reference is present."""
+    os.makedirs(REF_DIR, exist_ok=True)
+    binding = os.path.join(_HERE, "ref_quickjs.cpp")
+    tag = hashlib.sha1(open(binding, "rb").read()).hexdigest()[:16]
+    so = os.path.join(REF_DIR, f"libqjsref_{tag}.so")
+    if os.path.exists(so):
+        return so
+    if not os.path.isdir(QUICKJS_DIR):
+        return None
+    objs = []
+    for src in _QJS_SOURCES:
+        obj = os.path.join(REF_DIR, f"qjs_{src}.o")
+        subprocess.run(["gcc", "-O2", "-fPIC", "-w", "-D_GNU_SOURCE", "-DCONFIG_BIGNUM", '-DCONFIG_VERSION="2020-04-12"', "-c", os.path.join(QUICKJS_DIR, src), "-o", obj],
+                       check=True)
+        objs.append(obj)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", QUICKJS_DIR, binding] + objs + ["-lm", "-ldl", "-lpthread", "-o", so + ".tmp"], check=True)
+    os.replace(so + ".tmp", so)
+    for o in objs:
+        os.remove(o)
+    return so
