@@ -510,6 +510,63 @@ static void symbolic_solve_sym4(const Expr g[16], const Expr w[4], Expr out[4]) 
     }
 }
 
+// The same solve with the cofactors and the determinant multiplied out as polynomials over the atoms of the metric
+// entries (Graph::to_poly), so that everything that cancels in them cancels symbolically: for a Kerr-Schild form
+// eta + H l l the ten cofactors collapse to a few monomials in (H, l_i) each and the determinant to -(1 + H(l.l - 1)).
+// Returns false when the expansion would be too large; the caller keeps whichever arrangement has fewer operations.
+static bool symbolic_solve_sym4_poly(Graph& gr, const Expr g[16], const Expr w[4], Expr out[4]) {
+    typedef Graph::Poly Poly;
+    const size_t cap = 6000;
+    Poly P[4][4];
+    for (int i = 0; i < 4; i++)
+        for (int j = i; j < 4; j++) {
+            if (!gr.to_poly(g[i * 4 + j].id, P[i][j], cap)) return false;
+            P[j][i] = P[i][j];
+        }
+    bool ok = true;
+    auto mul = [&](const Poly& a, const Poly& b) { Poly r; if (!Graph::poly_mul(a, b, r, cap)) ok = false; return r; };
+    auto minor2 = [&](int r0, int r1, int c0, int c1) {   // P[r0][c0] P[r1][c1] - P[r1][c0] P[r0][c1]
+        Poly r = mul(P[r0][c0], P[r1][c1]);
+        Graph::poly_axpy(r, -1.0, mul(P[r1][c0], P[r0][c1]));
+        return r;
+    };
+    Poly s0 = minor2(0, 1, 0, 1), s1 = minor2(0, 1, 0, 2), s2 = minor2(0, 1, 0, 3), s3 = minor2(0, 1, 1, 2), s4 = minor2(0, 1, 1, 3), s5 = minor2(0, 1, 2, 3);
+    Poly c5 = minor2(2, 3, 2, 3), c4 = minor2(2, 3, 1, 3), c3 = minor2(2, 3, 1, 2), c2 = minor2(2, 3, 0, 3), c1 = minor2(2, 3, 0, 2), c0 = minor2(2, 3, 0, 1);
+    if (!ok) return false;
+    auto comb3 = [&](double sa, const Poly& a, const Poly& ma, double sb, const Poly& b, const Poly& mb, double sc, const Poly& c, const Poly& mc) {
+        Poly r;
+        Graph::poly_axpy(r, sa, mul(a, ma));
+        Graph::poly_axpy(r, sb, mul(b, mb));
+        Graph::poly_axpy(r, sc, mul(c, mc));
+        return r;
+    };
+    Poly det;
+    Graph::poly_axpy(det, 1.0, mul(s0, c5)); Graph::poly_axpy(det, -1.0, mul(s1, c4)); Graph::poly_axpy(det, 1.0, mul(s2, c3));
+    Graph::poly_axpy(det, 1.0, mul(s3, c2)); Graph::poly_axpy(det, -1.0, mul(s4, c1)); Graph::poly_axpy(det, 1.0, mul(s5, c0));
+    Poly adj[16];
+    adj[0] = comb3(1, P[1][1], c5, -1, P[1][2], c4, 1, P[1][3], c3);
+    adj[1] = comb3(-1, P[0][1], c5, 1, P[0][2], c4, -1, P[0][3], c3);
+    adj[2] = comb3(1, P[3][1], s5, -1, P[3][2], s4, 1, P[3][3], s3);
+    adj[3] = comb3(-1, P[2][1], s5, 1, P[2][2], s4, -1, P[2][3], s3);
+    adj[5] = comb3(1, P[0][0], c5, -1, P[0][2], c2, 1, P[0][3], c1);
+    adj[6] = comb3(-1, P[3][0], s5, 1, P[3][2], s2, -1, P[3][3], s1);
+    adj[7] = comb3(1, P[2][0], s5, -1, P[2][2], s2, 1, P[2][3], s1);
+    adj[10] = comb3(1, P[3][0], s4, -1, P[3][1], s2, 1, P[3][3], s0);
+    adj[11] = comb3(-1, P[2][0], s4, 1, P[2][1], s2, -1, P[2][3], s0);
+    adj[15] = comb3(1, P[2][0], s3, -1, P[2][1], s1, 1, P[2][2], s0);
+    if (!ok) return false;
+    Expr A[16];
+    const int upper[10] = {0, 1, 2, 3, 5, 6, 7, 10, 11, 15};
+    for (int k : upper) A[k] = Expr::from_id(gr.from_poly(adj[k]));
+    A[4] = A[1]; A[8] = A[2]; A[12] = A[3]; A[9] = A[6]; A[13] = A[7]; A[14] = A[11];
+    Expr nidet = Expr(-1.0) / Expr::from_id(gr.from_poly(det));
+    for (int i = 0; i < 4; i++) {
+        Expr sum = A[i * 4 + 0] * w[0] + A[i * 4 + 1] * w[1] + A[i * 4 + 2] * w[2] + A[i * 4 + 3] * w[3];
+        out[i] = sum * nidet;
+    }
+    return true;
+}
+
 static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction& fto, ScriptFunction& ffrom,
                              ScriptFunction& forigin, ScriptFunction* fperiod) {
     MetricDescriptor& d = m.desc;
@@ -669,6 +726,27 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
             for (int i = 0; i < 4; i++) { alt_raw[i] = a2[i].id; alt[i] = G.factor(a2[i].id, dist != 0); }
             consider(alt_raw);
             consider(alt);
+            // Third arrangement: the same P and S, with (v . grad) P_m taken as ONE forward-mode pass along v
+            // (Graph::diff_along) and grad S as ONE reverse-mode sweep (Graph::gradient): the tangents and
+            // adjoints of shared sub-expressions (r, H, l_i of a Kerr-Schild form) are computed once.
+            Expr w3[4], a4[4];
+            {
+                std::map<int, int> along;
+                for (int k = 0; k < 4; k++) along[v[k].id] = iv[k].id;
+                std::vector<int> gS = G.gradient(S.id, {v[0].id, v[1].id, v[2].id, v[3].id});
+                for (int mm = 0; mm < 4; mm++) w3[mm] = Expr::from_id(G.diff_along(P[mm].id, along)) - Expr(0.5) * Expr::from_id(gS[mm]);
+            }
+            symbolic_solve_sym4(g, w3, a4);
+            { int c_raw[4], c_fac[4]; for (int i = 0; i < 4; i++) { c_raw[i] = a4[i].id; c_fac[i] = G.factor(a4[i].id, dist != 0); } consider(c_raw); consider(c_fac); }
+            // every arrangement of w with the multiplied-out cofactors
+            for (const Expr* ww : {(const Expr*)w, (const Expr*)w2, (const Expr*)w3}) {
+                Expr a3[4];
+                if (!symbolic_solve_sym4_poly(G, g, ww, a3)) continue;
+                int p_raw[4], p_fac[4];
+                for (int i = 0; i < 4; i++) { p_raw[i] = a3[i].id; p_fac[i] = G.factor(a3[i].id, dist != 0); }
+                consider(p_raw);
+                consider(p_fac);
+            }
         }
     }
     // constant-theta specialisation (cl.cl:3294-3306): v3 = (float)(pi/2), iv3 = 0, a.z = 0

@@ -257,18 +257,32 @@ int Graph::make(Op op, int a, int b, int c) {
     return intern(n);
 }
 
-int Graph::diff(int id, int wrt) {
+int Graph::diff(int id, int wrt) { return diff_key(id, wrt); }
+
+int Graph::diff_along(int id, const std::map<int, int>& tangents) {
+    int key = -1;
+    for (size_t i = 0; i < tangent_sets_.size(); i++)
+        if (tangent_sets_[i] == tangents) key = -((int)i + 2);
+    if (key == -1) { tangent_sets_.push_back(tangents); key = -((int)tangent_sets_.size() + 1); }
+    return diff_key(id, key);
+}
+
+// wrt >= 0: partial derivative with respect to that variable node; wrt <= -2: tangent set -(wrt + 2)
+int Graph::diff_key(int id, int wrt) {
     auto key = std::make_pair(id, wrt);
     auto it = diff_memo_.find(key);
     if (it != diff_memo_.end()) return it->second;
     const Node n = nodes_[id];  // copy: nodes_ may reallocate
     int r;
-    auto D = [&](int x) { return diff(x, wrt); };
+    auto D = [&](int x) { return diff_key(x, wrt); };
     auto C = [&](double v) { return constant(v); };
     auto M = [&](Op op, int x, int y = -1, int z = -1) { return make(op, x, y, z); };
     switch (n.op) {
         case Op::Const: case Op::Param: r = C(0.0); break;
-        case Op::Var: r = C(id == wrt ? 1.0 : 0.0); break;
+        case Op::Var:
+            if (wrt >= 0) r = C(id == wrt ? 1.0 : 0.0);
+            else { const auto& ts = tangent_sets_[-(wrt + 2)]; auto f = ts.find(id); r = f == ts.end() ? C(0.0) : f->second; }
+            break;
         case Op::Add: r = M(Op::Add, D(n.a), D(n.b)); break;
         case Op::Sub: r = M(Op::Sub, D(n.a), D(n.b)); break;
         case Op::Mul: r = M(Op::Add, M(Op::Mul, D(n.a), n.b), M(Op::Mul, n.a, D(n.b))); break;
@@ -331,6 +345,90 @@ int Graph::diff(int id, int wrt) {
     return r;
 }
 
+std::vector<int> Graph::gradient(int id, const std::vector<int>& wrt) {
+    // reachable nodes, processed from the root down: children are created before their parents, so ids decrease
+    std::set<int> reach;
+    std::vector<int> stack{id};
+    while (!stack.empty()) {
+        int x = stack.back();
+        stack.pop_back();
+        if (!reach.insert(x).second) continue;
+        const Node& n = nodes_[x];
+        if (n.a >= 0) stack.push_back(n.a);
+        if (n.b >= 0) stack.push_back(n.b);
+        if (n.c >= 0) stack.push_back(n.c);
+    }
+    std::map<int, int> adj;
+    adj[id] = constant(1.0);
+    auto C = [&](double v) { return constant(v); };
+    auto M = [&](Op op, int x, int y = -1, int z = -1) { return make(op, x, y, z); };
+    auto push = [&](int child, int contribution) {
+        if (is_const(contribution, 0.0)) return;
+        auto it = adj.find(child);
+        if (it == adj.end()) adj[child] = contribution;
+        else it->second = M(Op::Add, it->second, contribution);
+    };
+    for (auto rit = reach.rbegin(); rit != reach.rend(); ++rit) {
+        const int x = *rit;
+        auto ai = adj.find(x);
+        if (ai == adj.end()) continue;
+        const int A = ai->second;
+        const Node n = nodes_[x];
+        switch (n.op) {
+            case Op::Const: case Op::Param: case Op::Var: break;
+            case Op::Add: push(n.a, A); push(n.b, A); break;
+            case Op::Sub: push(n.a, A); push(n.b, M(Op::Neg, A)); break;
+            case Op::Neg: push(n.a, M(Op::Neg, A)); break;
+            case Op::Mul: push(n.a, M(Op::Mul, A, n.b)); push(n.b, M(Op::Mul, A, n.a)); break;
+            case Op::Div: { int t = M(Op::Div, A, n.b); push(n.a, t); push(n.b, M(Op::Neg, M(Op::Mul, t, x))); break; }
+            case Op::Sin: push(n.a, M(Op::Mul, A, M(Op::Cos, n.a))); break;
+            case Op::Cos: push(n.a, M(Op::Neg, M(Op::Mul, A, M(Op::Sin, n.a)))); break;
+            case Op::Tan: { int cs = M(Op::Cos, n.a); push(n.a, M(Op::Div, A, M(Op::Mul, cs, cs))); break; }
+            case Op::Asin: push(n.a, M(Op::Div, A, M(Op::Sqrt, M(Op::Sub, C(1.0), M(Op::Mul, n.a, n.a))))); break;
+            case Op::Acos: push(n.a, M(Op::Neg, M(Op::Div, A, M(Op::Sqrt, M(Op::Sub, C(1.0), M(Op::Mul, n.a, n.a)))))); break;
+            case Op::Atan: push(n.a, M(Op::Div, A, M(Op::Add, C(1.0), M(Op::Mul, n.a, n.a)))); break;
+            case Op::Atan2: {
+                int y = n.a, xx = n.b;
+                int t = M(Op::Div, A, M(Op::Add, M(Op::Mul, xx, xx), M(Op::Mul, y, y)));
+                push(y, M(Op::Mul, t, xx));
+                push(xx, M(Op::Neg, M(Op::Mul, t, y)));
+                break;
+            }
+            case Op::Fabs: push(n.a, M(Op::Mul, A, M(Op::Sign, n.a))); break;
+            case Op::Log: push(n.a, M(Op::Div, A, n.a)); break;
+            case Op::Sqrt: push(n.a, M(Op::Div, A, M(Op::Mul, C(2.0), x))); break;
+            case Op::Exp: push(n.a, M(Op::Mul, A, x)); break;
+            case Op::Sinh: push(n.a, M(Op::Mul, A, M(Op::Cosh, n.a))); break;
+            case Op::Cosh: push(n.a, M(Op::Mul, A, M(Op::Sinh, n.a))); break;
+            case Op::Tanh: push(n.a, M(Op::Mul, A, M(Op::Sub, C(1.0), M(Op::Mul, x, x)))); break;
+            case Op::Pow:
+                if (is_const(n.b)) push(n.a, M(Op::Mul, A, M(Op::Mul, n.b, M(Op::Pow, n.a, C(cval(n.b) - 1.0)))));
+                else {
+                    int t = M(Op::Mul, A, x);
+                    push(n.a, M(Op::Div, M(Op::Mul, t, n.b), n.a));
+                    push(n.b, M(Op::Mul, t, M(Op::Log, n.a)));
+                }
+                break;
+            case Op::Select: push(n.b, M(Op::Select, n.a, A, C(0.0))); push(n.c, M(Op::Select, n.a, C(0.0), A)); break;
+            case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte: case Op::Sign: break;
+            case Op::Fmod: push(n.a, A); break;
+            case Op::Min: { int c = M(Op::Lt, n.a, n.b); push(n.a, M(Op::Select, c, A, C(0.0))); push(n.b, M(Op::Select, c, C(0.0), A)); break; }
+            case Op::Max: { int c = M(Op::Gt, n.a, n.b); push(n.a, M(Op::Select, c, A, C(0.0))); push(n.b, M(Op::Select, c, C(0.0), A)); break; }
+            case Op::CsqrtRe: case Op::CsqrtIm: {
+                int sr = M(Op::CsqrtRe, n.a, n.b), si = M(Op::CsqrtIm, n.a, n.b);
+                int t = M(Op::Div, A, M(Op::Mul, C(2.0), M(Op::Add, M(Op::Mul, sr, sr), M(Op::Mul, si, si))));
+                if (n.op == Op::CsqrtRe) { push(n.a, M(Op::Mul, t, sr)); push(n.b, M(Op::Mul, t, si)); }
+                else { push(n.a, M(Op::Neg, M(Op::Mul, t, si))); push(n.b, M(Op::Mul, t, sr)); }
+                break;
+            }
+            default: throw std::runtime_error("sym: gradient bad op");
+        }
+    }
+    std::vector<int> out;
+    for (int w : wrt) { auto it = adj.find(w); out.push_back(it == adj.end() ? constant(0.0) : it->second); }
+    return out;
+}
+
 int Graph::substitute(int id, const std::map<int, int>& repl) {
     std::unordered_map<int, int> memo;
     std::function<int(int)> go = [&](int x) -> int {
@@ -356,7 +454,114 @@ struct Term {
     double coef = 1.0;
     std::vector<int> factors;   // sorted node ids, repeats allowed
 };
+// x*y - x*y, 2ab + ab: terms with the same factor list are one term
+void merge_like_terms(std::vector<Term>& ts) {
+    std::map<std::vector<int>, double> acc;
+    std::vector<std::vector<int>> order;
+    for (auto& t : ts) {
+        auto it = acc.find(t.factors);
+        if (it == acc.end()) { acc[t.factors] = t.coef; order.push_back(t.factors); }
+        else it->second += t.coef;
+    }
+    if (order.size() == ts.size()) return;
+    ts.clear();
+    for (auto& f : order) {
+        double c = acc[f];
+        if (c != 0.0) { Term t; t.coef = c; t.factors = f; ts.push_back(t); }
+    }
+}
 }  // namespace
+
+void Graph::poly_axpy(Poly& acc, double alpha, const Poly& x) {
+    for (auto& kv : x.terms) {
+        double& c = acc.terms[kv.first];
+        c += alpha * kv.second;
+        if (c == 0.0) acc.terms.erase(kv.first);
+    }
+}
+
+bool Graph::poly_mul(const Poly& a, const Poly& b, Poly& out, size_t max_terms) {
+    Poly r;
+    for (auto& ka : a.terms)
+        for (auto& kb : b.terms) {
+            std::vector<int> m(ka.first.size() + kb.first.size());
+            std::merge(ka.first.begin(), ka.first.end(), kb.first.begin(), kb.first.end(), m.begin());
+            double& c = r.terms[m];
+            c += ka.second * kb.second;
+            if (r.terms.size() > max_terms) return false;
+        }
+    for (auto it = r.terms.begin(); it != r.terms.end();) it = (it->second == 0.0) ? r.terms.erase(it) : std::next(it);
+    out = r;
+    return true;
+}
+
+bool Graph::to_poly(int id, Poly& out, size_t max_terms) {
+    auto memo = poly_memo_.find(id);
+    if (memo != poly_memo_.end()) { out = memo->second; return true; }
+    const Node n = nodes_[id];
+    Poly r;
+    switch (n.op) {
+        case Op::Const:
+            if (n.val != 0.0) r.terms[{}] = n.val;
+            break;
+        case Op::Add: case Op::Sub: {
+            Poly a, b;
+            if (!to_poly(n.a, a, max_terms) || !to_poly(n.b, b, max_terms)) return false;
+            r = a;
+            poly_axpy(r, n.op == Op::Add ? 1.0 : -1.0, b);
+            break;
+        }
+        case Op::Neg: {
+            Poly a;
+            if (!to_poly(n.a, a, max_terms)) return false;
+            poly_axpy(r, -1.0, a);
+            break;
+        }
+        case Op::Mul: {
+            Poly a, b;
+            if (!to_poly(n.a, a, max_terms) || !to_poly(n.b, b, max_terms)) return false;
+            if (!poly_mul(a, b, r, max_terms)) return false;
+            break;
+        }
+        case Op::Pow: {
+            const Node e = nodes_[n.b];
+            if (e.op == Op::Const && e.val == std::floor(e.val) && e.val >= 1.0 && e.val <= 4.0) {
+                Poly a;
+                if (!to_poly(n.a, a, max_terms)) return false;
+                r = a;
+                for (int k = 1; k < (int)e.val; k++) { Poly t; if (!poly_mul(r, a, t, max_terms)) return false; r = t; }
+                break;
+            }
+            r.terms[{id}] = 1.0;
+            break;
+        }
+        default:
+            r.terms[{id}] = 1.0;   // an atom: variable, parameter, quotient, function value
+            break;
+    }
+    if (r.terms.size() > max_terms) return false;
+    poly_memo_[id] = r;
+    out = r;
+    return true;
+}
+
+int Graph::from_poly(const Poly& p) {
+    // one sum of plain products, built in a canonical order; `factor` then pulls the common factors out
+    int acc = -1;
+    std::vector<std::pair<std::vector<int>, double>> ts(p.terms.begin(), p.terms.end());
+    std::stable_sort(ts.begin(), ts.end(), [](const auto& a, const auto& b) { return (a.second > 0) > (b.second > 0); });
+    for (auto& t : ts) {
+        int prod = -1;
+        for (int f : t.first) prod = prod < 0 ? f : make(Op::Mul, prod, f);
+        double c = t.second;
+        bool neg = c < 0 && acc >= 0;
+        if (neg) c = -c;
+        int term = prod < 0 ? constant(c) : (c == 1.0 ? prod : make(Op::Mul, constant(c), prod));
+        acc = acc < 0 ? term : make(neg ? Op::Sub : Op::Add, acc, term);
+    }
+    if (acc < 0) return constant(0.0);
+    return factor(acc, false);
+}
 
 int Graph::factor(int id, bool distribute) {
     auto& memo_table = factor_memo_[distribute ? 1 : 0];
@@ -444,6 +649,7 @@ int Graph::factor(int id, bool distribute) {
             }
         };
         collect(id, 1.0);
+        merge_like_terms(terms);
         std::function<int(std::vector<Term>&)> build = [&](std::vector<Term>& ts) -> int {
             if (ts.empty()) return constant(0.0);
             // most frequent factor (counted once per term)

@@ -59,6 +59,13 @@ public:
 
     // d(id)/d(variable node `wrt`)
     int diff(int id, int wrt);
+    // Forward-mode derivative along a direction: every variable node in `tangents` carries the given tangent
+    // expression (others 0), so with {v_k -> iv_k} this is the directional derivative sum_k iv_k d/dv_k in ONE
+    // pass over the DAG (shared sub-expressions get one tangent each) instead of four gradients summed.
+    int diff_along(int id, const std::map<int, int>& tangents);
+    // Reverse-mode gradient: d(id)/d(wrt[i]) for all i in one adjoint sweep (about three times the cost of the
+    // expression itself, whatever the number of variables).
+    std::vector<int> gradient(int id, const std::vector<int>& wrt);
     // replace nodes by other nodes (bottom-up rebuild with re-simplification)
     int substitute(int id, const std::map<int, int>& repl);
     // does `id` depend on node `leaf`?
@@ -71,6 +78,17 @@ public:
     // With `distribute`, a product that contains a short sum is multiplied out first ((c + H l l) v ->
     // c v + H l l v) so that factors hidden inside it can be shared with the neighbouring terms.
     int factor(int id, bool distribute = false);
+    // Multivariate polynomial view of an expression.  `to_poly` multiplies sums and products out completely over
+    // "atoms" (every node that is not + - * neg, a constant or a small integer power), merging like terms, so that
+    // cancellations which only show after expansion - the cofactors and determinant of a metric with product
+    // structure, e.g. Kerr-Schild eta + H l l - happen symbolically.  Returns false if more than `max_terms`
+    // monomials appear.  `from_poly` rebuilds an expression with common factors pulled out (same greedy scheme as
+    // `factor`).  Same value as the input up to floating-point reassociation.
+    struct Poly { std::map<std::vector<int>, double> terms; };   // sorted atom ids (repeats = powers) -> coefficient
+    bool to_poly(int id, Poly& out, size_t max_terms = 20000);
+    int from_poly(const Poly& p);
+    static bool poly_mul(const Poly& a, const Poly& b, Poly& out, size_t max_terms = 20000);
+    static void poly_axpy(Poly& acc, double alpha, const Poly& x);   // acc += alpha * x
     // human readable infix (tests, debugging, classification decisions)
     std::string to_string(int id) const;
 
@@ -79,8 +97,11 @@ private:
     int simplify(Op op, int a, int b, int c, bool& done);
     std::vector<Node> nodes_;
     std::unordered_map<std::string, int> table_;
+    int diff_key(int id, int key);
     std::map<std::pair<int, int>, int> diff_memo_;
+    std::vector<std::map<int, int>> tangent_sets_;   // diff_along directions; key = -(index + 2)
     std::unordered_map<int, int> factor_memo_[2];
+    std::map<int, Poly> poly_memo_;
 };
 
 // value-semantics handle
