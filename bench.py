@@ -41,7 +41,7 @@ STRIPE_ROWS = 54
 # for ~30 ms of bulk work, and ~24 ms on 8 GPUs for ~4 ms of bulk work per GPU, so the count grows with the number of GPUs.
 _WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(4 if _WORLD == 1 else min(8, 2 * _WORLD + 2))))
-BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", "2"))
+BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", "3"))
 BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)
 

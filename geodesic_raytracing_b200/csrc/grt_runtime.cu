@@ -144,7 +144,7 @@ const char* kPrelude =
 std::string program_source(const grt::Metric& m, bool is_static, bool reparameterisation) {
     std::string s = kPrelude;
     s += reparameterisation ? "#define GRT_FEATURE_REPARAMETERISATION 1\n" : "#define GRT_FEATURE_REPARAMETERISATION 0\n";
-    if (const char* e = getenv("GRT_INTEGRATE_MIN_BLOCKS")) s += std::string("#define GRT_INTEGRATE_MIN_BLOCKS ") + std::to_string(atoi(e)) + "\n";
+    if (const char* e = getenv("GRT_INTEGRATE_MIN_BLOCKS")) s += std::string("// GRT_TIER_FIXED\n#define GRT_INTEGRATE_MIN_BLOCKS ") + std::to_string(atoi(e)) + "\n";
     s += GRT_SRC_STRUCTS;
     s += GRT_SRC_COMMON;
     s += grt::emit_metric_source(m, is_static);
@@ -153,14 +153,14 @@ std::string program_source(const grt::Metric& m, bool is_static, bool reparamete
 }
 
 std::vector<std::string> nvrtc_options(bool fast_math) {
-    std::vector<std::string> o = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-DGRT_NVRTC=1", "-diag-suppress=177,550"};
+    std::vector<std::string> o = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-DGRT_NVRTC=1", "-diag-suppress=177,550", "--ptxas-options=-v"};
     if (fast_math) o.push_back("--use_fast_math");
     return o;
 }
 
 // NVRTC -> cubin, with an on-disk cache keyed by hash(source + options + NVRTC version)
 // (the reference caches built programs through cl::build_program_with_cache, metric_manager.hpp:106)
-std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit) {
+std::vector<char> compile_cubin_raw(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit, std::string* path_out = nullptr) {
     std::vector<std::string> opts = nvrtc_options(fast_math);
     int major = 0, minor = 0;
     nvrtcVersion(&major, &minor);
@@ -170,13 +170,17 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
     char hex[40];
     snprintf(hex, sizeof hex, "%016llx%016llx", (unsigned long long)fnv1a(key, 14695981039346656037ull), (unsigned long long)fnv1a(key, 0x9e3779b97f4a7c15ull));
     std::string path = cache_dir() + "/" + name + "_" + hex + ".cubin";
+    if (path_out) *path_out = path;
     {
         std::ifstream f(path, std::ios::binary);
         if (f) {
             std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
             if (!data.empty()) {
                 if (cache_hit) *cache_hit = true;
-                if (log_out) *log_out = "cubin cache hit: " + path;
+                if (log_out) {
+                    std::ifstream lf(path + ".log", std::ios::binary);   // the ptxas resource report of the build that filled the cache
+                    *log_out = "cubin cache hit: " + path + "\n" + std::string((std::istreambuf_iterator<char>(lf)), std::istreambuf_iterator<char>());
+                }
                 return data;
             }
         }
@@ -216,8 +220,70 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
         std::ofstream f(tmp, std::ios::binary);
         f.write(cubin.data(), (std::streamsize)cubin.size());
     }
+    {
+        std::ofstream f(path + ".log", std::ios::binary);
+        f.write(log.data(), (std::streamsize)log.size());
+    }
     rename(tmp.c_str(), path.c_str());
     return cubin;
+}
+
+// registers and spill bytes of k_integrate from the `ptxas -v` report in an NVRTC log; false if absent
+bool integrate_resources(const std::string& log, int* regs, int* spill) {
+    size_t at = log.find("Function properties for k_integrate");
+    if (at == std::string::npos) return false;
+    int stack = 0, st = 0, ld = 0, r = 0;
+    size_t a = log.find("bytes stack frame", at), u = log.find("Used ", at);
+    if (a == std::string::npos || u == std::string::npos) return false;
+    size_t line = log.rfind('\n', a);
+    line = log.find_first_of("0123456789", line == std::string::npos ? 0 : line + 1);   // "ptxas         .     0 bytes stack frame, ..."
+    if (line == std::string::npos || sscanf(log.c_str() + line, "%d bytes stack frame, %d bytes spill stores, %d bytes spill loads", &stack, &st, &ld) != 3) return false;
+    if (sscanf(log.c_str() + u, "Used %d registers", &r) != 1) return false;
+    *regs = r;
+    *spill = stack + st + ld;
+    return true;
+}
+
+// Occupancy tier of the integration kernel.  The loop is bound by FP32 issue with long dependent chains, so more resident
+// warps per scheduler pay as long as nothing spills: after the free compile, the kernel is rebuilt with
+// __launch_bounds__(128, n) for the next one or two block-per-SM tiers and the highest tier that needs no stack and at most
+// a fifth fewer registers is kept (kerr_schild: 89 registers / 5 blocks -> 72 / 7, +5 % frames per second).  The choice is
+// remembered next to the cubins.  GRT_INTEGRATE_MIN_BLOCKS (environment) overrides, GRT_OCCUPANCY_TIER=0 disables.
+std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit) {
+    const char* off = getenv("GRT_OCCUPANCY_TIER");
+    if (src.find("// GRT_TIER_FIXED") != std::string::npos || (off && atoi(off) == 0)) return compile_cubin_raw(src, fast_math, name, log_out, cache_hit);
+    auto with_tier = [&](int n) { return "// GRT_TIER_FIXED\n#define GRT_INTEGRATE_MIN_BLOCKS " + std::to_string(n) + "\n" + src; };
+    char hex[24];
+    snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(src + (fast_math ? "f" : "p"), 14695981039346656037ull));
+    const std::string tier_path = cache_dir() + "/" + name + "_" + hex + ".tier";
+    {
+        std::ifstream f(tier_path);
+        int n = 0;
+        if (f >> n) return n > 0 ? compile_cubin_raw(with_tier(n), fast_math, name, log_out, cache_hit) : compile_cubin_raw(src, fast_math, name, log_out, cache_hit);
+    }
+    std::string log;
+    std::vector<char> best = compile_cubin_raw(src, fast_math, name, &log, cache_hit);
+    int regs = 0, spill = 0, chosen = 0;
+    std::string best_log = log;
+    if (integrate_resources(log, &regs, &spill) && regs > 0) {
+        auto blocks_for = [](int r) { return std::min(16, 65536 / (((r + 7) / 8 * 8) * 128)); };
+        const int base_blocks = blocks_for(regs);
+        for (int n = std::min(16, base_blocks + 2); n > base_blocks; n--) {
+            std::string tlog, tpath;
+            std::vector<char> cand;
+            try { cand = compile_cubin_raw(with_tier(n), fast_math, name, &tlog, nullptr, &tpath); } catch (const Error&) { continue; }
+            int r2 = 0, s2 = 0;
+            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 5 >= regs * 4 && blocks_for(r2) >= n) { best = cand; best_log = tlog; chosen = n; break; }
+            for (const char* ext : {"", ".log"}) remove((tpath + ext).c_str());                      // a rejected tier leaves nothing behind
+            remove((tpath.substr(0, tpath.size() - 6) + ".cu").c_str());
+        }
+    }
+    {
+        std::ofstream f(tier_path);
+        f << chosen << "\n";
+    }
+    if (log_out) *log_out = best_log;
+    return best;
 }
 
 struct Program {

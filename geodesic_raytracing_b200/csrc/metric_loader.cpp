@@ -697,9 +697,10 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         // (common factors pulled out) *before* they are differentiated, so metrics with product
         // structure - Kerr-Schild forms g = eta + H l l, conformally flat ones - never expand the
         // 40 separate partials.  The cheaper of the two arrangements is emitted.
-        size_t best_n = G.op_count(std::vector<int>(d.accel, d.accel + 4));
+        size_t best_n = G.instr_count(std::vector<int>(d.accel, d.accel + 4));
         auto consider = [&](const int cand[4]) {
-            size_t n = G.op_count(std::vector<int>(cand, cand + 4));
+            size_t n = G.instr_count(std::vector<int>(cand, cand + 4));
+            if (getenv("GRT_DEBUG_EMIT")) fprintf(stderr, "arrangement: %zu ops, %zu instructions\n", G.op_count(std::vector<int>(cand, cand + 4)), n);
             if (n < best_n) { best_n = n; for (int i = 0; i < 4; i++) d.accel[i] = cand[i]; }
         };
         const int base[4] = {d.accel[0], d.accel[1], d.accel[2], d.accel[3]};

@@ -727,6 +727,39 @@ size_t Graph::op_count(const std::vector<int>& outs) const {
     return cnt;
 }
 
+size_t Graph::instr_count(const std::vector<int>& outs) const {
+    std::set<int> seen;
+    std::map<int, int> uses;
+    std::function<void(int)> go = [&](int x) {
+        if (x < 0) return;
+        uses[x]++;
+        if (!seen.insert(x).second) return;
+        const Node& n = nodes_[x];
+        go(n.a); go(n.b); go(n.c);
+    };
+    for (int o : outs) go(o);
+    size_t cnt = 0;
+    std::set<int> fused;
+    for (int x : seen) {
+        const Node& n = nodes_[x];
+        switch (n.op) {
+            case Op::Const: case Op::Var: case Op::Param: case Op::Neg: break;
+            case Op::Div: cnt += 2; break;
+            case Op::Add: case Op::Sub: {
+                cnt++;
+                for (int ch : {n.a, n.b}) {
+                    int y = ch;
+                    if (nodes_[y].op == Op::Neg) y = nodes_[y].a;
+                    if (nodes_[y].op == Op::Mul && uses[y] == 1 && !fused.count(y)) { fused.insert(y); cnt--; break; }   // FMA: the product is free
+                }
+                break;
+            }
+            default: cnt++; break;
+        }
+    }
+    return cnt;
+}
+
 static const char* fn_name(Op op) {
     switch (op) {
         case Op::Sin: return "sin"; case Op::Cos: return "cos"; case Op::Tan: return "tan";

@@ -72,6 +72,9 @@ public:
     bool depends_on(int id, int leaf) const;
     // number of arithmetic nodes reachable from the outputs (flop-ish count, FMA not fused)
     size_t op_count(const std::vector<int>& outs) const;
+    // Estimated machine instructions: like op_count, but a single-use product feeding a sum is one FMA with it, a
+    // negation folds into the operand modifier of its consumer, and a quotient costs two (reciprocal + multiply).
+    size_t instr_count(const std::vector<int>& outs) const;
     // Algebraic clean-up of an expression: every maximal sum is flattened into signed product terms and
     // common factors are pulled out greedily (a*b*x + a*c*x -> a*x*(b + c)), recursively, bottom-up and
     // memoised so shared sub-expressions stay shared.  Same value up to floating-point reassociation.
