@@ -112,7 +112,7 @@ def lib() -> C.CDLL:
         "grt_metric_param_count": (ci, [vp]), "grt_metric_param_name": (cp, [vp, ci]), "grt_metric_param_default": (cf, [vp, ci]),
         "grt_metric_param_get": (cf, [vp, ci]), "grt_metric_param_set": (ci, [vp, ci, cf]),
         "grt_metric_get_info": (ci, [vp, C.POINTER(MetricInfo)]), "grt_metric_name": (cp, [vp]), "grt_metric_description": (cp, [vp]),
-        "grt_metric_source": (cp, [vp, ci]), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
+        "grt_metric_source": (cp, [vp, ci]), "grt_metric_eval_symbolic": (ci, [vp] + [vp] * 9), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
         "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]), "grt_set_metric_async": (ci, [vp, vp, ci]), "grt_build_poll": (ci, [vp]),
         "grt_set_fast_math": (ci, [vp, ci]), "grt_set_tuning": (ci, [vp, ci, ci]), "grt_set_frames_in_flight": (ci, [vp, ci]), "grt_set_features": (ci, [vp, C.POINTER(Features)]), "grt_get_features": (ci, [vp, C.POINTER(Features)]),
@@ -240,6 +240,13 @@ class Metric:
         if s is None:
             raise GrtError(-2, _err())
         return s.decode()
+
+    def eval_symbolic(self, pos, vel=(0, 0, 0, 0)) -> dict:
+        """Host-side float64 evaluation of the metric's symbolic expressions (plugin-layer diagnostic, grt.h)."""
+        p, v = np.ascontiguousarray(pos, np.float64), np.ascontiguousarray(vel, np.float64)
+        out = {"g": np.zeros(16), "dg": np.zeros(64), "accel": np.zeros(4), "accel_ref": np.zeros(4), "to_polar": np.zeros(4), "from_polar": np.zeros(4), "distance": np.zeros(1)}
+        _check(lib().grt_metric_eval_symbolic(self._h, p.ctypes.data, v.ctypes.data, *[a.ctypes.data for a in out.values()]))
+        return out
 
     def compile(self, is_static: bool = False, fast_math: bool = True) -> str:
         """NVRTC-compile for sm_100a into the cubin cache (needs no GPU). Returns the build log."""

@@ -971,6 +971,30 @@ const char* grt_metric_source(grt_metric* m, int is_static) {
     return rc == GRT_OK ? m->source[is_static ? 1 : 0].c_str() : nullptr;
 }
 
+int grt_metric_eval_symbolic(const grt_metric* m, const double pos[4], const double vel[4], double* g16, double* dg64, double* accel4, double* accel_ref4,
+                             double* to_polar4, double* from_polar4, double* distance1) {
+    return guard([&] {
+        if (!m || !pos) throw Error(GRT_E_INVALID, "null metric or position");
+        const grt::Metric& M = *m->m;
+        const grt::MetricDescriptor& d = M.desc;
+        std::map<std::string, double> env;
+        const char* vn[4] = {"v1", "v2", "v3", "v4"};
+        const char* ivn[4] = {"iv1", "iv2", "iv3", "iv4"};
+        const char* dvn[4] = {"dv1", "dv2", "dv3", "dv4"};
+        for (int i = 0; i < 4; i++) { env[vn[i]] = pos[i]; env[ivn[i]] = vel ? vel[i] : 0.0; env[dvn[i]] = vel ? vel[i] : 0.0; }
+        for (size_t i = 0; i < M.params.names.size(); i++) env[M.params.names[i]] = M.params.current_values[i];
+        auto put = [&](double* out, const int* ids, int n) { if (out) for (int i = 0; i < n; i++) out[i] = d.graph.eval(ids[i], env); };
+        put(g16, d.g, 16);
+        put(dg64, d.dg, 64);
+        put(accel4, d.accel, 4);
+        put(accel_ref4, d.accel_ref, 4);
+        put(to_polar4, d.to_polar, 4);
+        put(from_polar4, d.from_polar, 4);
+        put(distance1, &d.distance, 1);
+        return GRT_OK;
+    });
+}
+
 int grt_compile_metric(grt_metric* m, int is_static, int fast_math, const char** log_out) {
     return guard([&] {
         if (!m) throw Error(GRT_E_INVALID, "null metric");

@@ -760,6 +760,38 @@ size_t Graph::instr_count(const std::vector<int>& outs) const {
     return cnt;
 }
 
+double Graph::eval(int id, const std::map<std::string, double>& env) const {
+    std::map<int, double> memo;
+    std::function<double(int)> go = [&](int x) -> double {
+        auto it = memo.find(x);
+        if (it != memo.end()) return it->second;
+        const Node& n = nodes_[x];
+        double r = 0.0;
+        switch (n.op) {
+            case Op::Const: r = n.val; break;
+            case Op::Var: case Op::Param: { auto e = env.find(n.name); r = e == env.end() ? 0.0 : e->second; break; }
+            case Op::Add: r = go(n.a) + go(n.b); break;
+            case Op::Sub: r = go(n.a) - go(n.b); break;
+            case Op::Mul: r = go(n.a) * go(n.b); break;
+            case Op::Div: r = go(n.a) / go(n.b); break;
+            case Op::Neg: r = -go(n.a); break;
+            case Op::Select: r = go(n.a) != 0.0 ? go(n.b) : go(n.c); break;
+            case Op::CsqrtRe: case Op::CsqrtIm: {
+                std::complex<double> s = std::sqrt(std::complex<double>(go(n.a), go(n.b)));
+                r = n.op == Op::CsqrtRe ? s.real() : s.imag();
+                break;
+            }
+            case Op::Atan2: case Op::Pow: case Op::Fmod: case Op::Min: case Op::Max:
+            case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte:
+                r = fold2(n.op, go(n.a), go(n.b)); break;
+            default: r = fold1(n.op, go(n.a)); break;
+        }
+        memo[x] = r;
+        return r;
+    };
+    return go(id);
+}
+
 static const char* fn_name(Op op) {
     switch (op) {
         case Op::Sin: return "sin"; case Op::Cos: return "cos"; case Op::Tan: return "tan";

@@ -92,6 +92,8 @@ public:
     int from_poly(const Poly& p);
     static bool poly_mul(const Poly& a, const Poly& b, Poly& out, size_t max_terms = 20000);
     static void poly_axpy(Poly& acc, double alpha, const Poly& x);   // acc += alpha * x
+    // numeric value of an expression in double precision; variables / parameters by name (missing -> 0)
+    double eval(int id, const std::map<std::string, double>& env) const;
     // human readable infix (tests, debugging, classification decisions)
     std::string to_string(int id) const;
 

@@ -95,6 +95,15 @@ const char* grt_metric_description(const grt_metric*);
  * The string stays valid until the next call for the same metric. */
 const char* grt_metric_source(grt_metric*, int is_static);
 
+/* Plugin-layer diagnostic, host only, no device involved: evaluates the metric's symbolic expressions (what the
+ * emitted functions compute) in double precision at one point with the current parameter values - g (16, row-major),
+ * dg (64, [k*16 + i*4 + j] = d_k g_ij), the acceleration -Gamma^i_ab v^a v^b in the emitted arrangement and in the
+ * reference formulation (metric.hpp:184-244), to_polar / from_polar (4 each) and the origin distance of `pos` taken as
+ * polar coordinates.  Any output pointer may be NULL.  The tests use it to pin the script engine and the symbolic
+ * layer against the reference's own QuickJS engine running the same scripts; rendering never calls it. */
+int grt_metric_eval_symbolic(const grt_metric*, const double pos[4], const double vel[4], double* g16, double* dg64, double* accel4, double* accel_ref4,
+                             double* to_polar4, double* from_polar4, double* distance1);
+
 /* ---- (b2) device boundary ------------------------------------------------------------- */
 
 /* dynamic_feature_config (main.cpp:1123-1158, dynamic_feature_config.cpp:182-237); the

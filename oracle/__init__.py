@@ -320,3 +320,50 @@ def for_metric(metric, is_static: bool = False, native: bool = False) -> Oracle:
 def reference_for_metric(metric, native: bool = False) -> ClReference:
     """The reference's own cl.cl kernels (oracle/_ref) for a geodesic_raytracing_b200.Metric."""
     return ClReference(metric.source(False), _stem(metric), metric.params, native)
+
+
+class QuickJSReference:
+    """The reference's own JavaScript engine (vendored QuickJS, compiled from /root/reference/deps/quickjs into
+    oracle/_ref/ by ref_build.build_qjsref) running number.js and a script, with CShim/CMath bound to numeric dual
+    numbers (oracle/ref_quickjs.cpp).  `metric(js_path, pos)` -> g (16), dg (64, [k*16 + i*4 + j]) in float64."""
+
+    def __init__(self):
+        from . import ref_build
+        so = ref_build.build_qjsref()
+        if so is None or not os.path.exists(ref_build.NUMBER_JS):
+            raise FileNotFoundError("QuickJS reference needs /root/reference (number.js, deps/quickjs)")
+        self.number_js = ref_build.NUMBER_JS.encode()
+        self.lib = C.CDLL(so)
+        self.lib.qjsref_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_int]
+
+    def _run(self, path, kind, pos, params):
+        names = list(params.keys())
+        n = len(names)
+        c_names = (C.c_char_p * max(1, n))(*[k.encode() for k in names])
+        c_vals = (C.c_double * max(1, n))(*[float(params[k]) for k in names])
+        total = {0: 16, 1: 4, 2: 1}[kind]
+        out, dout = (C.c_double * total)(), (C.c_double * (total * 4))()
+        out_len, n_names = C.c_int(), C.c_int()
+        names_out = C.create_string_buffer(32 * 64)
+        defaults = (C.c_double * 32)()
+        err = C.create_string_buffer(1024)
+        p = (C.c_double * 4)(*[float(x) for x in pos])
+        rc = self.lib.qjsref_run(self.number_js, path.encode(), kind, p, n, c_names, c_vals, out, dout, C.byref(out_len), C.byref(n_names), names_out, defaults, err, 1024)
+        found = {names_out.raw[i * 64:(i + 1) * 64].split(b"\0")[0].decode(): defaults[i] for i in range(n_names.value)}
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return np.array(out[:]), np.array(dout[:]), out_len.value, found
+
+    def run(self, path, kind, pos, params=None):
+        """Two passes as the reference's sandbox implies: the first discovers `$cfg` names and `$default`s, the second
+        evaluates with the defaults overridden by `params`."""
+        _, _, _, found = self._run(path, kind, pos, {})
+        values = dict(found)
+        values.update(params or {})
+        o, d, n, found2 = self._run(path, kind, pos, values)
+        return o, d, n, found
+
+    def metric(self, js_path, pos, params=None):
+        g, dg, n, found = self.run(js_path, 0, pos, params)
+        return g, dg, n, found

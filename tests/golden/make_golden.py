@@ -4,6 +4,8 @@
 Run in a container where /root/reference is mounted. For each listed script the reference file is loaded
 unchanged through the plugin boundary, the CPU oracle is built on the generated functions, and g, dg, the
 reference-formulation acceleration (GEO_ACCEL) and the coordinate maps are evaluated at seeded points.
+`qjs_g` / `qjs_dg` come from the REFERENCE'S OWN JavaScript engine: the vendored QuickJS compiled from
+/root/reference/deps/quickjs, running number.js and the script with numeric dual numbers (oracle/ref_quickjs.cpp).
 The bundled content (geodesic_raytracing_b200/content) is tested against these vectors on machines that do
 not have the reference (tests/test_reference_scripts.py)."""
 import json
@@ -30,12 +32,26 @@ def points(name, n=4):
     return pos.astype(np.float32), vel.astype(np.float32)
 
 
+def script_of(name):
+    """js file of the metric whose JSON carries this friendly name (content_manager.cpp:263-278)."""
+    for f in sorted(os.listdir(REFERENCE)):
+        if f.endswith(".json"):
+            try:
+                if json.load(open(os.path.join(REFERENCE, f))).get("name") == name:
+                    return os.path.join(REFERENCE, f[:-5] + ".js")
+            except Exception:
+                pass
+    raise KeyError(name)
+
+
 def main():
     content = grt.Content(REFERENCE)
+    qjs = oracle.QuickJSReference()     # the reference's own JS engine (vendored QuickJS) on the reference's own scripts
     out = {}
     for name in NAMES:
         m = content.load_by_name(name)
         o = oracle.for_metric(m)
+        js = script_of(name)
         pos, vel = points(name)
         rec = {"params": m.param_names, "defaults": m.param_defaults, "info": {k: getattr(m.info, k) for k in
                ["is_big", "is_constant_theta", "use_prepass", "singular", "adaptive_precision", "detect_singularities", "coordinate_system", "has_periodicity"]},
@@ -48,7 +64,8 @@ def main():
             g, dg = o.metric_eval(p)
             a = o.accel(p, v)
             c = o.coords(p, v)
-            rec["points"].append({"pos": p.tolist(), "vel": v.tolist(), "g": g.tolist(), "dg": dg.tolist(), "accel_ref": a["ref"].tolist(),
+            qg, qdg, _, _ = qjs.metric(js, p.astype(np.float64))
+            rec["points"].append({"pos": p.tolist(), "vel": v.tolist(), "g": g.tolist(), "dg": dg.tolist(), "qjs_g": qg.tolist(), "qjs_dg": qdg.tolist(), "accel_ref": a["ref"].tolist(),
                                   "to_polar": c["to_polar"].tolist(), "from_polar": c["from_polar"].tolist(), "distance": c["distance"], "period": c["period"].tolist()})
         out[name] = rec
         print(name, "ok")
