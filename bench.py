@@ -40,8 +40,10 @@ STRIPE_ROWS = 54
 # frame (prepass -> first pass -> refinement, each as long as its slowest ray) with bulk work. One frame alone takes ~45 ms on 1 GPU
 # for ~30 ms of bulk work, and ~24 ms on 8 GPUs for ~4 ms of bulk work per GPU, so the count grows with the number of GPUs.
 _WORLD = int(os.environ.get("WORLD_SIZE", "1"))
-FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(4 if _WORLD == 1 else min(8, 2 * _WORLD + 2))))
-BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", "3"))
+# measured optima (tools/gpu_sweep_bench.sh, tools/gpu_sweep_scaling.sh; profiles/round1_scaling.md): slots in flight : blocks per SM and slot
+_DEFAULT_KNOBS = {1: (4, 3), 2: (6, 3), 4: (8, 2), 8: (8, 1)}.get(_WORLD, (min(8, 2 * _WORLD + 2), 2))
+FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(_DEFAULT_KNOBS[0])))
+BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS[1])))
 BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)
 
@@ -255,6 +257,10 @@ def run_ours(args):
     cam_pos, cam_quat = (0.0, 0.0, -4.0, 0.0), (-0.70710678, 0.0, 0.0, 0.70710678)
     ctx.set_camera(cam_pos, cam_quat)
     stripes = grt.interleaved_stripes(HEIGHT, rank, world, STRIPE_ROWS)
+    if world == 1 and os.environ.get("GRT_BENCH_EMULATE_WORLD"):
+        # diagnostic only (tools/gpu_probe_pipeline.sh): one GPU renders the stripes rank 0 of an N-GPU job would own, no gather -
+        # separates the per-rank pipeline from the collective when studying scaling
+        stripes = grt.interleaved_stripes(HEIGHT, 0, int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
     rows = sum(b - a for a, b in stripes)
     fmt = grt.GRT_FORMAT_RGBA8
     local = torch.empty((rows, WIDTH, 4), dtype=torch.uint8, device=device)
