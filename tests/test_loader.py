@@ -143,3 +143,40 @@ def test_sixteen_entry_returns_allow_holes_and_plain_numbers(grt, tmp_path, orac
 def test_load_by_unknown_name_fails(grt, content):
     with pytest.raises(grt.GrtError):
         content.load_by_name("no_such_metric")
+
+
+# ---- the emitted arrangement of the acceleration against the reference formulation, float64 on the host ----------------------
+# (grt_metric_eval_symbolic: plugin-layer diagnostic; the arrangement is chosen per metric among explicit partials /
+#  P-S form / forward-mode + reverse-mode form, each with the 2x2-minor or the multiplied-out cofactors - DESIGN.md 2)
+def _check_arrangement(metric, seed):
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    for _ in range(6):
+        pos = rng.uniform(0.7, 2.6, 4)
+        vel = rng.uniform(-1, 1, 4)
+        vel[0] = -1.0
+        if metric.info.is_constant_theta:
+            pos[2] = float(np.float32(np.pi / 2))
+            vel[2] = 0.0
+        e = metric.eval_symbolic(pos, vel)
+        a, r = e["accel"], e["accel_ref"]
+        if not (np.isfinite(a).all() and np.isfinite(r).all()):
+            assert np.array_equal(np.isfinite(a), np.isfinite(r))
+            continue
+        scale = max(1.0, np.abs(r).max())
+        worst = max(worst, np.abs(a - r).max() / scale)
+    return worst
+
+
+@pytest.mark.parametrize("name", ["minkowski", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre",
+                                  "double_schwarzschild"])
+def test_emitted_acceleration_equals_reference_formulation_in_float64(content, name):
+    assert _check_arrangement(content.load_by_name(name), 3) < 1e-9
+
+
+def test_emitted_acceleration_of_every_reference_metric(grt, have_reference):
+    if not have_reference:
+        pytest.skip("reference not mounted")
+    c = grt.Content("/root/reference/scripts")
+    for k, name in enumerate(c.metric_names()):
+        assert _check_arrangement(c.load_by_name(name), 40 + k) < 1e-8, name
