@@ -17,23 +17,27 @@ def main():
     os.makedirs(cache, exist_ok=True)
     os.environ["GRT_CACHE_DIR"] = cache
     content = grt.Content(folder)
-    print(f"{'metric':36s} {'ops(accel)':>10s} {'ops(ref)':>9s} {'regs':>5s} {'stack':>6s} {'build s':>8s}")
+    print(f"{'metric':36s} {'ops(accel)':>10s} {'ops(ref)':>9s} {'regs':>9s} {'stack':>6s} {'tier':>5s} {'build s':>8s}")
     for name in content.metric_names():
         m = content.load_by_name(name)
         before = set(os.listdir(cache))
         t = time.time()
         m.compile(False, True)
         dt = time.time() - t
-        new = [f for f in set(os.listdir(cache)) - before if f.endswith(".cubin")]
-        regs = stack = "?"
-        if new:
-            out = subprocess.run(["cuobjdump", "-res-usage", os.path.join(cache, new[0])], capture_output=True, text=True).stdout
+        added = set(os.listdir(cache)) - before
+        new = [f for f in added if f.endswith(".cubin")]
+        tier = [open(os.path.join(cache, f)).read().strip() for f in added if f.endswith(".tier")]
+        found = []
+        for f in new:   # the free compile and, if an occupancy tier was accepted, the tiered build that is actually used
+            out = subprocess.run(["cuobjdump", "-res-usage", os.path.join(cache, f)], capture_output=True, text=True).stdout
             i = out.find("k_integrate")
             if i >= 0:
-                regs = re.search(r"REG:(\d+)", out[i:]).group(1)
-                stack = re.search(r"STACK:(\d+)", out[i:]).group(1)
+                found.append((int(re.search(r"REG:(\d+)", out[i:]).group(1)), int(re.search(r"STACK:(\d+)", out[i:]).group(1))))
+        found.sort(reverse=True)
+        regs = "->".join(str(r) for r, _ in found) or "?"
+        stack = str(found[-1][1]) if found else "?"
         info = m.info
-        print(f"{name:36s} {info.flops_accel:10d} {info.flops_accel_reference:9d} {regs:>5s} {stack:>6s} {dt:8.1f}", flush=True)
+        print(f"{name:36s} {info.flops_accel:10d} {info.flops_accel_reference:9d} {regs:>9s} {stack:>6s} {(tier[0] if tier else '-'):>5s} {dt:8.1f}", flush=True)
 
 
 if __name__ == "__main__":
