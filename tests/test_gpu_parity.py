@@ -573,3 +573,32 @@ def test_frame_matches_reference_kernel_output(gpu_ctx, content, grt, name, case
     steps, rays, extra = gold[key + "counts"].tolist()
     assert abs(int(st.trial_steps) - steps) <= 0.03 * steps + 64
     assert abs(int(st.extra_rays) - extra) <= 0.10 * extra + 12
+
+
+def test_cpp_headless_host_renders_the_same_frame(gpu_ctx, content, grt, tmp_path):
+    """grt_headless (csrc/grt_headless.cpp): the C++ host over the C ABI that stands where the reference's main.cpp frame loop stands
+    (-bench <metric>, default camera, "Frametime Elapsed" lines, screenshot).  Same frame as the ctypes binding, byte for byte."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(grt.__file__), "grt_headless")
+    assert os.path.exists(exe), "make -C geodesic_raytracing_b200 builds grt_headless"
+    bg = grt.synthetic_background(1024, 512)
+    ppm_in, ppm_out = tmp_path / "sky.ppm", tmp_path / "frame.ppm"
+    with open(ppm_in, "wb") as f:
+        f.write(b"P6\n1024 512\n255\n" + np.ascontiguousarray(bg[..., :3]).tobytes())
+    w, h = 256, 144
+    r = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "kerr_schild", "-size", str(w), str(h), "-frames", "4", "-inflight", "2", "-background", str(ppm_in),
+                        "-out", str(ppm_out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("Frametime Elapsed: ") == 4          # the -bench line of main.cpp:2864-2871
+    data = open(ppm_out, "rb").read()
+    header = f"P6\n{w} {h}\n255\n".encode()
+    assert data.startswith(header)
+    got = np.frombuffer(data[len(header):], np.uint8).reshape(h, w, 3)
+    metric = content.load_by_name("kerr_schild")
+    bind(gpu_ctx, metric, bg)
+    want, _ = gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8)
+    assert np.array_equal(got, want[..., :3])
+    # loud failure paths: unknown metric, unknown parameter
+    bad = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "no such metric"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and "metric" in bad.stderr
