@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         "grt_metric_param_count": (ci, [vp]), "grt_metric_param_name": (cp, [vp, ci]), "grt_metric_param_default": (cf, [vp, ci]),
         "grt_metric_param_get": (cf, [vp, ci]), "grt_metric_param_set": (ci, [vp, ci, cf]),
         "grt_metric_get_info": (ci, [vp, C.POINTER(MetricInfo)]), "grt_metric_name": (cp, [vp]), "grt_metric_description": (cp, [vp]),
+        "grt_image_load_png": (vp, [cp, C.POINTER(ci), C.POINTER(ci)]), "grt_image_free": (None, [vp]),
         "grt_metric_source": (cp, [vp, ci]), "grt_metric_eval_symbolic": (ci, [vp] + [vp] * 9), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
         "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]), "grt_set_metric_async": (ci, [vp, vp, ci]), "grt_build_poll": (ci, [vp]),
@@ -486,6 +487,18 @@ def interleaved_stripes(height: int, rank: int, world: int, stripe_rows: int = 5
         if i % world == rank:
             out.append((y, min(height, y + stripe_rows)))
     return out
+
+
+def load_png(path: str) -> np.ndarray:
+    """PNG file -> HxWx4 uint8 (grt_image_load_png: the library's own decoder; the reference uses sf::Image)."""
+    w, h = C.c_int(), C.c_int()
+    p = lib().grt_image_load_png(os.fsencode(path), C.byref(w), C.byref(h))
+    if not p:
+        raise GrtError(-1, _err())
+    try:
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().grt_image_free(p)
 
 
 def synthetic_background(width: int = 4096, height: int = 2048, seed: int = 7) -> np.ndarray:

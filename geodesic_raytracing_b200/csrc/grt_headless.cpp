@@ -8,7 +8,7 @@
 // The window, ImGui, input and Steam parts of main.cpp are out of scope.
 //
 //   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K]
-//                [-param name value]... [-static] [-no-adaptive] [-redshift] [-geodesic tau] [-background file.ppm] [-out frame.ppm]
+//                [-param name value]... [-static] [-no-adaptive] [-redshift] [-geodesic tau] [-background file.png|file.ppm] [-out frame.ppm]
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -116,7 +116,13 @@ int main(int argc, char** argv) {
 
     std::vector<uint8_t> sky;
     int bw = 4096, bh = 2048;
-    if (background_path.empty() || !read_ppm(background_path.c_str(), sky, bw, bh)) sky = procedural_sky(bw, bh);
+    const bool is_png = background_path.size() > 4 && background_path.compare(background_path.size() - 4, 4, ".png") == 0;
+    if (is_png) {                                                 // backgrounds/nasa.png in the reference (main.cpp:233-234)
+        uint8_t* px = grt_image_load_png(background_path.c_str(), &bw, &bh);
+        if (!px) die("background");
+        sky.assign(px, px + (size_t)bw * bh * 4);
+        grt_image_free(px);
+    } else if (background_path.empty() || !read_ppm(background_path.c_str(), sky, bw, bh)) sky = procedural_sky(bw, bh);
     check(grt_set_background(ctx, sky.data(), bw, bh, 0), "background");
 
     grt_features feat;

@@ -405,6 +405,8 @@ struct grt_ctx {
     } build;
 };
 
+namespace grt { std::vector<uint8_t> load_png_rgba(const std::string& path, int* width, int* height); }   // png_loader.cpp
+
 namespace {
 
 void features_default(grt_features* f) {
@@ -970,6 +972,21 @@ const char* grt_metric_source(grt_metric* m, int is_static) {
     int rc = guard([&] { m->source[is_static ? 1 : 0] = grt::emit_metric_source(*m->m, is_static != 0); return GRT_OK; });
     return rc == GRT_OK ? m->source[is_static ? 1 : 0].c_str() : nullptr;
 }
+
+uint8_t* grt_image_load_png(const char* path, int* width, int* height) {
+    uint8_t* out = nullptr;
+    int rc = guard([&] {
+        if (!path || !width || !height) throw Error(GRT_E_INVALID, "null argument");
+        std::vector<uint8_t> px;
+        try { px = grt::load_png_rgba(path, width, height); } catch (const std::runtime_error& e) { throw Error(GRT_E_INVALID, e.what()); }
+        out = (uint8_t*)malloc(px.size());
+        if (!out) throw Error(GRT_E_INVALID, "out of memory");
+        memcpy(out, px.data(), px.size());
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? out : nullptr;
+}
+void grt_image_free(uint8_t* pixels) { free(pixels); }
 
 int grt_metric_eval_symbolic(const grt_metric* m, const double pos[4], const double vel[4], double* g16, double* dg64, double* accel4, double* accel_ref4,
                              double* to_polar4, double* from_polar4, double* distance1) {

@@ -175,6 +175,11 @@ int grt_get_features(const grt_ctx*, grt_features* out);
  * which = 0: the r >= 0 side (mip_background), 1: the r < 0 side (mip_background2);
  * if side 1 is never set it shares side 0 (graphics_settings.cpp:214-243). */
 int grt_set_background(grt_ctx*, const uint8_t* rgba, int width, int height, int which);
+/* Background file -> RGBA8 pixels for grt_set_background (the reference loads its backgrounds/ PNG files with sf::Image,
+ * graphics_settings.cpp:214-243, main.cpp:233-234): non-interlaced PNG, any colour type, 8/16 bit.  Host only.
+ * Returns a malloc'ed width*height*4 buffer the caller releases with grt_image_free, or NULL (grt_last_error). */
+uint8_t* grt_image_load_png(const char* path, int* width, int* height);
+void grt_image_free(uint8_t* pixels);
 /* device-resident variant (pixels already in HBM) */
 int grt_set_background_device(grt_ctx*, const void* rgba_device, int width, int height, int which);
 
