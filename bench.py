@@ -407,6 +407,31 @@ def run_ours(args):
             "clocks": clocks,
             "kernel_info": {k: v for k, v in ctx.kernel_info().items() if k in ("k_integrate", "integrate_blocks_per_sm")},
         }
+        if world == 1:
+            # SURVEY.md 8(d) asks for both operating modes: the same frame with adaptive sampling off (all 8.29 M rays traced, the
+            # clean ray-step rate), a side measurement after the headline numbers; never allowed to break the line
+            try:
+                ctx.set_features(adaptive_sampling=0)
+                full = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, device=device)
+                _, st_off = ctx.render(WIDTH, HEIGHT, fmt, out=full)                      # one frame alone, with statistics
+                outs_off = [full] + [torch.empty_like(full) for _ in range(min(FRAMES_IN_FLIGHT, 3) - 1)]
+                n_off = 4
+                ctx.synchronize(); torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True); e0.record(torch.cuda.current_stream(device))
+                ends_off = []
+                for k in range(n_off):
+                    ctx.render(WIDTH, HEIGHT, fmt, out=outs_off[k % len(outs_off)], stats=False)
+                    e = torch.cuda.Event(enable_timing=True); e.record(torch.cuda.ExternalStream(ctx.stream, device=device)); ends_off.append(e)
+                ctx.synchronize(); torch.cuda.synchronize()
+                ms_off = max(e0.elapsed_time(e) for e in ends_off) / n_off
+                line["full_sampling"] = {"mode": "adaptive sampling off: every pixel traced", "ray_steps": int(st_off.trial_steps), "rays_integrated": int(st_off.rays_integrated),
+                                         "ms_per_frame": ms_off, "fps": 1e3 / ms_off, "value": int(st_off.trial_steps) / ms_off / 1e3, "unit": "Mray-steps/s",
+                                         "frame_latency_ms": float(st_off.ms_total), "frames_timed": n_off}
+                del outs_off, full
+            except Exception as exc:   # noqa: BLE001
+                line["full_sampling"] = {"error": str(exc)}
+            finally:
+                ctx.set_features(adaptive_sampling=1)
         if world == 1 and not args.no_cpu_baseline:
             stride = 8
             orc, feat, cw, ch = cpu_baseline_sample(stride)
