@@ -50,3 +50,23 @@ def test_features_default(grt):
     f = grt.default_features()
     assert (f.universe_size, f.max_precision_radius, f.field_of_view, f.adaptive_sampling_threshold) == (20.0, 10.0, 90.0, 32.0)
     assert abs(f.min_step - 1e-6) < 1e-12 and f.adaptive_sampling == 1 and f.redshift == 0 and f.max_probes == 8 and f.use_prepass == -1
+
+
+def test_cpp_host_fails_loudly_without_a_gpu(grt):
+    """grt_headless (the C++ host over the C ABI) must not fall back to anything when no sm_100 GPU is usable."""
+    import os
+    import subprocess
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    exe = os.path.join(os.path.dirname(grt.__file__), "grt_headless")
+    assert os.path.exists(exe), "make -C geodesic_raytracing_b200 builds grt_headless"
+    r = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "kerr_schild", "-size", "64", "48", "-frames", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no usable CUDA device" in r.stderr
+    usage = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert usage.returncode == 2 and "usage" in usage.stderr
