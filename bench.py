@@ -220,7 +220,7 @@ def run_reference(args):
         "impl": "reference", "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": orc.kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "per_core": value / max(1, orc.info["threads"]), "kind": orc.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": ("oracle/_ref = the reference's cl.cl compiled as C++ for the host cores (g++ -O3 -march=x86-64-v3, OpenMP over work-items); no OpenCL runtime exists in this image"
                  if orc.kind == "reference" else "C++ restatement of the reference's OpenCL kernels (no prebuilt oracle/_ref library found)"),
@@ -437,7 +437,8 @@ def run_ours(args):
             orc, feat, cw, ch = cpu_baseline_sample(stride)
             r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
             line["cpu_baseline"] = {
-                "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"], "kind": orc.kind,
+                "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"],
+                "per_core": r["trial_steps"] / r["seconds"] / 1e6 / max(1, orc.info["threads"]), "kind": orc.kind,
                 "sample": f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw * ch} rays, {r['trial_steps']} ray-steps, {r['seconds']:.1f} s), integration stage, no prepass cull"}
         print(json.dumps(line), flush=True)
     if world > 1:
