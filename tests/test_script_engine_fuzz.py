@@ -148,3 +148,52 @@ def test_random_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_
                 assert not ok.any() or np.abs(got[ok] - want[ok]).max() <= 1e-9 * scale, (what, seed, np.abs(got[ok] - want[ok]).max(), js)
             checked += 1
     assert checked == 24
+
+
+def complex_script(seed):
+    """Scripts that go through complex values the way the double-Kerr family does (csqrt of a real, CMath.i, products, integer
+    powers, conjugates, Real / Imaginary / self_conjugate_multiply back to reals)."""
+    g = Gen(seed)
+    names = ["t", "x", "y", "z"]
+    e = lambda d=2: g.expr(names, d)   # noqa: E731
+    lines = ["function metric(t, x, y, z) {"]
+    lines.append(f"    var za = CMath.csqrt({e()} - {g.pick(['0.5', '2', '3.5'])});")                      # real or imaginary depending on the point
+    lines.append(f"    var zb = {e()} + CMath.i * ({e()});")
+    lines.append(f"    var zc = za * zb + {g.pick(['zb / (za * za + 3)', 'CMath.conjugate(zb) * 0.5', 'CMath.pow(zb, 2)', 'CMath.pow(za + 2, 3)', 'zb - za * 2'])};")
+    lines.append(f"    var zd = CMath.sqrt(zc * zc + {g.pick(['4', '9'])});")                                # complex square root away from the cut most of the time
+    lines.append("    var r0 = CMath.Real(zc), i0 = CMath.Imaginary(zc), m0 = CMath.self_conjugate_multiply(zd);")
+    lines.append(f"    var mix = CMath.Real(zd * CMath.conjugate(zb)) + CMath.Imaginary(za * {g.pick(['zb', 'zd', 'zc'])});")
+    lines.append("    return [-(1 + 0.01 * m0), 1 + 0.05 * r0, 1 + 0.05 * i0, 1 + 0.02 * mix];")
+    lines.append("}")
+    lines.append("metric")
+    return "\n".join(lines) + "\n"
+
+
+def test_complex_valued_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_path):
+    if not have_reference:
+        pytest.skip("reference not mounted")
+    try:
+        q = oracle_mod.QuickJSReference()
+    except FileNotFoundError:
+        pytest.skip("reference not mounted")
+    compared = 0
+    for seed in range(40):
+        js = complex_script(seed)
+        folder = write_folder(tmp_path / f"c{seed}", js)
+        path = os.path.join(folder, "probe.js")
+        m = grt.Content(folder).load(path)
+        rng = np.random.default_rng(seed)
+        for _ in range(3):
+            pos = rng.uniform(0.3, 1.6, 4)
+            g, dg, n, _ = q.metric(path, pos)
+            sym = m.eval_symbolic(pos)
+            assert np.isfinite(g).all() and np.isfinite(sym["g"]).all(), js
+            assert np.abs(sym["g"] - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), (seed, js, sym["g"] - g)
+            # numeric duals give 0 * inf = NaN where a constant sits on a branch point (csqrt(0.5 - 0.5)) and the symbolic derivative is an
+            # exact 0: whatever we leave undefined must be undefined there too, the defined entries must agree
+            assert not (np.isfinite(dg) & ~np.isfinite(sym["dg"])).any(), js
+            ok = np.isfinite(dg)
+            assert ok.mean() >= 0.5
+            assert np.abs(sym["dg"][ok] - dg[ok]).max() <= 1e-8 * max(1.0, np.abs(dg[ok]).max()), (seed, js)
+            compared += 1
+    assert compared == 120
