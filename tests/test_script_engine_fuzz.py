@@ -197,3 +197,38 @@ def test_complex_valued_scripts_agree_with_quickjs(grt, oracle_mod, have_referen
             assert np.abs(sym["dg"][ok] - dg[ok]).max() <= 1e-8 * max(1.0, np.abs(dg[ok]).max()), (seed, js)
             compared += 1
     assert compared == 120
+
+
+BAD_SCRIPTS = {
+    "tan of a complex value": "function f(t,x,y,z){ return [-1, CMath.tan(CMath.csqrt(x - 5)), 1, 1]; }\nf\n",
+    "log of a complex value": "function f(t,x,y,z){ return [-1, CMath.log(CMath.i * x), 1, 1]; }\nf\n",
+    "complex power with a variable exponent": "function f(t,x,y,z){ return [-1, CMath.Real(CMath.pow(CMath.i * x, y)), 1, 1]; }\nf\n",
+    "complex power with a fractional exponent": "function f(t,x,y,z){ return [-1, CMath.Real(CMath.pow(CMath.i * x, 1.5)), 1, 1]; }\nf\n",
+    "csqrt of a complex value": "function f(t,x,y,z){ return [-1, CMath.Real(CMath.csqrt(CMath.i * x)), 1, 1]; }\nf\n",
+    "comparison of complex values": "function f(t,x,y,z){ return [-1, CMath.lt(CMath.i * x, 1), 1, 1]; }\nf\n",
+    "three entries": "function f(t,x,y,z){ return [-1, 1, 1]; }\nf\n",
+    "not an array": "function f(t,x,y,z){ return x; }\nf\n",
+    "not a function": "var f = 3;\nf\n",
+    "syntax error": "function f(t,x,y,z){ return [-1, 1, 1, ; }\nf\n",
+    "undefined identifier": "function f(t,x,y,z){ return [-1, nothing_here * x, 1, 1]; }\nf\n",
+    "bad $cfg name": "function f(t,x,y,z){ var q = $cfg['a-b']; return [-1, q, 1, 1]; }\nf\n",
+}
+
+
+@pytest.mark.parametrize("what", sorted(BAD_SCRIPTS))
+def test_scripts_the_reference_engine_rejects_are_rejected(grt, oracle_mod, have_reference, tmp_path, what):
+    """Error behaviour at the plugin boundary (js_interop.cpp:171-184, 585-616, 753-760, 862-900): a script QuickJS + the reference's
+    bindings refuse must be refused by the product's loader too (GRT_E_SCRIPT with a message), never silently evaluated."""
+    if not have_reference:
+        pytest.skip("reference not mounted")
+    try:
+        q = oracle_mod.QuickJSReference()
+    except FileNotFoundError:
+        pytest.skip("reference not mounted")
+    folder = write_folder(tmp_path, BAD_SCRIPTS[what])
+    path = os.path.join(folder, "probe.js")
+    with pytest.raises(RuntimeError):
+        q.metric(path, [0.1, 1.2, 0.7, 0.4])
+    with pytest.raises(grt.GrtError) as err:
+        grt.Content(folder).load(path)
+    assert str(err.value)
