@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "grt_metric_param_get": (cf, [vp, ci]), "grt_metric_param_set": (ci, [vp, ci, cf]),
         "grt_metric_get_info": (ci, [vp, C.POINTER(MetricInfo)]), "grt_metric_name": (cp, [vp]), "grt_metric_description": (cp, [vp]),
         "grt_image_load_png": (vp, [cp, C.POINTER(ci), C.POINTER(ci)]), "grt_image_free": (None, [vp]),
+        "grt_metric_packed_params": (ci, [vp, vp, ci]),
         "grt_metric_source": (cp, [vp, ci]), "grt_metric_eval_symbolic": (ci, [vp] + [vp] * 9), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
         "grt_create": (vp, [ci]), "grt_destroy": (None, [vp]), "grt_set_metric": (ci, [vp, vp, ci]), "grt_update_params": (ci, [vp]), "grt_set_metric_async": (ci, [vp, vp, ci]), "grt_build_poll": (ci, [vp]),
@@ -231,6 +232,14 @@ class Metric:
     def params(self) -> List[float]:
         L = lib()
         return [L.grt_metric_param_get(self._h, i) for i in range(L.grt_metric_param_count(self._h))]
+
+    @property
+    def packed_params(self) -> List[float]:
+        """`struct grt_params` of the generated source: the named values followed by the derived parameters."""
+        n = _check(lib().grt_metric_packed_params(self._h, None, 0))
+        buf = (C.c_float * max(1, n))()
+        _check(lib().grt_metric_packed_params(self._h, buf, n))
+        return list(buf[:n])
 
     def set_param(self, name_or_index, value: float) -> None:
         idx = name_or_index if isinstance(name_or_index, int) else self.param_names.index(name_or_index)

@@ -367,7 +367,7 @@ struct grt_ctx {
     bool bound_use_prepass = false, bound_constant_theta = false;   // what the frame path needs of the bound metric
     std::map<std::string, std::unique_ptr<Program>> programs;
     Program* prog = nullptr;
-    float params[64] = {0};
+    float params[256] = {0};   // struct grt_params of the bound program: named $cfg values, then the derived parameters (pack_params)
 
     GrtCamera cam{};
     bool camera_dirty = true, camera_on_geodesic = false;
@@ -973,6 +973,16 @@ const char* grt_metric_source(grt_metric* m, int is_static) {
     return rc == GRT_OK ? m->source[is_static ? 1 : 0].c_str() : nullptr;
 }
 
+int grt_metric_packed_params(const grt_metric* m, float* out, int max_count) {
+    return guard([&] {
+        if (!m) throw Error(GRT_E_INVALID, "null metric");
+        std::vector<float> packed = grt::pack_params(*m->m);
+        if (out)
+            for (int i = 0; i < (int)packed.size() && i < max_count; i++) out[i] = packed[i];
+        return (int)packed.size();
+    });
+}
+
 uint8_t* grt_image_load_png(const char* path, int* width, int* height) {
     uint8_t* out = nullptr;
     int rc = guard([&] {
@@ -1135,6 +1145,13 @@ int grt_set_metric_async(grt_ctx* c, grt_metric* m, int is_static) {
     });
 }
 
+static void fill_params(grt_ctx* c, const grt::Metric& m) {
+    std::vector<float> packed = grt::pack_params(m);
+    if (packed.size() > sizeof(c->params) / sizeof(float)) throw Error(GRT_E_INVALID, "parameter block too large (named + derived > 256)");
+    memset(c->params, 0, sizeof c->params);
+    if (!packed.empty()) memcpy(c->params, packed.data(), packed.size() * sizeof(float));
+}
+
 int grt_build_poll(grt_ctx* c) {
     return guard([&] {
         if (!c) throw Error(GRT_E_INVALID, "null context");
@@ -1154,8 +1171,7 @@ int grt_build_poll(grt_ctx* c) {
         c->bound_constant_theta = m->m->constant_theta();
         c->prog = p;
         c->kernel_info = p->info;
-        memset(c->params, 0, sizeof c->params);
-        for (size_t i = 0; i < m->m->params.names.size(); i++) c->params[i] = m->m->params.current_values[i];
+        fill_params(c, *m->m);
         c->feat.max_acceleration_change = m->m->cfg.max_acceleration_change;
         c->camera_dirty = true;
         return 1;
@@ -1169,7 +1185,7 @@ int grt_update_params(grt_ctx* c) {
         need_program(c);
         const auto& p = c->metric->m->params;
         if (p.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
-        for (size_t i = 0; i < p.names.size(); i++) c->params[i] = p.current_values[i];
+        fill_params(c, *c->metric->m);
         if (c->is_static) c->prog = get_program(c, c->metric, true);   // literals changed: rebuild (metric_manager.hpp:153-167)
         c->kernel_info = c->prog->info;
         c->camera_dirty = true;
@@ -1189,8 +1205,7 @@ int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
         c->bound_constant_theta = m->m->constant_theta();
         c->prog = p;
         c->kernel_info = p->info;
-        memset(c->params, 0, sizeof c->params);
-        for (size_t i = 0; i < m->m->params.names.size(); i++) c->params[i] = m->m->params.current_values[i];
+        fill_params(c, *m->m);
         c->feat.max_acceleration_change = m->m->cfg.max_acceleration_change;   // metric_manager.hpp:50
         c->camera_dirty = true;
         c->camera_on_geodesic = false;

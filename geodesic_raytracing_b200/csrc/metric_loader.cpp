@@ -767,11 +767,46 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         d.radii[0] = d.to_polar[1];
         d.radii[1] = G.substitute(d.distance, repl);
     }
+    // derived parameters (see MetricDescriptor::derived)
+    {
+        std::vector<int> all(d.g, d.g + 16);
+        all.insert(all.end(), d.dg, d.dg + 64);
+        for (const int* arr : {d.to_polar, d.dto_polar, d.from_polar, d.dfrom_polar, d.period, d.accel, d.accel_ref}) all.insert(all.end(), arr, arr + 4);
+        all.push_back(d.distance);
+        all.push_back(d.radii[0]);
+        all.push_back(d.radii[1]);
+        std::map<int, int> kind;   // 0: constants only, 1: parameters (no variables), 2: depends on a variable
+        std::function<int(int)> classify = [&](int x) -> int {
+            if (x < 0) return 0;
+            auto it = kind.find(x);
+            if (it != kind.end()) return it->second;
+            const sym::Node n = G.node(x);
+            int k = n.op == sym::Op::Var ? 2 : (n.op == sym::Op::Param ? 1 : std::max(classify(n.a), std::max(classify(n.b), classify(n.c))));
+            kind[x] = k;
+            return k;
+        };
+        for (int o : all) classify(o);
+        auto is_op = [&](int x) { const sym::Node& n = G.node(x); return n.op != sym::Op::Const && n.op != sym::Op::Var && n.op != sym::Op::Param; };
+        std::set<int> maximal;
+        size_t param_only_ops = 0;
+        for (auto& kv : kind) {
+            const int x = kv.first;
+            if (kv.second == 1 && is_op(x)) param_only_ops++;
+            if (kv.second != 2) continue;
+            const sym::Node n = G.node(x);
+            for (int ch : {n.a, n.b, n.c})
+                if (ch >= 0 && kind[ch] == 1 && is_op(ch)) maximal.insert(ch);
+        }
+        for (int o : all)
+            if (kind[o] == 1 && is_op(o)) maximal.insert(o);
+        if (param_only_ops >= 16 && maximal.size() <= 160) d.derived.assign(maximal.begin(), maximal.end());
+    }
     std::vector<int> outs(d.g, d.g + 16);
     outs.insert(outs.end(), d.dg, d.dg + 64);
-    d.flops_expr = G.op_count(outs);
-    d.flops_accel = G.op_count(std::vector<int>(d.accel, d.accel + 4));
-    d.flops_accel_ref = G.op_count(std::vector<int>(d.accel_ref, d.accel_ref + 4));
+    // per-evaluation operation counts: derived parameters are inputs, not work
+    d.flops_expr = G.op_count(outs, &d.derived);
+    d.flops_accel = G.op_count(std::vector<int>(d.accel, d.accel + 4), &d.derived);
+    d.flops_accel_ref = G.op_count(std::vector<int>(d.accel_ref, d.accel_ref + 4), &d.derived);
 }
 
 std::unique_ptr<Metric> load_metric_from_script(const ContentManager& cm, const std::string& js_path) {
@@ -843,7 +878,15 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
     defflag("GRT_HAS_COORDINATE_PERIODICITY", d.has_period);
     defflag("GRT_USE_PREPASS", m.cfg.use_prepass);
     defflag("GRT_STATIC_PARAMS", is_static);
-    o << "#define GRT_NUM_PARAMS " << m.params.names.size() << "\n";
+    // named parameters, then the derived ones (MetricDescriptor::derived); the host fills the whole block (pack_params)
+    o << "#define GRT_NUM_PARAMS " << (m.params.names.size() + (is_static ? 0 : d.derived.size())) << "\n";
+    if (!d.derived.empty()) o << "#define GRT_NUM_NAMED_PARAMS " << m.params.names.size() << "\n";
+    if (!d.derived.empty()) {
+        std::map<std::string, double> env;
+        for (size_t i = 0; i < m.params.names.size(); i++) env[m.params.names[i]] = m.params.current_values[i];
+        for (size_t k = 0; k < d.derived.size(); k++)
+            opt.leaf_names[d.derived[k]] = is_static ? sym::float_literal((double)(float)G.eval(d.derived[k], env)) : "cfg.grt_d" + std::to_string(k);
+    }
     // principal complex square root (stable on both half planes): re >= 0 -> (t, im / 2t), else (|im| / 2t, +-t)
     o << "GRT_FN float grt_csqrt_re(float re, float im) { float t = GRT_SQRT(0.5f * (GRT_SQRT(re * re + im * im) + fabsf(re))); "
          "return re >= 0.0f ? t : (t > 0.0f ? GRT_DIV(fabsf(im), 2.0f * t) : 0.0f); }\n";
@@ -853,6 +896,8 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
     o << "struct grt_params {\n";
     if (m.params.names.empty()) o << "    float _unused;\n";
     for (auto& n : m.params.names) o << "    float " << n << ";\n";
+    if (!is_static)
+        for (size_t k = 0; k < d.derived.size(); k++) o << "    float grt_d" << k << ";\n";
     o << "};\n\n";
 
     auto fn = [&](const std::string& sig, const std::vector<std::pair<std::string, int>>& outs) {
@@ -895,6 +940,16 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
     fn_pos("void grt_accel(const float* p, const float* v, const grt_params& cfg, float* o)", pos_decl + vel_decl, vec4(d.accel));
     fn_pos("void grt_accel_ref(const float* p, const float* v, const grt_params& cfg, float* o)", pos_decl + vel_decl, vec4(d.accel_ref));
     return o.str();
+}
+
+std::vector<float> pack_params(const Metric& m) {
+    std::vector<float> out(m.params.current_values.begin(), m.params.current_values.end());
+    if (!m.desc.derived.empty()) {
+        std::map<std::string, double> env;
+        for (size_t i = 0; i < m.params.names.size(); i++) env[m.params.names[i]] = m.params.current_values[i];
+        for (int id : m.desc.derived) out.push_back((float)m.desc.graph.eval(id, env));
+    }
+    return out;
 }
 
 }  // namespace grt

@@ -79,6 +79,11 @@ struct MetricDescriptor {
     int accel_ref[4];             // -Gamma^mu_ab v^a v^b with symbolic inverse (metric.hpp:184-244)
     int accel[4];                 // same acceleration, lowered-index formulation (product kernels)
     int radii[2];                 // {polar r, distance-to-object} composed on native coordinates
+    // Derived parameters: maximal sub-expressions that depend on the `$cfg` parameters only (the double-Kerr family spends a
+    // quarter of its operations on them).  They are evaluated once on the host (float64) whenever a parameter changes and
+    // travel in the parameter block behind the named ones, instead of being recomputed - or kept live in registers - by every
+    // ray at every step.  Empty unless the metric has at least 16 such operations.
+    std::vector<int> derived;
     size_t flops_expr = 0;        // ops in the emitted g + dg DAG (SURVEY.md 8(d) F_expr)
     size_t flops_accel = 0;       // ops in the emitted lowered acceleration DAG
     size_t flops_accel_ref = 0;
@@ -100,5 +105,9 @@ std::unique_ptr<Metric> load_metric_from_script(const ContentManager& cm, const 
 // substitutes the current parameter values as literals (metric.hpp:494-547), otherwise the
 // functions read `cfg.<name>` from `struct grt_params`.
 std::string emit_metric_source(const Metric& m, bool is_static);
+
+// The parameter block the generated functions read (`struct grt_params`): the named parameters' current values followed by the
+// derived parameters evaluated from them.
+std::vector<float> pack_params(const Metric& m);
 
 }  // namespace grt

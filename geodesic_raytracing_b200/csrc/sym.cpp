@@ -713,8 +713,9 @@ bool Graph::depends_on(int id, int leaf) const {
     return go(id);
 }
 
-size_t Graph::op_count(const std::vector<int>& outs) const {
+size_t Graph::op_count(const std::vector<int>& outs, const std::vector<int>* leaves) const {
     std::set<int> seen;
+    if (leaves) seen.insert(leaves->begin(), leaves->end());
     size_t cnt = 0;
     std::function<void(int)> go = [&](int x) {
         if (x < 0 || !seen.insert(x).second) return;
@@ -850,12 +851,15 @@ std::string emit_block(const Graph& g, const std::vector<std::pair<std::string, 
     std::set<int> reach;
     std::function<void(int)> go = [&](int x) {
         if (x < 0 || !reach.insert(x).second) return;
+        if (opt.leaf_names.count(x)) return;   // a named leaf: nothing below it is needed
         const Node& n = g.node(x);
         go(n.a); go(n.b); go(n.c);
     };
     for (auto& o : outs) go(o.second);
 
     auto ref = [&](int x) -> std::string {
+        auto leaf = opt.leaf_names.find(x);
+        if (leaf != opt.leaf_names.end()) return leaf->second;
         const Node& n = g.node(x);
         switch (n.op) {
             case Op::Const: return float_literal(n.val);
@@ -872,7 +876,7 @@ std::string emit_block(const Graph& g, const std::vector<std::pair<std::string, 
     std::string out;
     for (int x : reach) {  // std::set iterates ascending = topological
         const Node& n = g.node(x);
-        if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param) continue;
+        if (n.op == Op::Const || n.op == Op::Var || n.op == Op::Param || opt.leaf_names.count(x)) continue;
         std::string rhs;
         auto A = [&]() { return ref(n.a); };
         auto B = [&]() { return ref(n.b); };

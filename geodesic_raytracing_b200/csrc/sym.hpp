@@ -71,7 +71,7 @@ public:
     // does `id` depend on node `leaf`?
     bool depends_on(int id, int leaf) const;
     // number of arithmetic nodes reachable from the outputs (flop-ish count, FMA not fused)
-    size_t op_count(const std::vector<int>& outs) const;
+    size_t op_count(const std::vector<int>& outs, const std::vector<int>* leaves = nullptr) const;   // `leaves`: nodes counted as inputs
     // Estimated machine instructions: like op_count, but a single-use product feeding a sum is one FMA with it, a
     // negation folds into the operand modifier of its consumer, and a quotient costs two (reciprocal + multiply).
     size_t instr_count(const std::vector<int>& outs) const;
@@ -173,6 +173,9 @@ struct EmitOptions {
     // `cfg->x` by a literal).
     std::string param_prefix = "cfg.";
     std::map<std::string, double> param_values;
+    // nodes emitted as a given text instead of being computed (derived parameters: sub-expressions of the parameters only,
+    // evaluated once on the host and handed to the kernels in the parameter block)
+    std::map<int, std::string> leaf_names;
     std::string tmp_prefix = "t";
     std::string indent = "    ";
 };

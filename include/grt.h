@@ -95,6 +95,12 @@ const char* grt_metric_description(const grt_metric*);
  * The string stays valid until the next call for the same metric. */
 const char* grt_metric_source(grt_metric*, int is_static);
 
+/* The parameter block the generated functions read (`struct grt_params` of grt_metric_source): the named `$cfg` values followed by
+ * the metric's derived parameters - sub-expressions of the parameters alone, evaluated on the host whenever a value changes so
+ * that no ray recomputes them (none for most metrics; the double-Kerr family has dozens).  Returns the number of floats;
+ * copies at most max_count of them when out is not NULL.  Code that runs the generated source elsewhere (the CPU oracle) uses it. */
+int grt_metric_packed_params(const grt_metric*, float* out, int max_count);
+
 /* Plugin-layer diagnostic, host only, no device involved: evaluates the metric's symbolic expressions (what the
  * emitted functions compute) in double precision at one point with the current parameter values - g (16, row-major),
  * dg (64, [k*16 + i*4 + j] = d_k g_ij), the acceleration -Gamma^i_ab v^a v^b in the emitted arrangement and in the

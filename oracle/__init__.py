@@ -31,7 +31,7 @@ class OracleFrameArgs(C.Structure):
     _fields_ = [
         ("width", C.c_int), ("height", C.c_int), ("camera_pos", C.c_float * 4), ("camera_quat", C.c_float * 4),
         ("basis_speed", C.c_float * 3), ("flip", C.c_int), ("use_given_camera", C.c_int), ("camera_generic", C.c_float * 4),
-        ("tetrad", C.c_float * 16), ("features", OracleFeatures), ("params", C.c_float * 32), ("max_probes", C.c_int),
+        ("tetrad", C.c_float * 16), ("features", OracleFeatures), ("params", C.c_float * 256), ("max_probes", C.c_int),
         ("use_prepass", C.c_int), ("bg1", C.c_void_p), ("bg1_w", C.c_int), ("bg1_h", C.c_int), ("bg2", C.c_void_p),
         ("bg2_w", C.c_int), ("bg2_h", C.c_int),
     ]
@@ -104,7 +104,7 @@ class Oracle:
                               "sizeof_lightray", "sizeof_render_data", "threads"], list(info)))
         assert self.info["sizeof_lightray"] == self._lightray_dtype.itemsize, self.info
         assert self.info["sizeof_render_data"] == self._rdata_dtype.itemsize, self.info
-        self.params = np.zeros(32, np.float32)
+        self.params = np.zeros(256, np.float32)
         self.params[:len(params)] = params
         L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
         L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
@@ -314,12 +314,12 @@ def _stem(metric) -> str:
 
 def for_metric(metric, is_static: bool = False, native: bool = False) -> Oracle:
     """Oracle for a geodesic_raytracing_b200.Metric (same generated functions as the CUDA program)."""
-    return Oracle(metric.source(is_static), _stem(metric) + ("_static" if is_static else ""), metric.params, native)
+    return Oracle(metric.source(is_static), _stem(metric) + ("_static" if is_static else ""), metric.packed_params, native)
 
 
 def reference_for_metric(metric, native: bool = False) -> ClReference:
     """The reference's own cl.cl kernels (oracle/_ref) for a geodesic_raytracing_b200.Metric."""
-    return ClReference(metric.source(False), _stem(metric), metric.params, native)
+    return ClReference(metric.source(False), _stem(metric), metric.packed_params, native)
 
 
 class QuickJSReference:

@@ -33,7 +33,7 @@ struct OracleFrameArgs {
     float camera_generic[4];
     float tetrad[16];
     OracleFeatures features;
-    float params[32];
+    float params[256];   // struct grt_params: named + derived values (grt_metric_packed_params)
     int max_probes;
     int use_prepass;        // -1: metric default (GRT_USE_PREPASS)
     const uint8_t* bg1; int bg1_w, bg1_h;

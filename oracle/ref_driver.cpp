@@ -144,7 +144,7 @@ struct OracleFrameArgs {
     float camera_generic[4];
     float tetrad[16];
     OracleFeatures features;
-    float params[32];
+    float params[256];   // struct grt_params: named + derived values (grt_metric_packed_params)
     int max_probes;
     int use_prepass;
     const uint8_t* bg1; int bg1_w, bg1_h;
@@ -208,8 +208,8 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
     const int width = a->width, height = a->height;
     const size_t LR = (size_t)clref_sizeof_lightray(), RD = (size_t)clref_sizeof_render_data();
     double t_start = now_s();
-    Buf<float> cfg_buf(32);
-    memcpy(cfg_buf.p, a->params, sizeof(float) * 32);
+    Buf<float> cfg_buf(256);
+    memcpy(cfg_buf.p, a->params, sizeof(float) * 256);
     const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
     Buf<FeatureBlock> dfg_buf(1);
     *dfg_buf.p = to_block(a->features);
@@ -311,8 +311,8 @@ int clref_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int
                            int* terminated_out, int* steps_out) {
     const int width = a->width, height = a->height;
     const size_t LR = (size_t)clref_sizeof_lightray();
-    Buf<float> cfg_buf(32);
-    memcpy(cfg_buf.p, a->params, sizeof(float) * 32);
+    Buf<float> cfg_buf(256);
+    memcpy(cfg_buf.p, a->params, sizeof(float) * 256);
     const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
     Buf<FeatureBlock> dfg_buf(1);
     *dfg_buf.p = to_block(a->features);
@@ -347,8 +347,8 @@ int clref_integrate_sample(const OracleFrameArgs* a, int x0, int y0, int cw, int
 // main.cpp:2675-2760: boost_tetrad -> init_inertial_ray -> get_geodesic_path -> 4x parallel_transport_quantity
 int clref_geodesic_snapshot(const float* camera_generic, const float* tetrad_in, const float* basis_speed, const OracleFeatures* f, const float* params,
                             int max_path_length, float* positions, float* velocities, float* ds, float* transported /* 4 * max * 4 */, float* boosted_tetrad) {
-    Buf<float> cfg_buf(32);
-    memcpy(cfg_buf.p, params, sizeof(float) * 32);
+    Buf<float> cfg_buf(256);
+    memcpy(cfg_buf.p, params, sizeof(float) * 256);
     const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
     Buf<FeatureBlock> dfg_buf(1);
     *dfg_buf.p = to_block(*f);
@@ -382,8 +382,8 @@ int clref_geodesic_snapshot(const float* camera_generic, const float* tetrad_in,
 void clref_geodesic_interpolate(const float* positions, const float* velocities, const float* ds, const float* transported, int max_path_length, int cnt,
                                 float target_time, int parallel_transport_observer, const float* basis_speed, const float* params, float* camera_generic_out,
                                 float* tetrad_out, float* velocity_out) {
-    Buf<float> cfg_buf(32);
-    memcpy(cfg_buf.p, params, sizeof(float) * 32);
+    Buf<float> cfg_buf(256);
+    memcpy(cfg_buf.p, params, sizeof(float) * 256);
     const dynamic_config* cfg = (const dynamic_config*)cfg_buf.p;
     size_t n = (size_t)std::max(cnt, 1);
     Buf<float4> pos(n), vel(n), t0(n), t1(n), t2(n), t3(n), cam(1), e0(1), e1(1), e2(1), e3(1), v(1);

@@ -602,3 +602,39 @@ def test_cpp_headless_host_renders_the_same_frame(gpu_ctx, content, grt, tmp_pat
     # loud failure paths: unknown metric, unknown parameter
     bad = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "no such metric"], capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and "metric" in bad.stderr
+
+
+def test_derived_parameters_on_the_device(gpu_ctx, oracle_mod, grt, background, tmp_path):
+    """A metric whose script spends most of its algebra on the $cfg parameters alone: the derived parameters are evaluated on the host and
+    reach the kernels through the parameter block (grt_metric_packed_params); frames and generated functions match the oracle, before and
+    after a parameter change without a rebuild."""
+    import os
+    from test_loader import PARAM_HEAVY_JS, write_folder
+    folder = write_folder(tmp_path, PARAM_HEAVY_JS, cfg='{"name": "probe", "inherit_settings": "spherical"}')
+    m = grt.Content(folder).load(os.path.join(folder, "probe.js"))
+    assert len(m.packed_params) > len(m.params) == 3
+    for trial in range(2):
+        orc = oracle_mod.for_metric(m)
+        base = bind(gpu_ctx, m, background, adaptive_sampling=0)
+        if trial:
+            gpu_ctx.update_params()
+        rng = np.random.default_rng(9)
+        pos = rng.uniform(1.5, 3.0, (16, 4)).astype(np.float32)
+        vel = rng.uniform(-1, 1, (16, 4)).astype(np.float32)
+        if m.info.is_constant_theta:
+            pos[:, 2] = np.float32(np.pi / 2)
+            vel[:, 2] = 0
+        g, dg, acc, pol, rad = gpu_ctx.eval_metric(pos, vel)
+        for i in range(len(pos)):
+            og, odg = orc.metric_eval(pos[i])
+            oa = orc.accel(pos[i], vel[i])
+            assert np.allclose(g[i], og, rtol=2e-4, atol=2e-5) and np.allclose(dg[i], odg, rtol=5e-4, atol=5e-4)
+            assert np.abs(acc[i] - oa["lowered"]).max() / (np.abs(oa["numeric"]).max() + 1e-4) < 1e-3
+        img, st = gpu_ctx.render(96, 64)
+        ref = orc.frame(96, 64, oracle_features(orc, base), background=background, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
+        rd = gpu_ctx.read_render_data(96, 64).reshape(64, 96)
+        assert (rd["terminated"] == ref["rdata"]["terminated"]).mean() >= 0.99
+        assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean() >= 0.97
+        assert abs(int(st.trial_steps) - ref["trial_steps"]) <= 0.02 * ref["trial_steps"] + 64
+        m.set_param("m", 0.3)          # smaller mass: the derived values change, the program does not
+        m.set_param("k", 0.9)

@@ -180,3 +180,61 @@ def test_emitted_acceleration_of_every_reference_metric(grt, have_reference):
     c = grt.Content("/root/reference/scripts")
     for k, name in enumerate(c.metric_names()):
         assert _check_arrangement(c.load_by_name(name), 40 + k) < 1e-8, name
+
+
+# ---- derived parameters (MetricDescriptor::derived): sub-expressions of the $cfg parameters alone travel in the parameter block --------
+PARAM_HEAVY_JS = """
+function f(t, r, theta, phi) {
+    $cfg.m.$default = 0.4; $cfg.q.$default = 0.25; $cfg.k.$default = 1.5;
+    var m = $cfg.m, q = $cfg.q, k = $cfg.k;
+    // a tower of parameter-only algebra, as the double-Kerr scripts have (roots of a cubic in the masses and spins)
+    var p1 = CMath.sqrt(m * m + q * q + k) * (m + 2 * q) / (1 + k * k);
+    var p2 = CMath.pow(p1 * p1 + m * q * k + 3, 1 / 3) - q / (2 + m * m);
+    var p3 = CMath.exp(-p2 * 0.1) * (p1 + p2) + CMath.sin(k) * CMath.cos(m + q);
+    var p4 = (p1 * p2 + p2 * p3 + p3 * p1) / (1 + p1 * p1 + p2 * p2 + p3 * p3);
+    var rs = 2 * m * (1 + 0.05 * p4);
+    var f0 = 1 - rs / r + p3 * 0.01 / (r * r);
+    return [-f0, 1 / f0, r * r * (1 + 0.001 * p2), r * r * CMath.sin(theta) * CMath.sin(theta)];
+}
+f
+"""
+
+
+def test_derived_parameters_travel_in_the_parameter_block(grt, oracle_mod, tmp_path):
+    folder = write_folder(tmp_path, PARAM_HEAVY_JS, cfg='{"name": "probe", "inherit_settings": "polar_base"}' if os.path.exists(os.path.join(grt.CONTENT_DIR, "polar_base.json")) else
+                          '{"name": "probe", "inherit_settings": "spherical"}')
+    m = grt.Content(folder).load(os.path.join(folder, "probe.js"))
+    assert m.param_names == ["m", "q", "k"]
+    packed = m.packed_params
+    assert len(packed) > 3 and packed[:3] == m.params                       # named values first, derived ones behind them
+    src = m.source(False)
+    assert f"#define GRT_NUM_PARAMS {len(packed)}" in src and "#define GRT_NUM_NAMED_PARAMS 3" in src and "float grt_d0;" in src
+    body = src[src.index("void grt_accel("):src.index("void grt_accel_ref(")]
+    assert "GRT_EXP" not in body and "GRT_POW" not in body                   # the parameter-only tower is not recomputed per evaluation
+    static = m.source(True)
+    assert "cfg." not in static[static.index("void grt_metric("):]           # static program: everything folded into literals
+    rng = np.random.default_rng(4)
+    for trial in range(2):
+        orc = oracle_mod.for_metric(m)                                       # the emitted fp32 functions with the packed block ...
+        orc_static = oracle_mod.for_metric(m, is_static=True)
+        for _ in range(4):
+            pos = rng.uniform(1.5, 3.0, 4)
+            vel = rng.uniform(-1, 1, 4)
+            e = m.eval_symbolic(pos, vel)                                    # ... against the float64 symbolic evaluation
+            for o in (orc, orc_static):
+                g, dg = o.metric_eval(pos.astype(np.float32))
+                a = o.accel(pos.astype(np.float32), vel.astype(np.float32))
+                assert np.allclose(g, e["g"], rtol=2e-5, atol=2e-5) and np.allclose(dg, e["dg"], rtol=2e-4, atol=2e-4)
+                assert np.allclose(a["lowered"], e["accel"], rtol=5e-4, atol=5e-4) and np.allclose(a["ref"], e["accel_ref"], rtol=5e-4, atol=5e-4)
+        before = list(packed)
+        m.set_param("k", 0.7 + 0.2 * trial)                                  # a parameter change re-evaluates the derived values
+        m.set_param("m", 0.55 - 0.1 * trial)
+        packed = m.packed_params
+        assert packed[:3] == m.params and packed[3:] != before[3:]
+
+
+def test_metrics_with_few_parameter_operations_have_no_derived_block(content):
+    for name in ["kerr_schild", "alcubierre", "schwarzschild", "double_schwarzschild"]:
+        m = content.load_by_name(name)
+        assert m.packed_params == m.params
+        assert "grt_d0" not in m.source(False)
