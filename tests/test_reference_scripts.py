@@ -180,3 +180,28 @@ def test_coordinate_and_origin_scripts_match_quickjs(grt, oracle_mod, have_refer
             assert np.allclose(sym["distance"], dist, rtol=1e-9, atol=1e-9, equal_nan=True), (origins[i % 2], sym["distance"], dist)
             checked += 1
     assert checked == 40
+
+
+@pytest.mark.parametrize("name", ["double_unequal_kerr", "double_kerr"])
+def test_double_kerr_family_with_derived_parameters(grt, oracle_mod, have_reference, name):
+    """BASELINE config 5's metric family: a quarter of the script's algebra depends on the parameters alone and travels as derived
+    parameters.  The emitted fp32 functions fed with the packed block agree with the float64 symbolic evaluation,
+    and a parameter change moves both together."""
+    if not have_reference:
+        pytest.skip("reference not mounted")
+    c = grt.Content(REFERENCE_SCRIPTS)
+    m = c.load_by_name(name)
+    assert len(m.packed_params) > len(m.params)
+    rng = np.random.default_rng(21)
+    for trial in range(2):
+        orc = oracle_mod.for_metric(m)
+        for _ in range(4):
+            pos = rng.uniform(0.7, 2.6, 4)
+            vel = rng.uniform(-1, 1, 4)
+            vel[0] = -1
+            e = m.eval_symbolic(pos, vel)
+            g, dg = orc.metric_eval(pos.astype(np.float32))
+            a = orc.accel(pos.astype(np.float32), vel.astype(np.float32))
+            for got, want in [(g, e["g"]), (dg, e["dg"]), (a["lowered"], e["accel"]), (a["ref"], e["accel_ref"])]:
+                assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+        m.set_param(0, m.params[0] * 1.2)
