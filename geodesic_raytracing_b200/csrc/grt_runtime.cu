@@ -23,6 +23,7 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -331,6 +332,7 @@ struct grt_metric {
     std::unique_ptr<grt::Metric> m;
     std::string source[2];
     std::string compile_log;
+    std::mutex text_mutex;   // guards source[] / compile_log: the returned pointers stay valid while the text is unchanged
 };
 
 // Everything one frame in flight owns.  Two slots alternate (the reference keeps two render_state
@@ -969,7 +971,14 @@ const char* grt_metric_name(const grt_metric* m) { return m ? m->m->cfg.name.c_s
 const char* grt_metric_description(const grt_metric* m) { return m ? m->m->cfg.description.c_str() : nullptr; }
 const char* grt_metric_source(grt_metric* m, int is_static) {
     if (!m) return nullptr;
-    int rc = guard([&] { m->source[is_static ? 1 : 0] = grt::emit_metric_source(*m->m, is_static != 0); return GRT_OK; });
+    // concurrent callers (build() compiles the program and the checker of one metric in parallel) must not see a string being
+    // reassigned: emit outside the lock, replace the stored text only when it really changed
+    int rc = guard([&] {
+        std::string text = grt::emit_metric_source(*m->m, is_static != 0);
+        std::lock_guard<std::mutex> lock(m->text_mutex);
+        if (m->source[is_static ? 1 : 0] != text) m->source[is_static ? 1 : 0] = std::move(text);
+        return GRT_OK;
+    });
     return rc == GRT_OK ? m->source[is_static ? 1 : 0].c_str() : nullptr;
 }
 
@@ -1030,7 +1039,10 @@ int grt_compile_metric(grt_metric* m, int is_static, int fast_math, const char**
         if (k != std::string::npos) stem = stem.substr(k + 1);
         k = stem.find_last_of('.');
         if (k != std::string::npos) stem = stem.substr(0, k);
-        compile_cubin(program_source(*m->m, is_static != 0, false), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &m->compile_log, nullptr);
+        std::string log;
+        compile_cubin(program_source(*m->m, is_static != 0, false), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &log, nullptr);
+        std::lock_guard<std::mutex> lock(m->text_mutex);
+        if (m->compile_log != log) m->compile_log = std::move(log);
         if (log_out) *log_out = m->compile_log.c_str();
         return GRT_OK;
     });
