@@ -349,6 +349,7 @@ struct FrameSlot {
     GrtCamera* d_cam = nullptr;
     std::vector<cudaEvent_t> events;
     GrtFrame frame{};
+    GrtCamera cam_staging{};   // pageable source of this slot's camera upload (copied to the driver's staging at the call)
     int last_first_pass = 0, last_extra = 0, last_pw = 0, last_ph = 0;
     bool last_prepass = false;
     bool used = false;
@@ -393,6 +394,7 @@ struct grt_ctx {
     int geo_count = 0;
     float4 geo_speed = make_float4(0, 0, 0, 0);
     int geo_parallel_transport = 1;
+    GrtCamera geo_cam_host{};    // the interpolated camera, read back by grt_set_camera_on_geodesic
 
     std::string launch_log, kernel_info;
 
@@ -612,7 +614,11 @@ void upload_camera(grt_ctx* c, Launcher& L) {
 // attached to a geodesic is copied from the master, which handle_interpolating_geodesic wrote
 void frame_camera(grt_ctx* c, FrameSlot& S, Launcher& L) {
     if (c->camera_on_geodesic) {
-        CK(cudaMemcpyAsync(S.d_cam, c->d_cam, sizeof(GrtCamera), cudaMemcpyDeviceToDevice, S.stream));
+        // the camera state handle_interpolating_geodesic produced, snapshotted on the host when it was computed: a frame queued
+        // now keeps this camera even if the master camera moves along the path before the frame runs (the reference keeps a
+        // camera buffer per render_state, render_state.hpp)
+        S.cam_staging = c->geo_cam_host;
+        CK(cudaMemcpyAsync(S.d_cam, &S.cam_staging, sizeof(GrtCamera), cudaMemcpyHostToDevice, S.stream));
         return;
     }
     CK(cudaMemcpyAsync(S.d_cam, &c->cam, sizeof(GrtCamera), cudaMemcpyHostToDevice, S.stream));
@@ -1328,7 +1334,8 @@ int grt_set_camera_on_geodesic(grt_ctx* c, float proper_time) {
         float4* vel_out = nullptr;
         void* a[] = {&c->d_cam, &c->geo, &proper_time, &pt, &vel_out, c->params};
         L.go(c->prog->k_geodesic_interpolate, 1, 32, a);
-        CK(cudaStreamSynchronize(c->stream));   // frames copy the master camera on their own streams
+        CK(cudaMemcpyAsync(&c->geo_cam_host, c->d_cam, sizeof(GrtCamera), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // frames upload this host copy on their own streams (frame_camera)
         c->camera_on_geodesic = true;
         return GRT_OK;
     });

@@ -91,12 +91,15 @@ class Oracle:
     _rdata_dtype = ORACLE_RENDER_DATA_DTYPE
     _lightray_dtype = ORACLE_LIGHTRAY_DTYPE
 
-    def __init__(self, metric_source: str, name: str, params: Sequence[float] = (), native: bool = False):
+    def __init__(self, metric_source: str, name: str, params: Sequence[float] = (), native: bool = False, threads: int = 0):
+        """`threads` > 0 sets the OpenMP thread count explicitly (a launcher such as torchrun exports OMP_NUM_THREADS=1)."""
         self.path = self._build(metric_source, name, native)
         L = C.CDLL(self.path)
         self.lib = L
-        for fn in ("info", "frame", "integrate_sample", "metric_eval", "tetrad_at", "geodesic_snapshot", "geodesic_interpolate"):   # one binding for both libraries
+        for fn in ("info", "set_threads", "frame", "frame_window", "integrate_sample", "metric_eval", "tetrad_at", "geodesic_snapshot", "geodesic_interpolate"):   # one binding for both libraries
             setattr(L, "oracle_" + fn, getattr(L, self._prefix + fn))
+        if threads:
+            L.oracle_set_threads(int(threads))
         info = (C.c_int * 16)()
         L.oracle_info(info)
         self._info_raw = list(info)
@@ -107,6 +110,7 @@ class Oracle:
         self.params = np.zeros(256, np.float32)
         self.params[:len(params)] = params
         L.oracle_frame.argtypes = [C.POINTER(OracleFrameArgs), C.POINTER(OracleFrameOut)]
+        L.oracle_frame_window.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OracleFrameOut)]
         L.oracle_integrate_sample.argtypes = [C.POINTER(OracleFrameArgs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
 
@@ -172,6 +176,23 @@ class Oracle:
             "t_integrate_s": o.t_integrate_s, "t_total_s": o.t_total_s, "t_render_s": o.t_render_s,
             "camera_generic": np.array(list(o.camera_generic), np.float32), "tetrad": np.array(list(o.tetrad), np.float32).reshape(4, 4),
         }
+
+    def frame_window(self, width, height, window, features, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678), background=None, background2=None, **kw):
+        """The window (x0, y0, x1, y1) of the width x height frame: same values as the full frame inside the window, but only the rays the
+        window depends on are integrated (the 1/16 prepass runs in full).  Returns window-sized `image` and `rdata`."""
+        x0, y0, x1, y1 = window
+        a = self._args(width, height, features, camera_pos, camera_quat, bg1=background, bg2=background2, **kw)
+        o = OracleFrameOut()
+        ww, wh = x1 - x0, y1 - y0
+        image = np.zeros((wh, ww, 4), np.float32) if background is not None else None
+        rdata = np.zeros(ww * wh, self._rdata_dtype)
+        o.image = image.ctypes.data if image is not None else None
+        o.rdata = rdata.ctypes.data
+        rc = self.lib.oracle_frame_window(C.byref(a), x0, y0, x1, y1, C.byref(o))
+        assert rc == 0, rc
+        return {"image": image, "rdata": rdata.reshape(wh, ww), "trial_steps": o.trial_steps, "rays_traced": o.rays_traced, "extra_rays": o.extra_rays,
+                "t_integrate_s": o.t_integrate_s, "t_total_s": o.t_total_s,
+                "camera_generic": np.array(list(o.camera_generic), np.float32), "tetrad": np.array(list(o.tetrad), np.float32).reshape(4, 4)}
 
     def integrate_sample(self, width, height, features, x0, y0, cw, ch, stride=1, camera_pos=(0, 0, -4, 0), camera_quat=(-0.70710678, 0, 0, 0.70710678)):
         a = self._args(width, height, features, camera_pos, camera_quat)
@@ -292,8 +313,8 @@ class ClReference(Oracle):
             raise FileNotFoundError(f"no prebuilt oracle/_ref/libclref_{name}_*.so for this metric source and /root/reference is not mounted")
         return so
 
-    def __init__(self, metric_source, name, params=(), native=False):
-        super().__init__(metric_source, name, params, native)
+    def __init__(self, metric_source, name, params=(), native=False, threads=0):
+        super().__init__(metric_source, name, params, native, threads)
         assert self._info_raw[11] == 1, "feature block layout mismatch"
 
     def step_verlet(self, pos, vel, acc, ds, features):
@@ -312,14 +333,14 @@ def _stem(metric) -> str:
     return os.path.splitext(os.path.basename(metric.name.replace(" ", "_").replace("(", "").replace(")", "")))[0]
 
 
-def for_metric(metric, is_static: bool = False, native: bool = False) -> Oracle:
+def for_metric(metric, is_static: bool = False, native: bool = False, threads: int = 0) -> Oracle:
     """Oracle for a geodesic_raytracing_b200.Metric (same generated functions as the CUDA program)."""
-    return Oracle(metric.source(is_static), _stem(metric) + ("_static" if is_static else ""), metric.packed_params, native)
+    return Oracle(metric.source(is_static), _stem(metric) + ("_static" if is_static else ""), metric.packed_params, native, threads)
 
 
-def reference_for_metric(metric, native: bool = False) -> ClReference:
+def reference_for_metric(metric, native: bool = False, threads: int = 0) -> ClReference:
     """The reference's own cl.cl kernels (oracle/_ref) for a geodesic_raytracing_b200.Metric."""
-    return ClReference(metric.source(False), _stem(metric), metric.packed_params, native)
+    return ClReference(metric.source(False), _stem(metric), metric.packed_params, native, threads)
 
 
 class QuickJSReference:

@@ -85,6 +85,15 @@ void oracle_info(int* out) {
 #endif
 }
 
+// bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: the thread count is set explicitly
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void oracle_metric_eval(const float* pos, const float* params, float* g16, float* dg64) {
     grt_params cfg = to_params(params);
     calculate_metric_big(from_arr(pos), g16, cfg);
@@ -141,11 +150,31 @@ void oracle_mip_level(const uint8_t* rgba, int w, int h, int level, uint8_t* out
     }
 }
 
-int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
+// `win` = {x0, y0, x1, y1}: only the rays a window of the frame depends on are integrated (the window grown by 6 pixels: Jacobian
+// +1, interpolation +2, refine stencil +-1 cell), the 1/16 prepass runs in full, and o->image / o->rdata receive the window only.
+// Inside the window every value equals that of the full frame - this is how frames of the BASELINE sizes are compared.
+static int frame_impl(const OracleFrameArgs* a, OracleFrameOut* o, const int* win) {
     const int width = a->width, height = a->height;
+    int ex0 = 0, ey0 = 0, ex1 = width, ey1 = height;
+    if (win) {
+        ex0 = std::max(0, (win[0] - 6) & ~1); ey0 = std::max(0, (win[1] - 6) & ~1);
+        ex1 = std::min(width, (win[2] + 7) & ~1); ey1 = std::min(height, (win[3] + 7) & ~1);
+    }
+    auto in_ext = [&](const lightray& r) { return r.sx >= ex0 && r.sx < ex1 && r.sy >= ey0 && r.sy < ey1; };
     Features dfg = to_features(a->features);
     grt_params cfg = to_params(a->params);
     double t_start = now_s();
+    // integrate the rays of `all` that lie in the extended window (all of them for a full frame)
+    auto integrate = [&](lightray* all, int count, Counters* cnt) -> int {
+        if (!win) { do_generic_rays(all, count, cfg, dfg, cnt); return count; }
+        std::vector<int> idx;
+        for (int i = 0; i < count; i++) if (in_ext(all[i])) idx.push_back(i);
+        std::vector<lightray> sub(idx.size());
+        for (size_t i = 0; i < idx.size(); i++) sub[i] = all[idx[i]];
+        do_generic_rays(sub.data(), (int)sub.size(), cfg, dfg, cnt);
+        for (size_t i = 0; i < idx.size(); i++) all[idx[i]] = sub[i];
+        return (int)sub.size();
+    };
 
     // camera (main.cpp:2244-2331)
     float4 camera_quat = from_arr(a->camera_quat);
@@ -187,9 +216,8 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
                                       0, e, cfg, dfg, 0);
     o->t_init_s = now_s() - t0 - o->t_integrate_s;
     double ti = now_s();
-    do_generic_rays(rays.data(), ray_count, cfg, dfg, &cnt);
+    o->rays_traced += integrate(rays.data(), ray_count, &cnt);
     o->t_integrate_s += now_s() - ti;
-    o->rays_traced += ray_count;
 
     std::vector<render_data> rdata((size_t)width * height);
     memset(rdata.data(), 0, sizeof(render_data) * rdata.size());
@@ -206,16 +234,19 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
         int extra_count = handle_adaptive_sampling(rays.data(), rdata.data(), extra.data(), camera_generic, camera_quat, e, width, height, cfg, dfg);
         o->t_adaptive_s = now_s() - t2;
         double t3 = now_s();
-        do_generic_rays(extra.data(), extra_count, cfg, dfg, &cnt);
+        int extra_traced = integrate(extra.data(), extra_count, &cnt);
         o->t_integrate_s += now_s() - t3;
         double t4 = now_s();
         calculate_render_data(extra.data(), extra_count, rdata.data(), width, height, cfg, dfg);
         o->t_render_data_s += now_s() - t4;
-        o->extra_rays = extra_count;
-        o->rays_traced += extra_count;
+        o->extra_rays = win ? extra_traced : extra_count;
+        o->rays_traced += extra_traced;
     }
-    if (o->rays) memcpy(o->rays, rays.data(), sizeof(lightray) * (size_t)ray_count);
-    if (o->rdata) memcpy(o->rdata, rdata.data(), sizeof(render_data) * rdata.size());
+    if (o->rays && !win) memcpy(o->rays, rays.data(), sizeof(lightray) * (size_t)ray_count);
+    if (o->rdata && !win) memcpy(o->rdata, rdata.data(), sizeof(render_data) * rdata.size());
+    const int wx0 = win ? win[0] : 0, wy0 = win ? win[1] : 0, wx1 = win ? win[2] : width, wy1 = win ? win[3] : height, ww = wx1 - wx0;
+    if (o->rdata && win)
+        for (int y = wy0; y < wy1; y++) memcpy(o->rdata + (size_t)(y - wy0) * ww, rdata.data() + (size_t)y * width + wx0, sizeof(render_data) * (size_t)ww);
 
     o->t_render_s = 0;
     if (o->image && a->bg1) {
@@ -228,10 +259,12 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
         (void)t5;
         // the framebuffer is cleared to nothing in the reference; every pixel id is written by `render`
 #pragma omp parallel for schedule(dynamic, 256)
-        for (int id = 0; id < width * height; id++) {
+        for (int k = 0; k < ww * (wy1 - wy0); k++) {
+            int id = (wy0 + k / ww) * width + wx0 + k % ww;
             int sx, sy;
             float4 px = render_pixel(rdata.data(), id, bg1, *bg2, width, height, a->max_probes, dfg, &sx, &sy);
-            float* dst = o->image + ((size_t)sy * width + sx) * 4;
+            if (sx < wx0 || sx >= wx1 || sy < wy0 || sy >= wy1) continue;   // (a record that was never written names pixel 0,0)
+            float* dst = o->image + ((size_t)(sy - wy0) * ww + (sx - wx0)) * 4;
             dst[0] = px.x; dst[1] = px.y; dst[2] = px.z; dst[3] = px.w;
         }
         o->t_render_s = now_s() - t6;
@@ -240,6 +273,13 @@ int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
     o->accepted_steps = cnt.accepted_steps;
     o->t_total_s = now_s() - t_start;
     return 0;
+}
+
+int oracle_frame(const OracleFrameArgs* a, OracleFrameOut* o) { return frame_impl(a, o, nullptr); }
+int oracle_frame_window(const OracleFrameArgs* a, int x0, int y0, int x1, int y1, OracleFrameOut* o) {
+    if (x0 < 0 || y0 < 0 || x1 > a->width || y1 > a->height || x1 <= x0 || y1 <= y0) return -1;
+    const int win[4] = {x0, y0, x1, y1};
+    return frame_impl(a, o, win);
 }
 
 // Bounded CPU-baseline sample: trace cw x ch rays at pixels (x0 + i*stride, y0 + j*stride) of the full

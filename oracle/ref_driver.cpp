@@ -97,11 +97,25 @@ template <typename F> void launch_1d(size_t gsize, size_t wgs, long long* steps,
     }
     if (steps) *steps += total;
 }
-template <typename F> void launch_2d(size_t gx, size_t gy, size_t lx, size_t ly, F&& body) {
+// a chosen subset of the work-items of a 1-D launch of global size gsize (id_of maps 0..count-1 to global ids)
+template <typename M, typename F> void launch_1d_ids(size_t count, size_t gsize, size_t wgs, M&& id_of, F&& body) {
+    size_t n = (gsize + wgs - 1) / wgs * wgs;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long k = 0; k < (long long)count; k++) {
+        size_t id = id_of((size_t)k);
+        clshim::work_item.gid[0] = id; clshim::work_item.gid[1] = 0;
+        clshim::work_item.lid[0] = id % wgs; clshim::work_item.grp[0] = id / wgs;
+        clshim::work_item.gsz[0] = n; clshim::work_item.lsz[0] = wgs;
+        body();
+    }
+}
+// 2-D launch; only the work-items with x0 <= gid0 < x1, y0 <= gid1 < y1 are run (the whole range by default)
+template <typename F> void launch_2d(size_t gx, size_t gy, size_t lx, size_t ly, size_t x0, size_t y0, size_t x1, size_t y1, F&& body) {
     size_t nx = (gx + lx - 1) / lx * lx, ny = (gy + ly - 1) / ly * ly;
+    x1 = std::min(x1, nx); y1 = std::min(y1, ny);
 #pragma omp parallel for schedule(dynamic, 1)
-    for (long long y = 0; y < (long long)ny; y++)
-        for (size_t x = 0; x < nx; x++) {
+    for (long long y = (long long)y0; y < (long long)y1; y++)
+        for (size_t x = x0; x < x1; x++) {
             clshim::work_item.gid[0] = x; clshim::work_item.gid[1] = (size_t)y;
             clshim::work_item.lid[0] = x % lx; clshim::work_item.lid[1] = (size_t)y % ly;
             clshim::work_item.grp[0] = x / lx; clshim::work_item.grp[1] = (size_t)y / ly;
@@ -184,6 +198,15 @@ void clref_info(int* out) {
     out[11] = clref_sizeof_features() == (int)sizeof(FeatureBlock);
 }
 
+// bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: the thread count is set explicitly
+void clref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 struct CameraState { Buf<float4> generic{1}, quat{1}, e0{1}, e1{1}, e2{1}, e3{1}; };
 
 static void setup_camera(const OracleFrameArgs* a, const dynamic_config* cfg, CameraState& c) {
@@ -204,8 +227,16 @@ static void setup_camera(const OracleFrameArgs* a, const dynamic_config* cfg, Ca
 }
 
 // One frame, main.cpp:2356-2526 (triangle rendering off).
-int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
+// `win` = {x0, y0, x1, y1}: a window of the frame (see oracle_capi.cpp frame_impl) - the same kernels, but only the rays the window
+// depends on go through do_generic_rays, handle_adaptive_sampling and render are enqueued over the window's sub-range of work-items,
+// and o->image / o->rdata receive the window only.  This is how frames of the BASELINE sizes are produced in seconds.
+static int frame_impl(const OracleFrameArgs* a, OracleFrameOut* o, const int* win) {
     const int width = a->width, height = a->height;
+    int ex0 = 0, ey0 = 0, ex1 = width, ey1 = height;
+    if (win) {
+        ex0 = std::max(0, (win[0] - 6) & ~1); ey0 = std::max(0, (win[1] - 6) & ~1);
+        ex1 = std::min(width, (win[2] + 7) & ~1); ey1 = std::min(height, (win[3] + 7) & ~1);
+    }
     const size_t LR = (size_t)clref_sizeof_lightray(), RD = (size_t)clref_sizeof_render_data();
     double t_start = now_s();
     Buf<float> cfg_buf(256);
@@ -229,12 +260,30 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
     o->rays_traced = 0; o->t_integrate_s = 0; o->extra_rays = 0; o->t_adaptive_s = 0; o->t_render_s = 0;
     const size_t wg = 64;   // workgroup_size 8x8 (graphics_settings.hpp:42)
 
-    auto execute_kernel = [&](char* rays, int* count) {   // main.cpp:139-205; global size {width*height}
+    long long last_traced = 0;
+    auto execute_kernel = [&](char* rays, int* count, bool windowed) {   // main.cpp:139-205; global size {width*height}
         memset(stored_ray_counts.p, 0, sizeof(int) * npx);
         double t = now_s();
-        launch_1d(npx, wg, &steps, [&] { do_generic_rays((lightray*)rays, count, tmin.p, tmax.p, cfg, dfg, width, height, 0, 0, nullptr, stored_ray_counts.p, 0); });
+        if (!windowed) {
+            launch_1d(npx, wg, &steps, [&] { do_generic_rays((lightray*)rays, count, tmin.p, tmax.p, cfg, dfg, width, height, 0, 0, nullptr, stored_ray_counts.p, 0); });
+            last_traced = *count;
+        } else {
+            // gather the rays of the extended window (lightray::sx, sy at bytes 76, 80: cl.cl:813-824), run the kernel on them, scatter back
+            std::vector<int> idx;
+            for (int i = 0; i < *count; i++) {
+                int sx = *(const int*)(rays + (size_t)i * LR + 76), sy = *(const int*)(rays + (size_t)i * LR + 80);
+                if (sx >= ex0 && sx < ex1 && sy >= ey0 && sy < ey1) idx.push_back(i);
+            }
+            RawBuf sub(idx.size(), LR);
+            Buf<int> sub_count(1);
+            for (size_t i = 0; i < idx.size(); i++) memcpy(sub.p + i * LR, rays + (size_t)idx[i] * LR, LR);
+            *sub_count.p = (int)idx.size();
+            launch_1d(idx.size(), wg, &steps, [&] { do_generic_rays((lightray*)sub.p, sub_count.p, tmin.p, tmax.p, cfg, dfg, width, height, 0, 0, nullptr, stored_ray_counts.p, 0); });
+            for (size_t i = 0; i < idx.size(); i++) memcpy(rays + (size_t)idx[i] * LR, sub.p + i * LR, LR);
+            last_traced = (long long)idx.size();
+        }
         o->t_integrate_s += now_s() - t;
-        o->rays_traced += *count;
+        o->rays_traced += last_traced;
     };
 
     double t0 = now_s();
@@ -247,7 +296,7 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
             init_rays_generic(cam.generic.p, cam.quat.p, (lightray*)rays_in.p, rays_count_in.p, prepass_width, prepass_height, termination_buffer.p, prepass_width,
                               prepass_height, isnap, cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, cfg, dfg, 1);
         });
-        execute_kernel(rays_in.p, rays_count_in.p);
+        execute_kernel(rays_in.p, rays_count_in.p, false);
         launch_1d(np, 256, nullptr, [&] { calculate_singularities((const lightray*)rays_in.p, rays_count_in.p, termination_buffer.p, prepass_width, prepass_height); });
     }
     if (o->termination) memcpy(o->termination, termination_buffer.p, sizeof(int) * (size_t)prepass_width * prepass_height);
@@ -257,7 +306,7 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
                           cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, cfg, dfg, 0);
     });
     o->t_init_s = now_s() - t0 - o->t_integrate_s;
-    execute_kernel(rays_in.p, rays_count_in.p);
+    execute_kernel(rays_in.p, rays_count_in.p, win != nullptr);
 
     *render_data_count.p = 0;
     double t1 = now_s();
@@ -267,12 +316,12 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
     if (a->features.adaptive_sampling) {   // main.cpp:2478-2511
         *rays_adaptive_count.p = 0;
         double t2 = now_s();
-        launch_2d((size_t)width / 2, (size_t)height / 2, 8, 8, [&] {
+        launch_2d((size_t)width / 2, (size_t)height / 2, 8, 8, (size_t)ex0 / 2, (size_t)ey0 / 2, (size_t)ex1 / 2, (size_t)ey1 / 2, [&] {
             handle_adaptive_sampling((const lightray*)rays_in.p, rays_count_in.p, (render_data*)rdata.p, render_data_count.p, (lightray*)rays_adaptive.p,
                                      rays_adaptive_count.p, cam.generic.p, cam.quat.p, cam.e0.p, cam.e1.p, cam.e2.p, cam.e3.p, width, height, cfg, dfg);
         });
         o->t_adaptive_s = now_s() - t2;
-        execute_kernel(rays_adaptive.p, rays_adaptive_count.p);
+        execute_kernel(rays_adaptive.p, rays_adaptive_count.p, false);   // every appended ray comes from a cell of the window
         double t4 = now_s();
         launch_1d(npx, 256, nullptr, [&] {
             calculate_render_data((const lightray*)rays_adaptive.p, rays_adaptive_count.p, (render_data*)rdata.p, render_data_count.p, width, height, cfg, dfg);
@@ -280,8 +329,11 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
         o->t_render_data_s += now_s() - t4;
         o->extra_rays = *rays_adaptive_count.p;
     }
-    if (o->rays) memcpy(o->rays, rays_in.p, LR * (size_t)*rays_count_in.p);
-    if (o->rdata) memcpy(o->rdata, rdata.p, RD * npx);
+    if (o->rays && !win) memcpy(o->rays, rays_in.p, LR * (size_t)*rays_count_in.p);
+    if (o->rdata && !win) memcpy(o->rdata, rdata.p, RD * npx);
+    const int wx0 = win ? win[0] : 0, wy0 = win ? win[1] : 0, wx1 = win ? win[2] : width, wy1 = win ? win[3] : height, ww = wx1 - wx0, wh = wy1 - wy0;
+    if (o->rdata && win)
+        for (int y = wy0; y < wy1; y++) memcpy((char*)o->rdata + (size_t)(y - wy0) * ww * RD, rdata.p + ((size_t)y * width + wx0) * RD, RD * (size_t)ww);
 
     if (o->image && a->bg1) {   // main.cpp:2513-2525
         oracle::MipImage m1 = oracle::build_mip_image(a->bg1, a->bg1_w, a->bg1_h);
@@ -292,15 +344,31 @@ int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) {
             l2 = padded_layers(m2);
             i2 = image2d_array_t{l2.data(), m2.width, m2.height, m2.levels};
         }
-        image2d_t out{o->image, width, height};
         double t6 = now_s();
-        launch_1d(npx, 256, nullptr, [&] { render((const render_data*)rdata.p, render_data_count.p, out, i1, i2, width, height, a->max_probes, cfg, dfg); });
+        if (!win) {
+            image2d_t out{o->image, width, height};
+            launch_1d(npx, 256, nullptr, [&] { render((const render_data*)rdata.p, render_data_count.p, out, i1, i2, width, height, a->max_probes, cfg, dfg); });
+        } else {
+            // render writes pixel (sx, sy) of its record: give it the full-size target, enqueue only the window's work-items, copy the window out
+            std::vector<float> full((size_t)npx * 4, 0.f);
+            image2d_t out{full.data(), width, height};
+            launch_1d_ids((size_t)ww * wh, npx, 256, [&](size_t k) { return (size_t)(wy0 + k / ww) * width + wx0 + k % ww; },
+                          [&] { render((const render_data*)rdata.p, render_data_count.p, out, i1, i2, width, height, a->max_probes, cfg, dfg); });
+            for (int y = wy0; y < wy1; y++) memcpy(o->image + (size_t)(y - wy0) * ww * 4, full.data() + ((size_t)y * width + wx0) * 4, sizeof(float) * 4 * (size_t)ww);
+        }
         o->t_render_s = now_s() - t6;
     }
     o->trial_steps = steps;
     o->accepted_steps = -1;   // the reference does not count them
     o->t_total_s = now_s() - t_start;
     return 0;
+}
+
+int clref_frame(const OracleFrameArgs* a, OracleFrameOut* o) { return frame_impl(a, o, nullptr); }
+int clref_frame_window(const OracleFrameArgs* a, int x0, int y0, int x1, int y1, OracleFrameOut* o) {
+    if (x0 < 0 || y0 < 0 || x1 > a->width || y1 > a->height || x1 <= x0 || y1 <= y0) return -1;
+    const int win[4] = {x0, y0, x1, y1};
+    return frame_impl(a, o, win);
 }
 
 // Bounded CPU-baseline sample for bench.py: rays of the pixels (x0 + i*stride, y0 + j*stride) of the

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 import geodesic_raytracing_b200 as grt  # noqa: E402
 import oracle  # noqa: E402
 
-W, H = 64, 48
+W, H = 128, 96
 BG_W, BG_H = 512, 256
 # name -> list of (tag, feature overrides, frame kwargs)
 CASES = {
@@ -26,6 +26,7 @@ CASES = {
     "alcubierre": [("redshift", {"redshift": 1}, {})],
     "wormhole (morris-thorne)": [("flip", {}, {"flip": True})],
     "kerr_boyer": [("default", {}, {})],
+    "double_unequal_kerr": [("default", {}, {})],
 }
 
 

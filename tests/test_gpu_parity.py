@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CAM_POS = (0.0, 0.0, -4.0, 0.0)
-METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild"]
+METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr"]
 
 
 def bind(gpu_ctx, metric, background, **features):
@@ -108,7 +108,7 @@ def compare_frame(gpu_ctx, metric, orc, background, w, h, min_term, min_px, **fe
 @pytest.mark.parametrize("adaptive", [0, 1])
 def test_frame_parity(gpu_ctx, oracles, background, name, adaptive):
     metric, orc = oracles(name)
-    compare_frame(gpu_ctx, metric, orc, background, 192, 128, 0.995, 0.99 if not adaptive else 0.97, adaptive_sampling=adaptive)
+    compare_frame(gpu_ctx, metric, orc, background, 256, 144, 0.995, 0.99, adaptive_sampling=adaptive)
 
 
 def test_minkowski_config1_is_exact_in_counts(gpu_ctx, oracles, background):
@@ -550,7 +550,7 @@ def test_frame_matches_reference_kernel_output(gpu_ctx, content, grt, name, case
     gpu_ctx.set_camera(kw.get("camera_pos", CAM_POS), kw.get("camera_quat", (-0.70710678, 0, 0, 0.70710678)), flip_r=kw.get("flip", False))
     gpu_ctx.set_observer_speed(kw.get("basis_speed", (0, 0, 0)))
     try:
-        w, h = 64, 48
+        from test_reference_kernels import W as w, H as h
         img, st = gpu_ctx.render(w, h)
         rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
     finally:
@@ -558,8 +558,7 @@ def test_frame_matches_reference_kernel_output(gpu_ctx, content, grt, name, case
         gpu_ctx.set_camera()
         gpu_ctx.set_background(bg, which=1)
     term = gold[key + "terminated"]
-    # 64x48: one pixel is 0.03 % of the frame and the shadow edge is ~2 % of it, so the bars sit a little below the 192x128 ones
-    assert (rd["terminated"] == term).mean() >= 0.985, (rd["terminated"] == term).mean()
+    assert (rd["terminated"] == term).mean() >= 0.995, (rd["terminated"] == term).mean()
     both = (rd["terminated"] == 1) & (term == 1)
     duv = np.abs(rd["tex_coord"] - gold[key + "tex_coord"])
     duv = np.minimum(duv, 1 - duv)[both]
@@ -569,7 +568,7 @@ def test_frame_matches_reference_kernel_output(gpu_ctx, content, grt, name, case
         dz = np.abs(rd["z_shift"][both] - gold[key + "z_shift"][both])
         assert (dz < 2e-3).mean() >= 0.99
     px = (np.abs(img[..., :3] - gold[key + "image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean()
-    assert px >= (0.95 if base["adaptive_sampling"] else 0.975), px
+    assert px >= 0.99, px
     steps, rays, extra = gold[key + "counts"].tolist()
     assert abs(int(st.trial_steps) - steps) <= 0.03 * steps + 64
     assert abs(int(st.extra_rays) - extra) <= 0.10 * extra + 12
@@ -638,3 +637,85 @@ def test_derived_parameters_on_the_device(gpu_ctx, oracle_mod, grt, background, 
         assert abs(int(st.trial_steps) - ref["trial_steps"]) <= 0.02 * ref["trial_steps"] + 64
         m.set_param("m", 0.3)          # smaller mass: the derived values change, the program does not
         m.set_param("k", 0.9)
+
+
+# ---- BASELINE.json configs 2-5 at their REAL sizes against the reference's own kernels ------------------------------------------
+# tests/golden/clref_windows.npz: windows of the 1920x1080 / 3840x2160 frames rendered by /root/reference/cl.cl itself (compiled as
+# C++ for the host; generator tests/golden/make_clref_windows.py) in the reference's default operating mode.  The CUDA path renders
+# the WHOLE frame at the real size; every window is compared with the bars of BASELINE.md: `terminated` >= 99.5 %, texture
+# coordinates of commonly finished pixels within 1e-3 for >= 99 %, linear RGB within 2/255 on >= 99 % of the pixels.
+@pytest.mark.parametrize("key", ["config2", "config3", "config4", "config5"])
+def test_real_size_frames_match_reference_kernel_windows(gpu_ctx, content, grt, key):
+    from test_reference_kernels import load_windows
+    z, meta = load_windows()
+    rec = meta[key]
+    metric = content.load_by_name(rec["metric"])
+    w, h = rec["size"]
+    bg = grt.synthetic_background(*rec["background"])
+    bind(gpu_ctx, metric, bg, **rec["features"])
+    gpu_ctx.set_background(bg[::-1].copy(), which=1)
+    try:
+        if "geodesic" in rec:
+            n = gpu_ctx.snapshot_geodesic(rec["geodesic"]["speed"], True)
+            assert n > 10
+            gpu_ctx.set_camera_on_geodesic(rec["geodesic"]["tau"])
+            cs = gpu_ctx.camera_state()
+            assert np.allclose(np.array(list(cs.pos_generic)), z[f"{key}|camera"], atol=5e-3)
+            assert np.allclose(np.array(list(cs.tetrad)).reshape(4, 4), z[f"{key}|tetrad"], atol=5e-3)
+        img, st = gpu_ctx.render(w, h)
+        rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
+    finally:
+        gpu_ctx.clear_camera_geodesic()
+        gpu_ctx.set_background(bg, which=1)
+    assert int(st.trial_steps) > 0
+    n_px = n_term = n_img = n_both = n_uv = 0
+    for i, (x0, y0, x1, y1) in enumerate(rec["windows"]):
+        k = f"{key}|{i}|"
+        term = z[k + "terminated"].astype(np.int32)
+        got = rd[y0:y1, x0:x1]
+        same = got["terminated"] == term
+        both = (got["terminated"] == 1) & (term == 1)
+        duv = np.abs(got["tex_coord"] - z[k + "tex_coord"])
+        duv = np.minimum(duv, 1 - duv)[both].max(axis=-1) if both.any() else np.zeros(0)
+        px = np.abs(img[y0:y1, x0:x1, :3] - z[k + "image"][..., :3]).max(axis=-1) <= 2.0 / 255.0
+        if both.any():
+            assert np.array_equal(got["side"][both], z[k + "side"].astype(np.int32)[both]), (key, i)
+            assert (np.abs(got["z_shift"][both] - z[k + "z_shift"][both]) < 2e-3).mean() >= 0.99, (key, i)
+        # every window on its own: a bar just below the pooled one (a 128x64 window across the shadow edge is mostly edge)
+        assert same.mean() >= 0.99, (key, i, "terminated", same.mean())
+        assert px.mean() >= 0.98, (key, i, "pixels", px.mean())
+        n_px += same.size; n_term += int(same.sum()); n_img += int(px.sum()); n_both += int(both.sum()); n_uv += int((duv < 1e-3).sum())
+    assert n_term / n_px >= 0.995, ("terminated", n_term / n_px)
+    assert n_img / n_px >= 0.99, ("pixels within 2/255", n_img / n_px)
+    assert n_both == 0 or n_uv / n_both >= 0.99, ("uv within 1e-3", n_uv / n_both)
+
+
+def test_queued_frame_keeps_its_geodesic_camera(gpu_ctx, oracles, background):
+    """A frame queued asynchronously with the camera at proper time t1 must not see the camera move to t2 afterwards (the reference
+    keeps one camera buffer per render_state): it equals the frame rendered synchronously at t1."""
+    import torch
+
+    metric, _ = oracles("alcubierre")
+    bind(gpu_ctx, metric, background, adaptive_sampling=0, redshift=1)
+    n = gpu_ctx.snapshot_geodesic(0.3, True)
+    assert n > 10
+    w, h = 512, 288
+    t1, t2 = 0.5, 6.0
+    try:
+        gpu_ctx.set_camera_on_geodesic(t1)
+        want1, _ = gpu_ctx.render(w, h)
+        gpu_ctx.set_camera_on_geodesic(t2)
+        want2, _ = gpu_ctx.render(w, h)
+        assert not np.array_equal(want1, want2)
+        gpu_ctx.set_frames_in_flight(4)
+        outs = [torch.empty((h, w, 4), dtype=torch.float32, device="cuda:0") for _ in range(6)]
+        for i, o in enumerate(outs):                       # alternate: queue a frame, move the camera at once
+            gpu_ctx.set_camera_on_geodesic(t1 if i % 2 == 0 else t2)
+            gpu_ctx.render(w, h, out=o, stats=False)
+        gpu_ctx.set_camera_on_geodesic(3.0)
+        gpu_ctx.synchronize()
+        for i, o in enumerate(outs):
+            assert np.array_equal(o.cpu().numpy(), want1 if i % 2 == 0 else want2), i
+    finally:
+        gpu_ctx.set_frames_in_flight(2)
+        gpu_ctx.clear_camera_geodesic()

@@ -7,7 +7,7 @@ import pytest
 
 
 def test_bundled_content_lists_in_sorting_order(content):
-    assert content.metric_names() == ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild"]
+    assert content.metric_names() == ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr"]
 
 
 def test_config_inheritance_and_flags(content):

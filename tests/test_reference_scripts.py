@@ -9,7 +9,7 @@ import pytest
 from conftest import REFERENCE_SCRIPTS
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_metric_vectors.json")))
-BUNDLED = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre"]
+BUNDLED = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_unequal_kerr"]
 
 
 def check_against_golden(metric, orc, rec, rtol=3e-5):
