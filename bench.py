@@ -5,17 +5,20 @@ A "step" is one frame of the hot path: camera/tetrad -> prepass -> init_rays -> 
 adaptive sampling -> integrate -> render_data -> render, in the reference's default operating mode (prepass as the
 metric's JSON asks, adaptive sampling on at threshold 32 - main.cpp:1123-1158, graphics_settings.hpp:39-40).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl reference]
 
-* value   Mray-steps/s: trial Verlet steps of the frame (SURVEY.md 8(d) unit of work) / device frame time, output and
-          all inputs resident in HBM, CUDA events on the launching stream, L2 flushed between frames.
-* e2e     the same metric with the frame delivered into pinned HOST memory through grt_render_stripes
-          (camera upload H2D, RGBA8 frame D2H, and for N > 1 the NCCL gather to rank 0, all inside the timed region).
-* N > 1   the frame is tiled in interleaved 54-row stripes over N ranks (one process per GPU, torchrun), every rank
-          traces its stripes (+ halo, + the redundant 1/16 prepass) and the finished tiles are gathered on rank 0 over
-          NCCL/NVLink; strong scaling: the work of ONE frame is fixed, value = its single-GPU step count / max-over-ranks time.
+* value   Mray-steps/s: trial Verlet steps of the frame (SURVEY.md 8(d) unit of work) / device frame time; every input
+          (background pyramid, camera, parameters) and the delivered frame stay in HBM; CUDA events on the frames' own
+          streams; frames are queued back to back with `frames_in_flight` frame slots busy.
+* e2e     the same metric with the camera uploaded (H2D) and the assembled frame delivered into pinned HOST memory on
+          rank 0 (D2H) for every frame, through grt_comm_render, host clock.
+* N > 1   the frame is tiled in interleaved 54-row stripes over N ranks (one process per GPU, torchrun). Every rank traces its
+          stripes (+ halo, + the redundant 1/16 prepass) and its render kernel stores the pixels straight into rank 0's frame over
+          NVLink (libgrt's grt_comm_*: peer-mapped frame, stream memory operations for the hand-shake, no collective kernel);
+          torch.distributed (NCCL) only carries the 64-byte IPC handles, the barriers and the max-over-ranks reductions.
+          Strong scaling: the work of ONE frame is fixed, value = its single-GPU step count / max-over-ranks time.
 * --impl reference   the reference's own integration kernel (oracle/_ref: /root/reference/cl.cl compiled as C++ for the host,
-          DESIGN.md) on all host cores, on a bounded pixel subsample of the same frame.
+          DESIGN.md) on all host cores (thread count set explicitly), on a bounded pixel subsample of the same frame.
 """
 import argparse
 import json
@@ -33,19 +36,23 @@ import numpy as np  # noqa: E402
 
 import geodesic_raytracing_b200 as grt  # noqa: E402
 
-WIDTH, HEIGHT = 3840, 2160
-METRIC_NAME = "kerr_schild"
 STRIPE_ROWS = 54
-# Frame slots the benchmark keeps busy (grt_set_frames_in_flight): enough frames to cover the latency-bound critical path of a
-# frame (prepass -> first pass -> refinement, each as long as its slowest ray) with bulk work. One frame alone takes ~45 ms on 1 GPU
-# for ~30 ms of bulk work, and ~24 ms on 8 GPUs for ~4 ms of bulk work per GPU, so the count grows with the number of GPUs.
+CAM_POS, CAM_QUAT = (0.0, 0.0, -4.0, 0.0), (-0.70710678, 0.0, 0.0, 0.70710678)
+# BASELINE.json `configs` (index = position in that list + 1; config 1 is the reference's CPU-only plumbing case)
+CONFIGS = {
+    2: dict(metric="schwarzschild", size=(1920, 1080), features={}, note="fixed camera"),
+    3: dict(metric="kerr_schild", size=(3840, 2160), features={}, note="headline config"),
+    4: dict(metric="alcubierre", size=(1920, 1080), features={"redshift": 1}, geodesic=dict(speed=0.3, tau=2.0), note="redshift + anisotropic filter on, camera attached to a geodesic"),
+    5: dict(metric="double_unequal_kerr", size=(3840, 2160), features={}, note="row-tiled over the GPUs of one box"),
+}
 _WORLD = int(os.environ.get("WORLD_SIZE", "1"))
-# measured optima (tools/gpu_sweep_bench.sh, tools/gpu_sweep_scaling.sh; profiles/round1_scaling.md): slots in flight : blocks per SM and slot
+# measured optima (tools/gpu_sweep_*.sh; profiles/round1_scaling.md, round2_*): frame slots in flight : integration blocks per SM and slot
 _DEFAULT_KNOBS = {1: (4, 3), 2: (6, 3), 4: (8, 2), 8: (8, 1)}.get(_WORLD, (min(8, 2 * _WORLD + 2), 2))
 FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(_DEFAULT_KNOBS[0])))
 BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS[1])))
-BYTES_PER_RAY = 96          # 56 B read + 40 B written per ray by the integration stage, 0 B per step
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived: SMs x lanes x FMA x clocks.max.sm (not in MEASURED_PEAKS.json)
+COMM_FRAMES = 8              # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
+BYTES_PER_RAY = 96           # 56 B read + 40 B written per ray by the integration stage, 0 B per step
+ISSUE_SLOTS_PER_CLOCK = 148 * 4   # one warp instruction per scheduler and clock
 
 
 def measured_peaks():
@@ -56,79 +63,31 @@ def measured_peaks():
 
 
 def ncu_facts():
-    """Per-launch DRAM bytes and per-step SASS instruction counts of k_integrate from the committed `ncu --set full`
-    capture of this same command (profiles/round1_ncu_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "round1_ncu_traffic.json")
-    return json.load(open(path)) if os.path.exists(path) else {}
-
-
-def fp32_microbench():
-    """FP32 pipe rate this GPU sustains on independent FFMA/FMUL chains (tools/microbench/fp32_pipes.cu, < 1 s): the
-    practical ceiling for an FP32-issue-bound kernel; MEASURED_PEAKS.json has no FP32 figure."""
-    exe = os.path.join(ROOT, "tools", "microbench", "fp32_pipes")
-    if not os.path.exists(exe):
-        return None
-    try:
-        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
-    except Exception:
-        return None
+    """Per-launch DRAM bytes, warp instructions per frame and per-step SASS instruction counts of k_integrate from the committed
+    `ncu --set full` capture of the headline command (newest profiles/round*_ncu_traffic.json)."""
     best = {}
-    for line in out.splitlines():
-        p = line.split()
-        if len(p) >= 9 and p[1] == "blocks/SM":
-            best[p[0]] = max(best.get(p[0], 0.0), float(p[6]) / 1e3)     # T lane-ops/s
-    return best or None
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+        if name.endswith("_ncu_traffic.json"):
+            best = json.load(open(os.path.join(ROOT, "profiles", name)))
+            best["file"] = "profiles/" + name
+    return best
 
 
-def workload_config(n_gpus):
+def workload_config(cfg_id, n_gpus):
+    cfg = CONFIGS[cfg_id]
+    w, h = cfg["size"]
     return {
-        "workload": f"{METRIC_NAME}.js {WIDTH}x{HEIGHT}, camera (0,0,-4,0) quat (-sin(pi/4),0,0,cos(pi/4)), fov 90, universe 20, a=-0.5 rs=1",
-        "mode": "reference defaults: prepass on (kerr_schild.json), adaptive sampling on (threshold 32), redshift off, anisotropy 8",
+        "workload": f"BASELINE config {cfg_id}: {cfg['metric']} {w}x{h} ({cfg['note']}); bundled script geodesic_raytracing_b200/content (a re-statement pinned by value against the reference's scripts/{cfg['metric']}.js, tests/golden/reference_metric_vectors.json); camera (0,0,-4,0) quat (-sin(pi/4),0,0,cos(pi/4)), fov 90, universe 20, default $cfg parameters",
+        "mode": "reference defaults: prepass as the metric's JSON asks, adaptive sampling on (threshold 32), anisotropy 8" + (", redshift on" if cfg["features"].get("redshift") else ", redshift off")
+                + (f", camera on a geodesic (speed {cfg['geodesic']['speed']}, proper time {cfg['geodesic']['tau']})" if "geodesic" in cfg else ""),
         "background": "synthetic 4096x2048 RGBA8 (the reference's nasa.png is not redistributable)",
         "out_format": "rgba8 (sRGB, the reference's screenshot encoding)",
-        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, interleaved {STRIPE_ROWS}-row stripes + halo, redundant prepass, NCCL gather to rank 0",
-        "l2": "256 MiB flush write queued before every frame; the per-frame working set (ray planes + shading records, > 260 MB) also exceeds the 126 MB L2",
-        "pipelining": f"frames are queued back to back, {FRAMES_IN_FLIGHT} in flight on the context's frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469); frame_latency_ms is the time of one frame alone",
+        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, interleaved {STRIPE_ROWS}-row stripes + halo, redundant prepass, peer stores into rank 0's frame (grt_comm_*), no collective kernel",
+        "l2": "inputs larger than L2: every frame reads and writes its slot's ray planes, work lists and shading records (> 260 MB per frame at 4K, 126 MB L2) and the frames in flight use different slots; no explicit flush",
+        "pipelining": f"frames are queued back to back, {FRAMES_IN_FLIGHT} in flight on the context's frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469); fps_at_2_in_flight and fps_latency (one frame at a time) are reported next to it",
         "integrate_blocks_per_sm_per_slot": BLOCKS_PER_SM,
         "fast_math": True,
     }
-
-
-def gather_frame(local, height, width, rank, world, stripe_rows, device, buffers=None):
-    """Gather every rank's stripes on rank 0 and reassemble the frame (rows, width, C). Returns the frame on rank 0, None elsewhere.
-    `buffers` (a dict the caller keeps per frame slot) makes the receive bucket and the frame persistent."""
-    import torch
-    import torch.distributed as dist
-
-    if world == 1:
-        return local
-    rows = [sum(b - a for a, b in grt.interleaved_stripes(height, r, world, stripe_rows)) for r in range(world)]
-    max_rows = max(rows)
-    if local.shape[0] < max_rows:
-        pad = torch.zeros((max_rows - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=device)
-        local = torch.cat([local, pad], 0)
-    buffers = buffers if buffers is not None else {}
-    if rank == 0 and "bucket" not in buffers:
-        buffers["bucket"] = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=device)
-        buffers["frame"] = torch.empty((height, width) + tuple(local.shape[2:]), dtype=local.dtype, device=device)
-    bucket = list(buffers["bucket"].unbind(0)) if rank == 0 else None
-    dist.gather(local, bucket, dst=0)
-    if rank != 0:
-        return None
-    frame = buffers["frame"]
-    n_stripes = -(-height // stripe_rows)
-    if height % stripe_rows == 0 and n_stripes % world == 0:
-        # regular interleave: stripe s = group * world + rank  ->  one strided copy
-        groups = n_stripes // world
-        src = buffers["bucket"].view(world, groups, stripe_rows, width, -1).permute(1, 0, 2, 3, 4)
-        frame.view(groups, world, stripe_rows, width, -1).copy_(src)
-    else:
-        for r in range(world):
-            row = 0
-            for (y0, y1) in grt.interleaved_stripes(height, r, world, stripe_rows):
-                frame[y0:y1] = bucket[r][row:row + (y1 - y0)]
-                row += y1 - y0
-    return frame
 
 
 class ClockSampler:
@@ -180,269 +139,351 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline_sample(stride, threads_note=True):
+def host_threads():
+    """Cores this process may use (the cgroup / affinity mask, not the machine's)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline_sample(cfg_id, stride):
     """The reference's own integration kernel (oracle/_ref: cl.cl's do_generic_rays compiled as C++ for the host, one OpenMP
-    iteration per work-item, all host cores) on a bounded subsample of the frame's rays: every `stride`-th pixel in x and y
-    of the 4K pixel grid, integration stage only (the stage that is > 90 % of a frame).  Falls back to the C++ restatement
-    (kind "port") when no oracle/_ref library was prebuilt."""
+    iteration per work-item) on a bounded subsample of the frame's rays: every `stride`-th pixel in x and y of the pixel grid,
+    integration stage only (the stage that is > 90 % of a frame).  The OpenMP thread count is set explicitly to the cores of this
+    process - a launcher such as torchrun exports OMP_NUM_THREADS=1.  Falls back to the C++ restatement (kind "port") when no
+    oracle/_ref library was prebuilt."""
     import oracle
 
+    cfg = CONFIGS[cfg_id]
     content = grt.Content(grt.CONTENT_DIR)
-    metric = content.load_by_name(METRIC_NAME)
+    metric = content.load_by_name(cfg["metric"])
+    threads = host_threads()
     try:
-        orc = oracle.reference_for_metric(metric, native=True)     # oracle/_ref: the reference's own cl.cl kernels, compiled for the host
+        orc = oracle.reference_for_metric(metric, native=True, threads=threads)     # oracle/_ref: the reference's own cl.cl kernels, compiled for the host
         orc.kind = "reference"
     except FileNotFoundError:
-        orc = oracle.for_metric(metric, native=True)               # the C++ restatement (bit-exact against oracle/_ref, tests/test_reference_kernels.py)
-        orc.kind = "port"
-    feat = orc.features(max_acceleration_change=metric.info.max_acceleration_change)
-    cw, ch = WIDTH // stride, HEIGHT // stride
-    return orc, feat, cw, ch
+        try:
+            orc = oracle.reference_for_metric(metric, threads=threads)              # the generic-ISA build of the same kernels
+            orc.kind = "reference"
+        except FileNotFoundError:
+            orc = oracle.for_metric(metric, native=True, threads=threads)           # the C++ restatement (bit-exact against oracle/_ref, tests/test_reference_kernels.py)
+            orc.kind = "port"
+    assert orc.info["threads"] == threads, (orc.info["threads"], threads)
+    feat = orc.features(max_acceleration_change=metric.info.max_acceleration_change, **cfg["features"])
+    w, h = cfg["size"]
+    return orc, feat, w // stride, h // stride
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                   # one CPU arm per job: the other ranks of a torchrun launch have nothing to add
+    cfg = CONFIGS[args.config]
+    w, h = cfg["size"]
     total = args.steps + args.warmup
     stride = 4 if total <= 4 else (8 if total <= 30 else 16)
-    orc, feat, cw, ch = cpu_baseline_sample(stride)
+    orc, feat, cw, ch = cpu_baseline_sample(args.config, stride)
     times, steps = [], 0
     for i in range(total):
-        r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
+        r = orc.integrate_sample(w, h, feat, 0, 0, cw, ch, stride)
         if i >= args.warmup:
             times.append(r["seconds"])
             steps += r["trial_steps"]
     t = sum(times)
     value = steps / t / 1e6
-    sample = f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw}x{ch} = {cw * ch} rays, {steps // max(1, args.steps)} ray-steps per step), integration stage, no prepass cull"
+    cores = orc.info["threads"]
+    sample = f"every {stride}th pixel in x and y of the {w}x{h} grid ({cw}x{ch} = {cw * ch} rays, {steps // max(1, args.steps)} ray-steps per step), integration stage, no prepass cull"
     line = {
         "impl": "reference", "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": orc.info["threads"], "per_core": value / max(1, orc.info["threads"]), "kind": orc.kind, "sample": sample},
+        "config": workload_config(args.config, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": cores, "per_core": value / max(1, cores), "kind": orc.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": ("oracle/_ref = the reference's cl.cl compiled as C++ for the host cores (g++ -O3 -march=x86-64-v3, OpenMP over work-items); no OpenCL runtime exists in this image"
+        "note": (f"oracle/_ref = the reference's cl.cl compiled as C++ for the host cores (g++ -O3 -march=x86-64-v3, OpenMP over work-items, {cores} threads set explicitly); no OpenCL runtime exists in this image. "
+                 "This arm is the integration stage alone on a pixel subsample without the prepass cull; the GPU arm's value is the whole frame (all stages) - the comparison is conservative for the GPU"
                  if orc.kind == "reference" else "C++ restatement of the reference's OpenCL kernels (no prebuilt oracle/_ref library found)"),
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    import torch
+class Job:
+    """One rank of the benchmark: context, communicator, frame submission and timing."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world != 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+    def __init__(self, args):
+        import torch
 
-    content = grt.Content(grt.CONTENT_DIR)
-    metric = content.load_by_name(METRIC_NAME)
-    ctx = grt.Context(local_rank)           # raises when libgrt.so or a B200 is missing: no fallback
-    ctx.set_fast_math(True)
-    ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
-    ctx.set_tuning(BLOCKS_PER_SM, 0)
-    ctx.set_metric(metric)
-    bg = grt.synthetic_background(4096, 2048)
-    bg_dev = torch.from_numpy(bg).to(device)
-    torch.cuda.synchronize()
-    ctx.set_background(bg_dev, 0, 4096, 2048)
-    cam_pos, cam_quat = (0.0, 0.0, -4.0, 0.0), (-0.70710678, 0.0, 0.0, 0.70710678)
-    ctx.set_camera(cam_pos, cam_quat)
-    stripes = grt.interleaved_stripes(HEIGHT, rank, world, STRIPE_ROWS)
-    if world == 1 and os.environ.get("GRT_BENCH_EMULATE_WORLD"):
-        # diagnostic only (tools/gpu_probe_pipeline.sh): one GPU renders the stripes rank 0 of an N-GPU job would own, no gather -
-        # separates the per-rank pipeline from the collective when studying scaling
-        stripes = grt.interleaved_stripes(HEIGHT, 0, int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
-    rows = sum(b - a for a, b in stripes)
-    fmt = grt.GRT_FORMAT_RGBA8
-    local = torch.empty((rows, WIDTH, 4), dtype=torch.uint8, device=device)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world != 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.device)
+            self.dist = dist
+        self.content = grt.Content(grt.CONTENT_DIR)
+        self.bg = grt.synthetic_background(4096, 2048)
+        self.seq = 0
+        self.ctx = None
 
-    # canonical work count of the frame (single-GPU trace of the whole frame), untimed
-    if rank == 0:
-        full = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, device=device)
-        _, st_full = ctx.render(WIDTH, HEIGHT, fmt, out=full)
-        frame_steps = int(st_full.trial_steps)
-        del full
-    else:
-        frame_steps = 0
-
-    # two output buffers: frames alternate between the context's two frame slots
-    locals_ = [local] + [torch.empty_like(local) for _ in range(FRAMES_IN_FLIGHT - 1)]
-    gather_bufs = [dict() for _ in range(FRAMES_IN_FLIGHT)]
-
-    def barrier():
-        ctx.synchronize()
+    def bind(self, cfg_id):
+        """A fresh context for one BASELINE config: metric, features, camera, background, communicator."""
+        torch = self.torch
+        cfg = CONFIGS[cfg_id]
+        if self.ctx is not None:
+            self.release()
+        self.cfg_id, self.cfg = cfg_id, cfg
+        self.w, self.h = cfg["size"]
+        self.metric = self.content.load_by_name(cfg["metric"])
+        ctx = grt.Context(self.local_rank)           # raises when libgrt.so or a B200 is missing: no fallback
+        ctx.set_fast_math(True)
+        ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
+        ctx.set_tuning(BLOCKS_PER_SM, 0)
+        ctx.set_metric(self.metric)
+        ctx.set_features(max_acceleration_change=self.metric.info.max_acceleration_change, **cfg["features"])
+        bg_dev = torch.from_numpy(self.bg).to(self.device)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ctx.set_background(bg_dev, 0, 4096, 2048)
+        ctx.set_camera(CAM_POS, CAM_QUAT)
+        if "geodesic" in cfg:
+            ctx.snapshot_geodesic(cfg["geodesic"]["speed"], True)
+            ctx.set_camera_on_geodesic(cfg["geodesic"]["tau"])
+        self.ctx = ctx
+        self.stripes = grt.interleaved_stripes(self.h, self.rank, self.world, STRIPE_ROWS)
+        if self.world == 1 and os.environ.get("GRT_BENCH_EMULATE_WORLD"):
+            # diagnostic only: one GPU renders the stripes rank 0 of an N-GPU job would own - separates the per-rank pipeline from the delivery
+            self.stripes = grt.interleaved_stripes(self.h, 0, int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
+        # canonical work count of the frame (single-GPU trace of the whole frame), untimed
+        self.frame_steps = 0
+        if self.rank == 0:
+            full = torch.empty((self.h, self.w, 4), dtype=torch.uint8, device=self.device)
+            _, st_full = ctx.render(self.w, self.h, grt.GRT_FORMAT_RGBA8, out=full)
+            self.frame_steps = int(st_full.trial_steps)
+            del full
+        # the communicator: rank 0 owns COMM_FRAMES frame buffers, every rank stores its stripes into them
+        handle = ctx.comm_init(self.rank, self.world, self.w, self.h, grt.GRT_FORMAT_RGBA8, COMM_FRAMES)
+        ctx.comm_connect(exchange_handles(handle, self.rank, self.world, self.device, self.dist))
+        self.seq = 0
+        self.host_out = [torch.empty((self.h, self.w, 4), dtype=torch.uint8).pin_memory() for _ in range(COMM_FRAMES)] if self.rank == 0 else None
 
-    def submit(k):
-        """Queue frame k (device-resident output; with N > 1 the NCCL gather to rank 0 is queued behind it). Returns its stream."""
-        flush.fill_(k & 1)                                        # evict L2 (256 MiB write) - see config.l2
-        ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
-        st = torch.cuda.ExternalStream(ctx.stream, device=device)
-        if world > 1:
-            with torch.cuda.stream(st):
-                gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device, gather_bufs[k % FRAMES_IN_FLIGHT])
-        return st
+    def release(self):
+        """Every rank unmaps the others' regions, then - behind a barrier - frees its own."""
+        self.barrier()
+        self.ctx.comm_disconnect()
+        self.barrier_host()
+        self.ctx.close()
+        self.ctx = None
 
-    def timed_batch(n_frames):
-        """ms for n_frames queued back to back (two in flight), measured with CUDA events: the start event is recorded on an idle
-        GPU, one end event behind the last frame of each frame slot."""
-        barrier()
+    def barrier_host(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def barrier(self):
+        self.ctx.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def submit(self, to_host=False):
+        """Queue the next frame on this rank (asynchronous): stripes rendered straight into the owner's frame buffer; with `to_host`
+        the camera is uploaded again (H2D) and rank 0 copies the assembled frame into pinned host memory (D2H) behind it."""
+        if to_host and "geodesic" not in self.cfg:
+            self.ctx.set_camera(CAM_POS, CAM_QUAT)          # per-frame camera upload on the frame's stream, as main.cpp:2244-2262
+        host = self.host_out[self.seq % COMM_FRAMES] if (to_host and self.rank == 0) else None
+        self.ctx.comm_render(self.stripes, self.seq, host)
+        self.seq += 1
+        return self.torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+
+    def timed_batch(self, n_frames, in_flight):
+        """ms for n_frames queued back to back with `in_flight` frame slots, CUDA events: the start event is recorded on an idle GPU,
+        one end event behind the last frame of each slot (on rank 0 that is behind the arrival of every rank's stripes). Max over ranks."""
+        torch = self.torch
+        self.barrier()
         start = torch.cuda.Event(enable_timing=True)
-        start.record(torch.cuda.current_stream(device))
+        start.record(torch.cuda.current_stream(self.device))
         ends = []
         for k in range(n_frames):
-            st = submit(k)
-            if k >= n_frames - FRAMES_IN_FLIGHT:
+            st = self.submit()
+            if k >= n_frames - in_flight:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record(st)
                 ends.append(e)
         for e in ends:
             e.synchronize()
-        barrier()
-        return max(start.elapsed_time(e) for e in ends)
+        self.barrier()
+        ms = torch.tensor([max(start.elapsed_time(e) for e in ends)], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
 
-    timed_batch(max(3, args.warmup))
-    sampler = ClockSampler(local_rank)
+    def measure(self, steps, warmup, in_flight):
+        self.barrier()
+        self.ctx.set_frames_in_flight(in_flight)
+        self.timed_batch(max(3, warmup), in_flight)
+        return self.timed_batch(steps, in_flight) / steps
+
+    def e2e(self, steps, in_flight):
+        torch = self.torch
+        self.barrier()
+        self.ctx.set_frames_in_flight(in_flight)
+        for _ in range(in_flight):
+            self.submit(to_host=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.submit(to_host=True)
+        self.barrier()
+        s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(s, op=self.dist.ReduceOp.MAX)
+        return float(s.item())
+
+
+def exchange_handles(handle, rank, world, device, dist):
+    """All ranks' communicator handles in rank order (64 bytes each): an all_gather over the job's process group."""
+    if world == 1:
+        return handle
+    import torch
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().tolist()) for p in parts)
+
+
+def run_ours(args):
+    job = Job(args)
+    torch, rank, world = job.torch, job.rank, job.world
+    job.bind(args.config)
+    ctx = job.ctx
+
+    sampler = ClockSampler(job.local_rank)
+    job.barrier()
+    ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
+    job.timed_batch(max(3, args.warmup), FRAMES_IN_FLIGHT)
     if rank == 0:
         sampler.start()
-    batch_ms = timed_batch(args.steps)
+    total_ms = job.timed_batch(args.steps, FRAMES_IN_FLIGHT)
     clocks = sampler.stop() if rank == 0 else None
-
-    # single-frame latency and per-stage times: one frame at a time, statistics read back
-    lat, last_stats = [], None
-    for _ in range(3):
-        barrier()
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        _, last_stats = ctx.render(WIDTH, HEIGHT, fmt, out=locals_[0], stats=True, stripes=stripes)
-        lat.append(last_stats.ms_total)
-    launches = last_stats.total_launches * args.steps
-    total_ms = torch.tensor([batch_ms], dtype=torch.float64, device=device)
-    steps_all = torch.tensor([float(last_stats.trial_steps)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(steps_all, op=dist.ReduceOp.SUM)
-    total_ms = float(total_ms.item())
+    launch_ms = ctx.integrate_launch_ms()                  # integration launches of the last frames of the timed region, while frames overlap
     ms_per_step = total_ms / args.steps
 
-    # end to end: every frame delivered into pinned HOST memory on rank 0 (two buffers, two frames in flight), host clock
-    host_out = [torch.empty((HEIGHT if world == 1 else rows, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(FRAMES_IN_FLIGHT)]
-    host_frame = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory() for _ in range(FRAMES_IN_FLIGHT)] if (world > 1 and rank == 0) else None
+    # the reference's depth (two render_state objects in flight) and one frame at a time
+    ms_2 = job.measure(args.steps, 1, 2) if FRAMES_IN_FLIGHT != 2 else ms_per_step
+    ms_1 = job.measure(max(4, args.steps // 2), 1, 1)
 
-    def submit_e2e(k):
-        ctx.set_camera(cam_pos, cam_quat)                      # per-frame camera upload (48 B H2D on the frame's stream), as main.cpp:2244-2262
-        if world == 1:
-            ctx.render(WIDTH, HEIGHT, fmt, out=host_out[k % FRAMES_IN_FLIGHT], stats=False)      # D2H queued behind the frame
-        else:
-            ctx.render(WIDTH, HEIGHT, fmt, out=locals_[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
-            st = torch.cuda.ExternalStream(ctx.stream, device=device)
-            with torch.cuda.stream(st):
-                frame = gather_frame(locals_[k % FRAMES_IN_FLIGHT], HEIGHT, WIDTH, rank, world, STRIPE_ROWS, device, gather_bufs[k % FRAMES_IN_FLIGHT])
-                if rank == 0:
-                    host_frame[k % FRAMES_IN_FLIGHT].copy_(frame, non_blocking=True)
-
-    for k in range(FRAMES_IN_FLIGHT):
-        submit_e2e(k)
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        submit_e2e(k)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    # per-stage times of one frame alone, statistics read back (this rank's stripes)
+    job.barrier()
+    ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
+    scratch = torch.empty((sum(b - a for a, b in job.stripes), job.w, 4), dtype=torch.uint8, device=job.device)
+    lat, last_stats = [], None
+    for _ in range(3):
+        job.barrier()
+        _, last_stats = ctx.render(job.w, job.h, grt.GRT_FORMAT_RGBA8, out=scratch, stats=True, stripes=job.stripes)
+        lat.append(last_stats.ms_total)
+    stage_log = ctx.launch_log()
+    steps_all = torch.tensor([float(last_stats.trial_steps)], dtype=torch.float64, device=job.device)
     if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+        job.dist.all_reduce(steps_all, op=job.dist.ReduceOp.SUM)
 
+    e2e_s = job.e2e(args.steps, FRAMES_IN_FLIGHT)
+    job.barrier()
+
+    line = None
     if rank == 0:
         peaks, peak_kind = measured_peaks()
+        frame_steps = job.frame_steps
         value = frame_steps * args.steps / (total_ms * 1e-3) / 1e6
         st = last_stats
-        rays_per_launch = (int(st.rays_integrated)) / max(1, st.integrate_launches)
-        integrate_ms = st.ms_integrate + st.ms_prepass          # prepass time is its integrate launch to within microseconds
-        algo_bytes = int(st.rays_integrated) * BYTES_PER_RAY            # all integrate launches of the frame
-        achieved_gbs = algo_bytes / (integrate_ms * 1e-3) / 1e9        # = per-launch bytes / mean launch duration
-        info = metric.info
-        flops_ref_step = info.flops_expr + 2090          # SURVEY.md 8(d): reference-formulation count, 16-component metric
-        flops_own_step = info.flops_accel + 110          # emitted lowered acceleration + Verlet update + step control + radii
-        gsteps = int(st.trial_steps) / (integrate_ms * 1e-3)
-        facts = ncu_facts()
-        micro = fp32_microbench() if (world == 1 and not args.no_cpu_baseline) else None   # side measurement, like the CPU baseline
-        fp_instr = facts.get("sass_fp_instr_per_step")
+        n_launch = max(1, st.integrate_launches)
+        rays_per_launch = int(st.rays_integrated) / n_launch
+        algo_bytes_per_launch = rays_per_launch * BYTES_PER_RAY
+        mean_launch_ms = float(np.mean(launch_ms)) if launch_ms else float("nan")
+        achieved_gbs = algo_bytes_per_launch / (mean_launch_ms * 1e-3) / 1e9
+        info = job.metric.info
+        facts = ncu_facts() if (args.config == 3 and world == 1) else {}      # the capture is of the headline command on one GPU
+        clk_hz = (clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        warp_instr = facts.get("warp_instructions_per_frame")
         line = {
             "metric": "ray_step_throughput", "value": value, "unit": "Mray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "frame_latency_ms": float(np.median(lat)), "frames_in_flight": FRAMES_IN_FLIGHT, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step, "frames_in_flight": FRAMES_IN_FLIGHT,
+            "fps_at_2_in_flight": 1e3 / ms_2, "fps_latency": 1e3 / ms_1, "frame_latency_ms": ms_1,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.config, world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
-                      "rank0_stage_ms": ctx.launch_log(), "sum_ranks_ray_steps": float(steps_all.item())},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": facts.get("mean_dram_bytes_per_launch"),
-                         "peak_kind": peak_kind, "kernel": "k_integrate (all integrate launches of one frame on rank 0)",
-                         "algorithmic_bytes_per_launch": algo_bytes / max(1, st.integrate_launches), "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the 3 integrate launches of a frame)", "launch_ms": integrate_ms / max(1, st.integrate_launches), "rays_per_launch": rays_per_launch,
-                         "note": "register-resident loop: 96 B per ray and 0 B per ray-step, so the HBM fraction is tiny by construction; the kernel is FP32-issue bound - see fp32"},
-            "fp32": {"gsteps_per_s_in_kernel": gsteps / 1e9, "flops_per_step_emitted": flops_own_step, "flops_per_step_reference_formulation": flops_ref_step,
-                     "achieved_tflops_emitted": gsteps * flops_own_step / 1e12, "achieved_tflops_reference_formulation": gsteps * flops_ref_step / 1e12,
-                     "peak_tflops_derived": FP32_PEAK_TFLOPS, "frac_emitted": gsteps * flops_own_step / 1e12 / FP32_PEAK_TFLOPS,
-                     "sass_fp_instr_per_step": fp_instr, "sass_instr_per_step": facts.get("sass_instr_per_step"),
-                     "sustained_gsteps_per_s": frame_steps * args.steps / (total_ms * 1e-3) / 1e9,
-                     "sustained_fp_tlaneops": (frame_steps * args.steps / (total_ms * 1e-3)) * fp_instr / 1e12 if fp_instr else None,
-                     "microbench_tlaneops": micro,
-                     "frac_of_microbench_ffma_fmul_mix": ((frame_steps * args.steps / (total_ms * 1e-3)) * fp_instr / 1e12 / micro["mix_fma_mul"]) if (fp_instr and micro and micro.get("mix_fma_mul")) else None,
-                     "note": "FP lane-op rate = ray-steps/s x FFMA+FMUL+FADD instructions per step (ncu); the microbenchmark is what independent FFMA/FMUL chains sustain on this GPU"},
-            "e2e": {"value": frame_steps * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s", "fps": args.steps / e2e_s, "h2d_bytes_per_step": 48,
-                    "d2h_bytes_per_step": HEIGHT * WIDTH * 4},
-            "gpu_launches": launches,
+                      "rank0_stage_ms_one_frame_alone": stage_log, "rank0_frame_alone_ms": float(np.median(lat)), "sum_ranks_ray_steps": float(steps_all.item())},
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                         "traffic": facts.get("mean_dram_bytes_per_launch"), "peak_kind": peak_kind,
+                         "kernel": "k_integrate", "algorithmic_bytes_per_launch": algo_bytes_per_launch, "rays_per_launch": rays_per_launch,
+                         "launch_ms": mean_launch_ms, "launches_timed": len(launch_ms),
+                         "launch_ms_basis": f"CUDA events around every k_integrate launch of the last {FRAMES_IN_FLIGHT} frames of the timed region (rank 0), frames overlapping as in `value`",
+                         "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the integrate launches of one frame; committed capture of this command, null when the run is not that command)",
+                         "note": "register-resident loop: 96 B per ray and 0 B per ray-step, so the HBM fraction is tiny by construction; the kernel is FP32-issue bound - see roofline_fp32"},
+            "roofline_fp32": {"bound": "issue", "unit": "G warp-instructions/s",
+                              "achieved": (warp_instr * args.steps / (total_ms * 1e-3) / 1e9) if warp_instr else None,
+                              "peak": ISSUE_SLOTS_PER_CLOCK * clk_hz / 1e9,
+                              "frac": (warp_instr * args.steps / (total_ms * 1e-3)) / (ISSUE_SLOTS_PER_CLOCK * clk_hz) if warp_instr else None,
+                              "warp_instructions_per_frame": warp_instr, "sass_instr_per_step": facts.get("sass_instr_per_step"), "sass_fp_instr_per_step": facts.get("sass_fp_instr_per_step"),
+                              "ops_per_step_emitted": info.flops_accel + 110, "ops_per_step_reference_formulation": info.flops_expr + 2090,
+                              "gsteps_per_s": frame_steps * args.steps / (total_ms * 1e-3) / 1e9,
+                              "source": (facts.get("file") or "no capture for this command") + ": smsp__inst_executed.sum over the frame's kernels (the frame is deterministic); clock = median clocks.sm sampled during the timed region; peak = 148 SMs x 4 schedulers x clock"},
+            "e2e": {"value": frame_steps * args.steps / e2e_s / 1e6, "unit": "Mray-steps/s", "fps": args.steps / e2e_s,
+                    "h2d_bytes_per_step": 48 if "geodesic" not in job.cfg else 0, "d2h_bytes_per_step": job.h * job.w * 4,
+                    "note": "whole frame through grt_comm_render into pinned host memory on rank 0; the reference arm it is compared with is the integration stage alone on a stride-8 pixel sample without prepass cull (conservative for the GPU)"},
+            "gpu_launches": int(st.total_launches) * args.steps,
             "clocks": clocks,
             "kernel_info": {k: v for k, v in ctx.kernel_info().items() if k in ("k_integrate", "integrate_blocks_per_sm")},
         }
-        if world == 1:
-            # SURVEY.md 8(d) asks for both operating modes: the same frame with adaptive sampling off (all 8.29 M rays traced, the
-            # clean ray-step rate), a side measurement after the headline numbers; never allowed to break the line
-            try:
-                ctx.set_features(adaptive_sampling=0)
-                full = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8, device=device)
-                _, st_off = ctx.render(WIDTH, HEIGHT, fmt, out=full)                      # one frame alone, with statistics
-                outs_off = [full] + [torch.empty_like(full) for _ in range(min(FRAMES_IN_FLIGHT, 3) - 1)]
-                n_off = 4
-                ctx.synchronize(); torch.cuda.synchronize()
-                e0 = torch.cuda.Event(enable_timing=True); e0.record(torch.cuda.current_stream(device))
-                ends_off = []
-                for k in range(n_off):
-                    ctx.render(WIDTH, HEIGHT, fmt, out=outs_off[k % len(outs_off)], stats=False)
-                    e = torch.cuda.Event(enable_timing=True); e.record(torch.cuda.ExternalStream(ctx.stream, device=device)); ends_off.append(e)
-                ctx.synchronize(); torch.cuda.synchronize()
-                ms_off = max(e0.elapsed_time(e) for e in ends_off) / n_off
-                line["full_sampling"] = {"mode": "adaptive sampling off: every pixel traced", "ray_steps": int(st_off.trial_steps), "rays_integrated": int(st_off.rays_integrated),
+
+    if args.config == 3 and not args.no_side_measurements:
+        # side measurements after the headline numbers; never allowed to break the line
+        side = {}
+        try:
+            if world == 1:
+                # SURVEY.md 8(d) asks for both operating modes: the same frame with adaptive sampling off (every pixel traced)
+                ctx.set_features(max_acceleration_change=job.metric.info.max_acceleration_change, adaptive_sampling=0)
+                full = torch.empty((job.h, job.w, 4), dtype=torch.uint8, device=job.device)
+                _, st_off = ctx.render(job.w, job.h, grt.GRT_FORMAT_RGBA8, out=full)
+                del full
+                ms_off = job.measure(6, 1, FRAMES_IN_FLIGHT)
+                side["full_sampling"] = {"mode": "adaptive sampling off: every pixel traced", "ray_steps": int(st_off.trial_steps), "rays_integrated": int(st_off.rays_integrated),
                                          "ms_per_frame": ms_off, "fps": 1e3 / ms_off, "value": int(st_off.trial_steps) / ms_off / 1e3, "unit": "Mray-steps/s",
-                                         "frame_latency_ms": float(st_off.ms_total), "frames_timed": n_off}
-                del outs_off, full
-            except Exception as exc:   # noqa: BLE001
-                line["full_sampling"] = {"error": str(exc)}
-            finally:
-                ctx.set_features(adaptive_sampling=1)
+                                         "frame_alone_ms": float(st_off.ms_total)}
+        except Exception as exc:   # noqa: BLE001
+            side["full_sampling"] = {"error": str(exc)}
+        try:
+            # BASELINE config 5 on the same GPUs: double_unequal_kerr 3840x2160, row-tiled (register-bound kernel: 167 registers, 3 blocks/SM)
+            job.bind(5)
+            ms5 = job.measure(8, 2, FRAMES_IN_FLIGHT)
+            ms5_1 = job.measure(4, 1, 1)
+            if rank == 0:
+                side["config5"] = {"workload": workload_config(5, world)["workload"], "ray_steps": job.frame_steps, "ms_per_step": ms5, "fps": 1e3 / ms5,
+                                   "value": job.frame_steps / ms5 / 1e3, "unit": "Mray-steps/s", "fps_latency": 1e3 / ms5_1, "n_gpus": world,
+                                   "kernel_info": {k: v for k, v in job.ctx.kernel_info().items() if k in ("k_integrate", "integrate_blocks_per_sm")}}
+        except Exception as exc:   # noqa: BLE001
+            side["config5"] = {"error": str(exc)}
+        if rank == 0:
+            line.update(side)
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             stride = 8
-            orc, feat, cw, ch = cpu_baseline_sample(stride)
-            r = orc.integrate_sample(WIDTH, HEIGHT, feat, 0, 0, cw, ch, stride)
+            orc, feat, cw, ch = cpu_baseline_sample(args.config, stride)
+            w, h = CONFIGS[args.config]["size"]
+            r = orc.integrate_sample(w, h, feat, 0, 0, cw, ch, stride)
             line["cpu_baseline"] = {
                 "value": r["trial_steps"] / r["seconds"] / 1e6, "unit": "Mray-steps/s", "cores": orc.info["threads"],
                 "per_core": r["trial_steps"] / r["seconds"] / 1e6 / max(1, orc.info["threads"]), "kind": orc.kind,
-                "sample": f"every {stride}th pixel in x and y of the {WIDTH}x{HEIGHT} grid ({cw * ch} rays, {r['trial_steps']} ray-steps, {r['seconds']:.1f} s), integration stage, no prepass cull"}
+                "sample": f"every {stride}th pixel in x and y of the {w}x{h} grid ({cw * ch} rays, {r['trial_steps']} ray-steps, {r['seconds']:.1f} s), integration stage, no prepass cull"}
         print(json.dumps(line), flush=True)
+    job.release()
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
 
 
 def main():
@@ -451,7 +492,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json config to time (default 3: the headline kerr_schild 4K frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-measurements", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

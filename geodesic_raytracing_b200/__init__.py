@@ -25,6 +25,7 @@ CONTENT_DIR = os.path.join(_HERE, "content")
 
 GRT_FORMAT_RGBA32F = 0
 GRT_FORMAT_RGBA8 = 1
+GRT_COMM_HANDLE_BYTES = 64
 
 COORDINATE_SYSTEMS = ("X_Y_THETA_PHI", "CARTESIAN", "CYLINDRICAL", "OTHER")
 
@@ -125,11 +126,15 @@ def lib() -> C.CDLL:
         "grt_render_rows": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, C.POINTER(Stats)]),
         "grt_render_stripes": (ci, [vp, ci, ci, pi, pi, ci, vp, ci, ci, C.POINTER(Stats)]),
         "grt_synchronize": (ci, [vp]), "grt_stream": (vp, [vp]),
+        "grt_comm_init": (ci, [vp, ci, ci, ci, ci, ci, ci, vp]), "grt_comm_connect": (ci, [vp, vp]), "grt_comm_connect_local": (ci, [C.POINTER(vp), ci]), "grt_comm_disconnect": (ci, [vp]),
+        "grt_comm_render": (ci, [vp, pi, pi, ci, C.c_uint, vp]), "grt_comm_frame": (vp, [vp, C.c_uint]),
+        "grt_interleaved_stripes": (ci, [ci, ci, ci, ci, pi, pi, ci]),
         "grt_get_camera_state": (ci, [vp, C.POINTER(CameraState)]),
         "grt_debug_ray_count": (ci, [vp, pi, pi]), "grt_debug_read_rays": (ci, [vp, vp, ci]), "grt_debug_read_render_data": (ci, [vp, vp, ci]),
         "grt_debug_read_prepass_mask": (ci, [vp, vp, ci, pi, pi]), "grt_debug_read_mip_level": (ci, [vp, ci, ci, vp, pi, pi, pi]),
         "grt_debug_read_geodesic": (ci, [vp, vp, vp, vp, vp, ci]),
         "grt_debug_eval_metric": (ci, [vp, vp, vp, ci, vp, vp, vp, vp, vp]), "grt_debug_tetrad_at": (ci, [vp, vp, ci, pf, ci, vp, vp]),
+        "grt_debug_integrate_launch_ms": (ci, [vp, pf, ci]),
         "grt_debug_kernel_info": (cp, [vp]), "grt_debug_launch_log": (cp, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -401,6 +406,47 @@ class Context:
     def synchronize(self) -> None:
         _check(lib().grt_synchronize(self._h))
 
+    # ---- one frame over several GPUs (grt.h: grt_comm_*) ------------------------------------------
+    def comm_init(self, rank: int, world: int, width: int, height: int, fmt: int = GRT_FORMAT_RGBA8, n_frames: int = 4) -> bytes:
+        """Allocate this rank's communication region (the frames too on rank 0); returns its IPC handle (GRT_COMM_HANDLE_BYTES)."""
+        h = (C.c_uint8 * GRT_COMM_HANDLE_BYTES)()
+        _check(lib().grt_comm_init(self._h, rank, world, width, height, fmt, n_frames, C.addressof(h)))
+        return bytes(h)
+
+    def comm_connect(self, handles: bytes) -> None:
+        """One process per GPU: `handles` = the handles of all ranks in rank order (world * GRT_COMM_HANDLE_BYTES bytes)."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        _check(lib().grt_comm_connect(self._h, C.addressof(buf)))
+
+    @staticmethod
+    def comm_connect_local(contexts: Sequence["Context"]) -> None:
+        """One process, several contexts (in rank order): peer access instead of IPC."""
+        arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+        _check(lib().grt_comm_connect_local(arr, len(contexts)))
+
+    def comm_disconnect(self) -> None:
+        """Unmap the other ranks' regions; every rank does this (then a barrier) before any rank closes its context."""
+        _check(lib().grt_comm_disconnect(self._h))
+
+    def comm_render(self, stripes: Sequence[Tuple[int, int]], seq: int, host_out=None) -> None:
+        """Render this rank's stripes of frame `seq` straight into the owner's frame buffer (asynchronous). On rank 0 `host_out`
+        (pinned) receives the assembled frame behind the last rank's stores."""
+        y0 = (C.c_int * len(stripes))(*[a for a, _ in stripes])
+        y1 = (C.c_int * len(stripes))(*[b for _, b in stripes])
+        _check(lib().grt_comm_render(self._h, y0, y1, len(stripes), seq, _ptr(host_out) if host_out is not None else None))
+
+    def integrate_launch_ms(self) -> List[float]:
+        """Durations (ms) of the integration launches of the most recent frame of every frame slot in use (waits for them)."""
+        buf = (C.c_float * 64)()
+        n = _check(lib().grt_debug_integrate_launch_ms(self._h, buf, 64))
+        return [buf[i] for i in range(min(n, 64))]
+
+    def comm_frame(self, seq: int) -> int:
+        p = lib().grt_comm_frame(self._h, seq)
+        if not p:
+            raise GrtError(-5, _err())
+        return p
+
     @property
     def stream(self) -> int:
         return lib().grt_stream(self._h) or 0
@@ -487,15 +533,11 @@ class Context:
 
 def interleaved_stripes(height: int, rank: int, world: int, stripe_rows: int = 54) -> List[Tuple[int, int]]:
     """Row stripes owned by `rank` when a frame is tiled over `world` GPUs: even-height stripes dealt
-    round-robin so the expensive rows around the hole are shared out."""
-    if world == 1:
-        return [(0, height)]
-    stripe_rows = max(2, stripe_rows - (stripe_rows & 1))
-    out = []
-    for i, y in enumerate(range(0, height, stripe_rows)):
-        if i % world == rank:
-            out.append((y, min(height, y + stripe_rows)))
-    return out
+    round-robin so the expensive rows around the hole are shared out (grt_interleaved_stripes)."""
+    cap = height // 2 + 2
+    y0, y1 = (C.c_int * cap)(), (C.c_int * cap)()
+    n = _check(lib().grt_interleaved_stripes(height, rank, world, stripe_rows, y0, y1, cap))
+    return [(y0[i], y1[i]) for i in range(n)]
 
 
 def load_png(path: str) -> np.ndarray:

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <future>
 #include <map>
 #include <memory>
@@ -60,6 +61,8 @@ struct Driver {
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;    // stream memory operations: no SM involved
+    CUresult (*StreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned) = nullptr;
     bool loaded = false;
 } g_drv;
 
@@ -77,6 +80,8 @@ void load_driver() {
     get("cuFuncGetAttribute", (void**)&g_drv.FuncGetAttribute);
     get("cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.OccupancyMaxActiveBlocksPerMultiprocessor);
     get("cuLaunchKernel", (void**)&g_drv.LaunchKernel);
+    get("cuStreamWaitValue32", (void**)&g_drv.StreamWaitValue32);
+    get("cuStreamWriteValue32", (void**)&g_drv.StreamWriteValue32);
     g_drv.loaded = true;
 }
 
@@ -125,25 +130,40 @@ std::string cache_dir() {
 }
 
 // ---- per-metric program ---------------------------------------------------------------------------
-const char* kPrelude =
+// Fast math is confined to what the integration loop uses: approximate division and square root, flush-to-zero and FMA
+// contraction come from the NVRTC options below, and the transcendental functions of the GENERATED metric code map to the
+// hardware intrinsics here.  The hand-written setup and shading kernels (ray construction, tetrads, hit angles, adaptive-sampling
+// interpolation) keep the precise sincosf / acosf / atan2f / tanf: they run once per ray, and their degenerate inputs (poles,
+// the equatorial row of a constant-theta metric, signed zeros) must round like the CPU oracle's libm does.
+const char* kPreludeCommon =
     "#define GRT_FN static __device__ __forceinline__\n"
+    "#define GRT_SQRT(a) sqrtf(a)\n"
+    "#define GRT_TANH(a) tanhf(a)\n"
+    "#define GRT_SIGN(a) ((a) > 0.0f ? 1.0f : ((a) < 0.0f ? -1.0f : 0.0f))\n"
+    "#define GRT_INF __int_as_float(0x7f800000)\n"
+    "#define GRT_NAN __int_as_float(0x7fffffff)\n";
+const char* kPreludeFast =
+    "#define GRT_DIV(a, b) __fdividef((a), (b))\n"      // div.approx (reciprocal + multiply); a plain `/` is div.full under --prec-div=false: three more instructions
+    "#define GRT_SIN(a) __sinf(a)\n"
+    "#define GRT_COS(a) __cosf(a)\n"
+    "#define GRT_TAN(a) __tanf(a)\n"
+    "#define GRT_LOG(a) __logf(a)\n"
+    "#define GRT_EXP(a) __expf(a)\n"
+    "#define GRT_POW(a, b) __powf(a, b)\n";
+const char* kPreludePrecise =
     "#define GRT_DIV(a, b) ((a) / (b))\n"
     "#define GRT_SIN(a) sinf(a)\n"
     "#define GRT_COS(a) cosf(a)\n"
     "#define GRT_TAN(a) tanf(a)\n"
     "#define GRT_LOG(a) logf(a)\n"
-    "#define GRT_SQRT(a) sqrtf(a)\n"
     "#define GRT_EXP(a) expf(a)\n"
-    "#define GRT_TANH(a) tanhf(a)\n"
-    "#define GRT_POW(a, b) powf(a, b)\n"
-    "#define GRT_SIGN(a) ((a) > 0.0f ? 1.0f : ((a) < 0.0f ? -1.0f : 0.0f))\n"
-    "#define GRT_INF __int_as_float(0x7f800000)\n"
-    "#define GRT_NAN __int_as_float(0x7fffffff)\n";
+    "#define GRT_POW(a, b) powf(a, b)\n";
 
 // `reparameterisation` is the one runtime feature the integration loop branches on every step; like the
 // reference's static program (-DFEATURE_name=value, dynamic_feature_config.cpp:122-180) it is baked in.
-std::string program_source(const grt::Metric& m, bool is_static, bool reparameterisation) {
-    std::string s = kPrelude;
+std::string program_source(const grt::Metric& m, bool is_static, bool reparameterisation, bool fast_math) {
+    std::string s = kPreludeCommon;
+    s += fast_math ? kPreludeFast : kPreludePrecise;
     s += reparameterisation ? "#define GRT_FEATURE_REPARAMETERISATION 1\n" : "#define GRT_FEATURE_REPARAMETERISATION 0\n";
     if (const char* e = getenv("GRT_INTEGRATE_MIN_BLOCKS")) s += std::string("// GRT_TIER_FIXED\n#define GRT_INTEGRATE_MIN_BLOCKS ") + std::to_string(atoi(e)) + "\n";
     s += GRT_SRC_STRUCTS;
@@ -155,7 +175,8 @@ std::string program_source(const grt::Metric& m, bool is_static, bool reparamete
 
 std::vector<std::string> nvrtc_options(bool fast_math) {
     std::vector<std::string> o = {"--gpu-architecture=sm_100a", "-lineinfo", "--std=c++17", "-DGRT_NVRTC=1", "-diag-suppress=177,550", "--ptxas-options=-v"};
-    if (fast_math) o.push_back("--use_fast_math");
+    if (fast_math)   // --use_fast_math minus its blanket sinf -> __sinf mapping (see the prelude)
+        for (const char* f : {"--ftz=true", "--prec-div=false", "--prec-sqrt=false", "--fmad=true"}) o.push_back(f);
     return o;
 }
 
@@ -348,6 +369,8 @@ struct FrameSlot {
     GrtStats* d_stats = nullptr;
     GrtCamera* d_cam = nullptr;
     std::vector<cudaEvent_t> events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> integrate_events;   // around every k_integrate launch of the slot's frames (created once, re-recorded)
+    int integrate_launches_last = 0;                                      // how many of them the slot's last frame used
     GrtFrame frame{};
     GrtCamera cam_staging{};   // pageable source of this slot's camera upload (copied to the driver's staging at the call)
     int last_first_pass = 0, last_extra = 0, last_pw = 0, last_ph = 0;
@@ -398,6 +421,22 @@ struct grt_ctx {
 
     std::string launch_log, kernel_info;
 
+    // Multi-GPU frame delivery: rank 0 owns the frames; every rank's k_render stores its stripes straight into
+    // them over NVLink (peer-mapped pointer), and the hand-shake is two words per frame buffer moved by stream memory
+    // operations and copy-engine writes - no kernel, no SM.  Every rank allocates one region with the same layout:
+    //   [0, 4096)   ready[n_frames][world]   written by rank r into the OWNER's region: seq + 1 of the last frame r delivered
+    //   [4096, 8192) freed[n_frames]          written by the owner into EVERY rank's region: seq + 1 of the last frame consumed
+    //   [8192, 12288) ring[1024]              local scratch: source words of the copy-engine writes
+    //   [12288, ...)  frames (owner only)
+    struct Comm {
+        bool active = false, connected = false, ipc = false;
+        int rank = 0, world = 1, n_frames = 0, w = 0, h = 0, format = 0;
+        size_t frame_bytes = 0;
+        DevBuf local;
+        std::vector<char*> base;      // every rank's region as mapped in this process (base[rank] == local.p)
+        unsigned ring_pos = 0;
+    } comm;
+
     // background build (metric_manager's soft recompile, metric_manager.hpp:153-219)
     struct PendingBuild {
         std::future<std::vector<char>> cubin;
@@ -444,7 +483,7 @@ Program* load_program(grt_ctx* c, const std::string& key, const std::vector<char
 
 Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
     const grt::Metric& m = *gm->m;
-    std::string src = program_source(m, is_static, c->feat.reparameterisation != 0);
+    std::string src = program_source(m, is_static, c->feat.reparameterisation != 0, c->fast_math);
     std::string key = program_key(c, src);
     auto it = c->programs.find(key);
     if (it != c->programs.end()) return it->second.get();
@@ -655,7 +694,17 @@ cudaEvent_t event_at(FrameSlot& S, size_t i) {
     return S.events[i];
 }
 
-int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n, void* out, int format, int out_is_device, grt_stats* stats) {
+// what grt_comm_render asks of a frame: stripes are written at their own rows of a whole frame (`out` is the frame), the stream waits
+// for `wait_addr` >= `wait_value` before the first pixel is stored, and `after` runs on the frame's stream behind the render kernels
+struct FrameDelivery {
+    bool frame_addressed = false;
+    unsigned* wait_addr = nullptr;
+    unsigned wait_value = 0;
+    std::function<void(cudaStream_t)> after;
+};
+
+int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int n, void* out, int format, int out_is_device, grt_stats* stats,
+                   const FrameDelivery* delivery = nullptr) {
     bind(c);
     need_program(c);
     if (w <= 0 || h <= 0 || w > 65535 || h > 65535 || n <= 0 || !out) throw Error(GRT_E_INVALID, "bad frame size, stripe list or output pointer");
@@ -752,7 +801,15 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         unsigned grid = std::min(persistent_grid, (unsigned)((max_items + 127) / 128));
         unsigned int* wc = S.d_counters + 8 + phase;
         void* args[] = {&rays, &f, &wl, &pool, &wc, &S.d_stats, &max_accel, c->params};
+        if ((int)S.integrate_events.size() <= L.integrate_launches) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            S.integrate_events.push_back({a, b});
+        }
+        CK(cudaEventRecord(S.integrate_events[L.integrate_launches].first, S.stream));
         L.go(P->k_integrate, grid, 128, args);
+        CK(cudaEventRecord(S.integrate_events[L.integrate_launches].second, S.stream));
         L.integrate_launches++;
     };
 
@@ -795,15 +852,20 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     }
     const GrtTexture* t1 = &c->tex[0].desc;
     const GrtTexture* t2 = c->tex[1].set ? &c->tex[1].desc : &c->tex[0].desc;
+    if (delivery && delivery->wait_addr) CU(g_drv.StreamWaitValue32((CUstream)S.stream, (CUdeviceptr)delivery->wait_addr, delivery->wait_value, CU_STREAM_WAIT_VALUE_GEQ));
     for (auto& st : c->stripes) {
-        grt_launch_render(d_rdata, &fr, &st, t1, t2, d_out, format, S.stream);
+        GrtRenderStripe target = st;
+        if (delivery && delivery->frame_addressed) target.out_offset_px = (unsigned long long)st.out_global0 * (unsigned long long)w;
+        grt_launch_render(d_rdata, &fr, &target, t1, t2, d_out, format, S.stream);
         L.launches++;
     }
     CK(cudaGetLastError());
+    if (delivery && delivery->after) delivery->after(S.stream);
     cudaEvent_t e_render = event_at(S, ev++);
     if (out_is_device != 1) CK(cudaMemcpyAsync(out, d_out, c->out_pixels * px_bytes, cudaMemcpyDeviceToHost, S.stream));
     cudaEvent_t e_end = event_at(S, ev++);
 
+    S.integrate_launches_last = L.integrate_launches;
     S.last_first_pass = fr.n_slots;
     S.last_pw = pw;
     S.last_ph = ph;
@@ -900,6 +962,7 @@ void ensure_geodesic(grt_ctx* c) {
 extern "C" {
 
 const char* grt_last_error(void) { return g_err.c_str(); }
+int grt_comm_disconnect(grt_ctx* c);
 const char* grt_version(void) { return "geodesic_raytracing_b200 0.1 (sm_100a)"; }
 
 grt_content* grt_content_create(void) { return new grt_content(); }
@@ -1046,7 +1109,7 @@ int grt_compile_metric(grt_metric* m, int is_static, int fast_math, const char**
         k = stem.find_last_of('.');
         if (k != std::string::npos) stem = stem.substr(0, k);
         std::string log;
-        compile_cubin(program_source(*m->m, is_static != 0, false), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &log, nullptr);
+        compile_cubin(program_source(*m->m, is_static != 0, false, fast_math != 0), fast_math != 0, stem + (is_static ? "_static" : "_dynamic"), &log, nullptr);
         std::lock_guard<std::mutex> lock(m->text_mutex);
         if (m->compile_log != log) m->compile_log = std::move(log);
         if (log_out) *log_out = m->compile_log.c_str();
@@ -1107,9 +1170,14 @@ void grt_destroy(grt_ctx* c) {
     for (auto& S : c->slots) {
         for (DevBuf* b : {&S.rays_pos, &S.rays_vel, &S.rays_acc, &S.rays_quat, &S.rays_aux, &S.pool_buf, &S.worklist, &S.rdata, &S.termination, &S.out}) b->release();
         for (auto e : S.events) cudaEventDestroy(e);
+        for (auto& e : S.integrate_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         cudaFree(S.d_cam);
         cudaFree(S.d_counters);
         if (S.stream) cudaStreamDestroy(S.stream);
+    }
+    if (c->comm.active) {
+        grt_comm_disconnect(c);
+        c->comm.local.release();
     }
     for (DevBuf* b : {&c->tables, &c->identity, &c->scratch, &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc}) b->release();
     cudaFree(c->d_cam);
@@ -1149,7 +1217,7 @@ int grt_set_metric_async(grt_ctx* c, grt_metric* m, int is_static) {
             c->build.cubin.wait();
             c->build.active = false;
         }
-        std::string src = program_source(*m->m, is_static != 0, c->feat.reparameterisation != 0);
+        std::string src = program_source(*m->m, is_static != 0, c->feat.reparameterisation != 0, c->fast_math);
         c->build.key = program_key(c, src);
         c->build.metric = m;
         c->build.is_static = is_static != 0;
@@ -1370,6 +1438,163 @@ int grt_synchronize(grt_ctx* c) {
 }
 void* grt_stream(grt_ctx* c) { return c ? (void*)c->last->stream : nullptr; }
 
+
+// ---- multi-GPU frame delivery ---------------------------------------------------------------------------
+namespace {
+constexpr size_t kCommReady = 0, kCommFreed = 4096, kCommRing = 8192, kCommFrames = 12288;
+
+unsigned* comm_ready(grt_ctx* c, int of_rank, int frame, int from_rank) { return (unsigned*)(c->comm.base[of_rank] + kCommReady) + (size_t)frame * c->comm.world + from_rank; }
+unsigned* comm_freed(grt_ctx* c, int of_rank, int frame) { return (unsigned*)(c->comm.base[of_rank] + kCommFreed) + frame; }
+
+// `value` -> *dst on `stream` without a kernel: a stream write-value into local memory, then (for a remote word) a 4-byte copy-engine write
+void comm_post(grt_ctx* c, cudaStream_t stream, unsigned* dst, bool remote, unsigned value) {
+    if (!remote) {
+        CU(g_drv.StreamWriteValue32((CUstream)stream, (CUdeviceptr)dst, value, CU_STREAM_WRITE_VALUE_DEFAULT));
+        return;
+    }
+    unsigned* src = (unsigned*)(c->comm.base[c->comm.rank] + kCommRing) + (c->comm.ring_pos++ & 1023u);
+    CU(g_drv.StreamWriteValue32((CUstream)stream, (CUdeviceptr)src, value, CU_STREAM_WRITE_VALUE_DEFAULT));
+    CK(cudaMemcpyAsync(dst, src, sizeof(unsigned), cudaMemcpyDeviceToDevice, stream));
+}
+}  // namespace
+
+int grt_comm_init(grt_ctx* c, int rank, int world, int width, int height, int format, int n_frames, uint8_t* handle_out) {
+    return guard([&] {
+        if (!c || world < 1 || rank < 0 || rank >= world || width <= 0 || height <= 0 || n_frames < 1) throw Error(GRT_E_INVALID, "bad communicator shape");
+        if (format != GRT_FORMAT_RGBA32F && format != GRT_FORMAT_RGBA8) throw Error(GRT_E_INVALID, "unknown output format");
+        if ((size_t)n_frames * world * sizeof(unsigned) > 4096 || (size_t)n_frames * sizeof(unsigned) > 4096) throw Error(GRT_E_INVALID, "too many frame buffers x ranks (n_frames * world <= 1024)");
+        if (c->comm.active) throw Error(GRT_E_STATE, "communicator already initialised");
+        bind(c);
+        auto& m = c->comm;
+        m.rank = rank; m.world = world; m.n_frames = n_frames; m.w = width; m.h = height; m.format = format;
+        m.frame_bytes = ((size_t)width * height * (format == GRT_FORMAT_RGBA32F ? 16 : 4) + 255) / 256 * 256;
+        const size_t bytes = kCommFrames + (rank == 0 ? m.frame_bytes * (size_t)n_frames : 0);
+        CK(cudaMalloc(&m.local.p, bytes));      // exactly this allocation is exported: not through DevBuf::ensure's rounding
+        m.local.cap = bytes;
+        CK(cudaMemset(m.local.p, 0, bytes));
+        m.base.assign(world, nullptr);
+        m.base[rank] = (char*)m.local.p;
+        if (handle_out) {
+            cudaIpcMemHandle_t hnd;
+            CK(cudaIpcGetMemHandle(&hnd, m.local.p));
+            static_assert(sizeof(hnd) == GRT_COMM_HANDLE_BYTES, "IPC handle size");
+            memcpy(handle_out, &hnd, sizeof hnd);
+        }
+        m.active = true;
+        m.connected = world == 1;
+        return GRT_OK;
+    });
+}
+
+int grt_comm_connect(grt_ctx* c, const uint8_t* handles) {
+    return guard([&] {
+        if (!c || !handles) throw Error(GRT_E_INVALID, "null argument");
+        auto& m = c->comm;
+        if (!m.active) throw Error(GRT_E_STATE, "grt_comm_init first");
+        bind(c);
+        for (int r = 0; r < m.world; r++) {
+            if (r == m.rank || m.base[r]) continue;
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, handles + (size_t)r * GRT_COMM_HANDLE_BYTES, sizeof hnd);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+            m.base[r] = (char*)p;
+        }
+        m.ipc = true;
+        m.connected = true;
+        return GRT_OK;
+    });
+}
+
+int grt_comm_connect_local(grt_ctx** ctxs, int n) {
+    return guard([&] {
+        if (!ctxs || n < 1) throw Error(GRT_E_INVALID, "null argument");
+        for (int i = 0; i < n; i++)
+            if (!ctxs[i] || !ctxs[i]->comm.active || ctxs[i]->comm.world != n || ctxs[i]->comm.rank != i) throw Error(GRT_E_STATE, "contexts must be initialised with grt_comm_init(rank = index, world = n)");
+        for (int i = 0; i < n; i++) {
+            bind(ctxs[i]);
+            for (int j = 0; j < n; j++) {
+                if (i == j) continue;
+                if (ctxs[i]->device != ctxs[j]->device) {
+                    int can = 0;
+                    CK(cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[j]->device));
+                    if (!can) throw Error(GRT_E_CUDA, "devices cannot access each other's memory");
+                    cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else CK(e);
+                }
+                ctxs[i]->comm.base[j] = (char*)ctxs[j]->comm.local.p;
+            }
+            ctxs[i]->comm.connected = true;
+        }
+        return GRT_OK;
+    });
+}
+
+int grt_comm_disconnect(grt_ctx* c) {
+    if (!c) { g_err = "null context"; return GRT_E_INVALID; }
+    auto& m = c->comm;
+    if (!m.active) return GRT_OK;
+    cudaSetDevice(c->device);
+    for (auto& S : c->slots) if (S.stream) cudaStreamSynchronize(S.stream);
+    for (int r = 0; r < (int)m.base.size(); r++) {
+        if (r == m.rank || !m.base[r]) continue;
+        if (m.ipc) cudaIpcCloseMemHandle(m.base[r]);
+        m.base[r] = nullptr;
+    }
+    m.connected = m.world == 1;
+    return GRT_OK;
+}
+
+int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, int* y0s, int* y1s, int max_stripes) {
+    if (height <= 0 || world < 1 || rank < 0 || rank >= world || !y0s || !y1s || max_stripes < 1) { g_err = "bad stripe request"; return GRT_E_INVALID; }
+    if (world == 1) { y0s[0] = 0; y1s[0] = height; return 1; }
+    stripe_rows = std::max(2, stripe_rows - (stripe_rows & 1));      // even: adaptive sampling works on 2x2 cells
+    int n = 0, i = 0;
+    for (int y = 0; y < height; y += stripe_rows, i++) {
+        if (i % world != rank) continue;
+        if (n == max_stripes) { g_err = "more stripes than max_stripes"; return GRT_E_INVALID; }
+        y0s[n] = y;
+        y1s[n] = std::min(height, y + stripe_rows);
+        n++;
+    }
+    return n;
+}
+
+void* grt_comm_frame(grt_ctx* c, unsigned seq) {
+    if (!c || !c->comm.active || c->comm.rank != 0) { g_err = "only the owner (rank 0) holds the frames"; return nullptr; }
+    return c->comm.base[0] + kCommFrames + (size_t)(seq % (unsigned)c->comm.n_frames) * c->comm.frame_bytes;
+}
+
+int grt_comm_render(grt_ctx* c, const int* y0s, const int* y1s, int n_stripes, unsigned seq, void* host_out) {
+    return guard([&] {
+        if (!c || !y0s || !y1s) throw Error(GRT_E_INVALID, "null argument");
+        auto& m = c->comm;
+        if (!m.active || !m.connected) throw Error(GRT_E_STATE, "communicator not connected: grt_comm_init, then grt_comm_connect / grt_comm_connect_local");
+        if (host_out && m.rank != 0) throw Error(GRT_E_INVALID, "only the owner (rank 0) delivers the frame to the host");
+        bind(c);
+        const int f = (int)(seq % (unsigned)m.n_frames);
+        char* frame = m.base[0] + kCommFrames + (size_t)f * m.frame_bytes;     // the owner's buffer, local or peer-mapped
+        FrameDelivery d;
+        d.frame_addressed = true;
+        if (seq >= (unsigned)m.n_frames) {        // the buffer's previous frame must have been consumed by the owner
+            d.wait_addr = comm_freed(c, m.rank, f);
+            d.wait_value = seq - (unsigned)m.n_frames + 1u;
+        }
+        d.after = [&, f](cudaStream_t stream) {
+            if (m.rank != 0) {
+                comm_post(c, stream, comm_ready(c, 0, f, m.rank), true, seq + 1u);          // my stripes of frame `seq` are in the owner's buffer
+                return;
+            }
+            for (int r = 1; r < m.world; r++)
+                CU(g_drv.StreamWaitValue32((CUstream)stream, (CUdeviceptr)comm_ready(c, 0, f, r), seq + 1u, CU_STREAM_WAIT_VALUE_GEQ));
+            if (host_out) CK(cudaMemcpyAsync(host_out, frame, (size_t)m.w * m.h * (m.format == GRT_FORMAT_RGBA32F ? 16 : 4), cudaMemcpyDeviceToHost, stream));
+            for (int r = 0; r < m.world; r++) comm_post(c, stream, comm_freed(c, r, f), r != 0, seq + 1u);   // the buffer may be written again
+        };
+        return render_stripes(c, m.w, m.h, y0s, y1s, n_stripes, frame, m.format, 1, nullptr, &d);
+    });
+}
+
 // ---- introspection ------------------------------------------------------------------------------------
 int grt_get_camera_state(grt_ctx* c, grt_camera_state* o) {
     return guard([&] {
@@ -1570,6 +1795,27 @@ int grt_debug_tetrad_at(grt_ctx* c, const float* positions, int count, const flo
         CK(cudaStreamSynchronize(c->stream));
         return GRT_OK;
     });
+}
+
+int grt_debug_integrate_launch_ms(grt_ctx* c, float* out, int max_count) {
+    int n = 0;
+    int rc = guard([&] {
+        if (!c) throw Error(GRT_E_INVALID, "null context");
+        bind(c);
+        sync_all(c);
+        for (int i = 0; i < c->n_slots; i++) {
+            FrameSlot& S = c->slots[i];
+            if (!S.used) continue;
+            for (int k = 0; k < S.integrate_launches_last; k++) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, S.integrate_events[k].first, S.integrate_events[k].second));
+                if (out && n < max_count) out[n] = ms;
+                n++;
+            }
+        }
+        return GRT_OK;
+    });
+    return rc == GRT_OK ? n : rc;
 }
 
 const char* grt_debug_kernel_info(grt_ctx* c) { return c ? c->kernel_info.c_str() : nullptr; }

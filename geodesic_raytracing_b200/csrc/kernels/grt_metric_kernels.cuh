@@ -236,7 +236,12 @@ static __device__ float4 theta_adjustment_quat(float3 pixel_direction, float4 po
     bx = norm3(norm3(bx - dot3(bx, by) * by));
     float3 plane_n = -norm3(cross3(bx, by));
     float angle_to_flat = acosf(plane_n.z);
-    return axis_angle_quat(norm3(cross3(plane_n, f3(0, 0, 1))), angle_to_flat * angle_sign);
+    // the orbital plane already is the equatorial plane (the centre row of the frame): the axis 0 / |0| is NaN where the
+    // cross product rounds to exactly zero.  Any axis in the plane gives the same physical ray (the hit is rotated back by
+    // the inverse), so take x; the reference's own result there is whatever rounding noise its device leaves in the axis.
+    float3 axis = cross3(plane_n, f3(0, 0, 1));
+    axis = dot3(axis, axis) > 0.0f ? norm3(axis) : f3(1, 0, 0);
+    return axis_angle_quat(axis, angle_to_flat * angle_sign);
 }
 static __device__ __forceinline__ float3 pixel_direction(int cx, int cy, const GrtFrame& fr, float4 camera_quat) {
     float width = (float)fr.full_w, height = (float)fr.full_h;
@@ -414,11 +419,11 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
     const float wmax = fmaxf(fmaxf(GRT_W_V1, GRT_W_V2), fmaxf(GRT_W_V3, GRT_W_V4));
     float ax = a.x * GRT_W_V1, ay = a.y * GRT_W_V2, az = a.z * GRT_W_V3, aw = a.w * GRT_W_V4;
     float e = sqrtf(ax * ax + ay * ay + az * az + aw * aw) * 0.01f;
-    e /= wmax;
+    e = GRT_DIV(e, wmax);
     float diff = e * 65536.0f;
     float floor_diff = max_acceleration * 65536.0f / (100000.0f * 100000.0f);
     if (diff < floor_diff) diff = floor_diff;
-    *next_ds = sqrtf((max_acceleration * 65536.0f) / diff);
+    *next_ds = sqrtf(GRT_DIV(max_acceleration * 65536.0f, diff));
     return diff;
 }
 
@@ -581,7 +586,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #endif
 #if !GRT_UNCONDITIONALLY_NONSINGULAR
 #if GRT_FEATURE_REPARAMETERISATION
-            drop = drop || (fabsf(vel.x / dlambda) > 1000.0f + f_in_x && fabsf(acc.x / dlambda) > 100.0f);
+            drop = drop || (fabsf(GRT_DIV(vel.x, dlambda)) > 1000.0f + f_in_x && fabsf(GRT_DIV(acc.x, dlambda)) > 100.0f);
 #else
             drop = drop || (fabsf(vel.x) > 1000.0f + f_in_x && fabsf(acc.x) > 100.0f);   // running_dlambda_dnew stays 1
 #endif
@@ -600,7 +605,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #if GRT_ADAPTIVE_PRECISION
                 ds = next_ds;
 #else
-                ds = lerpf(GRT_AMBIENT_PRECISION, GRT_SUBAMBIENT_PRECISION, (clampf(r_abs, 3.0f, new_max) - 3.0f) / (new_max - 3.0f));
+                ds = lerpf(GRT_AMBIENT_PRECISION, GRT_SUBAMBIENT_PRECISION, GRT_DIV(clampf(r_abs, 3.0f, new_max) - 3.0f, new_max - 3.0f));
 #endif
                 const bool inside = r_abs < new_max;
                 ds = inside ? fminf(ds, GRT_AMBIENT_PRECISION) : (0.1f * (r_abs - new_max) + GRT_AMBIENT_PRECISION);
@@ -615,7 +620,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                                  vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
 #if GRT_FEATURE_REPARAMETERISATION
                 {
-                    float K = 1.0f / fmaxf(fmaxf(fabsf(nvel.x), fabsf(nvel.y)), fmaxf(fabsf(nvel.z), fabsf(nvel.w)));
+                    float K = GRT_DIV(1.0f, fmaxf(fmaxf(fabsf(nvel.x), fabsf(nvel.y)), fmaxf(fabsf(nvel.z), fabsf(nvel.w))));
                     nvel = nvel * K;
                     nacc = nacc * (K * K);
                     dlambda *= K;
@@ -628,15 +633,15 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                     // calculate_ds_error (cl.cl:3431-3456)
                     float want;
                     float diff = accel_to_precision(nacc, max_acceleration, &want);
-                    float nds = 0.99f * ds * clampf(want / ds, 0.3f, 2.0f);
+                    float nds = 0.99f * ds * clampf(GRT_DIV(want, ds), 0.3f, 2.0f);
                     nds = fmaxf(nds, fr.min_step);
                     next_ds = nds;
 #if GRT_SINGULARITY_DETECTION
-                    if (nds == fr.min_step && (diff / 65536.0f) > max_acceleration * 10000.0f) { alive = false; accept = false; }
+                    if (nds == fr.min_step && (diff * (1.0f / 65536.0f)) > max_acceleration * 10000.0f) { alive = false; accept = false; }
 #else
                     (void)diff;
 #endif
-                    if (alive && nds < ds / 1.95f) accept = false;   // DS_SKIP: retry from the same state with the smaller step
+                    if (alive && nds < GRT_DIV(ds, 1.95f)) accept = false;   // DS_SKIP: retry from the same state with the smaller step
                 }
 #endif
                 if (accept) {

@@ -228,6 +228,33 @@ int grt_render_stripes(grt_ctx*, int width, int height, const int* y0s, const in
 int grt_synchronize(grt_ctx*);
 void* grt_stream(grt_ctx*);
 
+/* ---- one frame over several GPUs (replaces the single-context frame loop of main.cpp:1069-1095, 2244-2526) ----
+ * The frame is tiled in row stripes (grt_render_stripes); rank 0 OWNS the assembled frames.  Every rank's render kernel stores its
+ * stripes straight into the owner's frame buffer through a peer-mapped pointer (NVLink), and the hand-shake - "my stripes of frame
+ * seq are in", "buffer f may be written again" - is one word per buffer moved by stream memory operations and copy-engine writes:
+ * no collective kernel competes with the persistent integration blocks for SMs.
+ *   one process per GPU (torchrun): grt_comm_init on every rank -> exchange the GRT_COMM_HANDLE_BYTES handles (any byte transport,
+ *       e.g. torch.distributed.all_gather) -> grt_comm_connect(handles of all ranks in rank order);
+ *   one process, several contexts (grt_headless -gpus N): grt_comm_init on every context (handle_out may be NULL) ->
+ *       grt_comm_connect_local(contexts in rank order).
+ * grt_comm_render(rank's stripes, seq) is asynchronous on every rank; frames must be submitted with seq = 0, 1, 2, ... on all ranks.
+ * n_frames buffers rotate (seq % n_frames); a rank starts storing frame seq only after the owner has consumed frame seq - n_frames.
+ * On the owner, host_out (pinned memory, may be NULL) receives the assembled frame behind the last rank's stores; grt_comm_frame
+ * gives the device pointer of the buffer of frame seq, valid once the owner's stream has passed its wait (grt_synchronize, or order
+ * a consumer on grt_stream).  In the single-process form call the owner LAST for each frame if host_out is not pinned. */
+#define GRT_COMM_HANDLE_BYTES 64
+int grt_comm_init(grt_ctx*, int rank, int world, int width, int height, int format, int n_frames, uint8_t* handle_out /* GRT_COMM_HANDLE_BYTES or NULL */);
+int grt_comm_connect(grt_ctx*, const uint8_t* handles /* world * GRT_COMM_HANDLE_BYTES, rank order */);
+int grt_comm_connect_local(grt_ctx** contexts_in_rank_order, int n);
+/* Unmap the other ranks' regions (waits for this context's frames first). With one process per GPU every rank must disconnect
+ * BEFORE any rank destroys its context: freeing a region another process still has mapped is undefined in CUDA IPC. */
+int grt_comm_disconnect(grt_ctx*);
+int grt_comm_render(grt_ctx*, const int* y0s, const int* y1s, int n_stripes, unsigned seq, void* host_out);
+void* grt_comm_frame(grt_ctx*, unsigned seq);
+/* The stripes rank `rank` of `world` renders: interleaved `stripe_rows`-row stripes rank, rank + world, ... so that the expensive
+ * rows around the hole are dealt round-robin.  Writes up to max_stripes (y0, y1) pairs, returns the count. */
+int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, int* y0s, int* y1s, int max_stripes);
+
 /* ---- introspection for tests and tools --------------------------------------------------- */
 typedef struct grt_camera_state {
     float pos_generic[4];
@@ -262,6 +289,10 @@ int grt_debug_eval_metric(grt_ctx*, const float* positions, const float* velocit
                           float* radii2);
 int grt_debug_tetrad_at(grt_ctx*, const float* positions, int count, const float speed[3], int orient, float* tetrads16, int* timelike);
 
+/* Device time (ms) of every integration-kernel launch of the LAST frame of each frame slot in use (CUDA events on the slots' own
+ * streams), i.e. of the most recent frames_in_flight frames: launch durations as they are while frames overlap. Waits for the
+ * frames in flight. Returns the number of launches (writes at most max_count). */
+int grt_debug_integrate_launch_ms(grt_ctx*, float* out, int max_count);
 /* register count / spill info of the bound program's kernels: "name regs local_bytes;..." */
 const char* grt_debug_kernel_info(grt_ctx*);
 /* device time (ms) of each kernel launch of the last frame: "name:ms;..." */

@@ -1,4 +1,5 @@
-"""Host-side logic of the multi-GPU path on CPU: stripe partition and the world_size-2 gather (gloo)."""
+"""Host-side logic of the multi-GPU path on CPU: the stripe partition (computed in libgrt) and the world_size-2
+exchange of the communicator handles (gloo).  The delivery itself - peer stores into the owner's frame - is tested with -m gpu."""
 import os
 import socket
 
@@ -28,7 +29,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, h, w, rows, q):
+def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
 
@@ -37,28 +38,46 @@ def _worker(rank, world, port, h, w, rows, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
 
-    full = torch.arange(h * w * 4, dtype=torch.float32).reshape(h, w, 4)       # the frame every rank would agree on
-    stripes = bench.grt.interleaved_stripes(h, rank, world, rows)
-    local = torch.cat([full[a:b] for a, b in stripes], 0)
-    bufs = {}
-    for _ in range(2):      # twice: the second call reuses the persistent buffers
-        frame = bench.gather_frame(local, h, w, rank, world, rows, torch.device("cpu"), bufs)
-    if rank == 0:
-        q.put(bool(torch.equal(frame, full)))
+    # the host side of the multi-GPU path: every rank contributes its 64-byte communicator handle and receives all of them in rank
+    # order (what grt_comm_connect takes), and computes its own stripes; the frame delivery itself is device code (tests -m gpu)
+    handle = bytes([rank * 16 + (i % 16) for i in range(bench.grt.GRT_COMM_HANDLE_BYTES)])
+    for _ in range(2):
+        got = bench.exchange_handles(handle, rank, world, torch.device("cpu"), dist)
+    want = b"".join(bytes([r * 16 + (i % 16) for i in range(bench.grt.GRT_COMM_HANDLE_BYTES)]) for r in range(world))
+    stripes = bench.grt.interleaved_stripes(2160, rank, world, bench.STRIPE_ROWS)
+    rows = torch.tensor([sum(b - a for a, b in stripes)], dtype=torch.int64)
+    dist.all_reduce(rows)
+    q.put((rank, got == want, int(rows.item())))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("h, rows", [(100, 16), (128, 16)])   # ragged last stripe / regular interleave (single strided copy)
-def test_gather_reassembles_the_frame_world_size_2(h, rows):
+def test_handle_exchange_and_stripes_world_size_2():
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, h, 24, rows, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    assert q.get(timeout=5) is True
+    results = sorted(q.get(timeout=5) for _ in range(2))
+    assert results == [(0, True, 2160), (1, True, 2160)]
+
+
+def test_c_stripe_function_refuses_bad_requests(grt):
+    import ctypes as C
+    y0, y1 = (C.c_int * 4)(), (C.c_int * 4)()
+    L = grt.lib()
+    assert L.grt_interleaved_stripes(2160, 0, 8, 54, y0, y1, 4) < 0          # five stripes do not fit four slots
+    assert L.grt_interleaved_stripes(2160, 8, 8, 54, y0, y1, 4) < 0          # rank outside the world
+    assert L.grt_interleaved_stripes(100, 0, 1, 54, y0, y1, 4) == 1 and (y0[0], y1[0]) == (0, 100)
+
+
+def test_communicator_calls_fail_loudly_without_a_context(grt):
+    L = grt.lib()
+    assert L.grt_comm_init(None, 0, 2, 64, 64, 1, 2, None) < 0
+    assert L.grt_comm_render(None, None, None, 0, 0, None) < 0
+    assert L.grt_comm_frame(None, 0) is None
