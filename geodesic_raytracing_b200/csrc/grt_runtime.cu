@@ -1164,6 +1164,10 @@ void grt_destroy(grt_ctx* c) {
     if (!c) return;
     if (c->build.active) c->build.cubin.wait();
     cudaSetDevice(c->device);
+    if (c->comm.active) {      // while the slot streams still exist: disconnect waits for the frames in flight
+        grt_comm_disconnect(c);
+        c->comm.local.release();
+    }
     for (auto& S : c->slots) if (S.stream) cudaStreamSynchronize(S.stream);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
@@ -1174,10 +1178,6 @@ void grt_destroy(grt_ctx* c) {
         cudaFree(S.d_cam);
         cudaFree(S.d_counters);
         if (S.stream) cudaStreamDestroy(S.stream);
-    }
-    if (c->comm.active) {
-        grt_comm_disconnect(c);
-        c->comm.local.release();
     }
     for (DevBuf* b : {&c->tables, &c->identity, &c->scratch, &c->tex[0].data, &c->tex[1].data, &c->geo_pos, &c->geo_vel, &c->geo_ds, &c->geo_tr, &c->geo_misc}) b->release();
     cudaFree(c->d_cam);
