@@ -766,11 +766,11 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     // exchange pool of the integration kernel (see GrtPool): capacity = 4x the threads of the persistent grid
     GrtPool pool{};
     {
-        // sized for the largest persistent grid any tuning can ask for, so the ring layout (and the ready
-        // flags, which must never hold stale data) stays put when the tuning changes
+        // sized for the largest persistent grid any program and tuning can ask for, so the ring layout (and the ready
+        // flags, which must never hold stale data) stays put when the metric or the tuning changes
         unsigned cap = 1;
-        while (cap < (unsigned)(c->num_sms * P->integrate_blocks_per_sm) * 128u * 4u) cap <<= 1;
-        const size_t bytes = (size_t)cap * 84 + 64;
+        while (cap < (unsigned)(c->num_sms * 16) * 128u * 4u) cap <<= 1;      // the most blocks per SM any program can have: the layout never moves
+        const size_t bytes = (size_t)cap * 92 + 64;
         const bool fresh = S.pool_buf.cap < bytes;
         S.pool_buf.ensure(bytes);
         if (fresh) CK(cudaMemsetAsync(S.pool_buf.p, 0, S.pool_buf.cap, S.stream));   // tickets run on across launches; ready flags start at 0
@@ -782,7 +782,8 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
         pool.acc = (float4*)(p + (size_t)cap * 32);
         pool.misc = (float4*)(p + (size_t)cap * 48);
         pool.ids = (int4*)(p + (size_t)cap * 64);
-        pool.ready = c->donate_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 80) : nullptr;
+        pool.radii = (float2*)(p + (size_t)cap * 80);
+        pool.ready = c->donate_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 88) : nullptr;
         pool.mask = cap - 1;
         pool.donate_threshold = c->donate_threshold;
     }

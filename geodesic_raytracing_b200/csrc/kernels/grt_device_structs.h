@@ -31,6 +31,7 @@ struct GrtPool {
     float4* acc;
     float4* misc;   // {next_ds, accepted-step count (int bits), |v.t| at launch, running_dlambda_dnew}
     int4* ids;      // {slot, ku_uobsu (float bits), sy<<16|sx, -}
+    float2* radii;  // {|polar r|, |distance|} of the state (they travel with the ray: the loop computes them with the acceleration)
     unsigned int* ready;
     unsigned int* counters;
     unsigned int mask;

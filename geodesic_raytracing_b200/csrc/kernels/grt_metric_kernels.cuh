@@ -62,6 +62,14 @@ static __device__ __forceinline__ float4 accel_at(float4 pos, float4 vel, const 
     grt_accel(p, v, cfg, a);
     return f4(a[0], a[1], a[2], a[3]);
 }
+// acceleration and radii {polar r, distance to the object} of one point, evaluated as one block of generated code
+static __device__ __forceinline__ float4 accel_radii_at(float4 pos, float4 vel, const grt_params& cfg, float* polar_r, float* dist) {
+    float p[4] = {pos.x, pos.y, pos.z, pos.w}, v[4] = {vel.x, vel.y, vel.z, vel.w}, a[4], rr[2];
+    grt_accel_radii(p, v, cfg, a, rr);
+    *polar_r = rr[0];
+    *dist = rr[1];
+    return f4(a[0], a[1], a[2], a[3]);
+}
 static __device__ __forceinline__ float4 to_polar(float4 pos, const grt_params& cfg) {
     float p[4] = {pos.x, pos.y, pos.z, pos.w}, o[4];
     grt_to_polar(p, cfg, o);
@@ -453,9 +461,15 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
     bool alive = false, exhausted = false;
     int slot = 0, iter = 0;
     float4 pos = f4(0, 0, 0, 0), vel = pos, acc = pos;
-    float next_ds = 0.00001f, dlambda = 1.0f, f_in_x = 0.0f, r_abs, polar_r_abs, ku = 0.0f;
+    // r_abs / polar_r_abs: |distance to the object| and |polar r| of the CURRENT state.  They are evaluated once when a ray is
+    // loaded and from then on together with the acceleration of every trial position (grt_accel_radii), so the top-of-step
+    // checks never wait for them; a rejected step keeps the old ones.  Which code site produced them depends only on the
+    // ray's own history (first step: load site, later steps: step site), never on scheduling.
+    float next_ds = 0.00001f, dlambda = 1.0f, f_in_x = 0.0f, r_abs = 0.0f, polar_r_abs = 0.0f, ku = 0.0f;
     int sxsy = 0;
-    unsigned long long trial = 0, accepted = 0, nrays = 0, nfinished = 0;
+    // per-lane counters are 32 bit (a lane sees < 2^32 steps in any launch that ends within minutes); widened in the final reduction.
+    // accepted steps are counted per ray (iter) and added when the ray leaves the lane for good
+    unsigned int trial = 0, accepted = 0, nrays = 0, nfinished = 0;
     const float new_max = fr.max_precision_radius;
     unsigned int tail_tick = 0;
     int cooldown = 0;
@@ -492,6 +506,12 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                             iter = 0;
                             nrays++;
                             alive = true;
+                            {
+                                float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
+                                grt_radii(p, cfg, rr);
+                                polar_r_abs = fabsf(rr[0]);
+                                r_abs = fabsf(rr[1]);
+                            }
                         }
                     }
                 }
@@ -512,6 +532,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                         pool.acc[rec] = acc;
                         pool.misc[rec] = f4(next_ds, __int_as_float(iter), f_in_x, dlambda);
                         pool.ids[rec] = make_int4(slot, __float_as_int(ku), sxsy, 0);
+                        pool.radii[rec] = make_float2(polar_r_abs, r_abs);
                         __threadfence();
                         *(volatile unsigned int*)&pool.ready[rec] = ticket + 1u;
                         alive = false;
@@ -548,6 +569,9 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                         acc = __ldcg(&pool.acc[rec]);
                         float4 m = __ldcg(&pool.misc[rec]);
                         int4 ids = __ldcg(&pool.ids[rec]);
+                        float2 rr = __ldcg(&pool.radii[rec]);
+                        polar_r_abs = rr.x;
+                        r_abs = rr.y;
                         next_ds = m.x;
                         iter = __float_as_int(m.y);
                         f_in_x = m.z;
@@ -566,15 +590,6 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
             }
         }
         if (alive) {
-            // polar r and distance to the object of the current state (cl.cl:4062-4068).  Evaluated at this one
-            // place only: a second inlined copy may be contracted into FMAs differently, and a ray must not
-            // depend on which path (fresh load, exchange pool, previous step) brought it here.
-            {
-                float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
-                grt_radii(p, cfg, rr);
-                polar_r_abs = fabsf(rr[0]);
-                r_abs = fabsf(rr[1]);
-            }
             // ---- top-of-iteration checks on the current state (cl.cl:4088-4130) ----
             bool finish = polar_r_abs >= fr.universe_size;
 #if GRT_SINGULAR
@@ -593,12 +608,14 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #endif
             if (drop) {
                 alive = false;
+                accepted += (unsigned int)iter;
             } else if (finish) {
                 rays.pos[slot] = pos;
                 rays.vel[slot] = vel;
                 rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 1, sxsy);
                 nfinished++;
                 alive = false;
+                accepted += (unsigned int)iter;
             } else {
                 // ---- step size (cl.cl:4070-4086) ----
                 float ds;
@@ -614,7 +631,8 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                 float4 npos = f4(pos.x + vel.x * ds + acc.x * hds2, pos.y + vel.y * ds + acc.y * hds2,
                                  pos.z + vel.z * ds + acc.z * hds2, pos.w + vel.w * ds + acc.w * hds2);
                 float4 ivel = f4(vel.x + acc.x * ds, vel.y + acc.y * ds, vel.z + acc.z * ds, vel.w + acc.w * ds);
-                float4 nacc = accel_at(npos, ivel, cfg);
+                float n_polar_r, n_dist;
+                float4 nacc = accel_radii_at(npos, ivel, cfg, &n_polar_r, &n_dist);
                 const float hds = 0.5f * ds;
                 float4 nvel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds,
                                  vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
@@ -637,7 +655,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                     nds = fmaxf(nds, fr.min_step);
                     next_ds = nds;
 #if GRT_SINGULARITY_DETECTION
-                    if (nds == fr.min_step && (diff * (1.0f / 65536.0f)) > max_acceleration * 10000.0f) { alive = false; accept = false; }
+                    if (nds == fr.min_step && (diff * (1.0f / 65536.0f)) > max_acceleration * 10000.0f) { alive = false; accept = false; accepted += (unsigned int)iter; }
 #else
                     (void)diff;
 #endif
@@ -646,28 +664,30 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #endif
                 if (accept) {
                     pos = npos; vel = nvel; acc = nacc;
+                    polar_r_abs = fabsf(n_polar_r);
+                    r_abs = fabsf(n_dist);
 #if GRT_CONSTANT_THETA
                     pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
 #endif
-                    accepted++;
                     iter++;
-                    if (bad4(pos) || bad4(vel) || bad4(acc) || iter >= GRT_LOOP_LIMIT) alive = false;
+                    if (bad4(pos) || bad4(vel) || bad4(acc) || iter >= GRT_LOOP_LIMIT) { alive = false; accepted += (unsigned int)iter; }
                 }
             }
         }
     }
-    // statistics: warp reduce, one atomic per warp
+    // statistics: warp reduce in 64 bit, one atomic per warp
+    unsigned long long t64 = trial, a64 = accepted, r64 = nrays, f64 = nfinished;
     for (int o = 16; o > 0; o >>= 1) {
-        trial += __shfl_down_sync(FULL, trial, o);
-        accepted += __shfl_down_sync(FULL, accepted, o);
-        nrays += __shfl_down_sync(FULL, nrays, o);
-        nfinished += __shfl_down_sync(FULL, nfinished, o);
+        t64 += __shfl_down_sync(FULL, t64, o);
+        a64 += __shfl_down_sync(FULL, a64, o);
+        r64 += __shfl_down_sync(FULL, r64, o);
+        f64 += __shfl_down_sync(FULL, f64, o);
     }
     if (lane == 0 && stats) {
-        atomicAdd(&stats->trial_steps, trial);
-        atomicAdd(&stats->accepted_steps, accepted);
-        atomicAdd(&stats->rays_integrated, nrays);
-        atomicAdd(&stats->rays_finished, nfinished);
+        atomicAdd(&stats->trial_steps, t64);
+        atomicAdd(&stats->accepted_steps, a64);
+        atomicAdd(&stats->rays_integrated, r64);
+        atomicAdd(&stats->rays_finished, f64);
     }
 }
 

@@ -697,10 +697,31 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         // (common factors pulled out) *before* they are differentiated, so metrics with product
         // structure - Kerr-Schild forms g = eta + H l l, conformally flat ones - never expand the
         // 40 separate partials.  The cheaper of the two arrangements is emitted.
-        size_t best_n = G.instr_count(std::vector<int>(d.accel, d.accel + 4));
-        auto consider = [&](const int cand[4]) {
+        // every arrangement goes through the value-based merge (Graph::unify) before it is costed: mathematically equal
+        // sub-expressions that differ in form - the same l.v summed in three orders, a cofactor equal to a minor, |l|^2 = 1 -
+        // become one node or a constant.  GRT_UNIFY=0 switches the pass off (tools/compile_catalogue.py compares both).
+        std::map<std::string, double> param_env;
+        for (size_t i = 0; i < m.params.names.size(); i++) param_env[m.params.names[i]] = m.params.current_values[i];
+        const bool use_unify = !(getenv("GRT_UNIFY") && atoi(getenv("GRT_UNIFY")) == 0);
+        auto merged = [&](const int cand[4], int out[4]) {
+            std::vector<int> u(cand, cand + 4);
+            if (use_unify) u = G.unify(u, param_env);
+            for (int i = 0; i < 4; i++) out[i] = u[i];
+        };
+        size_t best_n;
+        {
+            int first[4];
+            merged(d.accel, first);
+            for (int i = 0; i < 4; i++) d.accel[i] = first[i];
+            best_n = G.instr_count(std::vector<int>(d.accel, d.accel + 4));
+        }
+        auto consider = [&](const int raw[4]) {
+            int cand[4];
+            merged(raw, cand);
             size_t n = G.instr_count(std::vector<int>(cand, cand + 4));
-            if (getenv("GRT_DEBUG_EMIT")) fprintf(stderr, "arrangement: %zu ops, %zu instructions\n", G.op_count(std::vector<int>(cand, cand + 4)), n);
+            if (getenv("GRT_DEBUG_EMIT"))
+                fprintf(stderr, "arrangement: %zu ops, %zu instructions (before the value-based merge %zu)\n", G.op_count(std::vector<int>(cand, cand + 4)), n,
+                        G.instr_count(std::vector<int>(raw, raw + 4)));
             if (n < best_n) { best_n = n; for (int i = 0; i < 4; i++) d.accel[i] = cand[i]; }
         };
         const int base[4] = {d.accel[0], d.accel[1], d.accel[2], d.accel[3]};
@@ -766,6 +787,17 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         if (m.constant_theta()) repl[v[2].id] = Expr((double)(float)(3.14159265358979323846 / 2)).id;  // polar_position.z = pi/2
         d.radii[0] = d.to_polar[1];
         d.radii[1] = G.substitute(d.distance, repl);
+        // the integration loop evaluates the radii of a point together with its acceleration (grt_accel_radii): merge the two
+        // DAGs by value so that r, rho^2 ... are computed once
+        if (!(getenv("GRT_UNIFY") && atoi(getenv("GRT_UNIFY")) == 0)) {
+            std::map<std::string, double> param_env;
+            for (size_t i = 0; i < m.params.names.size(); i++) param_env[m.params.names[i]] = m.params.current_values[i];
+            std::vector<int> all = {d.accel[0], d.accel[1], d.accel[2], d.accel[3], d.radii[0], d.radii[1]};
+            all = G.unify(all, param_env);
+            for (int i = 0; i < 4; i++) d.accel[i] = all[i];
+            d.radii[0] = all[4];
+            d.radii[1] = all[5];
+        }
     }
     // derived parameters (see MetricDescriptor::derived)
     {
@@ -938,6 +970,14 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
         fn_pos("void grt_period(const grt_params& cfg, float* o)", zero_decl, vec4(d.period));
     }
     fn_pos("void grt_accel(const float* p, const float* v, const grt_params& cfg, float* o)", pos_decl + vel_decl, vec4(d.accel));
+    {
+        // acceleration and radii of the same point in one straight-line block (shared sub-expressions computed once): what a step
+        // of the integration loop evaluates at the trial position
+        std::vector<std::pair<std::string, int>> both_outs = vec4(d.accel);
+        both_outs.push_back({"rr[0]", d.radii[0]});
+        both_outs.push_back({"rr[1]", d.radii[1]});
+        fn_pos("void grt_accel_radii(const float* p, const float* v, const grt_params& cfg, float* o, float* rr)", pos_decl + vel_decl, both_outs);
+    }
     fn_pos("void grt_accel_ref(const float* p, const float* v, const grt_params& cfg, float* o)", pos_decl + vel_decl, vec4(d.accel_ref));
     return o.str();
 }

@@ -2,6 +2,9 @@
 // See sym.hpp for what this replaces in the reference.
 #include "sym.hpp"
 
+#include <array>
+#include <cstring>
+
 #include <algorithm>
 #include <cmath>
 #include <complex>
@@ -759,6 +762,153 @@ size_t Graph::instr_count(const std::vector<int>& outs) const {
         }
     }
     return cnt;
+}
+
+// ---- value-based merging --------------------------------------------------------------------
+std::vector<int> Graph::unify(const std::vector<int>& outs, const std::map<std::string, double>& params) {
+    constexpr int K = 8;
+    constexpr double kTol = 1e-10;
+    // reachable nodes, ascending = topological
+    std::set<int> reach;
+    {
+        std::vector<int> stack(outs.begin(), outs.end());
+        while (!stack.empty()) {
+            int x = stack.back();
+            stack.pop_back();
+            if (x < 0 || !reach.insert(x).second) continue;
+            const Node& n = nodes_[x];
+            stack.push_back(n.a); stack.push_back(n.b); stack.push_back(n.c);
+        }
+    }
+    // deterministic sample generator (splitmix64)
+    uint64_t state = 0x9e3779b97f4a7c15ull;
+    auto rnd = [&]() {
+        uint64_t z = (state += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    };
+    using Vals = std::array<double, K>;
+    std::unordered_map<int, Vals> val;          // old id -> sample values
+    auto is_atom_op = [](Op op) {
+        switch (op) {
+            case Op::Select: case Op::Lt: case Op::Lte: case Op::Eq: case Op::Gt: case Op::Gte:
+            case Op::Fabs: case Op::Sign: case Op::Min: case Op::Max: case Op::Fmod: case Op::Atan2:
+            case Op::CsqrtRe: case Op::CsqrtIm:
+                return true;
+            default: return false;
+        }
+    };
+    auto finite = [](const Vals& v) { for (double x : v) if (!std::isfinite(x)) return false; return true; };
+    // representatives: new id + values, bucketed by the float rounding of |first sample|
+    struct Rep { int id; Vals v; };
+    std::unordered_map<uint32_t, std::vector<Rep>> buckets;
+    auto key_of = [](double x) { float f = (float)std::fabs(x); uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto close = [&](const Vals& a, const Vals& b, double sign) {
+        for (int k = 0; k < K; k++) {
+            double scale = std::max(std::fabs(a[k]), std::fabs(b[k]));
+            if (std::fabs(a[k] - sign * b[k]) > kTol * scale) return false;
+        }
+        return true;
+    };
+    auto find_rep = [&](const Vals& v, double* sign) -> int {
+        uint32_t k0 = key_of(v[0]);
+        for (uint32_t k : {k0, k0 + 1, k0 - 1}) {
+            auto it = buckets.find(k);
+            if (it == buckets.end()) continue;
+            for (const Rep& r : it->second) {
+                if (close(v, r.v, 1.0)) { *sign = 1.0; return r.id; }
+                if (close(v, r.v, -1.0)) { *sign = -1.0; return r.id; }
+            }
+        }
+        return -1;
+    };
+    std::unordered_map<int, int> repl;          // old id -> new id
+    for (int x : reach) {
+        const Node n = nodes_[x];
+        Vals v{};
+        if (n.op == Op::Const) {
+            v.fill(n.val);
+            val[x] = v;
+            repl[x] = x;
+            continue;                            // constants are never representatives: make() folds them
+        }
+        if (n.op == Op::Var || n.op == Op::Param) {
+            auto pit = params.find(n.name);
+            for (int k = 0; k < K; k++) {
+                if (n.op == Op::Param) {
+                    double base = pit == params.end() ? 0.0 : pit->second;
+                    v[k] = base == 0.0 ? 0.0 : base * (0.8 + 0.45 * rnd());      // a parameter that is exactly zero stays zero
+                } else {
+                    double mag = 0.6 + 1.9 * rnd();
+                    v[k] = (k >= K / 2 && rnd() < 0.5) ? -mag : mag;              // the first half all positive, the second with both signs
+                }
+            }
+            val[x] = v;
+            repl[x] = x;
+            buckets[key_of(v[0])].push_back({x, v});
+            continue;
+        }
+        const int a = n.a >= 0 ? repl.at(n.a) : -1, b = n.b >= 0 ? repl.at(n.b) : -1, c = n.c >= 0 ? repl.at(n.c) : -1;
+        int nx = (a == n.a && b == n.b && c == n.c) ? x : make(n.op, a, b, c);
+        if (is_atom_op(n.op)) {
+            // not analytic: an independent random atom (one per rebuilt node, so identical rebuilt nodes share it)
+            auto known = val.find(nx);
+            if (known != val.end() && nx != x) v = known->second;
+            else for (int k = 0; k < K; k++) v[k] = 0.5 + 1.5 * rnd();
+            val[x] = v;
+            val[nx] = v;
+            repl[x] = nx;
+            continue;
+        }
+        const Vals* va = n.a >= 0 ? &val.at(n.a) : nullptr;
+        const Vals* vb = n.b >= 0 ? &val.at(n.b) : nullptr;
+        for (int k = 0; k < K; k++) {
+            switch (n.op) {
+                case Op::Add: v[k] = (*va)[k] + (*vb)[k]; break;
+                case Op::Sub: v[k] = (*va)[k] - (*vb)[k]; break;
+                case Op::Mul: v[k] = (*va)[k] * (*vb)[k]; break;
+                case Op::Div: v[k] = (*va)[k] / (*vb)[k]; break;
+                case Op::Pow: v[k] = fold2(n.op, (*va)[k], (*vb)[k]); break;
+                default: v[k] = fold1(n.op, (*va)[k]); break;
+            }
+        }
+        val[x] = v;
+        if (!finite(v)) { repl[x] = nx; val[nx] = v; continue; }     // outside the sampled domain somewhere: leave it alone
+        if (nodes_[nx].op == Op::Const || nodes_[nx].op == Op::Var || nodes_[nx].op == Op::Param) { repl[x] = nx; continue; }
+        // a sum that cancels to rounding everywhere is zero
+        if (n.op == Op::Add || n.op == Op::Sub) {
+            bool zero = true;
+            for (int k = 0; k < K; k++)
+                if (std::fabs(v[k]) > 1e-11 * (std::fabs((*va)[k]) + std::fabs((*vb)[k]))) { zero = false; break; }
+            if (zero) { repl[x] = constant(0.0); continue; }
+        }
+        // the same number at every sample: a constant
+        {
+            double lo = v[0], hi = v[0];
+            for (double t : v) { lo = std::min(lo, t); hi = std::max(hi, t); }
+            double mean = 0.5 * (lo + hi);
+            if (hi - lo <= kTol * std::fabs(mean) && mean != 0.0) {
+                char buf[64];
+                snprintf(buf, sizeof buf, "%.11g", mean);        // snap: 0.99999999999999978 -> 1
+                repl[x] = constant(strtod(buf, nullptr));
+                continue;
+            }
+        }
+        double sign = 1.0;
+        int rep = find_rep(v, &sign);
+        if (rep >= 0 && rep != nx) {
+            repl[x] = sign > 0 ? rep : make(Op::Neg, rep);
+            continue;
+        }
+        repl[x] = nx;
+        val[nx] = v;
+        if (rep < 0) buckets[key_of(v[0])].push_back({nx, v});
+    }
+    std::vector<int> res;
+    for (int o : outs) res.push_back(repl.at(o));
+    return res;
 }
 
 double Graph::eval(int id, const std::map<std::string, double>& env) const {

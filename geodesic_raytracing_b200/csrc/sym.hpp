@@ -92,6 +92,18 @@ public:
     int from_poly(const Poly& p);
     static bool poly_mul(const Poly& a, const Poly& b, Poly& out, size_t max_terms = 20000);
     static void poly_axpy(Poly& acc, double alpha, const Poly& x);   // acc += alpha * x
+    // Value-based merging of sub-expressions (probabilistic identity testing).  The DAG reachable from `outs` is evaluated
+    // in double precision at a handful of random sample points (variables with both signs, parameters perturbed around their
+    // current values, every non-analytic node - select, comparisons, fabs, sign, min, max, fmod - replaced by an independent
+    // random atom so that what remains is analytic and equality on the samples means equality everywhere).  Then, bottom-up:
+    //   * a node whose value equals that of an earlier node at every sample IS that node (differently associated copies of
+    //     l.v, a cofactor that equals a minor computed elsewhere ...), a node equal to minus an earlier node is its negation;
+    //   * a node that is the same number at every sample is that constant (|l|^2 = 1 for the null vector of a Kerr-Schild form);
+    //   * a sum that cancels to rounding at every sample is zero.
+    // Hash-consing finds structurally equal sub-expressions; this finds the mathematically equal ones that no local rewrite
+    // rule reaches.  Same value as the input up to floating-point reassociation; returns the new ids of `outs`.
+    // `params`: current parameter values (name -> value).  Deterministic (fixed seed).
+    std::vector<int> unify(const std::vector<int>& outs, const std::map<std::string, double>& params);
     // numeric value of an expression in double precision; variables / parameters by name (missing -> 0)
     double eval(int id, const std::map<std::string, double>& env) const;
     // human readable infix (tests, debugging, classification decisions)

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 
+#ifndef ITERS
 #define ITERS 4096
+#endif
 #define CHAINS 8
 
 __global__ void k_ffma(float* out, float a, float b) {

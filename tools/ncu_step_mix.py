@@ -62,6 +62,9 @@ def main(path, out_path, which=1):
         "sass_fp_instr_per_step": round(fp / steps, 1),
         "sass_mix_per_step": {k: round(v / steps, 1) for k, v in execd.most_common(14)},
         "warp_steps_in_launch": steps,
+        "warp_instructions_per_frame": sum(float(r[idx["smsp__inst_executed.sum"]]) for r in rows),
+        "pipe_fma_pct": float(rows[which][idx["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]]),
+        "lanes_active_per_instruction": float(rows[which][idx["smsp__thread_inst_executed_per_inst_executed.ratio"]]),
         "registers": int(float(rows[which][idx["launch__registers_per_thread"]])),
         "issue_active_pct": float(rows[which][idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
         "note_instr": "warp-level SASS instructions executed per warp-step in the first-pass launch (ncu source page: all executed instructions / executions of the step body); FP = FFMA + FMUL + FADD",
