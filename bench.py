@@ -47,10 +47,10 @@ CONFIGS = {
 }
 _WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 # measured optima (tools/gpu_sweep_*.sh; profiles/round1_scaling.md, round2_*): frame slots in flight : integration blocks per SM and slot
-_DEFAULT_KNOBS = {1: (4, 3), 2: (6, 3), 4: (8, 2), 8: (8, 1)}.get(_WORLD, (min(8, 2 * _WORLD + 2), 2))
+_DEFAULT_KNOBS = {1: (4, 3), 2: (8, 2), 4: (8, 1), 8: (8, 1)}.get(_WORLD, (8, 1))
 FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(_DEFAULT_KNOBS[0])))
 BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS[1])))
-COMM_FRAMES = 8              # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
+COMM_FRAMES = 16             # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
 BYTES_PER_RAY = 96           # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 ISSUE_SLOTS_PER_CLOCK = 148 * 4   # one warp instruction per scheduler and clock
 
@@ -229,6 +229,7 @@ class Job:
         self.bg = grt.synthetic_background(4096, 2048)
         self.seq = 0
         self.ctx = None
+        self.submit_s, self.submits = 0.0, 0
 
     def bind(self, cfg_id):
         """A fresh context for one BASELINE config: metric, features, camera, background, communicator."""
@@ -256,7 +257,7 @@ class Job:
         self.stripes = grt.interleaved_stripes(self.h, self.rank, self.world, STRIPE_ROWS)
         if self.world == 1 and os.environ.get("GRT_BENCH_EMULATE_WORLD"):
             # diagnostic only: one GPU renders the stripes rank 0 of an N-GPU job would own - separates the per-rank pipeline from the delivery
-            self.stripes = grt.interleaved_stripes(self.h, 0, int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
+            self.stripes = grt.interleaved_stripes(self.h, int(os.environ.get("GRT_BENCH_EMULATE_RANK", "0")), int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
         # canonical work count of the frame (single-GPU trace of the whole frame), untimed
         self.frame_steps = 0
         if self.rank == 0:
@@ -296,7 +297,10 @@ class Job:
         if to_host and "geodesic" not in self.cfg:
             self.ctx.set_camera(CAM_POS, CAM_QUAT)          # per-frame camera upload on the frame's stream, as main.cpp:2244-2262
         host = self.host_out[self.seq % COMM_FRAMES] if (to_host and self.rank == 0) else None
+        t0 = time.perf_counter()
         self.ctx.comm_render(self.stripes, self.seq, host)
+        self.submit_s += time.perf_counter() - t0
+        self.submits += 1
         self.seq += 1
         return self.torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
 
@@ -318,7 +322,11 @@ class Job:
             e.synchronize()
         self.barrier()
         ms = torch.tensor([max(start.elapsed_time(e) for e in ends)], dtype=torch.float64, device=self.device)
+        self.last_rank_ms = [float(ms.item())]
         if self.world > 1:
+            parts = [torch.empty_like(ms) for _ in range(self.world)]
+            self.dist.all_gather(parts, ms)
+            self.last_rank_ms = [float(p.item()) for p in parts]       # every rank's own clock over the same frames
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -370,6 +378,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     total_ms = job.timed_batch(args.steps, FRAMES_IN_FLIGHT)
+    rank_ms = list(job.last_rank_ms)
     clocks = sampler.stop() if rank == 0 else None
     launch_ms = ctx.integrate_launch_ms()                  # integration launches of the last frames of the timed region, while frames overlap
     ms_per_step = total_ms / args.steps
@@ -417,7 +426,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.config, world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
-                      "rank0_stage_ms_one_frame_alone": stage_log, "rank0_frame_alone_ms": float(np.median(lat)), "sum_ranks_ray_steps": float(steps_all.item())},
+                      "rank0_stage_ms_one_frame_alone": stage_log, "rank0_frame_alone_ms": float(np.median(lat)), "sum_ranks_ray_steps": float(steps_all.item()),
+                      "timed_region_ms_by_rank": rank_ms, "host_ms_per_submit_rank0": 1e3 * job.submit_s / max(1, job.submits)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
                          "traffic": facts.get("mean_dram_bytes_per_launch"), "peak_kind": peak_kind,
                          "kernel": "k_integrate", "algorithmic_bytes_per_launch": algo_bytes_per_launch, "rays_per_launch": rays_per_launch,

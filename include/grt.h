@@ -169,7 +169,7 @@ int grt_set_fast_math(grt_ctx*, int enabled);
  * Defaults 3 and 0: measured best on the 4K kerr_schild frame (profiles/round1_tuning.md). */
 int grt_set_tuning(grt_ctx*, int blocks_per_sm, int donate_threshold);
 
-/* Frame slots that asynchronous frames rotate through (1..8, default 2 as the reference's two
+/* Frame slots that asynchronous frames rotate through (1..16, default 2 as the reference's two
  * render_state objects, main.cpp:1463-1469).  More slots fill the latency-bound stretches of a frame
  * (prepass, tails of the integration launches) with other frames' rays: throughput up, latency up. */
 int grt_set_frames_in_flight(grt_ctx*, int n);
@@ -231,8 +231,8 @@ void* grt_stream(grt_ctx*);
 /* ---- one frame over several GPUs (replaces the single-context frame loop of main.cpp:1069-1095, 2244-2526) ----
  * The frame is tiled in row stripes (grt_render_stripes); rank 0 OWNS the assembled frames.  Every rank's render kernel stores its
  * stripes straight into the owner's frame buffer through a peer-mapped pointer (NVLink), and the hand-shake - "my stripes of frame
- * seq are in", "buffer f may be written again" - is one word per buffer moved by stream memory operations and copy-engine writes:
- * no collective kernel competes with the persistent integration blocks for SMs.
+ * seq are in", "buffer f may be written again" - is one word per buffer moved by stream memory operations (cuStreamWriteValue32 to
+ * the peer-mapped word, cuStreamWaitValue32 on local words): no collective kernel competes with the persistent integration blocks for SMs.
  *   one process per GPU (torchrun): grt_comm_init on every rank -> exchange the GRT_COMM_HANDLE_BYTES handles (any byte transport,
  *       e.g. torch.distributed.all_gather) -> grt_comm_connect(handles of all ranks in rank order);
  *   one process, several contexts (grt_headless -gpus N): grt_comm_init on every context (handle_out may be NULL) ->
