@@ -113,7 +113,7 @@ def lib() -> C.CDLL:
         "grt_metric_param_count": (ci, [vp]), "grt_metric_param_name": (cp, [vp, ci]), "grt_metric_param_default": (cf, [vp, ci]),
         "grt_metric_param_get": (cf, [vp, ci]), "grt_metric_param_set": (ci, [vp, ci, cf]),
         "grt_metric_get_info": (ci, [vp, C.POINTER(MetricInfo)]), "grt_metric_name": (cp, [vp]), "grt_metric_description": (cp, [vp]),
-        "grt_image_load_png": (vp, [cp, C.POINTER(ci), C.POINTER(ci)]), "grt_image_free": (None, [vp]),
+        "grt_image_load_png": (vp, [cp, C.POINTER(ci), C.POINTER(ci)]), "grt_image_free": (None, [vp]), "grt_image_save_png": (ci, [cp, vp, ci, ci]),
         "grt_metric_packed_params": (ci, [vp, vp, ci]),
         "grt_metric_source": (cp, [vp, ci]), "grt_metric_eval_symbolic": (ci, [vp] + [vp] * 9), "grt_compile_metric": (ci, [vp, ci, ci, C.POINTER(cp)]),
         "grt_features_default": (None, [C.POINTER(Features)]),
@@ -538,6 +538,14 @@ def interleaved_stripes(height: int, rank: int, world: int, stripe_rows: int = 5
     y0, y1 = (C.c_int * cap)(), (C.c_int * cap)()
     n = _check(lib().grt_interleaved_stripes(height, rank, world, stripe_rows, y0, y1, cap))
     return [(y0[i], y1[i]) for i in range(n)]
+
+
+def save_png(path: str, rgba: np.ndarray) -> None:
+    """HxWx4 uint8 -> PNG file (grt_image_save_png: the reference's screenshot file format, main.cpp:2783-2812)."""
+    a = np.ascontiguousarray(rgba, np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("expected an HxWx4 uint8 image")
+    _check(lib().grt_image_save_png(path.encode(), a.ctypes.data, a.shape[1], a.shape[0]))
 
 
 def load_png(path: str) -> np.ndarray:

@@ -3,12 +3,15 @@
 // Stands where the reference's frame loop stands (/root/reference/main.cpp:1503-2871): content folders
 // (main.cpp:1562-1586), `-bench <metric>` / `-start <metric>` (main.cpp:956-986), the default camera
 // (main.cpp:664-673), the per-frame sequence (main.cpp:2244-2526) as one grt_render call, the
-// "Frametime Elapsed: %f" line of -bench (main.cpp:2864-2871) and the screenshot path
-// (main.cpp:2762-2831: linear -> sRGB, written here as a binary PPM instead of PNG).
-// The window, ImGui, input and Steam parts of main.cpp are out of scope.
+// "Frametime Elapsed: %f" line of -bench (main.cpp:2864-2871), the screenshot path (main.cpp:2762-2831: clamp, linear -> sRGB,
+// clamp, * 255, saved as ./screenshots/<metric>_<milliseconds>.png) and the settings file (main.cpp:240-254: settings.json with the
+// fields of graphics_settings.cpp:10-33).  With -gpus N the frame is tiled in row stripes over N devices of this box and assembled
+// on device 0 (grt_comm_*: one context per device, peer stores into device 0's frame) - the single-context frame loop of
+// main.cpp:1069-1095 over several GPUs.  The window, ImGui, input and Steam parts of main.cpp are out of scope.
 //
-//   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K]
-//                [-param name value]... [-static] [-no-adaptive] [-redshift] [-geodesic tau] [-background file.png|file.ppm] [-out frame.ppm]
+//   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K] [-gpus N | -devices 0,1,...]
+//                [-param name value]... [-static] [-no-adaptive] [-redshift] [-geodesic tau] [-background file.png|file.ppm]
+//                [-settings settings.json] [-save-settings settings.json] [-screenshot] [-out frame.png|frame.ppm]
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -19,9 +22,12 @@
 #include <utility>
 #include <vector>
 
+#include <sys/stat.h>
+
 #include <cuda_runtime.h>
 
 #include "grt.h"
+#include "mini_json.hpp"
 
 namespace {
 
@@ -60,6 +66,57 @@ bool read_ppm(const char* path, std::vector<uint8_t>& rgba, int& w, int& h) {
     return ok;
 }
 
+// the fields of struct graphics_settings that reach the hot path or the screenshot (graphics_settings.hpp:8-47, same defaults)
+struct Settings {
+    int width = 1920, height = 1080;
+    float field_of_view = 90.0f;
+    int screenshot_width = 1920, screenshot_height = 1080;
+    int supersample_factor = 2;
+    bool supersample = false;
+    int anisotropy = 8;
+    bool use_old_redshift = false, use_adaptive_sampling = true;
+    float adaptive_sampling_threshold = 32.0f;
+};
+
+// main.cpp:240-254: a missing file keeps the defaults, a broken one prints the reference's message and keeps the defaults
+bool load_settings(const std::string& path, Settings& st) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    fclose(f);
+    try {
+        mini_json::Value js = mini_json::parse(text);
+        auto num = [&](const char* k, auto& out) { if (const mini_json::Value* v = js.find(k)) out = (std::remove_reference_t<decltype(out)>)v->num; };
+        auto flag = [&](const char* k, bool& out) { if (const mini_json::Value* v = js.find(k)) out = v->b || v->num != 0; };
+        num("width", st.width); num("height", st.height); num("field_of_view", st.field_of_view);
+        num("screenshot_width", st.screenshot_width); num("screenshot_height", st.screenshot_height);
+        num("supersample_factor", st.supersample_factor); flag("supersample", st.supersample);
+        num("anisotropy", st.anisotropy); flag("use_old_redshift", st.use_old_redshift);
+        flag("use_adaptive_sampling", st.use_adaptive_sampling); num("adaptive_sampling_threshold", st.adaptive_sampling_threshold);
+        return true;
+    } catch (std::exception& ex) {
+        printf("Failed to load settings.json %s\n", ex.what());
+        return false;
+    }
+}
+void save_settings(const std::string& path, const Settings& st) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { fprintf(stderr, "grt_headless: cannot write %s\n", path.c_str()); return; }
+    fprintf(f, "{\"width\":%d,\"height\":%d,\"field_of_view\":%g,\"screenshot_width\":%d,\"screenshot_height\":%d,\"supersample\":%s,\"supersample_factor\":%d,"
+               "\"anisotropy\":%d,\"use_old_redshift\":%s,\"use_adaptive_sampling\":%s,\"adaptive_sampling_threshold\":%g}\n",
+            st.width, st.height, st.field_of_view, st.screenshot_width, st.screenshot_height, st.supersample ? "true" : "false", st.supersample_factor, st.anisotropy,
+            st.use_old_redshift ? "true" : "false", st.use_adaptive_sampling ? "true" : "false", st.adaptive_sampling_threshold);
+    fclose(f);
+}
+
+bool ends_with(const std::string& s, const char* suffix) {
+    size_t n = strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+
 void write_ppm(const char* path, const std::vector<uint8_t>& rgba, int w, int h) {
     FILE* f = fopen(path, "wb");
     if (!f) { fprintf(stderr, "grt_headless: cannot write %s\n", path); return; }
@@ -71,11 +128,12 @@ void write_ppm(const char* path, const std::vector<uint8_t>& rgba, int w, int h)
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string content_dir, metric_name = "kerr_schild", out_path, background_path;
-    int width = 1920, height = 1080, frames = 8, inflight = 2;
-    bool is_static = false, adaptive = true, redshift = false, print_frametime = false, on_geodesic = false;
+    std::string content_dir, metric_name = "kerr_schild", out_path, background_path, settings_path = "settings.json", save_settings_path;
+    int width = 0, height = 0, frames = 8, inflight = 2, gpus = 1;
+    bool is_static = false, adaptive = true, redshift = false, print_frametime = false, on_geodesic = false, screenshot = false, adaptive_given = false;
     float geodesic_tau = 0.0f;
     std::vector<std::pair<std::string, float>> params;
+    std::vector<int> devices;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&](int k = 1) -> const char* { if (i + k >= argc) { fprintf(stderr, "grt_headless: %s needs a value\n", a.c_str()); exit(2); } return argv[i + k]; };
@@ -85,18 +143,35 @@ int main(int argc, char** argv) {
         else if (a == "-size") { width = atoi(next(1)); height = atoi(next(2)); i += 2; }
         else if (a == "-frames") { frames = atoi(next()); i++; }
         else if (a == "-inflight") { inflight = atoi(next()); i++; }
+        else if (a == "-gpus") { gpus = atoi(next()); i++; }
+        else if (a == "-devices") {                                                          // explicit device list, e.g. 0,1,2,3 (a device may repeat: ranks then share it)
+            devices.clear();
+            for (const char* q = next(); *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+            gpus = (int)devices.size();
+            i++;
+        }
         else if (a == "-param") { params.push_back({next(1), (float)atof(next(2))}); i += 2; }
         else if (a == "-static") is_static = true;
-        else if (a == "-no-adaptive") adaptive = false;
+        else if (a == "-no-adaptive") { adaptive = false; adaptive_given = true; }
         else if (a == "-redshift") redshift = true;
         else if (a == "-geodesic") { on_geodesic = true; geodesic_tau = (float)atof(next()); i++; }
         else if (a == "-background") { background_path = next(); i++; }
+        else if (a == "-settings") { settings_path = next(); i++; }
+        else if (a == "-save-settings") { save_settings_path = next(); i++; }
+        else if (a == "-screenshot") screenshot = true;
         else if (a == "-out") { out_path = next(); i++; }
         else { fprintf(stderr, "grt_headless: unknown argument %s\n", a.c_str()); return 2; }
     }
-    if (content_dir.empty()) { fprintf(stderr, "usage: grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-out frame.ppm]\n"); return 2; }
+    if (content_dir.empty()) { fprintf(stderr, "usage: grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-gpus N] [-screenshot] [-out frame.png]\n"); return 2; }
+    if (gpus < 1 || gpus > 16) { fprintf(stderr, "grt_headless: -gpus must be 1..16\n"); return 2; }
 
     printf("Started (%s)\n", grt_version());
+    Settings sett;
+    if (load_settings(settings_path, sett)) printf("Loaded %s\n", settings_path.c_str());       // main.cpp:240-254
+    if (width <= 0 || height <= 0) { width = sett.width; height = sett.height; }
+    if (!adaptive_given) adaptive = sett.use_adaptive_sampling;
+    if (!save_settings_path.empty()) { sett.width = width; sett.height = height; save_settings(save_settings_path, sett); }
+
     grt_content* content = grt_content_create();
     check(grt_content_add_folder(content, content_dir.c_str()), "content folder");
     grt_metric* metric = grt_metric_load_by_name(content, metric_name.c_str());
@@ -107,69 +182,117 @@ int main(int argc, char** argv) {
         if (found < 0) { fprintf(stderr, "grt_headless: metric has no parameter %s\n", p.first.c_str()); return 2; }
         check(grt_metric_param_set(metric, found, p.second), "parameter");
     }
-    grt_ctx* ctx = grt_create(0);
-    if (!ctx) die("context");                                     // no CPU fallback: fails without an sm_100 GPU
-    auto t_build = std::chrono::steady_clock::now();
-    check(grt_set_metric(ctx, metric, is_static ? 1 : 0), "program build");
-    printf("Built %s program for %s in %.0f ms\n", is_static ? "static" : "dynamic", grt_metric_name(metric),
-           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
 
     std::vector<uint8_t> sky;
     int bw = 4096, bh = 2048;
-    const bool is_png = background_path.size() > 4 && background_path.compare(background_path.size() - 4, 4, ".png") == 0;
-    if (is_png) {                                                 // backgrounds/nasa.png in the reference (main.cpp:233-234)
+    if (ends_with(background_path, ".png")) {                     // backgrounds/nasa.png in the reference (main.cpp:233-234)
         uint8_t* px = grt_image_load_png(background_path.c_str(), &bw, &bh);
         if (!px) die("background");
         sky.assign(px, px + (size_t)bw * bh * 4);
         grt_image_free(px);
     } else if (background_path.empty() || !read_ppm(background_path.c_str(), sky, bw, bh)) sky = procedural_sky(bw, bh);
-    check(grt_set_background(ctx, sky.data(), bw, bh, 0), "background");
 
-    grt_features feat;
-    check(grt_get_features(ctx, &feat), "features");
-    feat.adaptive_sampling = adaptive ? 1 : 0;
-    feat.redshift = redshift ? 1 : 0;
-    check(grt_set_features(ctx, &feat), "features");
     const float pos[4] = {0.0f, 0.0f, -4.0f, 0.0f};                                   // main.cpp:669
     const float s = sinf(-3.14159265f / 4), c = cosf(-3.14159265f / 4);
     const float quat[4] = {s, 0.0f, 0.0f, c};                                          // axis (1,0,0), angle -pi/2 (main.cpp:670-673)
-    check(grt_set_camera(ctx, pos, quat, 0), "camera");
-    if (on_geodesic) {                                                                 // main.cpp:2675-2760, 2264-2297
-        int n = grt_snapshot_geodesic(ctx, 0.0f, 1);
-        check(n, "geodesic snapshot");
-        check(grt_set_camera_on_geodesic(ctx, geodesic_tau), "camera on geodesic");
-        printf("Camera on its geodesic at proper time %g (%d path points)\n", geodesic_tau, n);
-    }
-    check(grt_set_frames_in_flight(ctx, inflight), "frames in flight");
 
-    // one synchronous frame with statistics, then `frames` frames queued back to back into device buffers
+    // one context per device; rank 0 (device 0) owns the assembled frame
+    std::vector<grt_ctx*> ctxs(gpus, nullptr);
+    for (int r = 0; r < gpus; r++) {
+        grt_ctx* ctx = grt_create(devices.empty() ? r : devices[r]);
+        if (!ctx) die("context");                                 // no CPU fallback: fails without an sm_100 GPU
+        ctxs[r] = ctx;
+        auto t_build = std::chrono::steady_clock::now();
+        check(grt_set_metric(ctx, metric, is_static ? 1 : 0), "program build");
+        if (r == 0)
+            printf("Built %s program for %s in %.0f ms\n", is_static ? "static" : "dynamic", grt_metric_name(metric),
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
+        check(grt_set_background(ctx, sky.data(), bw, bh, 0), "background");
+        grt_features feat;
+        check(grt_get_features(ctx, &feat), "features");
+        feat.adaptive_sampling = adaptive ? 1 : 0;
+        feat.redshift = redshift ? 1 : 0;
+        feat.field_of_view = sett.field_of_view;
+        feat.max_probes = sett.anisotropy;
+        feat.use_old_redshift = sett.use_old_redshift ? 1 : 0;
+        feat.adaptive_sampling_threshold = sett.adaptive_sampling_threshold;
+        check(grt_set_features(ctx, &feat), "features");
+        check(grt_set_camera(ctx, pos, quat, 0), "camera");
+        if (on_geodesic) {                                                             // main.cpp:2675-2760, 2264-2297
+            int n = grt_snapshot_geodesic(ctx, 0.0f, 1);
+            check(n, "geodesic snapshot");
+            check(grt_set_camera_on_geodesic(ctx, geodesic_tau), "camera on geodesic");
+            if (r == 0) printf("Camera on its geodesic at proper time %g (%d path points)\n", geodesic_tau, n);
+        }
+        check(grt_set_frames_in_flight(ctx, inflight), "frames in flight");
+    }
+    grt_ctx* ctx = ctxs[0];
+
+    // one synchronous frame with statistics on device 0 (the whole frame), then `frames` frames queued back to back
     std::vector<uint8_t> host((size_t)width * height * 4);
     grt_stats st;
     check(grt_render(ctx, width, height, host.data(), GRT_FORMAT_RGBA8, GRT_OUT_HOST, &st), "render");
     printf("First frame: %.3f ms on the device (prepass %.3f, integrate %.3f, render %.3f), %llu ray-steps, %llu rays (%llu refinement)\n", st.ms_total, st.ms_prepass,
            st.ms_integrate, st.ms_render, (unsigned long long)st.trial_steps, (unsigned long long)st.rays_integrated, (unsigned long long)st.extra_rays);
-    std::vector<void*> dev(inflight, nullptr);
-    for (auto& d : dev) if (cudaMalloc(&d, host.size()) != cudaSuccess) { fprintf(stderr, "grt_headless: cudaMalloc failed\n"); return 1; }
+
+    // the frame loop: every device renders its interleaved stripes straight into device 0's frame buffer (grt_comm_render); the
+    // assembled frame lands in pinned host memory behind the last device's stores
+    std::vector<std::vector<int>> y0s(gpus), y1s(gpus);
+    for (int r = 0; r < gpus; r++) {
+        y0s[r].resize(height / 2 + 2);
+        y1s[r].resize(height / 2 + 2);
+        int n = grt_interleaved_stripes(height, r, gpus, 54, y0s[r].data(), y1s[r].data(), (int)y0s[r].size());
+        check(n, "stripes");
+        y0s[r].resize(n);
+        y1s[r].resize(n);
+        check(grt_comm_init(ctxs[r], r, gpus, width, height, GRT_FORMAT_RGBA8, std::max(2, inflight), nullptr), "communicator");
+    }
+    check(grt_comm_connect_local(ctxs.data(), gpus), "communicator connect");
+    if (gpus > 1) printf("Frame tiled over %d devices: %zu stripes of 54 rows on device 0\n", gpus, y0s[0].size());
+    std::vector<uint8_t*> pinned(std::max(2, inflight), nullptr);
+    for (auto& p : pinned) if (cudaHostAlloc((void**)&p, host.size(), cudaHostAllocDefault) != cudaSuccess) { fprintf(stderr, "grt_headless: cudaHostAlloc failed\n"); return 1; }
+    unsigned seq = 0;
     // frames go out in groups of `inflight` (one per frame slot, overlapping on the GPU); the host waits per group
     for (int k = 0; k < frames; k += inflight) {
         const int n = std::min(inflight, frames - k);
         auto t0 = std::chrono::steady_clock::now();
-        for (int j = 0; j < n; j++) {
-            check(grt_set_camera(ctx, pos, quat, 0), "camera");                       // the per-frame camera upload, main.cpp:2244-2262
-            check(grt_render(ctx, width, height, dev[j], GRT_FORMAT_RGBA8, GRT_OUT_DEVICE, nullptr), "render");
+        for (int j = 0; j < n; j++, seq++) {
+            for (int r = gpus - 1; r >= 0; r--) {                                      // the owner last
+                if (!on_geodesic) check(grt_set_camera(ctxs[r], pos, quat, 0), "camera");   // the per-frame camera upload, main.cpp:2244-2262
+                check(grt_comm_render(ctxs[r], y0s[r].data(), y1s[r].data(), (int)y0s[r].size(), seq, r == 0 ? pinned[seq % pinned.size()] : nullptr), "render");
+            }
         }
-        check(grt_synchronize(ctx), "synchronize");
+        for (int r = 0; r < gpus; r++) check(grt_synchronize(ctxs[r]), "synchronize");
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / n;
         if (print_frametime)
             for (int j = 0; j < n; j++) printf("Frametime Elapsed: %f\n", ms);       // main.cpp:2864-2871 (do-not-change string)
     }
-    check(grt_synchronize(ctx), "synchronize");
-    if (!out_path.empty()) {                                                           // screenshot, main.cpp:2762-2831
-        write_ppm(out_path.c_str(), host, width, height);
+    if (seq > 0) {
+        const uint8_t* last = pinned[(seq - 1) % pinned.size()];
+        if (memcmp(last, host.data(), host.size()) != 0) printf("note: the last frame of the loop differs from the first frame\n");
+        memcpy(host.data(), last, host.size());
+    }
+
+    // screenshot (main.cpp:2762-2831): screenshot_width x screenshot_height (times the supersample factor when supersampling is on),
+    // clamp -> lin_to_srgb -> clamp -> * 255 (the GRT_FORMAT_RGBA8 encoding), ./screenshots/<metric>_<milliseconds>.png
+    if (screenshot) {
+        const int sw = sett.screenshot_width * (sett.supersample ? sett.supersample_factor : 1), sh = sett.screenshot_height * (sett.supersample ? sett.supersample_factor : 1);
+        std::vector<uint8_t> shot((size_t)sw * sh * 4);
+        check(grt_render(ctx, sw, sh, shot.data(), GRT_FORMAT_RGBA8, GRT_OUT_HOST, nullptr), "screenshot render");
+        mkdir("./screenshots", 0755);
+        const long long millis = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+        std::string fname = "./screenshots/" + std::string(grt_metric_name(metric)) + "_" + std::to_string(millis) + ".png";
+        check(grt_image_save_png(fname.c_str(), shot.data(), sw, sh), "screenshot");
+        printf("Wrote %s (%dx%d)\n", fname.c_str(), sw, sh);
+    }
+    if (!out_path.empty()) {
+        if (ends_with(out_path, ".png")) check(grt_image_save_png(out_path.c_str(), host.data(), width, height), "png");
+        else write_ppm(out_path.c_str(), host, width, height);
         printf("Wrote %s (%dx%d)\n", out_path.c_str(), width, height);
     }
-    for (auto& d : dev) cudaFree(d);
-    grt_destroy(ctx);
+    for (auto& p : pinned) cudaFreeHost(p);
+    for (int r = 0; r < gpus; r++) check(grt_comm_disconnect(ctxs[r]), "disconnect");
+    for (int r = gpus - 1; r >= 0; r--) grt_destroy(ctxs[r]);
     grt_metric_destroy(metric);
     grt_content_destroy(content);
     return 0;

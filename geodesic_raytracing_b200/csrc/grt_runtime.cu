@@ -449,7 +449,10 @@ struct grt_ctx {
     } build;
 };
 
-namespace grt { std::vector<uint8_t> load_png_rgba(const std::string& path, int* width, int* height); }   // png_loader.cpp
+namespace grt {   // png_loader.cpp
+std::vector<uint8_t> load_png_rgba(const std::string& path, int* width, int* height);
+void save_png_rgba(const std::string& path, const uint8_t* rgba, int width, int height);
+}
 
 namespace {
 
@@ -1077,6 +1080,13 @@ uint8_t* grt_image_load_png(const char* path, int* width, int* height) {
     return rc == GRT_OK ? out : nullptr;
 }
 void grt_image_free(uint8_t* pixels) { free(pixels); }
+int grt_image_save_png(const char* path, const uint8_t* rgba, int width, int height) {
+    return guard([&] {
+        if (!path || !rgba) throw Error(GRT_E_INVALID, "null argument");
+        try { grt::save_png_rgba(path, rgba, width, height); } catch (const std::runtime_error& e) { throw Error(GRT_E_INVALID, e.what()); }
+        return GRT_OK;
+    });
+}
 
 int grt_metric_eval_symbolic(const grt_metric* m, const double pos[4], const double vel[4], double* g16, double* dg64, double* accel4, double* accel_ref4,
                              double* to_polar4, double* from_polar4, double* distance1) {

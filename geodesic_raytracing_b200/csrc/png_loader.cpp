@@ -117,4 +117,46 @@ std::vector<uint8_t> load_png_rgba(const std::string& path, int* width, int* hei
     return out;
 }
 
+
+// RGBA8 -> PNG (colour type 6, 8 bit, no interlace, filter 0 on every row, one zlib stream): the screenshot the reference writes with
+// sf::Image::saveToFile (/root/reference/main.cpp:2783-2812).
+void save_png_rgba(const std::string& path, const uint8_t* rgba, int width, int height) {
+    if (!rgba || width <= 0 || height <= 0) throw std::runtime_error("bad image");
+    std::vector<uint8_t> raw((size_t)height * ((size_t)width * 4 + 1));
+    for (int y = 0; y < height; y++) {
+        uint8_t* row = &raw[(size_t)y * ((size_t)width * 4 + 1)];
+        row[0] = 0;
+        memcpy(row + 1, rgba + (size_t)y * width * 4, (size_t)width * 4);
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) throw std::runtime_error("zlib compress failed");
+    z.resize(zlen);
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    auto put32 = [](uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; };
+    auto chunk = [&](const char* type, const uint8_t* data, size_t len) {
+        uint8_t hdr[8];
+        put32(hdr, (uint32_t)len);
+        memcpy(hdr + 4, type, 4);
+        fwrite(hdr, 1, 8, f);
+        if (len) fwrite(data, 1, len, f);
+        uLong crc = crc32(0L, (const Bytef*)type, 4);
+        if (len) crc = crc32(crc, data, (uInt)len);
+        uint8_t c[4];
+        put32(c, (uint32_t)crc);
+        fwrite(c, 1, 4, f);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    fwrite(sig, 1, 8, f);
+    uint8_t ihdr[13];
+    put32(ihdr, (uint32_t)width);
+    put32(ihdr + 4, (uint32_t)height);
+    ihdr[8] = 8; ihdr[9] = 6; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), z.size());
+    chunk("IEND", nullptr, 0);
+    if (fclose(f) != 0) throw std::runtime_error("cannot write " + path);
+}
+
 }  // namespace grt

@@ -186,6 +186,9 @@ int grt_set_background(grt_ctx*, const uint8_t* rgba, int width, int height, int
  * Returns a malloc'ed width*height*4 buffer the caller releases with grt_image_free, or NULL (grt_last_error). */
 uint8_t* grt_image_load_png(const char* path, int* width, int* height);
 void grt_image_free(uint8_t* pixels);
+/* RGBA8 pixels -> PNG file: the screenshot of main.cpp:2783-2812 (sf::Image::saveToFile). GRT_FORMAT_RGBA8 frames already carry the
+ * reference's screenshot encoding (clamp, linear -> sRGB, clamp, * 255 truncated, main.cpp:2791-2799). Host only. */
+int grt_image_save_png(const char* path, const uint8_t* rgba, int width, int height);
 /* device-resident variant (pixels already in HBM) */
 int grt_set_background_device(grt_ctx*, const void* rgba_device, int width, int height, int which);
 

@@ -598,6 +598,19 @@ def test_cpp_headless_host_renders_the_same_frame(gpu_ctx, content, grt, tmp_pat
     bind(gpu_ctx, metric, bg)
     want, _ = gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8)
     assert np.array_equal(got, want[..., :3])
+    # the frame tiled over two ranks (both on device 0 here: same protocol, the peer pointer is local), PNG output, and the screenshot
+    # path with a settings.json (main.cpp:240-254, 2762-2831)
+    (tmp_path / "settings.json").write_text('{"width": 256, "height": 144, "screenshot_width": 160, "screenshot_height": 90, "supersample": false, "anisotropy": 8}')
+    png_out = tmp_path / "frame.png"
+    r = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "kerr_schild", "-frames", "3", "-inflight", "2", "-devices", "0,0", "-background", str(ppm_in),
+                        "-out", str(png_out), "-screenshot"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "Loaded settings.json" in r.stdout and "tiled over 2 devices" in r.stdout and "differs" not in r.stdout
+    assert np.array_equal(grt.load_png(str(png_out)), want)                     # the assembled two-rank frame == the single-context frame
+    shots = list((tmp_path / "screenshots").glob("kerr_schild_*.png"))
+    assert len(shots) == 1
+    want_shot, _ = gpu_ctx.render(160, 90, grt.GRT_FORMAT_RGBA8)
+    assert np.array_equal(grt.load_png(str(shots[0])), want_shot)
     # loud failure paths: unknown metric, unknown parameter
     bad = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "no such metric"], capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and "metric" in bad.stderr

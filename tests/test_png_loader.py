@@ -59,3 +59,17 @@ def test_reference_backgrounds_decode_like_pil(grt, have_reference):
         assert got.shape == (size[1], size[0], 4)
         want = np.asarray(PIL_Image.open(path).convert("RGBA"))
         assert np.array_equal(got, want), rel
+
+
+def test_png_writer_round_trips(grt, tmp_path):
+    """grt_image_save_png (the screenshot file of main.cpp:2783-2812): what it writes, PIL and the library's own decoder read back."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for (w, h) in [(1, 1), (301, 157), (64, 2)]:
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        path = str(tmp_path / f"shot_{w}x{h}.png")
+        grt.save_png(path, img)
+        assert np.array_equal(np.array(Image.open(path).convert("RGBA")), img)
+        assert np.array_equal(grt.load_png(path), img)
+    with pytest.raises(grt.GrtError):
+        grt.save_png(str(tmp_path / "no_such_dir" / "x.png"), img)
