@@ -27,6 +27,12 @@ CASES = {
     "wormhole (morris-thorne)": [("flip", {}, {"flip": True})],
     "kerr_boyer": [("default", {}, {})],
     "double_unequal_kerr": [("default", {}, {})],
+    # the families of the reference catalogue with code paths of their own
+    "kerr_newman_schild": [("default", {}, {})],
+    "double_kerr": [("default", {}, {})],
+    "godel_cylindrical": [("default", {}, {"camera_pos": (0.0, 1.0, -3.0, 0.5)})],
+    "godel_cylindrical_forward": [("forward", {}, {"camera_pos": (0.0, 1.0, -3.0, 0.5)})],
+    "misner_4d": [("chronal", {}, {"camera_pos": (-2.0, 0.5, -4.0, 0.3)})],
 }
 
 

@@ -21,7 +21,7 @@ import oracle  # noqa: E402
 
 REFERENCE = "/root/reference/scripts"
 NAMES = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "wormhole (morris-thorne)", "kerr_schild", "alcubierre", "double_unequal_kerr", "kerr_boyer", "schwarzschild_ingoing_ef_hawking", "configurable_wormhole",
-         "krasnikov_tube", "misner_4d"]
+         "krasnikov_tube", "misner_4d", "godel_cylindrical", "kerr_newman_schild", "double_kerr"]
 
 
 def points(name, n=4):

@@ -11,7 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CAM_POS = (0.0, 0.0, -4.0, 0.0)
-METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr"]
+METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr",
+           "kerr_newman_schild", "double_kerr", "godel_cylindrical", "godel_cylindrical_forward", "misner_4d"]
 
 
 def bind(gpu_ctx, metric, background, **features):

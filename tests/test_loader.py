@@ -7,7 +7,8 @@ import pytest
 
 
 def test_bundled_content_lists_in_sorting_order(content):
-    assert content.metric_names() == ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr"]
+    assert content.metric_names() == ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr", "kerr_newman_schild", "double_kerr", "godel_cylindrical",
+                                      "godel_cylindrical_forward", "misner_4d"]
 
 
 def test_config_inheritance_and_flags(content):

@@ -9,7 +9,7 @@ import pytest
 from conftest import REFERENCE_SCRIPTS
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_metric_vectors.json")))
-BUNDLED = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_unequal_kerr"]
+BUNDLED = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_unequal_kerr", "kerr_newman_schild", "double_kerr", "godel_cylindrical", "misner_4d"]
 
 
 def check_against_golden(metric, orc, rec, rtol=3e-5):
@@ -46,6 +46,14 @@ def check_against_golden(metric, orc, rec, rtol=3e-5):
 def test_bundled_script_equals_reference_script_golden(oracles, name):
     metric, orc = oracles(name)
     check_against_golden(metric, orc, GOLDEN[name])
+
+
+def test_forward_geodesic_variant_is_the_same_metric(oracles):
+    """godel_forward.js/.json: the bundled Goedel metric with `follow_geodesics_forward` set (no reference metric sets that key; the variant
+    keeps the code path of cl.cl:3039-3051 under test).  Same g, dg, maps as the reference's godel_cylinder.js."""
+    metric, orc = oracles("godel_cylindrical_forward")
+    check_against_golden(metric, orc, GOLDEN["godel_cylindrical"])
+    assert "#define GRT_FORWARD_GEODESIC_PATH 1" in metric.source(False)
 
 
 def test_all_reference_scripts_load_unchanged(grt, have_reference):
