@@ -90,7 +90,58 @@ struct Lexer {
                 while (pos < src.size() && (isalnum((unsigned char)src[pos]) || src[pos] == '_' || src[pos] == '$')) pos++;
                 t.text = src.substr(s, pos - s);
                 t.type = kKeywords.count(t.text) ? Tok::Keyword : Tok::Ident;
-            } else if (c == '"' || c == '\'' || c == '`') {
+            } else if (c == '`') {
+                // template literal: `a${x}b` is emitted as the tokens ("a" + (x) + "b"), the pieces lexed recursively
+                if (!toks.empty() && !toks.back().nl_before && (toks.back().type == Tok::Ident || (toks.back().type == Tok::Punct && (toks.back().text == ")" || toks.back().text == "]"))))
+                    fail("tagged template literals are not supported by the metric script interpreter");
+                pos++;
+                auto push_punct = [&](const char* s) { Token k; k.type = Tok::Punct; k.text = s; k.line = line; toks.push_back(k); };
+                t.type = Tok::Punct; t.text = "("; toks.push_back(t);
+                std::string piece;
+                bool first = true;
+                auto flush = [&]() {
+                    if (!first) push_punct("+");
+                    Token k; k.type = Tok::Str; k.text = piece; k.line = line; toks.push_back(k);
+                    piece.clear();
+                    first = false;
+                };
+                while (true) {
+                    if (pos >= src.size()) fail("unterminated template literal");
+                    char ch = src[pos++];
+                    if (ch == '`') break;
+                    if (ch == '\\' && pos < src.size()) {
+                        char e = src[pos++];
+                        switch (e) { case 'n': piece += '\n'; break; case 't': piece += '\t'; break; case 'r': piece += '\r'; break; case '\n': line++; break; default: piece += e; }
+                    } else if (ch == '$' && pos < src.size() && src[pos] == '{') {
+                        pos++;
+                        size_t start = pos;
+                        int depth = 1;
+                        while (pos < src.size() && depth > 0) {
+                            if (src[pos] == '{') depth++;
+                            else if (src[pos] == '}') depth--;
+                            else if (src[pos] == '\n') line++;
+                            if (depth > 0) pos++;
+                        }
+                        if (pos >= src.size()) fail("unterminated ${ in template literal");
+                        std::string inner = src.substr(start, pos - start);
+                        pos++;
+                        flush();
+                        push_punct("+");
+                        push_punct("(");
+                        Lexer sub(inner, name);
+                        sub.line = line;
+                        sub.run();
+                        for (auto& k : sub.toks) if (k.type != Tok::End) toks.push_back(k);
+                        push_punct(")");
+                    } else {
+                        if (ch == '\n') line++;
+                        piece += ch;
+                    }
+                }
+                flush();
+                push_punct(")");
+                continue;
+            } else if (c == '"' || c == '\'') {
                 char q = c;
                 pos++;
                 std::string out;
@@ -139,7 +190,11 @@ enum class K {
     Num, Str, Ident, ArrayLit, ObjectLit, Func, Member, Index, Call, New, Unary, Update, Binary,
     Logical, Assign, Cond, Comma, This, Literal,
     VarDecl, FuncDecl, Return, If, For, ForIn, ForOf, While, DoWhile, Break, Continue, Block,
-    ExprStmt, Empty, Throw, Try
+    ExprStmt, Empty, Throw, Try,
+    Spread,      // ...expr in a call, an array literal or an object literal
+    Switch,      // kids[0] discriminant, then Case nodes
+    Case,        // kids[0] test (Empty for `default`), then the statements
+    Class        // s = name, kids[0] = parent expression or Empty, members in `members`
 };
 
 struct Node;
@@ -151,6 +206,10 @@ struct FuncDef {
     NodeP body;             // Block, or an expression for concise arrows
     bool is_arrow = false;
     bool expr_body = false;
+    std::vector<NodeP> defaults;          // parallel to params (null: none): `function f(a, b = 2)`
+    std::string rest;                     // `...rest`
+    std::string source;                   // name of the script that defines the function (error messages of later calls)
+    std::vector<NodeP> prologue;          // destructuring parameters: declarations run before the body
     std::vector<std::string> hoisted_vars;
     std::vector<const Node*> hoisted_funcs;
 };
@@ -163,6 +222,8 @@ struct Node {
     bool flag = false;      // Update: prefix; Literal: bool value
     std::vector<NodeP> kids;
     std::unique_ptr<FuncDef> fn;
+    struct ClassMember { std::string name; std::unique_ptr<FuncDef> fn; bool is_static = false; char accessor = 0; };   // accessor: 'g' getter, 's' setter
+    std::vector<ClassMember> members;       // Class
     Node(K kind, int ln) : k(kind), line(ln) {}
 };
 
@@ -247,16 +308,118 @@ struct Parser {
         return prog;
     }
 
-    std::unique_ptr<FuncDef> function_rest(const std::string& fname) {
-        auto f = std::make_unique<FuncDef>();
-        f->name = fname;
-        expect_punct("(");
+    int tmp_counter = 0;
+    std::string fresh(const char* stem) { return std::string("$") + stem + std::to_string(tmp_counter++); }
+    NodeP ident_node(const std::string& nm) { auto n = mk(K::Ident); n->s = nm; return n; }
+
+    // Binding pattern -> plain declarations.  `[a, b = 1, ...r]` and `{x, y: z = 3}` (nested patterns allowed) read from the
+    // variable `src`; every bound name becomes an Ident declaration with its initialiser appended to `decls`.
+    void bind_pattern(std::vector<NodeP>& decls, const std::string& src) {
+        auto with_default = [&](std::function<NodeP()> access) -> NodeP {
+            if (!eat_punct("=")) return access();
+            auto test = mk(K::Binary);
+            test->s = "===";
+            test->kids.push_back(access());
+            auto undef = mk(K::Literal);
+            undef->s = "undefined";
+            test->kids.push_back(std::move(undef));
+            auto c = mk(K::Cond);
+            c->kids.push_back(std::move(test));
+            c->kids.push_back(assignment());
+            c->kids.push_back(access());
+            return c;
+        };
+        auto bind_target = [&](std::function<NodeP()> access) {
+            if (is_punct("[") || is_punct("{")) {
+                // nested pattern: a temporary holds the element (its own default applies to the whole sub-pattern)
+                std::string tmp = fresh("d");
+                std::vector<NodeP> inner;
+                bind_pattern(inner, tmp);
+                auto d = ident_node(tmp);
+                d->kids.push_back(with_default(access));
+                decls.push_back(std::move(d));
+                for (auto& x : inner) decls.push_back(std::move(x));
+                return;
+            }
+            auto d = ident_node(ident_name());
+            d->kids.push_back(with_default(access));
+            decls.push_back(std::move(d));
+        };
+        if (eat_punct("[")) {
+            int index = 0;
+            while (!is_punct("]")) {
+                if (eat_punct(",")) { index++; continue; }          // hole
+                if (eat_punct("...")) {
+                    auto d = ident_node(ident_name());
+                    auto call = mk(K::Call);
+                    auto m = mk(K::Member);
+                    m->s = "slice";
+                    m->kids.push_back(ident_node(src));
+                    call->kids.push_back(std::move(m));
+                    auto from = mk(K::Num);
+                    from->num = index;
+                    call->kids.push_back(std::move(from));
+                    d->kids.push_back(std::move(call));
+                    decls.push_back(std::move(d));
+                    break;
+                }
+                const int at = index++;
+                bind_target([&, at]() { auto ix = mk(K::Index); ix->kids.push_back(ident_node(src)); auto k = mk(K::Num); k->num = at; ix->kids.push_back(std::move(k)); return NodeP(std::move(ix)); });
+                if (!eat_punct(",")) break;
+            }
+            expect_punct("]");
+        } else if (eat_punct("{")) {
+            while (!is_punct("}")) {
+                if (is_punct("...")) fail("rest properties in object patterns are not supported by the metric script interpreter");
+                const bool was_ident = t[p].type == Tok::Ident;
+                std::string key = property_name();
+                auto access = [&, key]() { auto m = mk(K::Member); m->s = key; m->kids.push_back(ident_node(src)); return NodeP(std::move(m)); };
+                if (eat_punct(":")) bind_target(access);
+                else {
+                    if (!was_ident) fail("expected ':' after a quoted or numeric property name in a pattern");
+                    auto d = ident_node(key);
+                    d->kids.push_back(with_default(access));
+                    decls.push_back(std::move(d));
+                }
+                if (!eat_punct(",")) break;
+            }
+            expect_punct("}");
+        } else fail("expected a binding pattern");
+    }
+
+    // formal parameters after '(' up to and including ')': names, defaults, a rest parameter, destructuring patterns
+    void parameters(FuncDef& f) {
         while (!is_punct(")")) {
-            f->params.push_back(ident_name());
-            if (eat_punct("=")) fail("default parameters are not supported");
+            if (eat_punct("...")) {
+                f.rest = ident_name();
+                break;
+            }
+            if (is_punct("[") || is_punct("{")) {
+                std::string tmp = fresh("p");
+                std::vector<NodeP> decls;
+                bind_pattern(decls, tmp);
+                f.params.push_back(tmp);
+                f.defaults.push_back(eat_punct("=") ? assignment() : nullptr);
+                auto d = mk(K::VarDecl);
+                d->s = "let";
+                d->kids = std::move(decls);
+                f.prologue.push_back(std::move(d));
+            } else {
+                f.params.push_back(ident_name());
+                f.defaults.push_back(eat_punct("=") ? assignment() : nullptr);
+            }
             if (!eat_punct(",")) break;
         }
         expect_punct(")");
+    }
+
+    std::unique_ptr<FuncDef> function_rest(const std::string& fname) {
+        auto f = std::make_unique<FuncDef>();
+        f->name = fname;
+        f->source = name;
+        if (is_punct("*")) fail("generator functions are not supported by the metric script interpreter");
+        expect_punct("(");
+        parameters(*f);
         f->body = block();
         collect_hoisted(f->body.get(), *f, true);
         return f;
@@ -277,6 +440,17 @@ struct Parser {
         auto d = mk(K::VarDecl);
         d->s = t[p++].text;  // var/let/const
         do {
+            if (is_punct("[") || is_punct("{")) {       // destructuring: const [a, b] = pair;  const {x, y} = point;
+                std::string tmp = fresh("d");
+                std::vector<NodeP> decls;
+                bind_pattern(decls, tmp);
+                if (!eat_punct("=")) fail("a destructuring declaration needs an initialiser");
+                auto src = ident_node(tmp);
+                src->kids.push_back(assignment());
+                d->kids.push_back(std::move(src));
+                for (auto& x : decls) d->kids.push_back(std::move(x));
+                continue;
+            }
             auto one = mk(K::Ident);
             one->s = ident_name();
             if (eat_punct("=")) one->kids.push_back(assignment());
@@ -293,6 +467,7 @@ struct Parser {
         if (is_kw("function")) {
             auto n = mk(K::FuncDecl);
             p++;
+            if (is_punct("*")) fail("generator functions are not supported by the metric script interpreter");
             n->s = ident_name();
             n->fn = function_rest(n->s);
             return n;
@@ -325,6 +500,27 @@ struct Parser {
                 bool decl = t[p].type == Tok::Keyword;
                 std::string declkind = decl ? t[p].text : "";
                 if (decl) p++;
+                if (decl && (is_punct("[") || is_punct("{"))) {        // for (const [k, v] of pairs)
+                    std::string tmp = fresh("it");
+                    std::vector<NodeP> decls;
+                    bind_pattern(decls, tmp);
+                    if (!is_kw("of")) fail("a destructuring loop variable needs 'of'");
+                    auto n = std::make_unique<Node>(K::ForOf, ln);
+                    p++;
+                    n->s = tmp;
+                    n->flag = true;
+                    n->num = 1;
+                    n->kids.push_back(expression());
+                    expect_punct(")");
+                    auto body = mk(K::Block);
+                    auto d = mk(K::VarDecl);
+                    d->s = declkind == "var" ? "let" : declkind;
+                    d->kids = std::move(decls);
+                    body->kids.push_back(std::move(d));
+                    body->kids.push_back(statement());
+                    n->kids.push_back(std::move(body));
+                    return n;
+                }
                 if (t[p].type == Tok::Ident) {
                     std::string vname = t[p].text;
                     p++;
@@ -394,7 +590,43 @@ struct Parser {
             if (eat_kw("finally")) n->kids.push_back(block());
             return n;
         }
-        if (is_kw("class") || is_kw("switch")) fail("'" + t[p].text + "' is not supported by the metric script interpreter");
+        if (is_kw("switch")) {
+            auto n = mk(K::Switch);
+            p++;
+            expect_punct("(");
+            n->kids.push_back(expression());
+            expect_punct(")");
+            expect_punct("{");
+            bool seen_default = false;
+            while (!is_punct("}")) {
+                auto c = mk(K::Case);
+                if (eat_kw("default")) {
+                    if (seen_default) fail("more than one default clause");
+                    seen_default = true;
+                    c->kids.push_back(mk(K::Empty));
+                } else {
+                    if (!eat_kw("case")) fail("expected 'case' or 'default'");
+                    c->kids.push_back(expression());
+                }
+                expect_punct(":");
+                while (!is_kw("case") && !is_kw("default") && !is_punct("}")) {
+                    if (t[p].type == Tok::End) fail("unterminated switch");
+                    c->kids.push_back(statement());
+                }
+                n->kids.push_back(std::move(c));
+            }
+            expect_punct("}");
+            return n;
+        }
+        if (is_kw("class")) {
+            auto c = class_rest();
+            if (c->s.empty()) fail("a class declaration needs a name");
+            return c;
+        }
+        if (t[p].type == Tok::Ident && (t[p].text == "async" || t[p].text == "yield" || t[p].text == "await") && t[p + 1].type != Tok::Punct)
+            fail("'" + t[p].text + "' is not supported by the metric script interpreter");
+        if (t[p].type == Tok::Ident && t[p + 1].type == Tok::Punct && t[p + 1].text == ":")
+            fail("labelled statements are not supported by the metric script interpreter");
         auto e = mk(K::ExprStmt);
         e->kids.push_back(expression());
         consume_semicolon();
@@ -433,14 +665,11 @@ struct Parser {
         auto n = mk(K::Func);
         auto f = std::make_unique<FuncDef>();
         f->is_arrow = true;
-        if (t[p].type == Tok::Ident) f->params.push_back(t[p++].text);
+        f->source = name;
+        if (t[p].type == Tok::Ident) { f->params.push_back(t[p++].text); f->defaults.push_back(nullptr); }
         else {
             expect_punct("(");
-            while (!is_punct(")")) {
-                f->params.push_back(ident_name());
-                if (!eat_punct(",")) break;
-            }
-            expect_punct(")");
+            parameters(*f);
         }
         expect_punct("=>");
         if (is_punct("{")) f->body = block();
@@ -558,13 +787,46 @@ struct Parser {
         return e;
     }
 
+    NodeP maybe_spread() {
+        if (is_punct("...")) {
+            auto sp = mk(K::Spread);
+            p++;
+            sp->kids.push_back(assignment());
+            return sp;
+        }
+        return assignment();
+    }
+
     void arguments(Node& call) {
         expect_punct("(");
         while (!is_punct(")")) {
-            call.kids.push_back(assignment());
+            call.kids.push_back(maybe_spread());
             if (!eat_punct(",")) break;
         }
         expect_punct(")");
+    }
+
+    // after the `class` keyword: [name] [extends expr] { constructor(..){..}  m(..){..}  static s(..){..}  get x(){..}  set x(v){..} }
+    NodeP class_rest() {
+        auto c = mk(K::Class);
+        p++;
+        if (t[p].type == Tok::Ident) c->s = t[p++].text;
+        if (t[p].type == Tok::Ident && t[p].text == "extends") { p++; c->kids.push_back(call_member()); }
+        else c->kids.push_back(mk(K::Empty));
+        expect_punct("{");
+        while (!is_punct("}")) {
+            if (eat_punct(";")) continue;
+            Node::ClassMember m;
+            if (t[p].type == Tok::Ident && t[p].text == "static" && !(t[p + 1].type == Tok::Punct && t[p + 1].text == "(")) { m.is_static = true; p++; }
+            if (t[p].type == Tok::Ident && (t[p].text == "get" || t[p].text == "set") && !(t[p + 1].type == Tok::Punct && t[p + 1].text == "(")) { m.accessor = t[p].text[0]; p++; }
+            if (is_punct("*") || is_punct("[") || is_punct("#")) fail("generator, computed and private class members are not supported by the metric script interpreter");
+            m.name = property_name();
+            if (!is_punct("(")) fail("class fields are not supported by the metric script interpreter (assign them in the constructor)");
+            m.fn = function_rest(m.name);
+            c->members.push_back(std::move(m));
+        }
+        expect_punct("}");
+        return c;
     }
 
     NodeP call_member() {
@@ -621,9 +883,11 @@ struct Parser {
             if (tk.text == "null") { auto n = mk(K::Literal); n->s = "null"; p++; return n; }
             if (tk.text == "undefined") { auto n = mk(K::Literal); n->s = "undefined"; p++; return n; }
             if (tk.text == "of") { auto n = mk(K::Ident); n->s = tk.text; p++; return n; }
+            if (tk.text == "class") return class_rest();
             if (tk.text == "function") {
                 auto n = mk(K::Func);
                 p++;
+                if (is_punct("*")) fail("generator functions are not supported by the metric script interpreter");
                 std::string fname;
                 if (t[p].type == Tok::Ident) fname = t[p++].text;
                 n->fn = function_rest(fname);
@@ -641,7 +905,7 @@ struct Parser {
             p++;
             while (!is_punct("]")) {
                 if (is_punct(",")) { a->kids.push_back(mk(K::Literal)); a->kids.back()->s = "hole"; p++; continue; }
-                a->kids.push_back(assignment());
+                a->kids.push_back(maybe_spread());
                 if (!eat_punct(",")) break;
             }
             expect_punct("]");
@@ -651,6 +915,16 @@ struct Parser {
             auto o = mk(K::ObjectLit);
             p++;
             while (!is_punct("}")) {
+                if (is_punct("...")) {                    // {...base, x: 1}
+                    auto key = mk(K::Str);
+                    key->s = "...";
+                    p++;
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(assignment());
+                    if (!eat_punct(",")) break;
+                    continue;
+                }
+                if (is_punct("[")) fail("computed property names are not supported by the metric script interpreter");
                 auto key = mk(K::Str);
                 bool was_ident = t[p].type == Tok::Ident;
                 key->s = property_name();
@@ -776,6 +1050,63 @@ struct Evaluator {
     Comp exec_block(const std::vector<NodeP>& body, EnvP& env);
     Value call_function(const Node* n, const Value& fn, const Value& self, std::vector<Value>& args);
     void assign_to(const Node* target, EnvP& env, const Value& v);
+
+    // one argument / array element: `...expr` contributes every element of the array it evaluates to
+    void push_arg(const Node* k, EnvP& env, std::vector<Value>& out) {
+        if (k->k != K::Spread) { out.push_back(eval(k, env)); return; }
+        Value v = eval(k->kids[0].get(), env);
+        if (v.type == Value::String) { for (char c : v.str) out.push_back(Value(std::string(1, c))); return; }
+        if (v.type != Value::Obj || v.obj->kind != Object::Array) fail(k, "TypeError: spread needs an array");
+        out.insert(out.end(), v.obj->arr.begin(), v.obj->arr.end());
+    }
+
+    // class C [extends B] { ... } -> a constructor object: props["prototype"] holds the methods (getters / setters under "$get$name" /
+    // "$set$name"), static members are properties of the constructor, `klass` links to the parent class
+    Value make_class(const Node* n, EnvP& env) {
+        Value parent;
+        if (n->kids[0]->k != K::Empty) {
+            parent = eval(n->kids[0].get(), env);
+            if (parent.type != Value::Obj || parent.obj->kind != Object::Function) fail(n, "TypeError: class extends value is not a constructor");
+        }
+        EnvP cenv = new_env(env, false);        // `super` and the class's own name are visible to its methods
+        auto proto = Interp::make_object();
+        auto ctor = std::make_shared<Object>();
+        ctor->kind = Object::Function;
+        ctor->is_class = true;
+        ctor->env = cenv;
+        const FuncDef* ctor_def = nullptr;
+        if (parent.type == Value::Obj) {
+            ctor->klass = parent.obj;
+            auto pp = parent.obj->props.find("prototype");
+            if (pp != parent.obj->props.end() && pp->second.type == Value::Obj) proto->props = pp->second.obj->props;     // inherited methods
+            for (auto& kv : parent.obj->props) if (kv.first != "prototype") ctor->props[kv.first] = kv.second;              // inherited statics
+            // `super`: callable (the parent constructor on the current `this`) and carrying the parent's methods
+            auto sup = std::make_shared<Object>(*parent.obj);
+            sup->is_class = false;
+            sup->props.clear();
+            if (pp != parent.obj->props.end() && pp->second.type == Value::Obj) sup->props = pp->second.obj->props;
+            cenv->vars["super"] = Value(sup);
+        }
+        for (auto& m : n->members) {
+            if (m.name == "constructor" && !m.is_static && !m.accessor) { ctor_def = m.fn.get(); continue; }
+            auto f = std::make_shared<Object>();
+            f->kind = Object::Function;
+            f->def = m.fn.get();
+            f->env = cenv;
+            std::string key = m.accessor == 'g' ? "$get$" + m.name : (m.accessor == 's' ? "$set$" + m.name : m.name);
+            (m.is_static ? ctor->props : proto->props)[key] = Value(f);
+        }
+        static const FuncDef empty_ctor = [] { FuncDef d; d.body = std::make_unique<Node>(K::Block, 0); return d; }();
+        if (!ctor_def && parent.type == Value::Obj) {
+            // default derived constructor: constructor(...args) { super(...args); }
+            ctor->def = parent.obj->def ? parent.obj->def : &empty_ctor;
+            ctor->env = parent.obj->def ? parent.obj->env : cenv;
+        } else ctor->def = ctor_def ? ctor_def : &empty_ctor;
+        ctor->props["prototype"] = Value(proto);
+        Value cv(ctor);
+        if (!n->s.empty()) cenv->vars[n->s] = cv;
+        return cv;
+    }
 };
 
 Value Evaluator::array_method(const Node* n, const ObjP& a, const std::string& key) {
@@ -885,6 +1216,16 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
     }
     auto it = o->props.find(key);
     if (it != o->props.end()) return it->second;
+    for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a getter of the instance's class (or a parent's)
+        auto pr = c->props.find("prototype");
+        if (pr == c->props.end() || pr->second.type != Value::Obj) break;
+        auto g = pr->second.obj->props.find("$get$" + key);
+        if (g != pr->second.obj->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
+    }
+    if (o->kind == Object::Function && o->is_class) {        // static getter
+        auto g = o->props.find("$get$" + key);
+        if (g != o->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
+    }
     if ((o->kind == Object::Function || o->kind == Object::Native) && key == "call") {
         Value fn = objv;
         return Value(Interp::make_native([fn](Interp& ip, const Value&, std::vector<Value>& args) {
@@ -914,6 +1255,12 @@ void Evaluator::set_prop(const Node* n, const Value& objv, const std::string& ke
             o->arr[idx] = v;
             return;
         }
+    }
+    for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a setter of the instance's class (or a parent's)
+        auto pr = c->props.find("prototype");
+        if (pr == c->props.end() || pr->second.type != Value::Obj) break;
+        auto st = pr->second.obj->props.find("$set$" + key);
+        if (st != pr->second.obj->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
     }
     o->props[key] = v;
 }
@@ -968,7 +1315,13 @@ Value Evaluator::binary_op(const Node* n, const std::string& op, const Value& a,
         if (b.obj->kind == Object::Array && array_index(k, idx)) return Value(idx < b.obj->arr.size());
         return Value(b.obj->props.count(k) > 0);
     }
-    if (op == "instanceof") return Value(false);
+    if (op == "instanceof") {
+        if (b.type != Value::Obj || (b.obj->kind != Object::Function && b.obj->kind != Object::Native)) fail(n, "TypeError: right-hand side of 'instanceof' is not callable");
+        if (a.type != Value::Obj) return Value(false);
+        for (const Object* c = a.obj->klass.get(); c; c = c->klass.get())
+            if (c == b.obj.get()) return Value(true);
+        return Value(false);
+    }
     double x = Interp::to_number(a), y = Interp::to_number(b);
     if (op == "-") return Value(x - y);
     if (op == "*") return Value(x * y);
@@ -1007,9 +1360,16 @@ Value Evaluator::call_function(const Node* n, const Value& fn, const Value& self
     const FuncDef* def = fn.obj->def;
     EnvP env = new_env(fn.obj->env, true);
     env->this_val = fn.obj->is_arrow ? fn.obj->bound_this : self;
-    for (size_t i = 0; i < def->params.size(); i++) env->vars[def->params[i]] = i < args.size() ? args[i] : Value();
+    for (size_t i = 0; i < def->params.size(); i++) {
+        Value v = i < args.size() ? args[i] : Value();
+        if (v.is_undefined() && i < def->defaults.size() && def->defaults[i]) v = eval(def->defaults[i].get(), env);   // earlier parameters are in scope
+        env->vars[def->params[i]] = v;
+    }
+    if (!def->rest.empty())
+        env->vars[def->rest] = Value(Interp::make_array(args.size() > def->params.size() ? std::vector<Value>(args.begin() + def->params.size(), args.end()) : std::vector<Value>()));
     if (!def->is_arrow) env->vars["arguments"] = Value(Interp::make_array(args));
     hoist(*def, env);
+    for (auto& d : def->prologue) exec(d.get(), env);
     Value result;
     try {
         if (def->expr_body) result = eval(def->body.get(), env);
@@ -1041,14 +1401,26 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
         case K::Ident: return get_var(n, env, n->s);
         case K::ArrayLit: {
             std::vector<Value> items;
-            for (auto& k : n->kids) items.push_back(eval(k.get(), env));
+            for (auto& k : n->kids) push_arg(k.get(), env, items);
             return Value(Interp::make_array(items));
         }
         case K::ObjectLit: {
             auto o = Interp::make_object();
-            for (size_t i = 0; i + 1 < n->kids.size(); i += 2) o->props[n->kids[i]->s] = eval(n->kids[i + 1].get(), env);
+            for (size_t i = 0; i + 1 < n->kids.size(); i += 2) {
+                Value v = eval(n->kids[i + 1].get(), env);
+                if (n->kids[i]->s == "..." && n->kids[i + 1]->k != K::Str) {      // {...base}
+                    if (v.type == Value::Obj) {
+                        if (v.obj->kind == Object::Array) for (size_t k = 0; k < v.obj->arr.size(); k++) o->props[std::to_string(k)] = v.obj->arr[k];
+                        for (auto& kv : v.obj->props) o->props[kv.first] = kv.second;
+                    }
+                    continue;
+                }
+                o->props[n->kids[i]->s] = v;
+            }
             return Value(o);
         }
+        case K::Spread: fail(n, "SyntaxError: '...' is only valid in a call, an array literal or an object literal");
+        case K::Class: return make_class(n, env);
         case K::Func: return make_closure(n->fn.get(), env);
         case K::Member: return get_prop(n, eval(n->kids[0].get(), env), n->s);
         case K::Index: {
@@ -1067,18 +1439,29 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
                 self = eval(callee->kids[0].get(), env);
                 fn = get_prop(callee, self, key_of(eval(callee->kids[1].get(), env)));
             } else fn = eval(callee, env);
+            // super(...) and super.method(...) run with the current `this`
+            if ((callee->k == K::Ident && callee->s == "super") || (callee->k == K::Member && callee->kids[0]->k == K::Ident && callee->kids[0]->s == "super")) self = env->this_val;
             std::vector<Value> args;
-            for (size_t i = 1; i < n->kids.size(); i++) args.push_back(eval(n->kids[i].get(), env));
+            for (size_t i = 1; i < n->kids.size(); i++) push_arg(n->kids[i].get(), env, args);
             if (fn.type != Value::Obj) fail(n, "TypeError: " + (callee->k == K::Ident ? "'" + callee->s + "'" : std::string("expression")) + " is not a function");
+            if (fn.obj->is_class && !(callee->k == K::Ident && callee->s == "super")) fail(n, "TypeError: class constructors must be invoked with 'new'");
             return call_function(n, fn, self, args);
         }
         case K::New: {
             Value ctor = eval(n->kids[0].get(), env);
             std::vector<Value> args;
-            for (size_t i = 1; i < n->kids.size(); i++) args.push_back(eval(n->kids[i].get(), env));
+            for (size_t i = 1; i < n->kids.size(); i++) push_arg(n->kids[i].get(), env, args);
             if (ctor.type != Value::Obj) fail(n, "TypeError: not a constructor");
             if (ctor.obj->kind == Object::Native) return ctor.obj->native(in, Value(), args);
             Value self(Interp::make_object());
+            if (ctor.obj->is_class) {
+                // no prototype chain in this interpreter: an instance carries its class (instanceof, getters) and gets the methods copied in
+                self.obj->klass = ctor.obj;
+                auto proto = ctor.obj->props.find("prototype");
+                if (proto != ctor.obj->props.end() && proto->second.type == Value::Obj)
+                    for (auto& kv : proto->second.obj->props)
+                        if (kv.first.compare(0, 5, "$get$") != 0 && kv.first.compare(0, 5, "$set$") != 0) self.obj->props[kv.first] = kv.second;
+            }
             Value r = call_function(n, ctor, self, args);
             return r.type == Value::Obj ? r : self;
         }
@@ -1189,6 +1572,30 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
             return Comp::Normal;
         }
         case K::FuncDecl: return Comp::Normal;  // hoisted
+        case K::Class: {
+            env->vars[n->s] = make_class(n, env);
+            return Comp::Normal;
+        }
+        case K::Switch: {
+            Value d = eval(n->kids[0].get(), env);
+            EnvP inner = new_env(env, false);
+            size_t start = n->kids.size(), fallback = n->kids.size();
+            for (size_t i = 1; i < n->kids.size() && start == n->kids.size(); i++) {
+                const Node* c = n->kids[i].get();
+                if (c->kids[0]->k == K::Empty) { fallback = i; continue; }
+                if (strict_equal(d, eval(c->kids[0].get(), inner))) start = i;
+            }
+            if (start == n->kids.size()) start = fallback;
+            for (size_t i = start; i < n->kids.size(); i++) {        // fall through until a break
+                const Node* c = n->kids[i].get();
+                for (size_t k = 1; k < c->kids.size(); k++) {
+                    Comp r = exec(c->kids[k].get(), inner);
+                    if (r == Comp::Break) return Comp::Normal;
+                    if (r != Comp::Normal) return r;
+                }
+            }
+            return Comp::Normal;
+        }
         case K::Return:
             ret = n->kids.empty() ? Value() : eval(n->kids[0].get(), env);
             return Comp::Return;
@@ -1484,7 +1891,9 @@ Value Interp::eval(const std::string& source, const std::string& name) {
 }
 
 Value Interp::call(const Value& fn, const Value& self, std::vector<Value> args) {
-    Evaluator ev(*this, "<call>");
+    // errors raised while the function runs name the script that defines it, like the errors of its first evaluation
+    const bool scripted = fn.type == Value::Obj && fn.obj->kind == Object::Function && fn.obj->def && !fn.obj->def->source.empty();
+    Evaluator ev(*this, scripted ? fn.obj->def->source : std::string("<call>"));
     try {
         return ev.call_function(nullptr, fn, self, args);
     } catch (Thrown& th) {

@@ -6,8 +6,12 @@
 // engine and the reference's vendored one must not be copied, so the plugin boundary
 //  is served by this interpreter: operator overloading on host objects is a
 // first-class hook instead of the bignum extension, everything else is plain JavaScript:
-// var/let/const with hoisting, functions/closures/arrows, if/for/while/do, arrays, objects,
-// Math.*, the usual operators, automatic semicolon insertion.  The completion value of a
+// var/let/const with hoisting, functions/closures/arrows, default and rest parameters, destructuring declarations and
+// parameters, spread in calls / array / object literals, template literals, if/for/for-in/for-of/while/do/switch, try/catch,
+// classes (constructor, methods, static methods, getters, extends + super), arrays with the usual methods, objects, Math.*,
+// the usual operators, automatic semicolon insertion.  What is not implemented (generators, async, regular expressions,
+// labels, destructuring assignment without a declaration, class fields, tagged templates, optional chaining) is refused with
+// a SyntaxError that names the script and the line - never skipped silently.  The completion value of a
 // script (the value of its last expression statement) is what `eval` returns, which is how the
 // reference obtains the metric function (/root/reference/js_interop.cpp:738-742).
 #pragma once
@@ -66,6 +70,8 @@ struct Object {
     NativeFn native;                        // Native
     int host_tag = 0;                       // Host: type tag chosen by the embedder
     std::shared_ptr<void> host;             // Host payload
+    ObjP klass;                             // instance: the class (constructor object) that built it; class: its parent class
+    bool is_class = false;                  // a constructor made by `class`: props["prototype"] holds its methods
     // property hooks for Host objects (return true when handled)
     std::function<bool(Interp&, const std::string&, Value&)> get_hook;
     std::function<bool(Interp&, const std::string&, const Value&)> set_hook;

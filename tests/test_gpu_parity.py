@@ -11,6 +11,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 CAM_POS = (0.0, 0.0, -4.0, 0.0)
+# Misner space wants the camera in the chronal region (camera time < 0, scripts/misner_4d.json); at the default camera its
+# coordinate map takes the logarithm of zero
+CAMERAS = {"misner_4d": (-2.0, 0.5, -4.0, 0.3)}
+
+
+def camera_of(metric):
+    return CAMERAS.get(metric.name, CAM_POS)
+
 METRICS = ["minkowski", "schwarzschild_fast", "schwarzschild", "schwarzschild_skewed", "schwarzschild_ingoing_ef", "kerr_schild", "kerr_boyer", "wormhole (morris-thorne)", "alcubierre", "double_schwarzschild", "double_unequal_kerr",
            "kerr_newman_schild", "double_kerr", "godel_cylindrical", "godel_cylindrical_forward", "misner_4d"]
 
@@ -19,7 +27,7 @@ def bind(gpu_ctx, metric, background, **features):
     gpu_ctx.set_fast_math(True)
     gpu_ctx.set_metric(metric)
     gpu_ctx.set_background(background)
-    gpu_ctx.set_camera()
+    gpu_ctx.set_camera(camera_of(metric))
     gpu_ctx.clear_camera_geodesic()
     base = dict(universe_size=20.0, max_precision_radius=10.0, min_step=1e-6, adaptive_sampling_threshold=32.0, field_of_view=90.0, redshift=0, reparameterisation=0,
                 use_old_redshift=0, adaptive_sampling=1, max_probes=8, use_prepass=-1, max_acceleration_change=metric.info.max_acceleration_change)
@@ -61,13 +69,14 @@ def test_camera_tetrad_matches(gpu_ctx, oracles, background, name):
     metric, orc = oracles(name)
     bind(gpu_ctx, metric, background)
     cs = gpu_ctx.camera_state()
-    gen, tet = orc.camera(CAM_POS)
+    gen, tet = orc.camera(camera_of(metric))
     assert np.allclose(np.array(list(cs.pos_generic)), gen, atol=1e-5)
+    assert np.isfinite(gen).all()
     assert np.allclose(np.array(list(cs.tetrad)).reshape(4, 4), tet, atol=2e-4), name
     # a boosted observer too
     gpu_ctx.set_observer_speed((0.3, -0.2, 0.1))
     cs = gpu_ctx.camera_state()
-    gen, tet = orc.camera(CAM_POS, basis_speed=(0.3, -0.2, 0.1))
+    gen, tet = orc.camera(camera_of(metric), basis_speed=(0.3, -0.2, 0.1))
     assert np.allclose(np.array(list(cs.tetrad)).reshape(4, 4), tet, atol=5e-4), name
     gpu_ctx.set_observer_speed((0, 0, 0))
     # tetrads at arbitrary points, unoriented (the per-hit emitter frame of calculate_render_data)
@@ -81,7 +90,7 @@ def test_camera_tetrad_matches(gpu_ctx, oracles, background, name):
 def compare_frame(gpu_ctx, metric, orc, background, w, h, min_term, min_px, **features):
     base = bind(gpu_ctx, metric, background, **features)
     img, st = gpu_ctx.render(w, h)
-    ref = orc.frame(w, h, oracle_features(orc, base), background=background, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
+    ref = orc.frame(w, h, oracle_features(orc, base), camera_pos=camera_of(metric), background=background, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
     rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
     ord_ = ref["rdata"]
     agree = (rd["terminated"] == ord_["terminated"]).mean()

@@ -9,6 +9,14 @@ import pytest
 from test_loader import write_folder
 
 
+def m_path(tmp_path):
+    """The probe script metric_diag wrote (test_loader.write_folder puts it into <tmp>/content)."""
+    for root, _, files in os.walk(str(tmp_path)):
+        if "probe.js" in files:
+            return os.path.join(root, "probe.js")
+    raise FileNotFoundError("probe.js")
+
+
 def metric_diag(grt, oracle_mod, tmp_path, js, pos=(0.3, 1.5, 0.7, 0.4)):
     folder = write_folder(tmp_path, js)
     m = grt.Content(folder).load(os.path.join(folder, "probe.js"))
@@ -76,3 +84,133 @@ def test_runaway_script_is_stopped(grt, tmp_path):
     folder = write_folder(tmp_path, "function f(t, x, y, z) { while (true) {} }\nf")
     with pytest.raises(grt.GrtError):
         grt.Content(folder).load(os.path.join(folder, "probe.js"))
+
+
+# ---- the ES2015+ surface QuickJS 2020-04-12 accepts and plugin authors may use -------------------------------------------------
+# every script returns a diagonal metric whose entries are built with the construct under test; expected values are computed by hand,
+# and where the reference is mounted the same script runs in the reference's own QuickJS (oracle/ref_quickjs.cpp) and must agree.
+MODERN_SCRIPTS = {
+    "template literals": ("""
+        function f(t, x, y, z) {
+            const n = 3, label = `k${n}-${1 + 1}`;
+            const tbl = {"k3-2": 2.5};
+            const multi = `a
+b`;
+            return [-1, tbl[label] * x, multi.length + 0 * y, `${n}${n}` * 1 + 0 * z];
+        }
+        f""", [-1, 2.5 * 1.5, 3, 33]),
+    "default and rest parameters": ("""
+        function scale(v, k = 2, m = k + 1) { return v * k + m; }
+        const total = (first, ...rest) => rest.reduce((s, q) => s + q, first);
+        function f(t, x, y, z) {
+            return [-1, scale(x), scale(x, 3), total(1, 2, 3, 4) + scale(0, undefined, 5) + 0 * z];
+        }
+        f""", [-1, 1.5 * 2 + 3, 1.5 * 3 + 4, 15]),
+    "destructuring declarations": ("""
+        function f(t, x, y, z) {
+            const [a, b = 7, , c, ...tail] = [x, undefined, 99, y, 1, 2, 3];
+            const {p, q: {r, s = 4}, w = 10} = {p: 2, q: {r: 3}};
+            let [[m, n], {k}] = [[1, 2], {k: 5}];
+            return [-1, a + b, c * p + r + s + w, tail.length + m + n + k + 0 * z];
+        }
+        f""", [-1, 1.5 + 7, 0.7 * 2 + 3 + 4 + 10, 3 + 1 + 2 + 5]),
+    "destructuring parameters and for-of": ("""
+        function norm2([u, v], {weight = 2} = {}) { return (u * u + v * v) * weight; }
+        function f(t, x, y, z) {
+            let acc = 0;
+            for (const [k, v] of [[1, x], [2, y]]) acc = acc + k * v;
+            let keys = 0;
+            for (const {id} of [{id: 3}, {id: 4}]) keys += id;
+            return [-1, norm2([x, y]), acc, keys + norm2([1, 1], {weight: 0.5}) + 0 * z];
+        }
+        f""", [-1, (1.5 ** 2 + 0.7 ** 2) * 2, 1.5 + 2 * 0.7, 7 + 1]),
+    "spread": ("""
+        function add3(a, b, c) { return a + b + c; }
+        function f(t, x, y, z) {
+            const base = [x, y];
+            const more = [...base, z, ...[1, 2]];
+            const o = {...{a: 1, b: 2}, b: 3, ...{c: 4}};
+            return [-1, add3(...base, 1), more.length + more[2], o.a + o.b + o.c + Math.max(...[1, 5, 2]) + 0 * z];
+        }
+        f""", [-1, 1.5 + 0.7 + 1, 5 + 0.4, 1 + 3 + 4 + 5]),
+    "switch": ("""
+        function kind(n) {
+            let r = 0;
+            switch (n) {
+                case 1: r += 1;
+                case 2: r += 10; break;
+                case "2": r += 100; break;
+                default: r += 1000;
+                case 3: r += 5;
+            }
+            return r;
+        }
+        function f(t, x, y, z) { return [-1, kind(1) + 0 * x, kind(2) + kind("2") + 0 * y, kind(7) + kind(3) + 0 * z]; }
+        f""", [-1, 11, 110, 1005 + 5]),
+    "classes": ("""
+        class Vec {
+            constructor(a, b) { this.a = a; this.b = b; }
+            dot(o) { return this.a * o.a + this.b * o.b; }
+            get norm2() { return this.dot(this); }
+            set first(v) { this.a = v * 2; }
+            static unit() { return new Vec(1, 0); }
+        }
+        class Weighted extends Vec {
+            constructor(a, b, w) { super(a, b); this.w = w; }
+            dot(o) { return super.dot(o) * this.w; }
+        }
+        class Plain extends Vec {}
+        function f(t, x, y, z) {
+            const v = new Vec(x, y), u = new Weighted(x, y, 2), q = new Plain(3, 4);
+            const e = Vec.unit();
+            e.first = 4;
+            const kinds = (u instanceof Vec ? 1 : 0) + (u instanceof Weighted ? 10 : 0) + (v instanceof Weighted ? 100 : 0) + (q instanceof Vec ? 1000 : 0);
+            return [-1, v.norm2, u.dot(v), q.norm2 + e.a + kinds + 0 * z];
+        }
+        f""", [-1, 1.5 ** 2 + 0.7 ** 2, (1.5 ** 2 + 0.7 ** 2) * 2, 25 + 8 + 1011]),
+    "class expression and closures": ("""
+        const make = (k) => class { constructor(v) { this.v = v; } times() { return this.v * k; } };
+        const Twice = make(2), Thrice = make(3);
+        function f(t, x, y, z) { return [-1, new Twice(x).times(), new Thrice(y).times(), (typeof Twice === "function" ? 1 : 0) + 0 * z]; }
+        f""", [-1, 3.0, 2.1, 1]),
+}
+
+
+@pytest.mark.parametrize("what", sorted(MODERN_SCRIPTS))
+def test_modern_javascript_constructs(grt, oracle_mod, have_reference, tmp_path, what):
+    js, want = MODERN_SCRIPTS[what]
+    pos = (0.3, 1.5, 0.7, 0.4)
+    g, m = metric_diag(grt, oracle_mod, tmp_path, js, pos)
+    assert np.allclose(np.diag(g), want, rtol=1e-6), (what, np.diag(g), want)
+    if have_reference:
+        try:
+            q = oracle_mod.QuickJSReference()
+        except FileNotFoundError:
+            return
+        qg, qdg, _, _ = q.metric(m_path(tmp_path), np.array(pos, np.float64))
+        sym = m.eval_symbolic(pos)
+        assert np.abs(sym["g"] - qg).max() <= 1e-9 * max(1.0, np.abs(qg).max()), what
+        assert np.abs(sym["dg"] - qdg).max() <= 1e-8 * max(1.0, np.abs(qdg).max()), what
+
+
+REFUSED = {
+    "generator function": ("function* gen() { yield 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "generator"),
+    "async function": ("async function g() { return 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "async"),
+    "class field": ("class A { n = 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "class fields"),
+    "tagged template": ("function tag(s) { return 1; }\nfunction f(t,x,y,z){ return [-1, tag`a`, 1, 1]; }\nf", "tagged template"),
+    "labelled statement": ("function f(t,x,y,z){ outer: for (var i = 0; i < 2; i++) {} return [-1,1,1,1]; }\nf", "labelled"),
+    "computed property name": ("function f(t,x,y,z){ var k = 'a'; var o = {[k]: 1}; return [-1,1,1,1]; }\nf", "computed property"),
+    "destructuring assignment": ("function f(t,x,y,z){ var a, b; [a, b] = [1, 2]; return [-1,a,b,1]; }\nf", "assignment target"),
+    "class called without new": ("class A {}\nfunction f(t,x,y,z){ A(); return [-1,1,1,1]; }\nf", "'new'"),
+}
+
+
+@pytest.mark.parametrize("what", sorted(REFUSED))
+def test_unsupported_javascript_is_refused_loudly(grt, tmp_path, what):
+    """What the interpreter does not implement is a SyntaxError (or TypeError) naming the script and the line - never skipped."""
+    js, needle = REFUSED[what]
+    folder = write_folder(tmp_path, js)
+    with pytest.raises(grt.GrtError) as e:
+        grt.Content(folder).load(os.path.join(folder, "probe.js"))
+    msg = e.value.message
+    assert needle in msg and "probe.js:" in msg, msg

@@ -10,7 +10,7 @@ from test_loader import write_folder
 
 
 class Gen:
-    """Seeded generator of JavaScript in the dialect the reference's scripts use (ES5 functions and `var`, a little ES6)."""
+    """Seeded generator of JavaScript in the dialect the reference's scripts use (ES5 functions and `var`, and the ES2015+ constructs the interpreter implements)."""
 
     UNARY = ["CMath.sin", "CMath.cos", "CMath.exp", "CMath.tanh", "CMath.sinh", "CMath.cosh", "CMath.atan", "CMath.fabs"]
 
@@ -64,6 +64,12 @@ class Gen:
             f"var mk = function(s) {{ return function(v) {{ return v * s + {c}; }}; }}; var f2 = mk(2), f3 = mk(-3); return f2({a}) + f3({b});",
             f"var r = {a}; var flag = (Math.floor(2.7) == 2 && !(1 > 2)) || false; if (flag) {{ r = r + {b}; }} else {{ r = r - {b}; }} do {{ r = r * 0.5; }} while (false); return r;",
             f"var xs = [{a}, {b}].map(function(v) {{ return v * 2; }}); var s = xs.reduce((p, v) => p + v, 0); return s + [1, 2, 3].indexOf(3) + (typeof s === 'object' ? 1 : 0);",
+            # ES2015+: destructuring, defaults, rest / spread, template literals, switch, classes
+            f"const [p0, p1 = {c}, ...more] = [{a}, undefined, {b}, 2]; const {{u, v: {{w = 3}}}} = {{u: p0, v: {{}}}}; return u * w + p1 + more.length * more[0];",
+            f"function lin(v, k = {n}, ...extra) {{ return extra.reduce((s, e) => s + e, v * k); }} const args = [{a}, undefined, {b}]; return lin(...args) + lin({c}, 2) + [...args, 1].length;",
+            f"const tag = `n${{{n}}}`; let r; switch (tag) {{ case 'n2': r = {a}; break; case 'n3': r = {b}; break; default: r = {c}; }} const tbl = {{n2: 2, n3: 3, n4: 4}}; return r * tbl[tag] + `${{1}}${{2}}` * 1;",
+            f"class Acc {{ constructor(s) {{ this.s = s; }} add(v) {{ this.s = this.s + v; return this; }} get doubled() {{ return this.s * 2; }} static of(v) {{ return new Acc(v); }} }} "
+            f"class Neg extends Acc {{ add(v) {{ return super.add(-v); }} }} return Acc.of({a}).add({b}).doubled + new Neg({c}).add({b}).s;",
         ]
         body = bodies[self.force_body] if self.force_body is not None else self.pick(bodies)
         return f"(function() {{ {body} }})()"
@@ -129,7 +135,7 @@ def test_random_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_
     checked = 0
     for k in range(12):
         seed = 1000 * block + k
-        js = Gen(seed, force_body=(k % 6) if block % 2 else None).script()
+        js = Gen(seed, force_body=(k % 10) if block % 2 else None).script()
         assert block % 2 == 0 or "(function() {" in js
         folder = write_folder(tmp_path / f"s{seed}", js)
         path = os.path.join(folder, "probe.js")

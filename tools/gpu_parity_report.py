@@ -11,7 +11,7 @@ import geodesic_raytracing_b200 as grt  # noqa: E402
 import oracle  # noqa: E402
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
-from test_gpu_parity import METRICS, bind, oracle_features  # noqa: E402
+from test_gpu_parity import METRICS, bind, camera_of, oracle_features  # noqa: E402
 
 
 def main():
@@ -25,7 +25,7 @@ def main():
         for adaptive in (0, 1):
             base = bind(ctx, metric, bg, adaptive_sampling=adaptive)
             img, st = ctx.render(w, h)
-            ref = orc.frame(w, h, oracle_features(orc, base), background=bg, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
+            ref = orc.frame(w, h, oracle_features(orc, base), camera_pos=camera_of(metric), background=bg, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
             rd = ctx.read_render_data(w, h).reshape(h, w)
             o = ref["rdata"]
             agree = (rd["terminated"] == o["terminated"]).mean()
