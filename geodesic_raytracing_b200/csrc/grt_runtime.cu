@@ -271,9 +271,19 @@ bool integrate_resources(const std::string& log, int* regs, int* spill) {
 // __launch_bounds__(128, n) for the next one or two block-per-SM tiers and the highest tier that needs no stack and at most
 // a fifth fewer registers is kept (kerr_schild: 89 registers / 5 blocks -> 72 / 7, +5 % frames per second).  The choice is
 // remembered next to the cubins.  GRT_INTEGRATE_MIN_BLOCKS (environment) overrides, GRT_OCCUPANCY_TIER=0 disables.
-std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit) {
+std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit, std::vector<std::string>* files_out = nullptr) {
     const char* off = getenv("GRT_OCCUPANCY_TIER");
-    if (src.find("// GRT_TIER_FIXED") != std::string::npos || (off && atoi(off) == 0)) return compile_cubin_raw(src, fast_math, name, log_out, cache_hit);
+    auto note_files = [&](const std::string& cubin_path, const std::string& tier) {      // what a superseded static program leaves in the cache
+        if (!files_out) return;
+        *files_out = {cubin_path, cubin_path + ".log", cubin_path.substr(0, cubin_path.size() - 6) + ".cu"};
+        if (!tier.empty()) files_out->push_back(tier);
+    };
+    if (src.find("// GRT_TIER_FIXED") != std::string::npos || (off && atoi(off) == 0)) {
+        std::string path;
+        auto r = compile_cubin_raw(src, fast_math, name, log_out, cache_hit, &path);
+        note_files(path, "");
+        return r;
+    }
     auto with_tier = [&](int n) { return "// GRT_TIER_FIXED\n#define GRT_INTEGRATE_MIN_BLOCKS " + std::to_string(n) + "\n" + src; };
     char hex[24];
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(src + (fast_math ? "f" : "p"), 14695981039346656037ull));
@@ -281,10 +291,15 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
     {
         std::ifstream f(tier_path);
         int n = 0;
-        if (f >> n) return n > 0 ? compile_cubin_raw(with_tier(n), fast_math, name, log_out, cache_hit) : compile_cubin_raw(src, fast_math, name, log_out, cache_hit);
+        if (f >> n) {
+            std::string path;
+            auto r = n > 0 ? compile_cubin_raw(with_tier(n), fast_math, name, log_out, cache_hit, &path) : compile_cubin_raw(src, fast_math, name, log_out, cache_hit, &path);
+            note_files(path, tier_path);
+            return r;
+        }
     }
-    std::string log;
-    std::vector<char> best = compile_cubin_raw(src, fast_math, name, &log, cache_hit);
+    std::string log, best_path;
+    std::vector<char> best = compile_cubin_raw(src, fast_math, name, &log, cache_hit, &best_path);
     int regs = 0, spill = 0, chosen = 0;
     std::string best_log = log;
     if (integrate_resources(log, &regs, &spill) && regs > 0) {
@@ -295,7 +310,12 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
             std::vector<char> cand;
             try { cand = compile_cubin_raw(with_tier(n), fast_math, name, &tlog, nullptr, &tpath); } catch (const Error&) { continue; }
             int r2 = 0, s2 = 0;
-            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 5 >= regs * 4 && blocks_for(r2) >= n) { best = cand; best_log = tlog; chosen = n; break; }
+            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 5 >= regs * 4 && blocks_for(r2) >= n) {
+                if (files_out) for (const char* ext : {"", ".log"}) remove((best_path + ext).c_str());      // the free compile is not the one kept
+                if (files_out) remove((best_path.substr(0, best_path.size() - 6) + ".cu").c_str());
+                best = cand; best_log = tlog; best_path = tpath; chosen = n;
+                break;
+            }
             for (const char* ext : {"", ".log"}) remove((tpath + ext).c_str());                      // a rejected tier leaves nothing behind
             remove((tpath.substr(0, tpath.size() - 6) + ".cu").c_str());
         }
@@ -305,6 +325,7 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
         f << chosen << "\n";
     }
     if (log_out) *log_out = best_log;
+    note_files(best_path, tier_path);
     return best;
 }
 
@@ -315,6 +336,7 @@ struct Program {
     int integrate_blocks_per_sm = 1;
     std::string info;
     std::string key;
+    std::vector<std::string> cache_files;   // static programs: their files in the cubin cache (removed when the program is superseded)
 };
 
 struct DevBuf {
@@ -393,6 +415,7 @@ struct grt_ctx {
     bool bound_use_prepass = false, bound_constant_theta = false;   // what the frame path needs of the bound metric
     std::map<std::string, std::unique_ptr<Program>> programs;
     Program* prog = nullptr;
+    std::string static_key;      // key of the one static-parameter program kept loaded (a parameter slider in static mode must not grow memory)
     float params[256] = {0};   // struct grt_params of the bound program: named $cfg values, then the derived parameters (pack_params)
 
     GrtCamera cam{};
@@ -491,8 +514,11 @@ Program* get_program(grt_ctx* c, grt_metric* gm, bool is_static) {
     std::string key = program_key(c, src);
     auto it = c->programs.find(key);
     if (it != c->programs.end()) return it->second.get();
-    std::vector<char> cubin = compile_cubin(src, c->fast_math, program_stem(m, is_static), &gm->compile_log, nullptr);
-    return load_program(c, key, cubin);
+    std::vector<std::string> files;
+    std::vector<char> cubin = compile_cubin(src, c->fast_math, program_stem(m, is_static), &gm->compile_log, nullptr, is_static ? &files : nullptr);
+    Program* p = load_program(c, key, cubin);
+    p->cache_files = std::move(files);
+    return p;
 }
 
 // cubin -> module + kernel handles (needs the device; the NVRTC step above does not)
@@ -520,6 +546,26 @@ Program* load_program(grt_ctx* c, const std::string& key, const std::vector<char
     Program* raw = p.get();
     c->programs[key] = std::move(p);
     return raw;
+}
+
+void sync_all(grt_ctx* c);
+
+// A context keeps ONE static-parameter program: every new set of literals is a new module, and the superseded one is unloaded
+// once the frames in flight have drained (the reference replaces its single static program, metric_manager.hpp:153-219).  Its
+// files in the on-disk cache are removed too, so a parameter slider in static mode grows neither device memory nor the disk.
+void retire_static_program(grt_ctx* c, Program* incoming, bool incoming_is_static) {
+    if (!incoming_is_static || incoming->key == c->static_key) return;
+    if (!c->static_key.empty()) {
+        auto it = c->programs.find(c->static_key);
+        if (it != c->programs.end() && it->second.get() != incoming) {
+            sync_all(c);
+            if (c->prog == it->second.get()) c->prog = nullptr;
+            if (it->second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(it->second->mod);
+            for (const std::string& f : it->second->cache_files) remove(f.c_str());
+            c->programs.erase(it);
+        }
+    }
+    c->static_key = incoming->key;
 }
 
 struct Launcher {
@@ -1259,9 +1305,19 @@ int grt_build_poll(grt_ctx* c) {
         std::vector<char> cubin = c->build.cubin.get();   // rethrows a compile error as GRT_E_COMPILE
         bind(c);
         grt_metric* m = c->build.metric;
-        m->compile_log = *c->build.log;
-        auto it = c->programs.find(c->build.key);
-        Program* p = it != c->programs.end() ? it->second.get() : load_program(c, c->build.key, cubin);
+        {
+            std::lock_guard<std::mutex> lock(m->text_mutex);
+            m->compile_log = *c->build.log;
+        }
+        // the program was specialised on the features and the fast-math setting of the REQUEST: if they changed meanwhile
+        // (grt_set_features / grt_set_fast_math between request and poll) the finished cubin is not the program to bind
+        Program* p = nullptr;
+        if (program_key(c, program_source(*m->m, c->build.is_static, c->feat.reparameterisation != 0, c->fast_math)) != c->build.key) p = get_program(c, m, c->build.is_static);
+        else {
+            auto it = c->programs.find(c->build.key);
+            p = it != c->programs.end() ? it->second.get() : load_program(c, c->build.key, cubin);
+        }
+        retire_static_program(c, p, c->build.is_static);
         // swap: frames already queued keep the module they were launched with
         c->metric = m;
         c->is_static = c->build.is_static;
@@ -1284,7 +1340,11 @@ int grt_update_params(grt_ctx* c) {
         const auto& p = c->metric->m->params;
         if (p.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
         fill_params(c, *c->metric->m);
-        if (c->is_static) c->prog = get_program(c, c->metric, true);   // literals changed: rebuild (metric_manager.hpp:153-167)
+        if (c->is_static) {   // literals changed: rebuild (metric_manager.hpp:153-167); the reference replaces its single static program
+            Program* p = get_program(c, c->metric, true);
+            retire_static_program(c, p, true);
+            c->prog = p;
+        }
         c->kernel_info = c->prog->info;
         c->camera_dirty = true;
         return GRT_OK;
@@ -1297,6 +1357,7 @@ int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
         bind(c);
         if (m->m->params.names.size() > 64) throw Error(GRT_E_INVALID, "too many $cfg parameters (max 64)");
         Program* p = get_program(c, m, is_static != 0);
+        retire_static_program(c, p, is_static != 0);
         c->metric = m;
         c->is_static = is_static != 0;
         c->bound_use_prepass = m->m->cfg.use_prepass;

@@ -826,3 +826,28 @@ def test_communicator_of_one_rank_is_the_plain_frame(gpu_ctx, oracles, backgroun
             c.comm_init(0, 1, w, h, grt.GRT_FORMAT_RGBA8, 2)      # already initialised
     finally:
         c.close()
+
+
+def test_static_parameter_slider_keeps_one_program(gpu_ctx, content, background, tmp_path, monkeypatch):
+    """Static-parameter mode compiles a program per set of literals (metric.hpp:494-547); moving a slider must not pile up modules or
+    cache files: the superseded static program is unloaded and its files removed (the reference replaces its single static program)."""
+    import glob
+    monkeypatch.setenv("GRT_CACHE_DIR", str(tmp_path))
+    metric = content.load_by_name("schwarzschild")
+    bind(gpu_ctx, metric, background, adaptive_sampling=0)
+    gpu_ctx.set_metric(metric, is_static=True)
+    gpu_ctx.set_features(max_acceleration_change=metric.info.max_acceleration_change, adaptive_sampling=0)
+    frames = []
+    for rs in (1.0, 0.9, 0.8, 0.7, 0.6):
+        metric.set_param("rs", rs)
+        gpu_ctx.update_params()
+        img, _ = gpu_ctx.render(96, 64)
+        frames.append(img.copy())
+    assert not np.array_equal(frames[0], frames[-1])
+    statics = glob.glob(str(tmp_path / "*_static_*.cubin"))
+    assert 1 <= len(statics) <= 2, statics           # the live one (and at most the tier probe's sibling), not five
+    metric.set_param("rs", 1.0)
+    gpu_ctx.update_params()
+    again, _ = gpu_ctx.render(96, 64)
+    assert np.array_equal(again, frames[0])
+    gpu_ctx.set_metric(metric, is_static=False)
