@@ -67,7 +67,8 @@ struct GrtFrame {
     int n_slots;            // tiles_x * tiles_y * 32 first-pass ray slots (padding slots are terminated=3)
     const int* row_global;      // [n_rows]  local row -> full-frame row
     const int* local_of_global; // [full_h]  full-frame row -> local row, -1 when not held
-    const int* cellrow_refine;  // [grid_h]  adaptive sampling: 1 = this cell row feeds output pixels
+    const int* cellrow_refine;  // [grid_h]  adaptive sampling: 1 = this cell row feeds output pixels; in the 1/16 prepass launch:
+                                //           1 = a cull test of this GPU reads this prepass row (others are not traced)
     int prepass_w, prepass_h;
     int use_prepass_mask;   // main pass consults the prepass termination mask
     int flip_geodesic_direction;

@@ -385,7 +385,8 @@ extern "C" __global__ void __launch_bounds__(128) k_init_rays(GrtRays rays, GrtF
     if (slot >= fr.n_slots) return;
     int gx, gy;
     grt_cell_of(slot, fr.tiles_x, gx, gy);
-    const bool real = gx < fr.grid_w && gy < fr.grid_h;
+    bool real = gx < fr.grid_w && gy < fr.grid_h;
+    if (real && is_prepass) real = fr.cellrow_refine[gy] != 0;     // prepass rows no cull test of this GPU reads are not traced
     int terminated = 3;
     bool hot = false;
     if (real) {

@@ -265,21 +265,43 @@ def test_camera_on_geodesic(gpu_ctx, oracles, background):
     q = np.array([-0.70710678, 0, 0, 0.70710678])
     fwd = np.array([2 * (q[0] * q[2] + q[3] * q[1]), 2 * (q[1] * q[2] - q[3] * q[0]), 1 - 2 * (q[0] ** 2 + q[1] ** 2)])
     opos, ovel, ods, otr, _ = orc.geodesic_snapshot(np.array(list(cs.pos_generic)), np.array(list(cs.tetrad)).reshape(4, 4), fwd * 0.2, oracle_features(orc, base))
-    m = min(n, len(opos))
-    assert abs(n - len(opos)) <= max(3, 0.02 * n)
-    k = m // 2
-    assert np.allclose(pos[:k], opos[:k], rtol=2e-3, atol=2e-3)
-    assert np.allclose(vel[:k], ovel[:k], rtol=5e-3, atol=5e-3)
-    assert np.allclose(tr[:, :k], otr[:, :k], rtol=1e-2, atol=1e-2)
-    tau = float(np.sum(ds[: m // 4]))
+    assert n == len(opos)
+    compare_geodesic_paths((pos, vel, ds, tr), (opos, ovel, ods, otr))
+    # the camera interpolated at three proper times, the last one in the final quarter of the path (cl.cl:2738-2872)
+    total = float(np.sum(ods))
+    for frac in (0.2, 0.6, 0.95):
+        tau = total * frac
+        gpu_ctx.set_camera_on_geodesic(tau)
+        cam, tet, _ = orc.geodesic_interpolate(opos, ovel, ods, otr, tau, True, fwd * 0.2)
+        cs2 = gpu_ctx.camera_state()
+        assert np.allclose(np.array(list(cs2.pos_generic)), cam, atol=1e-3), frac
+        assert np.allclose(np.array(list(cs2.tetrad)).reshape(4, 4), tet, atol=1e-3), frac
+    tau = total * 0.6
     gpu_ctx.set_camera_on_geodesic(tau)
     img, _ = gpu_ctx.render(128, 96)
-    cam, tet, _ = orc.geodesic_interpolate(opos, ovel, ods, otr.transpose(0, 1, 2), tau, True, fwd * 0.2)
-    cs2 = gpu_ctx.camera_state()
-    assert np.allclose(np.array(list(cs2.pos_generic)), cam, atol=5e-3)
+    cam, tet, _ = orc.geodesic_interpolate(opos, ovel, ods, otr, tau, True, fwd * 0.2)
     ref = orc.frame(128, 96, oracle_features(orc, base), background=background, given_camera=(cam, tet))
-    assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2 / 255).mean() >= 0.98
+    assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2 / 255).mean() >= 0.99
     gpu_ctx.clear_camera_geodesic()
+
+
+def compare_geodesic_paths(gpu, orc_path):
+    """The WHOLE recorded path of get_geodesic_path + parallel_transport_quantity (cl.cl:4735-4940, 2569-2620) against the oracle's.
+    Two fp32 integrations of the same ODE separate with arc length, so the tolerance grows along the path: tight over the first
+    half, looser to the end (measured on a B200, tools/gpu_diag3.py: positions <= 3e-3 and velocities <= 1.1e-3 relative at the very
+    end of the worst path, step sizes <= 1.5e-4; transported tetrads <= 5e-4 over the first half and <= 5e-2 in absolute terms where
+    an infalling observer's tetrad components grow without bound near the horizon)."""
+    (pos, vel, ds, tr), (opos, ovel, ods, otr) = gpu, orc_path
+    n = len(opos)
+    assert len(pos) == n
+    half = n // 2
+    for k, (tp, tv, tt, tds) in ((half, (1e-3, 1e-3, 2e-3, 1e-4)), (n, (1e-2, 5e-3, 0.1, 1e-3))):
+        pscale = np.abs(opos[:k]).max(axis=0) + 1e-3
+        vscale = np.abs(ovel[:k]).max(axis=0) + 1e-3
+        assert (np.abs(pos[:k] - opos[:k]) / pscale).max() <= tp, k
+        assert (np.abs(vel[:k] - ovel[:k]) / vscale).max() <= tv, k
+        assert np.abs(tr[:, :k] - otr[:, :k]).max() <= tt * max(1.0, float(np.abs(otr[:, :k]).max())), k
+        assert (np.abs(ds[:k] - ods[:k]) / (np.abs(ods[:k]) + 1e-9)).max() <= tds, k
 
 
 def test_frame_properties_at_headline_size(gpu_ctx, oracles, grt):
@@ -523,12 +545,9 @@ def test_geodesic_camera_paths(gpu_ctx, oracles, background, name, speed):
     q = np.array([-0.70710678, 0, 0, 0.70710678])
     fwd = np.array([2 * (q[0] * q[2] + q[3] * q[1]), 2 * (q[1] * q[2] - q[3] * q[0]), 1 - 2 * (q[0] ** 2 + q[1] ** 2)])
     opos, ovel, ods, otr, _ = orc.geodesic_snapshot(np.array(list(cs.pos_generic)), np.array(list(cs.tetrad)).reshape(4, 4), fwd * speed, oracle_features(orc, base))
-    assert n > 20 and abs(n - len(opos)) <= max(3, 0.03 * n), (n, len(opos))
-    k = min(n, len(opos)) // 3          # compare the first third: the two integrations separate slowly afterwards
-    assert np.allclose(pos[:k], opos[:k], rtol=3e-3, atol=3e-3)
-    assert np.allclose(vel[:k], ovel[:k], rtol=1e-2, atol=1e-2)
-    assert np.allclose(ds[:k], ods[:k], rtol=2e-2, atol=1e-6)
-    assert np.allclose(tr[:, :k], otr[:, :k], rtol=2e-2, atol=2e-2)
+    assert n > 20 and n == len(opos), (n, len(opos))
+    compare_geodesic_paths((pos, vel, ds, tr), (opos, ovel, ods, otr))
+    k = n // 3
     # the transported tetrad stays orthonormal along the path (a property the oracle shares, checked on the GPU result)
     for i in (0, k // 2, k - 1):
         g, _ = orc.metric_eval(pos[i])
