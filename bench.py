@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 
 import geodesic_raytracing_b200 as grt  # noqa: E402
 
-STRIPE_ROWS = 54
+STRIPE_ROWS = int(os.environ.get("GRT_BENCH_STRIPE_ROWS", "54"))
 CAM_POS, CAM_QUAT = (0.0, 0.0, -4.0, 0.0), (-0.70710678, 0.0, 0.0, 0.70710678)
 # BASELINE.json `configs` (index = position in that list + 1; config 1 is the reference's CPU-only plumbing case)
 CONFIGS = {

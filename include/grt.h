@@ -254,8 +254,9 @@ int grt_comm_connect_local(grt_ctx** contexts_in_rank_order, int n);
 int grt_comm_disconnect(grt_ctx*);
 int grt_comm_render(grt_ctx*, const int* y0s, const int* y1s, int n_stripes, unsigned seq, void* host_out);
 void* grt_comm_frame(grt_ctx*, unsigned seq);
-/* The stripes rank `rank` of `world` renders: interleaved `stripe_rows`-row stripes rank, rank + world, ... so that the expensive
- * rows around the hole are dealt round-robin.  Writes up to max_stripes (y0, y1) pairs, returns the count. */
+/* The stripes rank `rank` of `world` renders: `stripe_rows`-row stripes dealt one per rank within every group of `world` consecutive
+ * stripes, the position rotating by three from group to group, so that the cheap and the expensive rows of a frame are shared out
+ * evenly.  Writes up to max_stripes (y0, y1) pairs in ascending order, returns the count. */
 int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, int* y0s, int* y1s, int max_stripes);
 
 /* ---- introspection for tests and tools --------------------------------------------------- */

@@ -17,8 +17,9 @@ def test_interleaved_stripes_partition_the_frame(grt):
                         assert y0 % 2 == 0 and (y1 % 2 == 0 or y1 == h) and y0 < y1 <= h
                         seen[y0:y1] += 1
                 assert (seen == 1).all(), (h, world, rows)
-    assert grt.interleaved_stripes(2160, 0, 8, 54)[:2] == [(0, 54), (432, 486)]
-    assert len(grt.interleaved_stripes(2160, 3, 8, 54)) == 5
+    assert grt.interleaved_stripes(2160, 0, 8, 54)[:3] == [(0, 54), (702, 756), (972, 1026)]      # position 0, then 5, then 2: rotating by three
+    assert all(len(grt.interleaved_stripes(2160, r, 8, 54)) == 5 for r in range(8))
+    assert grt.interleaved_stripes(2160, 1, 2, 54)[:3] == [(54, 108), (108, 162), (270, 324)]
 
 
 def _free_port():
