@@ -129,6 +129,10 @@ def lib() -> C.CDLL:
         "grt_comm_init": (ci, [vp, ci, ci, ci, ci, ci, ci, vp]), "grt_comm_connect": (ci, [vp, vp]), "grt_comm_connect_local": (ci, [C.POINTER(vp), ci]), "grt_comm_disconnect": (ci, [vp]),
         "grt_comm_render": (ci, [vp, pi, pi, ci, C.c_uint, vp]), "grt_comm_frame": (vp, [vp, C.c_uint]),
         "grt_interleaved_stripes": (ci, [ci, ci, ci, ci, pi, pi, ci]),
+        "grt_group_create": (vp, [pi, ci]), "grt_group_destroy": (None, [vp]), "grt_group_size": (ci, [vp]), "grt_group_ctx": (vp, [vp, ci]),
+        "grt_group_set_metric": (ci, [vp, vp, ci]), "grt_group_update_params": (ci, [vp]), "grt_group_set_features": (ci, [vp, C.POINTER(Features)]),
+        "grt_group_set_background": (ci, [vp, vp, ci, ci, ci]), "grt_group_set_camera": (ci, [vp, pf, pf, ci]), "grt_group_set_frames_in_flight": (ci, [vp, ci]),
+        "grt_group_render": (ci, [vp, ci, ci, ci, vp]), "grt_group_frame": (vp, [vp]), "grt_group_synchronize": (ci, [vp]),
         "grt_get_camera_state": (ci, [vp, C.POINTER(CameraState)]),
         "grt_debug_ray_count": (ci, [vp, pi, pi]), "grt_debug_read_rays": (ci, [vp, vp, ci]), "grt_debug_read_render_data": (ci, [vp, vp, ci]),
         "grt_debug_read_prepass_mask": (ci, [vp, vp, ci, pi, pi]), "grt_debug_read_mip_level": (ci, [vp, ci, ci, vp, pi, pi, pi]),
@@ -529,6 +533,57 @@ class Context:
     def launch_log(self) -> dict:
         s = (lib().grt_debug_launch_log(self._h) or b"").decode()
         return {k: float(v) for k, v in (item.split(":") for item in filter(None, s.split(";")))}
+
+
+class Group:
+    """Several devices of one box driven as one renderer (grt_group_*): rank 0 = devices[0] owns the assembled frame."""
+
+    def __init__(self, devices: Sequence[int]):
+        arr = (C.c_int * len(devices))(*devices)
+        self._g = lib().grt_group_create(arr, len(devices))
+        if not self._g:
+            raise GrtError(-3, _err())
+        self.size = len(devices)
+
+    def close(self):
+        if getattr(self, "_g", None):
+            lib().grt_group_destroy(self._g)
+            self._g = None
+
+    __del__ = close
+
+    def set_metric(self, metric: "Metric", is_static: bool = False):
+        _check(lib().grt_group_set_metric(self._g, metric._h, int(is_static)))
+
+    def set_features(self, **kw):
+        f = Features()
+        lib().grt_features_default(C.byref(f))
+        for k, v in kw.items():
+            if not hasattr(f, k):
+                raise AttributeError(k)
+            setattr(f, k, v)
+        _check(lib().grt_group_set_features(self._g, C.byref(f)))
+
+    def set_background(self, rgba: np.ndarray, which: int = 0):
+        a = np.ascontiguousarray(rgba, np.uint8)
+        _check(lib().grt_group_set_background(self._g, a.ctypes.data, a.shape[1], a.shape[0], which))
+
+    def set_camera(self, pos=(0.0, 0.0, -4.0, 0.0), quat=(-0.70710678, 0.0, 0.0, 0.70710678), flip_r: bool = False):
+        p, q = (C.c_float * 4)(*pos), (C.c_float * 4)(*quat)
+        _check(lib().grt_group_set_camera(self._g, p, q, int(flip_r)))
+
+    def set_frames_in_flight(self, n: int):
+        _check(lib().grt_group_set_frames_in_flight(self._g, n))
+
+    def render(self, width: int, height: int, fmt: int = GRT_FORMAT_RGBA8, host_out=None):
+        """Queue one frame on all devices (asynchronous); `host_out` (pinned) receives the assembled frame."""
+        _check(lib().grt_group_render(self._g, width, height, fmt, _ptr(host_out) if host_out is not None else None))
+
+    def frame_ptr(self) -> int:
+        return lib().grt_group_frame(self._g) or 0
+
+    def synchronize(self):
+        _check(lib().grt_group_synchronize(self._g))
 
 
 def interleaved_stripes(height: int, rank: int, world: int, stripe_rows: int = 54) -> List[Tuple[int, int]]:

@@ -6,7 +6,7 @@
 // "Frametime Elapsed: %f" line of -bench (main.cpp:2864-2871), the screenshot path (main.cpp:2762-2831: clamp, linear -> sRGB,
 // clamp, * 255, saved as ./screenshots/<metric>_<milliseconds>.png) and the settings file (main.cpp:240-254: settings.json with the
 // fields of graphics_settings.cpp:10-33).  With -gpus N the frame is tiled in row stripes over N devices of this box and assembled
-// on device 0 (grt_comm_*: one context per device, peer stores into device 0's frame) - the single-context frame loop of
+// on device 0 (grt_group_*: one context per device, peer stores into device 0's frame) - the single-context frame loop of
 // main.cpp:1069-1095 over several GPUs.  The window, ImGui, input and Steam parts of main.cpp are out of scope.
 //
 //   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K] [-gpus N | -devices 0,1,...]
@@ -196,37 +196,36 @@ int main(int argc, char** argv) {
     const float s = sinf(-3.14159265f / 4), c = cosf(-3.14159265f / 4);
     const float quat[4] = {s, 0.0f, 0.0f, c};                                          // axis (1,0,0), angle -pi/2 (main.cpp:670-673)
 
-    // one context per device; rank 0 (device 0) owns the assembled frame
-    std::vector<grt_ctx*> ctxs(gpus, nullptr);
-    for (int r = 0; r < gpus; r++) {
-        grt_ctx* ctx = grt_create(devices.empty() ? r : devices[r]);
-        if (!ctx) die("context");                                 // no CPU fallback: fails without an sm_100 GPU
-        ctxs[r] = ctx;
-        auto t_build = std::chrono::steady_clock::now();
-        check(grt_set_metric(ctx, metric, is_static ? 1 : 0), "program build");
-        if (r == 0)
-            printf("Built %s program for %s in %.0f ms\n", is_static ? "static" : "dynamic", grt_metric_name(metric),
-                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
-        check(grt_set_background(ctx, sky.data(), bw, bh, 0), "background");
-        grt_features feat;
-        check(grt_get_features(ctx, &feat), "features");
-        feat.adaptive_sampling = adaptive ? 1 : 0;
-        feat.redshift = redshift ? 1 : 0;
-        feat.field_of_view = sett.field_of_view;
-        feat.max_probes = sett.anisotropy;
-        feat.use_old_redshift = sett.use_old_redshift ? 1 : 0;
-        feat.adaptive_sampling_threshold = sett.adaptive_sampling_threshold;
-        check(grt_set_features(ctx, &feat), "features");
-        check(grt_set_camera(ctx, pos, quat, 0), "camera");
-        if (on_geodesic) {                                                             // main.cpp:2675-2760, 2264-2297
-            int n = grt_snapshot_geodesic(ctx, 0.0f, 1);
+    // the devices as one renderer (grt_group_*): one context per device, rank 0 owns the assembled frame
+    if (devices.empty()) for (int r = 0; r < gpus; r++) devices.push_back(r);
+    grt_group* group = grt_group_create(devices.data(), gpus);
+    if (!group) die("context");                                   // no CPU fallback: fails without an sm_100 GPU
+    grt_ctx* ctx = grt_group_ctx(group, 0);
+    auto t_build = std::chrono::steady_clock::now();
+    check(grt_group_set_metric(group, metric, is_static ? 1 : 0), "program build");
+    printf("Built %s program for %s in %.0f ms\n", is_static ? "static" : "dynamic", grt_metric_name(metric),
+           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
+    check(grt_group_set_background(group, sky.data(), bw, bh, 0), "background");
+    grt_features feat;
+    check(grt_get_features(ctx, &feat), "features");
+    feat.adaptive_sampling = adaptive ? 1 : 0;
+    feat.redshift = redshift ? 1 : 0;
+    feat.field_of_view = sett.field_of_view;
+    feat.max_probes = sett.anisotropy;
+    feat.use_old_redshift = sett.use_old_redshift ? 1 : 0;
+    feat.adaptive_sampling_threshold = sett.adaptive_sampling_threshold;
+    check(grt_group_set_features(group, &feat), "features");
+    check(grt_group_set_camera(group, pos, quat, 0), "camera");
+    if (on_geodesic) {                                                                 // main.cpp:2675-2760, 2264-2297: every device integrates the same path
+        int n = 0;
+        for (int r = 0; r < gpus; r++) {
+            n = grt_snapshot_geodesic(grt_group_ctx(group, r), 0.0f, 1);
             check(n, "geodesic snapshot");
-            check(grt_set_camera_on_geodesic(ctx, geodesic_tau), "camera on geodesic");
-            if (r == 0) printf("Camera on its geodesic at proper time %g (%d path points)\n", geodesic_tau, n);
+            check(grt_set_camera_on_geodesic(grt_group_ctx(group, r), geodesic_tau), "camera on geodesic");
         }
-        check(grt_set_frames_in_flight(ctx, inflight), "frames in flight");
+        printf("Camera on its geodesic at proper time %g (%d path points)\n", geodesic_tau, n);
     }
-    grt_ctx* ctx = ctxs[0];
+    check(grt_group_set_frames_in_flight(group, inflight), "frames in flight");
 
     // one synchronous frame with statistics on device 0 (the whole frame), then `frames` frames queued back to back
     std::vector<uint8_t> host((size_t)width * height * 4);
@@ -235,20 +234,9 @@ int main(int argc, char** argv) {
     printf("First frame: %.3f ms on the device (prepass %.3f, integrate %.3f, render %.3f), %llu ray-steps, %llu rays (%llu refinement)\n", st.ms_total, st.ms_prepass,
            st.ms_integrate, st.ms_render, (unsigned long long)st.trial_steps, (unsigned long long)st.rays_integrated, (unsigned long long)st.extra_rays);
 
-    // the frame loop: every device renders its interleaved stripes straight into device 0's frame buffer (grt_comm_render); the
-    // assembled frame lands in pinned host memory behind the last device's stores
-    std::vector<std::vector<int>> y0s(gpus), y1s(gpus);
-    for (int r = 0; r < gpus; r++) {
-        y0s[r].resize(height / 2 + 2);
-        y1s[r].resize(height / 2 + 2);
-        int n = grt_interleaved_stripes(height, r, gpus, 54, y0s[r].data(), y1s[r].data(), (int)y0s[r].size());
-        check(n, "stripes");
-        y0s[r].resize(n);
-        y1s[r].resize(n);
-        check(grt_comm_init(ctxs[r], r, gpus, width, height, GRT_FORMAT_RGBA8, std::max(2, inflight), nullptr), "communicator");
-    }
-    check(grt_comm_connect_local(ctxs.data(), gpus), "communicator connect");
-    if (gpus > 1) printf("Frame tiled over %d devices: %zu stripes of 54 rows on device 0\n", gpus, y0s[0].size());
+    // the frame loop: every device renders its stripes straight into device 0's frame buffer; the assembled frame lands in pinned
+    // host memory behind the last device's stores
+    if (gpus > 1) printf("Frame tiled over %d devices\n", gpus);
     std::vector<uint8_t*> pinned(std::max(2, inflight), nullptr);
     for (auto& p : pinned) if (cudaHostAlloc((void**)&p, host.size(), cudaHostAllocDefault) != cudaSuccess) { fprintf(stderr, "grt_headless: cudaHostAlloc failed\n"); return 1; }
     unsigned seq = 0;
@@ -257,12 +245,10 @@ int main(int argc, char** argv) {
         const int n = std::min(inflight, frames - k);
         auto t0 = std::chrono::steady_clock::now();
         for (int j = 0; j < n; j++, seq++) {
-            for (int r = gpus - 1; r >= 0; r--) {                                      // the owner last
-                if (!on_geodesic) check(grt_set_camera(ctxs[r], pos, quat, 0), "camera");   // the per-frame camera upload, main.cpp:2244-2262
-                check(grt_comm_render(ctxs[r], y0s[r].data(), y1s[r].data(), (int)y0s[r].size(), seq, r == 0 ? pinned[seq % pinned.size()] : nullptr), "render");
-            }
+            if (!on_geodesic) check(grt_group_set_camera(group, pos, quat, 0), "camera");   // the per-frame camera upload, main.cpp:2244-2262
+            check(grt_group_render(group, width, height, GRT_FORMAT_RGBA8, pinned[seq % pinned.size()]), "render");
         }
-        for (int r = 0; r < gpus; r++) check(grt_synchronize(ctxs[r]), "synchronize");
+        check(grt_group_synchronize(group), "synchronize");
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / n;
         if (print_frametime)
             for (int j = 0; j < n; j++) printf("Frametime Elapsed: %f\n", ms);       // main.cpp:2864-2871 (do-not-change string)
@@ -291,8 +277,7 @@ int main(int argc, char** argv) {
         printf("Wrote %s (%dx%d)\n", out_path.c_str(), width, height);
     }
     for (auto& p : pinned) cudaFreeHost(p);
-    for (int r = 0; r < gpus; r++) check(grt_comm_disconnect(ctxs[r]), "disconnect");
-    for (int r = gpus - 1; r >= 0; r--) grt_destroy(ctxs[r]);
+    grt_group_destroy(group);
     grt_metric_destroy(metric);
     grt_content_destroy(content);
     return 0;

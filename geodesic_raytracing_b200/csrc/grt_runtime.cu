@@ -1689,6 +1689,89 @@ int grt_comm_render(grt_ctx* c, const int* y0s, const int* y1s, int n_stripes, u
     });
 }
 
+// ---- a group of contexts driven as one renderer -------------------------------------------------------------
+struct grt_group {
+    std::vector<grt_ctx*> ctx;
+    std::vector<std::vector<int>> y0s, y1s;
+    int w = 0, h = 0, format = -1, frames = 2;
+    unsigned seq = 0;
+    bool connected = false;
+};
+
+namespace {
+int for_each_ctx(grt_group* g, const std::function<int(grt_ctx*)>& f) {
+    if (!g) { g_err = "null group"; return GRT_E_INVALID; }
+    for (grt_ctx* c : g->ctx) { int rc = f(c); if (rc < 0) return rc; }
+    return GRT_OK;
+}
+void group_disconnect(grt_group* g) {
+    for (grt_ctx* c : g->ctx) grt_comm_disconnect(c);
+    for (grt_ctx* c : g->ctx)
+        if (c->comm.active) { cudaSetDevice(c->device); c->comm.local.release(); c->comm = grt_ctx::Comm(); }
+    g->connected = false;
+}
+}  // namespace
+
+grt_group* grt_group_create(const int* devices, int ndev) {
+    if (!devices || ndev < 1 || ndev > 64) { g_err = "bad device list"; return nullptr; }
+    auto g = new grt_group();
+    for (int i = 0; i < ndev; i++) {
+        grt_ctx* c = grt_create(devices[i]);
+        if (!c) { grt_group_destroy(g); return nullptr; }
+        g->ctx.push_back(c);
+    }
+    g->y0s.resize(ndev);
+    g->y1s.resize(ndev);
+    return g;
+}
+void grt_group_destroy(grt_group* g) {
+    if (!g) return;
+    group_disconnect(g);
+    for (int r = (int)g->ctx.size() - 1; r >= 0; r--) grt_destroy(g->ctx[r]);
+    delete g;
+}
+int grt_group_size(const grt_group* g) { return g ? (int)g->ctx.size() : 0; }
+grt_ctx* grt_group_ctx(grt_group* g, int rank) { return (g && rank >= 0 && rank < (int)g->ctx.size()) ? g->ctx[rank] : nullptr; }
+int grt_group_set_metric(grt_group* g, grt_metric* m, int is_static) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_set_metric(c, m, is_static); }); }
+int grt_group_update_params(grt_group* g) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_update_params(c); }); }
+int grt_group_set_features(grt_group* g, const grt_features* f) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_set_features(c, f); }); }
+int grt_group_set_background(grt_group* g, const uint8_t* rgba, int w, int h, int which) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_set_background(c, rgba, w, h, which); }); }
+int grt_group_set_camera(grt_group* g, const float pos[4], const float quat[4], int flip_r) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_set_camera(c, pos, quat, flip_r); }); }
+int grt_group_set_frames_in_flight(grt_group* g, int n) {
+    int rc = for_each_ctx(g, [&](grt_ctx* c) { return grt_set_frames_in_flight(c, n); });
+    if (rc == GRT_OK && n != g->frames) { g->frames = n; if (g->connected) group_disconnect(g); }     // the frame buffers follow the depth
+    return rc;
+}
+int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
+    if (!g) { g_err = "null group"; return GRT_E_INVALID; }
+    const int n = (int)g->ctx.size();
+    if (!g->connected || w != g->w || h != g->h || format != g->format) {
+        // (re)build the communicator for this frame shape: every rank's region, then the peer pointers
+        if (g->connected) group_disconnect(g);
+        for (int r = 0; r < n; r++) {
+            g->y0s[r].assign(h / 2 + 2, 0);
+            g->y1s[r].assign(h / 2 + 2, 0);
+            int k = grt_interleaved_stripes(h, r, n, 54, g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size());
+            if (k < 0) return k;
+            g->y0s[r].resize(k);
+            g->y1s[r].resize(k);
+            int rc = grt_comm_init(g->ctx[r], r, n, w, h, format, std::max(2, g->frames), nullptr);
+            if (rc < 0) return rc;
+        }
+        int rc = grt_comm_connect_local(g->ctx.data(), n);
+        if (rc < 0) return rc;
+        g->w = w; g->h = h; g->format = format; g->seq = 0; g->connected = true;
+    }
+    for (int r = n - 1; r >= 0; r--) {       // the owner last: its stream then waits for stores that are already queued
+        int rc = grt_comm_render(g->ctx[r], g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size(), g->seq, r == 0 ? host_out : nullptr);
+        if (rc < 0) return rc;
+    }
+    g->seq++;
+    return GRT_OK;
+}
+void* grt_group_frame(grt_group* g) { return (g && g->connected && g->seq > 0) ? grt_comm_frame(g->ctx[0], g->seq - 1) : nullptr; }
+int grt_group_synchronize(grt_group* g) { return for_each_ctx(g, [&](grt_ctx* c) { return grt_synchronize(c); }); }
+
 // ---- introspection ------------------------------------------------------------------------------------
 int grt_get_camera_state(grt_ctx* c, grt_camera_state* o) {
     return guard([&] {

@@ -259,6 +259,26 @@ void* grt_comm_frame(grt_ctx*, unsigned seq);
  * evenly.  Writes up to max_stripes (y0, y1) pairs in ascending order, returns the count. */
 int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, int* y0s, int* y1s, int max_stripes);
 
+/* A group: the contexts of several devices of one box driven as one renderer from one thread - what SURVEY.md 8(b2) writes as
+ * grt_create(const int* devices, int ndev).  Rank 0 = devices[0] owns the assembled frame.  The setters broadcast to every context;
+ * grt_group_render queues ONE frame on all devices (interleaved stripes of grt_interleaved_stripes with 54 rows, peer stores into
+ * rank 0's frame, asynchronous) and, when host_out is given (pinned memory), the copy of the assembled frame behind it.
+ * grt_group_ctx gives the context of a rank for everything else (statistics, introspection).  A device may appear more than once. */
+typedef struct grt_group grt_group;
+grt_group* grt_group_create(const int* devices, int ndev);
+void grt_group_destroy(grt_group*);
+int grt_group_size(const grt_group*);
+grt_ctx* grt_group_ctx(grt_group*, int rank);
+int grt_group_set_metric(grt_group*, grt_metric*, int is_static);
+int grt_group_update_params(grt_group*);
+int grt_group_set_features(grt_group*, const grt_features*);
+int grt_group_set_background(grt_group*, const uint8_t* rgba, int width, int height, int which);
+int grt_group_set_camera(grt_group*, const float pos_txyz[4], const float quat_xyzw[4], int flip_r);
+int grt_group_set_frames_in_flight(grt_group*, int n);
+int grt_group_render(grt_group*, int width, int height, int format, void* host_out);
+void* grt_group_frame(grt_group*);          /* device pointer (on devices[0]) of the most recently queued frame's buffer */
+int grt_group_synchronize(grt_group*);
+
 /* ---- introspection for tests and tools --------------------------------------------------- */
 typedef struct grt_camera_state {
     float pos_generic[4];

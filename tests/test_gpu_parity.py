@@ -634,7 +634,7 @@ def test_cpp_headless_host_renders_the_same_frame(gpu_ctx, content, grt, tmp_pat
     r = subprocess.run([exe, "-content", grt.CONTENT_DIR, "-bench", "kerr_schild", "-frames", "3", "-inflight", "2", "-devices", "0,0", "-background", str(ppm_in),
                         "-out", str(png_out), "-screenshot"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr
-    assert "Loaded settings.json" in r.stdout and "tiled over 2 devices" in r.stdout and "differs" not in r.stdout
+    assert "Loaded settings.json" in r.stdout and "tiled over 2 devices" in r.stdout and "differs" not in r.stdout, r.stdout
     assert np.array_equal(grt.load_png(str(png_out)), want)                     # the assembled two-rank frame == the single-context frame
     shots = list((tmp_path / "screenshots").glob("kerr_schild_*.png"))
     assert len(shots) == 1
@@ -870,3 +870,30 @@ def test_static_parameter_slider_keeps_one_program(gpu_ctx, content, background,
     again, _ = gpu_ctx.render(96, 64)
     assert np.array_equal(again, frames[0])
     gpu_ctx.set_metric(metric, is_static=False)
+
+
+def test_group_of_devices_renders_as_one(gpu_ctx, oracles, background, grt):
+    """grt_group_* (grt_create(devices, ndev)): several contexts driven as one renderer from one thread; the frame
+    assembled on rank 0 equals the single-context frame, also after the frame shape and the pipeline depth change."""
+    import torch
+
+    metric, _ = oracles("kerr_schild")
+    group = grt.Group([0, 0, 0])          # three ranks on one device: same protocol, peer pointers are local
+    try:
+        group.set_metric(metric)
+        group.set_features(max_acceleration_change=metric.info.max_acceleration_change)
+        group.set_background(background)
+        group.set_camera()
+        for (w, h), depth in (((256, 160), 2), ((192, 128), 3)):
+            bind(gpu_ctx, metric, background)
+            want, _ = gpu_ctx.render(w, h, grt.GRT_FORMAT_RGBA8)
+            group.set_frames_in_flight(depth)
+            host = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(5)]
+            for o in host:
+                group.render(w, h, grt.GRT_FORMAT_RGBA8, o)
+            group.synchronize()
+            for o in host:
+                assert np.array_equal(o.numpy(), want), (w, h)
+            assert group.frame_ptr() != 0
+    finally:
+        group.close()
