@@ -143,6 +143,7 @@ const char* kPreludeCommon =
     "#define GRT_INF __int_as_float(0x7f800000)\n"
     "#define GRT_NAN __int_as_float(0x7fffffff)\n";
 const char* kPreludeFast =
+    "#define GRT_FAST_STEP_CONTROL 1\n"     // the step-size chain of the loop in its shortest form (rsqrt, no division): see accel_to_precision
     "#define GRT_DIV(a, b) __fdividef((a), (b))\n"      // div.approx (reciprocal + multiply); a plain `/` is div.full under --prec-div=false: three more instructions
     "#define GRT_SIN(a) __sinf(a)\n"
     "#define GRT_COS(a) __cosf(a)\n"
@@ -151,6 +152,7 @@ const char* kPreludeFast =
     "#define GRT_EXP(a) __expf(a)\n"
     "#define GRT_POW(a, b) __powf(a, b)\n";
 const char* kPreludePrecise =
+    "#define GRT_FAST_STEP_CONTROL 0\n"
     "#define GRT_DIV(a, b) ((a) / (b))\n"
     "#define GRT_SIN(a) sinf(a)\n"
     "#define GRT_COS(a) cosf(a)\n"

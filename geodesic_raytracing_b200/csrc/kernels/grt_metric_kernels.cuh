@@ -432,7 +432,13 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
     float diff = e * 65536.0f;
     float floor_diff = max_acceleration * 65536.0f / (100000.0f * 100000.0f);
     if (diff < floor_diff) diff = floor_diff;
+#if GRT_FAST_STEP_CONTROL
+    // sqrt(K / diff) as sqrt(K) * rsqrt(diff): one MUFU on the step's dependency chain instead of reciprocal + multiply + square root
+    // (the reference takes native_sqrt of a native divide here, cl.cl:3424: device approximations either way)
+    *next_ds = sqrtf(max_acceleration * 65536.0f) * rsqrtf(diff);
+#else
     *next_ds = sqrtf(GRT_DIV(max_acceleration * 65536.0f, diff));
+#endif
     return diff;
 }
 
@@ -475,8 +481,10 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
     unsigned int tail_tick = 0;
     int cooldown = 0;
 
-    for (;;) {
-        unsigned dead = __ballot_sync(FULL, !alive);
+    for (unsigned int turn = 0;; turn++) {
+        // free lanes are looked for every second turn: the vote and the branch on it sit on the dependency chain of every step (a lone
+        // warp's step is latency-bound), and a lane that waits one more turn for its next ray costs nothing measurable
+        unsigned dead = (turn & 1u) ? 0u : __ballot_sync(FULL, !alive);
         if (dead) {
             if (!exhausted) {
                 int ndead = __popc(dead), leader = __ffs(dead) - 1;
@@ -652,7 +660,12 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
                     // calculate_ds_error (cl.cl:3431-3456)
                     float want;
                     float diff = accel_to_precision(nacc, max_acceleration, &want);
+#if GRT_FAST_STEP_CONTROL
+                    // 0.99 ds clamp(want / ds, 0.3, 2) = clamp(0.99 want, 0.297 ds, 1.98 ds) for ds > 0: no division on the chain
+                    float nds = fminf(fmaxf(0.99f * want, (0.99f * 0.3f) * ds), (0.99f * 2.0f) * ds);
+#else
                     float nds = 0.99f * ds * clampf(GRT_DIV(want, ds), 0.3f, 2.0f);
+#endif
                     nds = fmaxf(nds, fr.min_step);
                     next_ds = nds;
 #if GRT_SINGULARITY_DETECTION
@@ -660,7 +673,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #else
                     (void)diff;
 #endif
-                    if (alive && nds < GRT_DIV(ds, 1.95f)) accept = false;   // DS_SKIP: retry from the same state with the smaller step
+                    if (alive && nds < ds * (1.0f / 1.95f)) accept = false;   // DS_SKIP: retry from the same state with the smaller step
                 }
 #endif
                 if (accept) {
