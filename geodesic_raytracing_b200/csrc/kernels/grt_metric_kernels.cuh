@@ -485,7 +485,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
         // free lanes are looked for every second turn: the vote and the branch on it sit on the dependency chain of every step (a lone
         // warp's step is latency-bound), and a lane that waits one more turn for its next ray costs nothing measurable
         unsigned dead = (turn & 1u) ? 0u : __ballot_sync(FULL, !alive);
-        if (dead) {
+        if (__builtin_expect(dead != 0u, 0)) {      // the step below is the fall-through path: taken branches cost a lone warp an instruction fetch
             if (!exhausted) {
                 int ndead = __popc(dead), leader = __ffs(dead) - 1;
                 unsigned int base = 0;
@@ -615,10 +615,10 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
             drop = drop || (fabsf(vel.x) > 1000.0f + f_in_x && fabsf(acc.x) > 100.0f);   // running_dlambda_dnew stays 1
 #endif
 #endif
-            if (drop) {
+            if (__builtin_expect(drop, 0)) {
                 alive = false;
                 accepted += (unsigned int)iter;
-            } else if (finish) {
+            } else if (__builtin_expect(finish, 0)) {
                 rays.pos[slot] = pos;
                 rays.vel[slot] = vel;
                 rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 1, sxsy);
