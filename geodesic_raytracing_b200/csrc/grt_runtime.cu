@@ -271,7 +271,7 @@ bool integrate_resources(const std::string& log, int* regs, int* spill) {
 // Occupancy tier of the integration kernel.  The loop is bound by FP32 issue with long dependent chains, so more resident
 // warps per scheduler pay as long as nothing spills: after the free compile, the kernel is rebuilt with
 // __launch_bounds__(128, n) for the next one or two block-per-SM tiers and the highest tier that needs no stack and at most
-// a fifth fewer registers is kept (kerr_schild: 89 registers / 5 blocks -> 72 / 7, +5 % frames per second).  The choice is
+// a quarter fewer registers is kept (kerr_schild: 93 registers / 5 blocks -> 72 / 7, +5 % frames per second).  The choice is
 // remembered next to the cubins.  GRT_INTEGRATE_MIN_BLOCKS (environment) overrides, GRT_OCCUPANCY_TIER=0 disables.
 std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit, std::vector<std::string>* files_out = nullptr) {
     const char* off = getenv("GRT_OCCUPANCY_TIER");
@@ -312,7 +312,7 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
             std::vector<char> cand;
             try { cand = compile_cubin_raw(with_tier(n), fast_math, name, &tlog, nullptr, &tpath); } catch (const Error&) { continue; }
             int r2 = 0, s2 = 0;
-            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 5 >= regs * 4 && blocks_for(r2) >= n) {
+            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 4 >= regs * 3 && blocks_for(r2) >= n) {
                 if (files_out) for (const char* ext : {"", ".log"}) remove((best_path + ext).c_str());      // the free compile is not the one kept
                 if (files_out) remove((best_path.substr(0, best_path.size() - 6) + ".cu").c_str());
                 best = cand; best_log = tlog; best_path = tpath; chosen = n;
@@ -386,7 +386,7 @@ struct grt_metric {
 // launches) are filled with the next frame's rays.
 struct FrameSlot {
     cudaStream_t stream = nullptr;
-    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, pool_buf, worklist, rdata, termination, out;
+    DevBuf rays_pos, rays_vel, rays_acc, rays_quat, rays_aux, worklist, rdata, termination, out;
     // counters (zeroed every frame): [4] extra ray count; [8 + phase] work counter and [16 + 2 * phase], [17 + 2 * phase]
     // hot / cold work-list lengths of phase 0 (prepass), 1 (first pass), 2 (refinement); then GrtStats
     unsigned int* d_counters = nullptr;
@@ -415,6 +415,7 @@ struct grt_ctx {
     grt_metric* metric = nullptr;          // only dereferenced by grt_update_params / feature-driven rebuilds
     bool is_static = false;
     bool bound_use_prepass = false, bound_constant_theta = false;   // what the frame path needs of the bound metric
+    float bound_wmax = 1.0f;     // largest acceleration weight of the bound metric (GRT_W_V1..4): step-control constants of GrtFrame
     std::map<std::string, std::unique_ptr<Program>> programs;
     Program* prog = nullptr;
     std::string static_key;      // key of the one static-parameter program kept loaded (a parameter slider in static mode must not grow memory)
@@ -428,7 +429,6 @@ struct grt_ctx {
     DevBuf tables, identity, scratch;
     int identity_len = 0;
     int blocks_per_sm = 3;           // 128-thread blocks of the integration kernel per SM and frame slot; 0 = as many as fit (GRT_BLOCKS_PER_SM)
-    int donate_threshold = 0;   // a warp donates its rays to the exchange pool at this many live lanes or fewer; 0 = no exchange (GRT_DONATE_THRESHOLD)
 
     // geometry cache
     std::vector<int> geom_key;
@@ -592,6 +592,18 @@ void fill_frame_features(grt_ctx* c, GrtFrame& fr) {
     fr.max_acceleration_change = f.max_acceleration_change;
     fr.max_precision_radius = f.max_precision_radius;
     fr.min_step = f.min_step;
+    {
+        // step-size control of the integration loop in its folded form (k_integrate, GRT_FAST_STEP_CONTROL), from
+        // acceleration_to_precision / calculate_ds_error (cl.cl:3400-3456) with S = sum (a_i w_i)^2:
+        //   diff = 655.36 / wmax * sqrt(S), floored at K / 1e10 with K = 65536 max_acceleration_change
+        //   0.99 * sqrt(K / diff) = sc_want * S^(-1/4);  singular when diff / 65536 > 1e4 max_acceleration_change
+        const double K = 65536.0 * (double)f.max_acceleration_change, k = 655.36 / (double)c->bound_wmax;
+        const double floor_diff = K / 1e10, sing = 1e4 * 65536.0 * (double)f.max_acceleration_change;
+        auto clampf = [](double v) { return (float)std::min(v, 3.0e38); };
+        fr.sc_floor = clampf((floor_diff / k) * (floor_diff / k));
+        fr.sc_want = clampf(0.99 * std::sqrt(K / k));
+        fr.sc_singular = clampf((sing / k) * (sing / k));
+    }
     fr.adaptive_sampling_threshold = f.adaptive_sampling_threshold;
     fr.field_of_view = f.field_of_view;
     fr.redshift = f.redshift;
@@ -829,30 +841,6 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     const int* null_count = nullptr;
     float max_accel = c->feat.max_acceleration_change;
     const unsigned persistent_grid = (unsigned)(c->num_sms * (c->blocks_per_sm > 0 ? std::min(c->blocks_per_sm, P->integrate_blocks_per_sm) : P->integrate_blocks_per_sm));
-    // exchange pool of the integration kernel (see GrtPool): capacity = 4x the threads of the persistent grid
-    GrtPool pool{};
-    {
-        // sized for the largest persistent grid any program and tuning can ask for, so the ring layout (and the ready
-        // flags, which must never hold stale data) stays put when the metric or the tuning changes
-        unsigned cap = 1;
-        while (cap < (unsigned)(c->num_sms * 16) * 128u * 4u) cap <<= 1;      // the most blocks per SM any program can have: the layout never moves
-        const size_t bytes = (size_t)cap * 92 + 64;
-        const bool fresh = S.pool_buf.cap < bytes;
-        S.pool_buf.ensure(bytes);
-        if (fresh) CK(cudaMemsetAsync(S.pool_buf.p, 0, S.pool_buf.cap, S.stream));   // tickets run on across launches; ready flags start at 0
-        char* p = (char*)S.pool_buf.p;
-        pool.counters = (unsigned int*)p;
-        p += 64;
-        pool.pos = (float4*)p;
-        pool.vel = (float4*)(p + (size_t)cap * 16);
-        pool.acc = (float4*)(p + (size_t)cap * 32);
-        pool.misc = (float4*)(p + (size_t)cap * 48);
-        pool.ids = (int4*)(p + (size_t)cap * 64);
-        pool.radii = (float2*)(p + (size_t)cap * 80);
-        pool.ready = c->donate_threshold > 0 ? (unsigned int*)(p + (size_t)cap * 88) : nullptr;
-        pool.mask = cap - 1;
-        pool.donate_threshold = c->donate_threshold;
-    }
     // work lists (see GrtWorkList): one int buffer reused by the three phases, which run back to back
     S.worklist.ensure(sizeof(int) * std::max<size_t>({(size_t)fr.n_slots, extra_cap, use_prepass ? (size_t)pf.n_slots : (size_t)1}));
     auto worklist = [&](int phase, size_t capacity) {
@@ -867,7 +855,7 @@ int render_stripes(grt_ctx* c, int w, int h, const int* y0s, const int* y1s, int
     auto integrate = [&](GrtFrame& f, GrtWorkList& wl, int phase, size_t max_items) {
         unsigned grid = std::min(persistent_grid, (unsigned)((max_items + 127) / 128));
         unsigned int* wc = S.d_counters + 8 + phase;
-        void* args[] = {&rays, &f, &wl, &pool, &wc, &S.d_stats, &max_accel, c->params};
+        void* args[] = {&rays, &f, &wl, &wc, &S.d_stats, &max_accel, c->params};
         if ((int)S.integrate_events.size() <= L.integrate_launches) {
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a));
@@ -1223,7 +1211,6 @@ grt_ctx* grt_create(int device) {
         }
         c->last = &c->slots[0];
         if (const char* e = getenv("GRT_BLOCKS_PER_SM")) c->blocks_per_sm = atoi(e);
-        if (const char* e = getenv("GRT_DONATE_THRESHOLD")) c->donate_threshold = atoi(e);
         // default camera (main.cpp:664-673)
         c->cam.pos_cart = make_float4(0, 0, -4, 0);
         c->cam.quat = make_float4(-0.70710678f, 0, 0, 0.70710678f);
@@ -1246,7 +1233,7 @@ void grt_destroy(grt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->programs) if (kv.second->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(kv.second->mod);
     for (auto& S : c->slots) {
-        for (DevBuf* b : {&S.rays_pos, &S.rays_vel, &S.rays_acc, &S.rays_quat, &S.rays_aux, &S.pool_buf, &S.worklist, &S.rdata, &S.termination, &S.out}) b->release();
+        for (DevBuf* b : {&S.rays_pos, &S.rays_vel, &S.rays_acc, &S.rays_quat, &S.rays_aux, &S.worklist, &S.rdata, &S.termination, &S.out}) b->release();
         for (auto e : S.events) cudaEventDestroy(e);
         for (auto& e : S.integrate_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
         cudaFree(S.d_cam);
@@ -1268,7 +1255,6 @@ int grt_set_fast_math(grt_ctx* c, int enabled) {
 int grt_set_tuning(grt_ctx* c, int blocks_per_sm, int donate_threshold) {
     if (!c || blocks_per_sm < 0 || blocks_per_sm > 32 || donate_threshold < 0 || donate_threshold > 31) { g_err = "tuning out of range (blocks_per_sm 0..32, donate_threshold 0..31)"; return GRT_E_INVALID; }
     c->blocks_per_sm = blocks_per_sm;
-    c->donate_threshold = donate_threshold;
     return GRT_OK;
 }
 
@@ -1339,6 +1325,7 @@ int grt_build_poll(grt_ctx* c) {
         c->is_static = c->build.is_static;
         c->bound_use_prepass = m->m->cfg.use_prepass;
         c->bound_constant_theta = m->m->constant_theta();
+        { double w[4]; grt::acceleration_weights(*m->m, w); c->bound_wmax = (float)std::max(std::max(w[0], w[1]), std::max(w[2], w[3])); }
         c->prog = p;
         c->kernel_info = p->info;
         fill_params(c, *m->m);
@@ -1378,6 +1365,7 @@ int grt_set_metric(grt_ctx* c, grt_metric* m, int is_static) {
         c->is_static = is_static != 0;
         c->bound_use_prepass = m->m->cfg.use_prepass;
         c->bound_constant_theta = m->m->constant_theta();
+        { double w[4]; grt::acceleration_weights(*m->m, w); c->bound_wmax = (float)std::max(std::max(w[0], w[1]), std::max(w[2], w[3])); }
         c->prog = p;
         c->kernel_info = p->info;
         fill_params(c, *m->m);

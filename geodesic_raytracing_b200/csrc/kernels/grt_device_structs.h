@@ -19,25 +19,6 @@ struct GrtRays {
     int4* aux;
 };
 
-// Exchange pool of the integration kernel: a ring of in-flight ray records (80 B of loop state per
-// ray, SoA) through which sparse warps hand their surviving rays to warps with free lanes, so warps
-// stay converged under divergent step counts.  Tickets are reserved with atomicAdd on counters[0]
-// (push) and claimed with atomicCAS on counters[1] (pop); ready[ticket & mask] == ticket + 1 once
-// the record is visible.  Capacity (mask + 1) exceeds the threads of the persistent grid several
-// times over: only rays in flight are ever outstanding.
-struct GrtPool {
-    float4* pos;
-    float4* vel;
-    float4* acc;
-    float4* misc;   // {next_ds, accepted-step count (int bits), |v.t| at launch, running_dlambda_dnew}
-    int4* ids;      // {slot, ku_uobsu (float bits), sy<<16|sx, -}
-    float2* radii;  // {|polar r|, |distance|} of the state (they travel with the ray: the loop computes them with the acceleration)
-    unsigned int* ready;
-    unsigned int* counters;
-    unsigned int mask;
-    int donate_threshold;   // a warp with this many live lanes or fewer (after the queue ran dry) gives its rays away
-};
-
 // Work list of one integration phase: the slots of the rays that really have to be traced (culled
 // and padding slots never enter it), "hot" rays - the ones expected to run longest, next to the
 // shadow - filled in from the front and the rest from the back, so the kernel starts the long rays
@@ -74,6 +55,7 @@ struct GrtFrame {
     int flip_geodesic_direction;
     int max_probes;
     float universe_size, max_acceleration_change, max_precision_radius, min_step;
+    float sc_floor, sc_want, sc_singular;   // step-size control constants folded on the host (fill_frame_features)
     float adaptive_sampling_threshold, field_of_view;
     int redshift, reparameterisation, use_old_redshift, adaptive_sampling;
 };

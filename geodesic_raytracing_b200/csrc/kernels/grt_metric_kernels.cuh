@@ -442,255 +442,237 @@ static __device__ __forceinline__ float accel_to_precision(float4 a, float max_a
     return diff;
 }
 
-// The integration loop.  Each lane owns one ray; a lane whose ray ends stores it and immediately
-// pulls the next fresh slot from `work_counter` (warp-aggregated atomicAdd), so lanes never idle
-// waiting for the slowest ray of their warp.  Ray state lives in registers; HBM traffic is one
-// 64-byte load and (for finished rays) one 48-byte store per ray, zero bytes per step.
-//
-// Live-ray compaction: step counts range from ~50 to the 16384 cap, so once the work queue is dry
-// the surviving long rays are scattered a few per warp.  A warp that is down to
-// `pool.donate_threshold` live lanes pushes their loop state into the exchange pool (ballot-ranked,
-// one atomicAdd per warp) and any warp with free lanes claims records from it, so the survivors
-// are re-packed into full warps without leaving the kernel.  A donor always tries to claim after
-// it pushed, so a record is never orphaned; results do not depend on which lane runs a ray.
-static __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+#if GRT_FAST_STEP_CONTROL
+// NaN or Inf among eight values: max.NaN keeps a NaN, |x| > FLT_MAX catches an infinity.  abs sits inside the asm and without
+// .ftz, so that it folds into the operand modifiers whatever the build's denormal mode; ptxas fuses each pair of two-input
+// maxima into one FMNMX3 (the three-input PTX form itself is refused by the NVRTC 12.8 a process gets when PyTorch's bundled
+// copy was loaded before the toolkit's 12.9): five instructions for the eight values.
+static __device__ __forceinline__ float absmax_nan3(float a, float b, float c) {
+    float r;
+    asm("{ .reg .f32 x, y, z; abs.f32 x, %1; abs.f32 y, %2; abs.f32 z, %3; max.NaN.f32 x, x, y; max.NaN.f32 %0, x, z; }" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+static __device__ __forceinline__ float absmax_nan2(float a, float b) {
+    float r;
+    asm("{ .reg .f32 x, y; abs.f32 x, %1; abs.f32 y, %2; max.NaN.f32 %0, x, y; }" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+static __device__ __forceinline__ bool bad8(float4 a, float4 b) {
+    const float m = absmax_nan2(absmax_nan3(a.x, a.y, a.z), absmax_nan3(b.x, b.y, absmax_nan3(a.w, b.z, b.w)));
+    return !(m <= 3.402823466e+38f);
+}
+// sum (a_i w_i)^2 of the step-size control (the weights are literals of the generated program)
+static __device__ __forceinline__ float weighted_accel_sq(float4 a) {
+    const float ax = a.x * GRT_W_V1, ay = a.y * GRT_W_V2, az = a.z * GRT_W_V3, aw = a.w * GRT_W_V4;
+    return ax * ax + ay * ay + az * az + aw * aw;
+}
+#endif
 
+// A cleanly terminated ray goes back to its slot (cl.cl:4088-4130).  Not inlined: the loads of the three plane pointers would
+// otherwise be hoisted to the top of every step.
+static __device__ __noinline__ void store_finished_ray(float4* pos_at, float4* vel_at, int4* aux_at, float4 pos, float4 vel, int4 aux) {
+    *pos_at = pos;
+    *vel_at = vel;
+    *aux_at = aux;
+}
+
+// The integration loop.  Each lane owns one ray; a lane whose ray ends stores it and immediately
+// pulls the next item of the work list (atomicAdd aggregated over the lanes that are free at that
+// moment), so lanes never idle waiting for the slowest ray of their warp.  Ray state lives in
+// registers; HBM traffic is one 64-byte load and (for finished rays) one 48-byte store per ray,
+// zero bytes per step.  A lane that finds the list dry leaves the loop on its own and waits for the
+// rest of its warp at the final reduction; results do not depend on which lane runs a ray.
 #ifndef GRT_INTEGRATE_MIN_BLOCKS
 #define GRT_INTEGRATE_MIN_BLOCKS 1
 #endif
-extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_integrate(GrtRays rays, GrtFrame fr, GrtWorkList wl, GrtPool pool, unsigned int* work_counter, GrtStats* stats,
+extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_integrate(GrtRays rays, GrtFrame fr, GrtWorkList wl, unsigned int* work_counter, GrtStats* stats,
                                                               float max_acceleration, grt_params cfg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lanes_below = (1u << lane) - 1u;
     const unsigned int n_hot = *wl.n_hot, count = n_hot + *wl.n_cold;
 
-    bool alive = false, exhausted = false;
-    int slot = 0, iter = 0;
+    bool exhausted = false;
+    int slot = 0;
+    int iter = -1;      // accepted steps of the ray this lane holds; -1: the lane holds no ray
     float4 pos = f4(0, 0, 0, 0), vel = pos, acc = pos;
     // r_abs / polar_r_abs: |distance to the object| and |polar r| of the CURRENT state.  They are evaluated once when a ray is
     // loaded and from then on together with the acceleration of every trial position (grt_accel_radii), so the top-of-step
     // checks never wait for them; a rejected step keeps the old ones.  Which code site produced them depends only on the
     // ray's own history (first step: load site, later steps: step site), never on scheduling.
-    float next_ds = 0.00001f, dlambda = 1.0f, f_in_x = 0.0f, r_abs = 0.0f, polar_r_abs = 0.0f, ku = 0.0f;
+    // drop_limit = 1000 + |velocity.x| of the ray as loaded (the f_in_x of cl.cl:4061)
+    float next_ds = 0.00001f, dlambda = 1.0f, drop_limit = 0.0f, r_abs = 0.0f, polar_r_abs = 0.0f, ku = 0.0f;
     int sxsy = 0;
     // per-lane counters are 32 bit (a lane sees < 2^32 steps in any launch that ends within minutes); widened in the final reduction.
-    // accepted steps are counted per ray (iter) and added when the ray leaves the lane for good
-    unsigned int trial = 0, accepted = 0, nrays = 0, nfinished = 0;
+    // accepted steps = trial steps - the trials that were not accepted (retries, singularity kills): those are counted on their own rare paths
+    unsigned int trial = 0, not_accepted = 0, nrays = 0, nfinished = 0;
     const float new_max = fr.max_precision_radius;
-    unsigned int tail_tick = 0;
-    int cooldown = 0;
 
-    for (unsigned int turn = 0;; turn++) {
-        // free lanes are looked for every second turn: the vote and the branch on it sit on the dependency chain of every step (a lone
-        // warp's step is latency-bound), and a lane that waits one more turn for its next ray costs nothing measurable
-        unsigned dead = (turn & 1u) ? 0u : __ballot_sync(FULL, !alive);
-        if (__builtin_expect(dead != 0u, 0)) {      // the step below is the fall-through path: taken branches cost a lone warp an instruction fetch
-            if (!exhausted) {
-                int ndead = __popc(dead), leader = __ffs(dead) - 1;
-                unsigned int base = 0;
-                if (lane == leader) base = atomicAdd(work_counter, (unsigned int)ndead);
-                base = __shfl_sync(FULL, base, leader);
-                exhausted = base + ndead >= count;
-                if (!alive) {
-                    unsigned int mine = base + __popc(dead & lanes_below);
-                    if (mine < count) {
-                        slot = wl.slots[mine < n_hot ? (int)mine : wl.capacity - 1 - (int)(mine - n_hot)];
-                        int4 aux = rays.aux[slot];
-                        {
-                            pos = rays.pos[slot];
-                            vel = rays.vel[slot];
-                            acc = rays.acc[slot];
-                            ku = __int_as_float(aux.x);
-                            sxsy = aux.w;
+    for (;;) {
+        if (__builtin_expect(iter < 0, 0)) {      // the step below is the fall-through path: taken branches cost a lone warp an instruction fetch
+            if (exhausted) break;
+            // ---- pull the next item: one atomicAdd for all the lanes that are free right now ----
+            const unsigned idle = __activemask();
+            const int nidle = __popc(idle), leader = __ffs(idle) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (unsigned int)nidle);
+            base = __shfl_sync(idle, base, leader);
+            exhausted = base + nidle >= count;
+            const unsigned int mine = base + __popc(idle & lanes_below);
+            if (mine >= count) break;
+            slot = wl.slots[mine < n_hot ? (int)mine : wl.capacity - 1 - (int)(mine - n_hot)];
+            const int4 aux = rays.aux[slot];
+            pos = rays.pos[slot];
+            vel = rays.vel[slot];
+            acc = rays.acc[slot];
+            ku = __int_as_float(aux.x);
+            sxsy = aux.w;
 #if GRT_CONSTANT_THETA
-                            pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
+            pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
 #endif
-                            f_in_x = fabsf(vel.x);
-                            next_ds = 0.00001f;
+            drop_limit = 1000.0f + fabsf(vel.x);
+            next_ds = 0.00001f;
 #if GRT_ADAPTIVE_PRECISION
-                            (void)accel_to_precision(acc, max_acceleration, &next_ds);
+#if GRT_FAST_STEP_CONTROL
+            next_ds = (1.0f / 0.99f) * fr.sc_want * rsqrtf(sqrtf(fmaxf(weighted_accel_sq(acc), fr.sc_floor)));
+#else
+            (void)accel_to_precision(acc, max_acceleration, &next_ds);
 #endif
-                            dlambda = 1.0f;
-                            iter = 0;
-                            nrays++;
-                            alive = true;
-                            {
-                                float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
-                                grt_radii(p, cfg, rr);
-                                polar_r_abs = fabsf(rr[0]);
-                                r_abs = fabsf(rr[1]);
-                            }
-                        }
-                    }
-                }
-            } else if (pool.ready && (dead == FULL || (tail_tick++ & 7u) == 0u)) {
-                // ---- queue is dry: exchange rays through the pool (rate limited to every 8th step) ----
-                unsigned live = ~dead;
-                int nlive = __popc(live);
-                bool donated = false;
-                if (nlive > 0 && nlive <= pool.donate_threshold && cooldown == 0) {
-                    int leader = __ffs(live) - 1;
-                    unsigned int base = 0;
-                    if (lane == leader) base = atomicAdd(&pool.counters[0], (unsigned int)nlive);
-                    base = __shfl_sync(FULL, base, leader);
-                    if (alive) {
-                        const unsigned int ticket = base + __popc(live & lanes_below), rec = ticket & pool.mask;
-                        pool.pos[rec] = pos;
-                        pool.vel[rec] = vel;
-                        pool.acc[rec] = acc;
-                        pool.misc[rec] = f4(next_ds, __int_as_float(iter), f_in_x, dlambda);
-                        pool.ids[rec] = make_int4(slot, __float_as_int(ku), sxsy, 0);
-                        pool.radii[rec] = make_float2(polar_r_abs, r_abs);
-                        __threadfence();
-                        *(volatile unsigned int*)&pool.ready[rec] = ticket + 1u;
-                        alive = false;
-                    }
-                    donated = true;
-                    dead = FULL;
-                    __nanosleep(2000);   // let other sparse warps add theirs before anyone claims
-                } else if (cooldown > 0) cooldown--;
-                // claim up to one record per free lane
-                const int want = __popc(dead);
-                unsigned int base = 0, n = 0;
-                if (lane == 0) {
-                    unsigned int pop = ld_volatile_u32(&pool.counters[1]);
-                    for (;;) {
-                        unsigned int push = ld_volatile_u32(&pool.counters[0]);
-                        n = min((unsigned int)want, push - pop);
-                        if (n == 0) break;
-                        unsigned int old = atomicCAS(&pool.counters[1], pop, pop + n);
-                        if (old == pop) break;
-                        pop = old;
-                    }
-                    base = pop;
-                }
-                base = __shfl_sync(FULL, base, 0);
-                n = __shfl_sync(FULL, n, 0);
-                if (!alive) {
-                    const unsigned int rank = __popc(dead & lanes_below);
-                    if (rank < n) {
-                        const unsigned int ticket = base + rank, rec = ticket & pool.mask;
-                        while (ld_volatile_u32(&pool.ready[rec]) != ticket + 1u) {}
-                        __threadfence();
-                        pos = __ldcg(&pool.pos[rec]);
-                        vel = __ldcg(&pool.vel[rec]);
-                        acc = __ldcg(&pool.acc[rec]);
-                        float4 m = __ldcg(&pool.misc[rec]);
-                        int4 ids = __ldcg(&pool.ids[rec]);
-                        float2 rr = __ldcg(&pool.radii[rec]);
-                        polar_r_abs = rr.x;
-                        r_abs = rr.y;
-                        next_ds = m.x;
-                        iter = __float_as_int(m.y);
-                        f_in_x = m.z;
-                        dlambda = m.w;
-                        slot = ids.x;
-                        ku = __int_as_float(ids.y);
-                        sxsy = ids.z;
-                        alive = true;
-                    }
-                }
-                if (donated && (int)n <= nlive) cooldown = 8;   // nobody to merge with: do not churn
-            }
-            if (!__any_sync(FULL, alive)) {
-                if (exhausted) break;
-                continue;
+#endif
+            dlambda = 1.0f;
+            iter = 0;
+            nrays++;
+            {
+                float p[4] = {pos.x, pos.y, pos.z, pos.w}, rr[2];
+                grt_radii(p, cfg, rr);
+                polar_r_abs = fabsf(rr[0]);
+                r_abs = fabsf(rr[1]);
             }
         }
-        if (alive) {
-            // ---- top-of-iteration checks on the current state (cl.cl:4088-4130) ----
-            bool finish = polar_r_abs >= fr.universe_size;
+        // ---- one trial Verlet step of this lane's ray (cl.cl:4070-4247) ----
+        // ---- top-of-iteration checks on the current state (cl.cl:4088-4130) ----
+        bool finish = polar_r_abs >= fr.universe_size;
 #if GRT_SINGULAR
-            finish = finish || (polar_r_abs < GRT_SINGULAR_TERMINATOR);
+        finish = finish || (polar_r_abs < GRT_SINGULAR_TERMINATOR);
 #endif
-            bool drop = false;
+        bool drop = false;
 #if GRT_HAS_CYLINDRICAL_SINGULARITY
-            drop = pos.y < GRT_CYLINDRICAL_TERMINATOR;
+        drop = pos.y < GRT_CYLINDRICAL_TERMINATOR;
 #endif
 #if !GRT_UNCONDITIONALLY_NONSINGULAR
 #if GRT_FEATURE_REPARAMETERISATION
-            drop = drop || (fabsf(GRT_DIV(vel.x, dlambda)) > 1000.0f + f_in_x && fabsf(GRT_DIV(acc.x, dlambda)) > 100.0f);
+        drop = drop || (fabsf(GRT_DIV(vel.x, dlambda)) > drop_limit && fabsf(GRT_DIV(acc.x, dlambda)) > 100.0f);
 #else
-            drop = drop || (fabsf(vel.x) > 1000.0f + f_in_x && fabsf(acc.x) > 100.0f);   // running_dlambda_dnew stays 1
+        drop = drop || (fabsf(vel.x) > drop_limit && fabsf(acc.x) > 100.0f);   // running_dlambda_dnew stays 1
 #endif
 #endif
-            if (__builtin_expect(drop, 0)) {
-                alive = false;
-                accepted += (unsigned int)iter;
-            } else if (__builtin_expect(finish, 0)) {
-                rays.pos[slot] = pos;
-                rays.vel[slot] = vel;
-                rays.aux[slot] = make_int4(__float_as_int(ku), __float_as_int(dlambda), 1, sxsy);
-                nfinished++;
-                alive = false;
-                accepted += (unsigned int)iter;
-            } else {
-                // ---- step size (cl.cl:4070-4086) ----
-                float ds;
-#if GRT_ADAPTIVE_PRECISION
-                ds = next_ds;
-#else
-                ds = lerpf(GRT_AMBIENT_PRECISION, GRT_SUBAMBIENT_PRECISION, GRT_DIV(clampf(r_abs, 3.0f, new_max) - 3.0f, new_max - 3.0f));
-#endif
-                const bool inside = r_abs < new_max;
-                ds = inside ? fminf(ds, GRT_AMBIENT_PRECISION) : (0.1f * (r_abs - new_max) + GRT_AMBIENT_PRECISION);
-                // ---- velocity Verlet (cl.cl:3273-3346) ----
-                const float hds2 = 0.5f * ds * ds;
-                float4 npos = f4(pos.x + vel.x * ds + acc.x * hds2, pos.y + vel.y * ds + acc.y * hds2,
-                                 pos.z + vel.z * ds + acc.z * hds2, pos.w + vel.w * ds + acc.w * hds2);
-                float4 ivel = f4(vel.x + acc.x * ds, vel.y + acc.y * ds, vel.z + acc.z * ds, vel.w + acc.w * ds);
-                float n_polar_r, n_dist;
-                float4 nacc = accel_radii_at(npos, ivel, cfg, &n_polar_r, &n_dist);
-                const float hds = 0.5f * ds;
-                float4 nvel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds,
-                                 vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
-#if GRT_FEATURE_REPARAMETERISATION
-                {
-                    float K = GRT_DIV(1.0f, fmaxf(fmaxf(fabsf(nvel.x), fabsf(nvel.y)), fmaxf(fabsf(nvel.z), fabsf(nvel.w))));
-                    nvel = nvel * K;
-                    nacc = nacc * (K * K);
-                    dlambda *= K;
-                }
-#endif
-                trial++;
-                bool accept = true;
-#if GRT_ADAPTIVE_PRECISION
-                if (inside) {
-                    // calculate_ds_error (cl.cl:3431-3456)
-                    float want;
-                    float diff = accel_to_precision(nacc, max_acceleration, &want);
-#if GRT_FAST_STEP_CONTROL
-                    // 0.99 ds clamp(want / ds, 0.3, 2) = clamp(0.99 want, 0.297 ds, 1.98 ds) for ds > 0: no division on the chain
-                    float nds = fminf(fmaxf(0.99f * want, (0.99f * 0.3f) * ds), (0.99f * 2.0f) * ds);
-#else
-                    float nds = 0.99f * ds * clampf(GRT_DIV(want, ds), 0.3f, 2.0f);
-#endif
-                    nds = fmaxf(nds, fr.min_step);
-                    next_ds = nds;
-#if GRT_SINGULARITY_DETECTION
-                    if (nds == fr.min_step && (diff * (1.0f / 65536.0f)) > max_acceleration * 10000.0f) { alive = false; accept = false; accepted += (unsigned int)iter; }
-#else
-                    (void)diff;
-#endif
-                    if (alive && nds < ds * (1.0f / 1.95f)) accept = false;   // DS_SKIP: retry from the same state with the smaller step
-                }
-#endif
-                if (accept) {
-                    pos = npos; vel = nvel; acc = nacc;
-                    polar_r_abs = fabsf(n_polar_r);
-                    r_abs = fabsf(n_dist);
-#if GRT_CONSTANT_THETA
-                    pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
-#endif
-                    iter++;
-                    if (bad4(pos) || bad4(vel) || bad4(acc) || iter >= GRT_LOOP_LIMIT) { alive = false; accepted += (unsigned int)iter; }
-                }
-            }
+        if (__builtin_expect(drop, 0)) {
+            iter = -1;
+            continue;
         }
+        if (__builtin_expect(finish, 0)) {
+            store_finished_ray(rays.pos + slot, rays.vel + slot, rays.aux + slot, pos, vel, make_int4(__float_as_int(ku), __float_as_int(dlambda), 1, sxsy));
+            nfinished++;
+            iter = -1;
+            continue;
+        }
+        // ---- step size (cl.cl:4070-4086) ----
+        float ds;
+#if GRT_ADAPTIVE_PRECISION
+        ds = next_ds;
+#else
+        ds = lerpf(GRT_AMBIENT_PRECISION, GRT_SUBAMBIENT_PRECISION, GRT_DIV(clampf(r_abs, 3.0f, new_max) - 3.0f, new_max - 3.0f));
+#endif
+        const bool inside = r_abs < new_max;
+        ds = inside ? fminf(ds, GRT_AMBIENT_PRECISION) : (0.1f * (r_abs - new_max) + GRT_AMBIENT_PRECISION);
+        // ---- velocity Verlet (cl.cl:3273-3346) ----
+        const float hds2 = 0.5f * ds * ds;
+        float4 npos = f4(pos.x + vel.x * ds + acc.x * hds2, pos.y + vel.y * ds + acc.y * hds2,
+                         pos.z + vel.z * ds + acc.z * hds2, pos.w + vel.w * ds + acc.w * hds2);
+        float4 ivel = f4(vel.x + acc.x * ds, vel.y + acc.y * ds, vel.z + acc.z * ds, vel.w + acc.w * ds);
+        float n_polar_r, n_dist;
+        float4 nacc = accel_radii_at(npos, ivel, cfg, &n_polar_r, &n_dist);
+        const float hds = 0.5f * ds;
+        trial++;
+#if GRT_FAST_STEP_CONTROL && !GRT_FEATURE_REPARAMETERISATION
+        // The folded arrangement.  The new velocity is not an input of the step control, so it is formed after the verdict, straight
+        // into the state registers; a NaN or Inf of the new acceleration shows in the new velocity (v + (a + a') ds / 2 with ds > 0),
+        // so the check of position and velocity covers it.
+#if GRT_ADAPTIVE_PRECISION
+        {
+            // calculate_ds_error (cl.cl:3431-3456) with the constants of fill_frame_features:
+            //   0.99 ds clamp(want / ds, 0.3, 2) = clamp(0.99 want, 0.297 ds, 1.98 ds),  0.99 want = sc_want * S^(-1/4)
+            // Evaluated for every step and applied inside the precision radius only (a select instead of a branch around it:
+            // nearly all steps are inside).
+            const float S = fmaxf(weighted_accel_sq(nacc), fr.sc_floor);
+            float nds = fminf(fmaxf(fr.sc_want * rsqrtf(sqrtf(S)), (0.99f * 0.3f) * ds), (0.99f * 2.0f) * ds);
+            nds = fmaxf(nds, fr.min_step);
+            next_ds = inside ? nds : next_ds;
+#if GRT_SINGULARITY_DETECTION
+            if (__builtin_expect(inside && nds == fr.min_step && S > fr.sc_singular, 0)) { iter = -1; not_accepted++; continue; }
+#endif
+            if (__builtin_expect(inside && nds < ds * (1.0f / 1.95f), 0)) { not_accepted++; continue; }   // DS_SKIP: retry from the same state with the smaller step
+        }
+#endif
+        vel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds, vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
+        pos = npos; acc = nacc;
+        polar_r_abs = fabsf(n_polar_r);
+        r_abs = fabsf(n_dist);
+#if GRT_CONSTANT_THETA
+        pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
+#endif
+        iter++;
+        if (__builtin_expect(bad8(pos, vel) || iter >= GRT_LOOP_LIMIT, 0)) iter = -1;
+#else
+        float4 nvel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds,
+                         vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
+#if GRT_FEATURE_REPARAMETERISATION
+        {
+            float K = GRT_DIV(1.0f, fmaxf(fmaxf(fabsf(nvel.x), fabsf(nvel.y)), fmaxf(fabsf(nvel.z), fabsf(nvel.w))));
+            nvel = nvel * K;
+            nacc = nacc * (K * K);
+            dlambda *= K;
+        }
+#endif
+        bool accept = true, dead = false;
+#if GRT_ADAPTIVE_PRECISION
+        if (inside) {
+            // calculate_ds_error (cl.cl:3431-3456)
+            float want;
+            float diff = accel_to_precision(nacc, max_acceleration, &want);
+#if GRT_FAST_STEP_CONTROL
+            // 0.99 ds clamp(want / ds, 0.3, 2) = clamp(0.99 want, 0.297 ds, 1.98 ds) for ds > 0: no division on the chain
+            float nds = fminf(fmaxf(0.99f * want, (0.99f * 0.3f) * ds), (0.99f * 2.0f) * ds);
+#else
+            float nds = 0.99f * ds * clampf(GRT_DIV(want, ds), 0.3f, 2.0f);
+#endif
+            nds = fmaxf(nds, fr.min_step);
+            next_ds = nds;
+#if GRT_SINGULARITY_DETECTION
+            if (nds == fr.min_step && (diff * (1.0f / 65536.0f)) > max_acceleration * 10000.0f) { dead = true; accept = false; }
+#else
+            (void)diff;
+#endif
+            if (!dead && nds < ds * (1.0f / 1.95f)) accept = false;   // DS_SKIP: retry from the same state with the smaller step
+        }
+#endif
+        if (accept) {
+            pos = npos; vel = nvel; acc = nacc;
+            polar_r_abs = fabsf(n_polar_r);
+            r_abs = fabsf(n_dist);
+#if GRT_CONSTANT_THETA
+            pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
+#endif
+            iter++;
+            if (bad4(pos) || bad4(vel) || bad4(acc) || iter >= GRT_LOOP_LIMIT) iter = -1;
+        } else {
+            not_accepted++;
+            if (dead) iter = -1;
+        }
+#endif
     }
     // statistics: warp reduce in 64 bit, one atomic per warp
-    unsigned long long t64 = trial, a64 = accepted, r64 = nrays, f64 = nfinished;
+    unsigned long long t64 = trial, a64 = trial - not_accepted, r64 = nrays, f64 = nfinished;
     for (int o = 16; o > 0; o >>= 1) {
         t64 += __shfl_down_sync(FULL, t64, o);
         a64 += __shfl_down_sync(FULL, a64, o);

@@ -876,6 +876,13 @@ std::unique_ptr<Metric> load_metric_from_script(const ContentManager& cm, const 
 // ------------------------------------------------------------------------------------------
 // Emission (replaces build_argument_string, metric.hpp:725-959)
 // ------------------------------------------------------------------------------------------
+// W_V1..4 (metric.hpp:849-869): weights of the acceleration components in the step-size control
+void acceleration_weights(const Metric& m, double w[4]) {
+    w[0] = w[1] = w[2] = w[3] = 1;
+    if (m.cfg.system == CoordinateSystem::X_Y_THETA_PHI) { w[2] = 8; w[3] = m.constant_theta() ? 8 : 32; }
+    else if (m.cfg.system == CoordinateSystem::CYLINDRICAL) { w[2] = 8; }
+}
+
 std::string emit_metric_source(const Metric& m, bool is_static) {
     const MetricDescriptor& d = m.desc;
     const Graph& G = d.graph;
@@ -899,9 +906,8 @@ std::string emit_metric_source(const Metric& m, bool is_static) {
     defflag("GRT_ADAPTIVE_PRECISION", m.cfg.adaptive_precision);
     defflag("GRT_SINGULARITY_DETECTION", m.cfg.adaptive_precision && m.cfg.detect_singularities);
     // W_V1..4 (metric.hpp:849-869)
-    double w[4] = {1, 1, 1, 1};
-    if (m.cfg.system == CoordinateSystem::X_Y_THETA_PHI) { w[2] = 8; w[3] = const_theta ? 8 : 32; }
-    else if (m.cfg.system == CoordinateSystem::CYLINDRICAL) { w[2] = 8; }
+    double w[4];
+    acceleration_weights(m, w);
     deffloat("GRT_W_V1", w[0]); deffloat("GRT_W_V2", w[1]); deffloat("GRT_W_V3", w[2]); deffloat("GRT_W_V4", w[3]);
     defflag("GRT_FORWARD_GEODESIC_PATH", m.cfg.follow_geodesics_forward);
     defflag("GRT_HAS_CYLINDRICAL_SINGULARITY", m.cfg.has_cylindrical_singularity);

@@ -106,6 +106,10 @@ std::unique_ptr<Metric> load_metric_from_script(const ContentManager& cm, const 
 // functions read `cfg.<name>` from `struct grt_params`.
 std::string emit_metric_source(const Metric& m, bool is_static);
 
+// W_V1..4 of the step-size control (metric.hpp:849-869); the generated program carries them as GRT_W_V1..4, the host needs
+// their maximum for the step-control constants of GrtFrame.
+void acceleration_weights(const Metric& m, double w[4]);
+
 // The parameter block the generated functions read (`struct grt_params`): the named parameters' current values followed by the
 // derived parameters evaluated from them.
 std::vector<float> pack_params(const Metric& m);

@@ -163,10 +163,11 @@ int grt_compile_metric(grt_metric*, int is_static, int fast_math, const char** l
 int grt_set_fast_math(grt_ctx*, int enabled);
 
 /* Scheduling of the integration kernel (results do not depend on it): `blocks_per_sm` 128-thread
- * blocks of the persistent grid per SM (0 = as many as fit: throughput; fewer = lower per-step
- * latency for the longest rays); once the work queue is dry, a warp with `donate_threshold` live rays
- * or fewer hands them to warps with free lanes through the exchange pool (0 disables the exchange).
- * Defaults 3 and 0: measured best on the 4K kerr_schild frame (profiles/round1_tuning.md). */
+ * blocks of the persistent grid per SM and frame slot (0 = as many as fit: throughput; fewer = lower
+ * per-step latency for the longest rays).  Default 3: measured best on the 4K kerr_schild frame
+ * (profiles/round1_tuning.md).  `donate_threshold` (0..31) is accepted and ignored: it steered the
+ * in-kernel exchange of surviving rays between warps, which never paid for its atomics and was taken
+ * out of the loop in round 2 (profiles/round2_tuning.md); the argument stays so callers need not change. */
 int grt_set_tuning(grt_ctx*, int blocks_per_sm, int donate_threshold);
 
 /* Frame slots that asynchronous frames rotate through (1..16, default 2 as the reference's two

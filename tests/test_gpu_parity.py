@@ -412,7 +412,8 @@ def test_frames_in_flight_do_not_interfere(gpu_ctx, oracles, background):
 
 
 def test_scheduling_knobs_do_not_change_results(gpu_ctx, oracles, background):
-    """Occupancy and the in-kernel live-ray exchange only move rays between lanes: images are bit-identical."""
+    """How many blocks share an SM only moves rays between lanes: images and step counts are bit-identical (the second argument of
+    grt_set_tuning is accepted and ignored since the in-kernel ray exchange was taken out)."""
     metric, _ = oracles("kerr_schild")
     bind(gpu_ctx, metric, background)
     w, h = 256, 160
@@ -422,7 +423,7 @@ def test_scheduling_knobs_do_not_change_results(gpu_ctx, oracles, background):
         gpu_ctx.set_tuning(blocks, donate)
         img, st = gpu_ctx.render(w, h)
         assert np.array_equal(img, ref), (blocks, donate)
-        assert int(st.trial_steps) == int(st0.trial_steps) and int(st.rays_finished) == int(st0.rays_finished)
+        assert int(st.trial_steps) == int(st0.trial_steps) and int(st.rays_finished) == int(st0.rays_finished) and int(st.accepted_steps) == int(st0.accepted_steps)
     gpu_ctx.set_tuning(3, 0)
 
 
