@@ -271,7 +271,7 @@ bool integrate_resources(const std::string& log, int* regs, int* spill) {
 // Occupancy tier of the integration kernel.  The loop is bound by FP32 issue with long dependent chains, so more resident
 // warps per scheduler pay as long as nothing spills: after the free compile, the kernel is rebuilt with
 // __launch_bounds__(128, n) for the next one or two block-per-SM tiers and the highest tier that needs no stack and at most
-// a quarter fewer registers is kept (kerr_schild: 93 registers / 5 blocks -> 72 / 7, +5 % frames per second).  The choice is
+// three tenths fewer registers is kept (kerr_schild: 87 registers / 5 blocks -> 72 / 7, +5 % frames per second; double_unequal_kerr: 179 / 2 -> 128 / 4, +4 % over 150 / 3).  The choice is
 // remembered next to the cubins.  GRT_INTEGRATE_MIN_BLOCKS (environment) overrides, GRT_OCCUPANCY_TIER=0 disables.
 std::vector<char> compile_cubin(const std::string& src, bool fast_math, const std::string& name, std::string* log_out, bool* cache_hit, std::vector<std::string>* files_out = nullptr) {
     const char* off = getenv("GRT_OCCUPANCY_TIER");
@@ -312,7 +312,7 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
             std::vector<char> cand;
             try { cand = compile_cubin_raw(with_tier(n), fast_math, name, &tlog, nullptr, &tpath); } catch (const Error&) { continue; }
             int r2 = 0, s2 = 0;
-            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 4 >= regs * 3 && blocks_for(r2) >= n) {
+            if (integrate_resources(tlog, &r2, &s2) && s2 == 0 && r2 * 10 >= regs * 7 && blocks_for(r2) >= n) {
                 if (files_out) for (const char* ext : {"", ".log"}) remove((best_path + ext).c_str());      // the free compile is not the one kept
                 if (files_out) remove((best_path.substr(0, best_path.size() - 6) + ".cu").c_str());
                 best = cand; best_log = tlog; best_path = tpath; chosen = n;

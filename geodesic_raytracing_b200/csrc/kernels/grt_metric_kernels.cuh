@@ -468,8 +468,11 @@ static __device__ __forceinline__ float weighted_accel_sq(float4 a) {
 }
 #endif
 
-// A cleanly terminated ray goes back to its slot (cl.cl:4088-4130).  Not inlined: the loads of the three plane pointers would
-// otherwise be hoisted to the top of every step.
+// iter = -1 (the lane holds no ray) written where a ray ends.  Volatile, so that the compiler keeps the write on the rare path
+// that ends the ray instead of writing -1 speculatively at the top of every step and restoring the count at the bottom.
+#define GRT_RELEASE_LANE(iter) asm volatile("mov.s32 %0, -1;" : "=r"(iter))
+
+// A cleanly terminated ray goes back to its slot (cl.cl:4088-4130).  Out of line: a rare path, kept out of the loop's code.
 static __device__ __noinline__ void store_finished_ray(float4* pos_at, float4* vel_at, int4* aux_at, float4 pos, float4 vel, int4 aux) {
     *pos_at = pos;
     *vel_at = vel;
@@ -567,13 +570,13 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
 #endif
 #endif
         if (__builtin_expect(drop, 0)) {
-            iter = -1;
+            GRT_RELEASE_LANE(iter);
             continue;
         }
         if (__builtin_expect(finish, 0)) {
             store_finished_ray(rays.pos + slot, rays.vel + slot, rays.aux + slot, pos, vel, make_int4(__float_as_int(ku), __float_as_int(dlambda), 1, sxsy));
             nfinished++;
-            iter = -1;
+            GRT_RELEASE_LANE(iter);
             continue;
         }
         // ---- step size (cl.cl:4070-4086) ----
@@ -586,13 +589,21 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
         const bool inside = r_abs < new_max;
         ds = inside ? fminf(ds, GRT_AMBIENT_PRECISION) : (0.1f * (r_abs - new_max) + GRT_AMBIENT_PRECISION);
         // ---- velocity Verlet (cl.cl:3273-3346) ----
+        const float hds = 0.5f * ds;
+#if GRT_FAST_STEP_CONTROL && !GRT_FEATURE_REPARAMETERISATION
+        // through the half-step velocity w = v + a ds/2:  x' = x + w ds,  v~ = w + a ds/2,  v' = w + a' ds/2  (sixteen FMAs instead of
+        // twenty multiply-adds and four additions; the same polynomial as the reference's, associated differently)
+        const float4 hvel = f4(vel.x + acc.x * hds, vel.y + acc.y * hds, vel.z + acc.z * hds, vel.w + acc.w * hds);
+        float4 npos = f4(pos.x + hvel.x * ds, pos.y + hvel.y * ds, pos.z + hvel.z * ds, pos.w + hvel.w * ds);
+        float4 ivel = f4(hvel.x + acc.x * hds, hvel.y + acc.y * hds, hvel.z + acc.z * hds, hvel.w + acc.w * hds);
+#else
         const float hds2 = 0.5f * ds * ds;
         float4 npos = f4(pos.x + vel.x * ds + acc.x * hds2, pos.y + vel.y * ds + acc.y * hds2,
                          pos.z + vel.z * ds + acc.z * hds2, pos.w + vel.w * ds + acc.w * hds2);
         float4 ivel = f4(vel.x + acc.x * ds, vel.y + acc.y * ds, vel.z + acc.z * ds, vel.w + acc.w * ds);
+#endif
         float n_polar_r, n_dist;
         float4 nacc = accel_radii_at(npos, ivel, cfg, &n_polar_r, &n_dist);
-        const float hds = 0.5f * ds;
         trial++;
 #if GRT_FAST_STEP_CONTROL && !GRT_FEATURE_REPARAMETERISATION
         // The folded arrangement.  The new velocity is not an input of the step control, so it is formed after the verdict, straight
@@ -609,12 +620,12 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
             nds = fmaxf(nds, fr.min_step);
             next_ds = inside ? nds : next_ds;
 #if GRT_SINGULARITY_DETECTION
-            if (__builtin_expect(inside && nds == fr.min_step && S > fr.sc_singular, 0)) { iter = -1; not_accepted++; continue; }
+            if (__builtin_expect(inside && nds == fr.min_step && S > fr.sc_singular, 0)) { GRT_RELEASE_LANE(iter); not_accepted++; continue; }
 #endif
             if (__builtin_expect(inside && nds < ds * (1.0f / 1.95f), 0)) { not_accepted++; continue; }   // DS_SKIP: retry from the same state with the smaller step
         }
 #endif
-        vel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds, vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);
+        vel = f4(hvel.x + nacc.x * hds, hvel.y + nacc.y * hds, hvel.z + nacc.z * hds, hvel.w + nacc.w * hds);
         pos = npos; acc = nacc;
         polar_r_abs = fabsf(n_polar_r);
         r_abs = fabsf(n_dist);
@@ -622,7 +633,7 @@ extern "C" __global__ void __launch_bounds__(128, GRT_INTEGRATE_MIN_BLOCKS) k_in
         pos.z = GRT_PI_F / 2; vel.z = 0; acc.z = 0;
 #endif
         iter++;
-        if (__builtin_expect(bad8(pos, vel) || iter >= GRT_LOOP_LIMIT, 0)) iter = -1;
+        if (__builtin_expect(bad8(pos, vel) || iter >= GRT_LOOP_LIMIT, 0)) GRT_RELEASE_LANE(iter);
 #else
         float4 nvel = f4(vel.x + (acc.x + nacc.x) * hds, vel.y + (acc.y + nacc.y) * hds,
                          vel.z + (acc.z + nacc.z) * hds, vel.w + (acc.w + nacc.w) * hds);

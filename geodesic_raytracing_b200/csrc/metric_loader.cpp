@@ -831,7 +831,7 @@ static void build_descriptor(Metric& m, ScriptFunction& fmetric, ScriptFunction&
         }
         for (int o : all)
             if (kind[o] == 1 && is_op(o)) maximal.insert(o);
-        if (param_only_ops >= 16 && maximal.size() <= 160) d.derived.assign(maximal.begin(), maximal.end());
+        if (param_only_ops >= 1 && maximal.size() <= 160) d.derived.assign(maximal.begin(), maximal.end());
     }
     std::vector<int> outs(d.g, d.g + 16);
     outs.insert(outs.end(), d.dg, d.dg + 64);

@@ -234,8 +234,17 @@ def test_derived_parameters_travel_in_the_parameter_block(grt, oracle_mod, tmp_p
         assert packed[:3] == m.params and packed[3:] != before[3:]
 
 
-def test_metrics_with_few_parameter_operations_have_no_derived_block(content):
-    for name in ["kerr_schild", "alcubierre", "schwarzschild", "double_schwarzschild"]:
+def test_parameter_only_products_travel_in_the_parameter_block(content):
+    """Even a single parameter-only operation (the a * a of Kerr-Schild) is evaluated on the host: a parameter lives in a uniform
+    register, so a * a in the loop costs a move and a multiply per use.  A metric whose parameters only meet variables has no block."""
+    m = content.load_by_name("kerr_schild")
+    named = m.params
+    a = named[m.param_names.index("a")]
+    assert m.packed_params[:len(named)] == named and len(m.packed_params) > len(named)
+    assert any(abs(d - a * a) < 1e-6 for d in m.packed_params[len(named):])
+    src = m.source(False)
+    body = src[src.index("void grt_accel_radii("):src.index("void grt_accel_ref(")]
+    assert "cfg.a * cfg.a" not in body and "cfg.grt_d0" in src
+    for name in ["minkowski", "schwarzschild_fast"]:
         m = content.load_by_name(name)
-        assert m.packed_params == m.params
-        assert "grt_d0" not in m.source(False)
+        assert m.packed_params == m.params and "grt_d0" not in m.source(False)
