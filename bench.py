@@ -28,6 +28,9 @@ import sys
 import tempfile
 import time
 
+# one hardware work queue per frame slot's stream (the default 8 serialises the slots beyond the eighth); has to be in the environment
+# before CUDA is initialised in this process (libgrt sets it too, for hosts that do not load PyTorch first)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -47,9 +50,13 @@ CONFIGS = {
 }
 _WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 # measured optima (tools/gpu_sweep_*.sh; profiles/round1_scaling.md, round2_*): frame slots in flight : integration blocks per SM and slot
-_DEFAULT_KNOBS = {1: (4, 3), 2: (8, 2), 4: (8, 1), 8: (8, 1)}.get(_WORLD, (8, 1))
+_DEFAULT_KNOBS = {1: (4, 3)}.get(_WORLD, (12, 1))
 FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(_DEFAULT_KNOBS[0])))
 BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS[1])))
+# 1: stripes dealt by measured cost (grt_balanced_stripes).  Off by default: at 8 GPUs the heaviest rank ends where it was (one-GPU
+# emulation of all eight ranks, profiles/round2_scaling.md) - every rank re-traces the prepass rows its stripes need, a rank's prepass
+# work depends on where its stripes lie, and that tenth of the work is not additive over stripes
+BALANCE = os.environ.get("GRT_BENCH_BALANCE", "0") != "0"
 COMM_FRAMES = 16             # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
 BYTES_PER_RAY = 96           # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 ISSUE_SLOTS_PER_CLOCK = 148 * 4   # one warp instruction per scheduler and clock
@@ -82,7 +89,8 @@ def workload_config(cfg_id, n_gpus):
                 + (f", camera on a geodesic (speed {cfg['geodesic']['speed']}, proper time {cfg['geodesic']['tau']})" if "geodesic" in cfg else ""),
         "background": "synthetic 4096x2048 RGBA8 (the reference's nasa.png is not redistributable)",
         "out_format": "rgba8 (sRGB, the reference's screenshot encoding)",
-        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, interleaved {STRIPE_ROWS}-row stripes + halo, redundant prepass, peer stores into rank 0's frame (grt_comm_*), no collective kernel",
+        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, {STRIPE_ROWS}-row stripes + halo dealt to the ranks " + ("by measured cost, longest first (grt_balanced_stripes; profile measured during set-up)" if BALANCE else "interleaved")
+                       + ", partial prepass per rank, peer stores into rank 0's frame (grt_comm_*), no collective kernel",
         "l2": "inputs larger than L2: every frame reads and writes its slot's ray planes, work lists and shading records (> 260 MB per frame at 4K, 126 MB L2) and the frames in flight use different slots; no explicit flush",
         "pipelining": f"frames are queued back to back, {FRAMES_IN_FLIGHT} in flight on the context's frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469); fps_at_2_in_flight and fps_latency (one frame at a time) are reported next to it",
         "integrate_blocks_per_sm_per_slot": BLOCKS_PER_SM,
@@ -91,7 +99,7 @@ def workload_config(cfg_id, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + event reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + event reasons during the warm-up frames and the timed region, every 50 ms (B200_PROFILING.md recipe)."""
 
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -104,7 +112,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -254,10 +262,18 @@ class Job:
             ctx.snapshot_geodesic(cfg["geodesic"]["speed"], True)
             ctx.set_camera_on_geodesic(cfg["geodesic"]["tau"])
         self.ctx = ctx
-        self.stripes = grt.interleaved_stripes(self.h, self.rank, self.world, STRIPE_ROWS)
-        if self.world == 1 and os.environ.get("GRT_BENCH_EMULATE_WORLD"):
-            # diagnostic only: one GPU renders the stripes rank 0 of an N-GPU job would own - separates the per-rank pipeline from the delivery
-            self.stripes = grt.interleaved_stripes(self.h, int(os.environ.get("GRT_BENCH_EMULATE_RANK", "0")), int(os.environ["GRT_BENCH_EMULATE_WORLD"]), STRIPE_ROWS)
+        # Optionally (GRT_BENCH_BALANCE=1) the stripes are dealt by measured cost (sort-first with feedback: the trial steps of every half
+        # stripe of this view, rendered one by one during set-up - what an interactive host refreshes now and then).  Untimed; the
+        # numbers are a deterministic function of program, features and camera, so every rank measures the same profile itself.
+        emu_world = int(os.environ.get("GRT_BENCH_EMULATE_WORLD", "0")) if self.world == 1 else 0
+        part_world, part_rank = (emu_world, int(os.environ.get("GRT_BENCH_EMULATE_RANK", "0"))) if emu_world else (self.world, self.rank)
+        # (emulation, diagnostic only: one GPU renders the stripes one rank of an N-GPU job would own - the per-rank pipeline without the delivery)
+        self.stripe_costs = None
+        if part_world > 1 and BALANCE:
+            self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
+            self.stripes = grt.balanced_stripes(self.h, part_rank, part_world, self.stripe_costs, STRIPE_ROWS)
+        else:
+            self.stripes = grt.interleaved_stripes(self.h, part_rank, part_world, STRIPE_ROWS)
         # canonical work count of the frame (single-GPU trace of the whole frame), untimed
         self.frame_steps = 0
         if self.rank == 0:
@@ -374,9 +390,9 @@ def run_ours(args):
     job.barrier()
     ctx.set_frames_in_flight(FRAMES_IN_FLIGHT)
     warmup = max(3, args.warmup, FRAMES_IN_FLIGHT + 1)       # every frame slot allocates its buffers on first use: warm all of them
-    job.timed_batch(warmup, FRAMES_IN_FLIGHT)
     if rank == 0:
-        sampler.start()
+        sampler.start()       # from the warm-up frames on (the same load): at 8 GPUs the timed region alone is shorter than one sampling period
+    job.timed_batch(warmup, FRAMES_IN_FLIGHT)
     total_ms = job.timed_batch(args.steps, FRAMES_IN_FLIGHT)
     rank_ms = list(job.last_rank_ms)
     clocks = sampler.stop() if rank == 0 else None
@@ -385,7 +401,9 @@ def run_ours(args):
 
     # the reference's depth (two render_state objects in flight) and one frame at a time
     ms_2 = job.measure(args.steps, 1, 2) if FRAMES_IN_FLIGHT != 2 else ms_per_step
+    ctx.set_tuning(3, 0)                                   # one frame at a time: three blocks per SM whatever the pipelined setting is
     ms_1 = job.measure(max(4, args.steps // 2), 1, 1)
+    ctx.set_tuning(BLOCKS_PER_SM, 0)
 
     # per-stage times of one frame alone, statistics read back (this rank's stripes)
     job.barrier()
@@ -427,7 +445,7 @@ def run_ours(args):
             "config": workload_config(args.config, world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
                       "rank0_stage_ms_one_frame_alone": stage_log, "rank0_frame_alone_ms": float(np.median(lat)), "sum_ranks_ray_steps": float(steps_all.item()),
-                      "timed_region_ms_by_rank": rank_ms, "host_ms_per_submit_rank0": 1e3 * job.submit_s / max(1, job.submits)},
+                      "timed_region_ms_by_rank": rank_ms, "stripes_rank0": job.stripes, "stripe_costs_mray_steps": [round(c / 1e6, 2) for c in job.stripe_costs] if job.stripe_costs else None, "host_ms_per_submit_rank0": 1e3 * job.submit_s / max(1, job.submits)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
                          "traffic": facts.get("mean_dram_bytes_per_launch"), "peak_kind": peak_kind,
                          "kernel": "k_integrate", "algorithmic_bytes_per_launch": algo_bytes_per_launch, "rays_per_launch": rays_per_launch,

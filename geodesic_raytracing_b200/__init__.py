@@ -129,10 +129,13 @@ def lib() -> C.CDLL:
         "grt_comm_init": (ci, [vp, ci, ci, ci, ci, ci, ci, vp]), "grt_comm_connect": (ci, [vp, vp]), "grt_comm_connect_local": (ci, [C.POINTER(vp), ci]), "grt_comm_disconnect": (ci, [vp]),
         "grt_comm_render": (ci, [vp, pi, pi, ci, C.c_uint, vp]), "grt_comm_frame": (vp, [vp, C.c_uint]),
         "grt_interleaved_stripes": (ci, [ci, ci, ci, ci, pi, pi, ci]),
+        "grt_measure_stripe_costs": (ci, [vp, ci, ci, ci, C.POINTER(C.c_double), ci]),
+        "grt_balanced_stripes": (ci, [ci, ci, ci, ci, C.POINTER(C.c_double), ci, pi, pi, ci]),
         "grt_group_create": (vp, [pi, ci]), "grt_group_destroy": (None, [vp]), "grt_group_size": (ci, [vp]), "grt_group_ctx": (vp, [vp, ci]),
         "grt_group_set_metric": (ci, [vp, vp, ci]), "grt_group_update_params": (ci, [vp]), "grt_group_set_features": (ci, [vp, C.POINTER(Features)]),
         "grt_group_set_background": (ci, [vp, vp, ci, ci, ci]), "grt_group_set_camera": (ci, [vp, pf, pf, ci]), "grt_group_set_frames_in_flight": (ci, [vp, ci]),
         "grt_group_render": (ci, [vp, ci, ci, ci, vp]), "grt_group_frame": (vp, [vp]), "grt_group_synchronize": (ci, [vp]),
+        "grt_group_rebalance": (ci, [vp, ci, ci]),
         "grt_get_camera_state": (ci, [vp, C.POINTER(CameraState)]),
         "grt_debug_ray_count": (ci, [vp, pi, pi]), "grt_debug_read_rays": (ci, [vp, vp, ci]), "grt_debug_read_render_data": (ci, [vp, vp, ci]),
         "grt_debug_read_prepass_mask": (ci, [vp, vp, ci, pi, pi]), "grt_debug_read_mip_level": (ci, [vp, ci, ci, vp, pi, pi, pi]),
@@ -310,6 +313,14 @@ class Context:
     # ---- program / features -----------------------------------------------------------------
     def set_fast_math(self, enabled: bool) -> None:
         _check(lib().grt_set_fast_math(self._h, int(enabled)))
+
+    def measure_stripe_costs(self, width: int, height: int, stripe_rows: int = 54) -> List[float]:
+        """Trial ray-steps of every half stripe of the frame rendered by itself (grt_measure_stripe_costs; two numbers per stripe):
+        the cost profile grt_balanced_stripes deals the stripes by."""
+        cap = height + 4
+        cost = (C.c_double * cap)()
+        n = _check(lib().grt_measure_stripe_costs(self._h, width, height, stripe_rows, cost, cap))
+        return [cost[i] for i in range(n)]
 
     def set_tuning(self, blocks_per_sm: int, donate_threshold: int) -> None:
         """Scheduling knobs of the integration kernel (never change results): see grt_set_tuning in include/grt.h."""
@@ -592,6 +603,16 @@ def interleaved_stripes(height: int, rank: int, world: int, stripe_rows: int = 5
     cap = height // 2 + 2
     y0, y1 = (C.c_int * cap)(), (C.c_int * cap)()
     n = _check(lib().grt_interleaved_stripes(height, rank, world, stripe_rows, y0, y1, cap))
+    return [(y0[i], y1[i]) for i in range(n)]
+
+
+def balanced_stripes(height: int, rank: int, world: int, costs, stripe_rows: int = 54) -> List[Tuple[int, int]]:
+    """Row stripes owned by `rank` when the stripes are dealt by measured cost, longest first (grt_balanced_stripes);
+    `costs` = Context.measure_stripe_costs(...) of the frame, the same numbers on every rank."""
+    cap = height // 2 + 2
+    y0, y1 = (C.c_int * cap)(), (C.c_int * cap)()
+    cost = (C.c_double * len(costs))(*[float(x) for x in costs])
+    n = _check(lib().grt_balanced_stripes(height, rank, world, stripe_rows, cost, len(costs), y0, y1, cap))
     return [(y0[i], y1[i]) for i in range(n)]
 
 

@@ -1184,6 +1184,12 @@ void grt_features_default(grt_features* f) { if (f) features_default(f); }
 grt_ctx* grt_create(int device) {
     grt_ctx* c = nullptr;
     int rc = guard([&] {
+        // Frames in flight live on one stream each, and streams beyond the device's hardware work queues (8 by default) are
+        // multiplexed onto shared queues, which serialises frames that should overlap: 12 - 16 slots only pay with more queues
+        // (one-GPU emulation of rank 0 of 8: 3.89 -> 3.44 ms per frame).  Read by the driver when it creates the device's context,
+        // so it has to be in the environment before the first CUDA call of the process (a host that initialises CUDA earlier, e.g.
+        // through PyTorch, sets it itself: bench.py does).  Never overrides the user's value.
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) throw Error(GRT_E_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
@@ -1645,6 +1651,122 @@ int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, in
     return n;
 }
 
+namespace {
+// rows [y0, y1) of stripe i and of its two halves (even heights: adaptive sampling works on 2x2 cells)
+struct StripeRows { int y0, mid, y1; };
+StripeRows stripe_rows_of(int i, int stripe_rows, int height) {
+    const int y0 = i * stripe_rows, y1 = std::min(height, y0 + stripe_rows);
+    int mid = y0 + ((y1 - y0) / 2 & ~1);
+    if (mid <= y0 || mid >= y1) mid = y1;          // too short to split
+    return {y0, mid, y1};
+}
+}  // namespace
+
+int grt_measure_stripe_costs(grt_ctx* c, int width, int height, int stripe_rows, double* cost_out, int max_costs) {
+    if (!c || !cost_out || width <= 0 || height <= 0 || max_costs < 1) { g_err = "bad stripe cost request"; return GRT_E_INVALID; }
+    stripe_rows = std::max(2, stripe_rows - (stripe_rows & 1));
+    const int n = (height + stripe_rows - 1) / stripe_rows;
+    if (2 * n > max_costs) { g_err = "more half stripes than max_costs"; return GRT_E_INVALID; }
+    DevBuf scratch;
+    int rc = guard([&] {
+        bind(c);
+        scratch.ensure((size_t)stripe_rows * (size_t)width * 4);
+        return GRT_OK;
+    });
+    if (rc != GRT_OK) return rc;
+    for (int i = 0; i < n && rc == GRT_OK; i++) {
+        const StripeRows r = stripe_rows_of(i, stripe_rows, height);
+        const int y0s[2] = {r.y0, r.mid}, y1s[2] = {r.mid, r.y1};
+        for (int half = 0; half < 2 && rc == GRT_OK; half++) {
+            cost_out[2 * i + half] = 0.0;
+            if (y1s[half] <= y0s[half]) continue;
+            grt_stats st{};
+            rc = grt_render_stripes(c, width, height, &y0s[half], &y1s[half], 1, scratch.p, GRT_FORMAT_RGBA8, GRT_OUT_DEVICE, &st);
+            cost_out[2 * i + half] = (double)st.trial_steps;
+        }
+    }
+    scratch.release();
+    return rc == GRT_OK ? 2 * n : rc;
+}
+
+int grt_balanced_stripes(int height, int rank, int world, int stripe_rows, const double* cost, int n_cost, int* y0s, int* y1s, int max_stripes) {
+    if (!cost) return grt_interleaved_stripes(height, rank, world, stripe_rows, y0s, y1s, max_stripes);
+    if (height <= 0 || world < 1 || rank < 0 || rank >= world || !y0s || !y1s || max_stripes < 1) { g_err = "bad stripe request"; return GRT_E_INVALID; }
+    if (world == 1) { y0s[0] = 0; y1s[0] = height; return 1; }
+    stripe_rows = std::max(2, stripe_rows - (stripe_rows & 1));
+    const int n = (height + stripe_rows - 1) / stripe_rows;
+    if (n_cost != 2 * n) { g_err = "stripe cost vector does not match the stripe count of this height (two halves per stripe)"; return GRT_E_INVALID; }
+    // Items: whole stripes, except that a stripe heavier than 3/10 of a rank's fair share goes in as its two halves (the rows tangent to
+    // the shadow's edge: two such stripes of a 4K kerr_schild frame carry 150 M of the 240 M ray-steps a rank of eight should get).  A
+    // half rendered alone pays its own halo; a whole stripe pays one halo for both, hence the discount on the sum.
+    struct Item { int y0, y1; double cost; };
+    std::vector<Item> items;
+    double total = 0.0;
+    for (int i = 0; i < 2 * n; i++) total += std::max(0.0, cost[i]);
+    const double fair = total / world, halo = 6.0;
+    for (int i = 0; i < n; i++) {
+        const StripeRows r = stripe_rows_of(i, stripe_rows, height);
+        const double top = std::max(0.0, cost[2 * i]), bottom = std::max(0.0, cost[2 * i + 1]);
+        if (r.mid < r.y1 && top + bottom > 0.3 * fair) {
+            items.push_back({r.y0, r.mid, top});
+            items.push_back({r.mid, r.y1, bottom});
+        } else {
+            const double rows = (double)(r.y1 - r.y0);
+            items.push_back({r.y0, r.y1, (top + bottom) * (r.mid < r.y1 ? (rows + halo) / (rows + 2.0 * halo) : 1.0)});
+        }
+    }
+    const int m = (int)items.size();
+    std::vector<int> order(m), owner(m, 0), held(world, 0);
+    for (int i = 0; i < m; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cost > items[b].cost; });
+    std::vector<double> load(world, 0.0);
+    // Nearly the same number of items on every rank: what an item costs on top of its rays - halo rows, its share of the prepass,
+    // launches - is then about the same everywhere and drops out of the comparison.
+    const int cap = (m + world - 1) / world + 1;
+    for (int i : order) {
+        int best = -1;
+        for (int r = 0; r < world; r++)
+            if (held[r] < cap && (best < 0 || load[r] < load[best])) best = r;
+        owner[i] = best;
+        load[best] += items[i].cost;
+        held[best]++;
+    }
+    // refinement: exchange one item of the heaviest rank against one item of another rank while that lowers the larger of the two
+    // loads (the counts stay as they are); deterministic, a few dozen exchanges at most for the stripes of a 4K frame
+    for (int round = 0; round < 4 * m; round++) {
+        int p = 0;
+        for (int r = 1; r < world; r++) if (load[r] > load[p]) p = r;
+        double best_peak = load[p];
+        int best_a = -1, best_b = -1;
+        for (int a = 0; a < m; a++) {
+            if (owner[a] != p) continue;
+            for (int b = 0; b < m; b++) {
+                const int q = owner[b];
+                if (q == p) continue;
+                const double peak = std::max(load[p] - items[a].cost + items[b].cost, load[q] - items[b].cost + items[a].cost);
+                if (peak < best_peak - 1e-9 * std::max(1.0, load[p])) { best_peak = peak; best_a = a; best_b = b; }
+            }
+        }
+        if (best_a < 0) break;
+        const int q = owner[best_b];
+        load[p] += items[best_b].cost - items[best_a].cost;
+        load[q] += items[best_a].cost - items[best_b].cost;
+        owner[best_a] = q;
+        owner[best_b] = p;
+    }
+    // this rank's items in ascending order, neighbours merged into one stripe (one halo less)
+    int k = 0;
+    for (int i = 0; i < m; i++) {
+        if (owner[i] != rank) continue;
+        if (k > 0 && y1s[k - 1] == items[i].y0) { y1s[k - 1] = items[i].y1; continue; }
+        if (k == max_stripes) { g_err = "more stripes than max_stripes"; return GRT_E_INVALID; }
+        y0s[k] = items[i].y0;
+        y1s[k] = items[i].y1;
+        k++;
+    }
+    return k;
+}
+
 void* grt_comm_frame(grt_ctx* c, unsigned seq) {
     if (!c || !c->comm.active || c->comm.rank != 0) { g_err = "only the owner (rank 0) holds the frames"; return nullptr; }
     return c->comm.base[0] + kCommFrames + (size_t)(seq % (unsigned)c->comm.n_frames) * c->comm.frame_bytes;
@@ -1686,6 +1808,7 @@ struct grt_group {
     int w = 0, h = 0, format = -1, frames = 2;
     unsigned seq = 0;
     bool connected = false;
+    std::vector<double> pending_cost;      // grt_group_rebalance before the first frame of a shape: used when the communicator is built
 };
 
 namespace {
@@ -1741,7 +1864,8 @@ int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
         for (int r = 0; r < n; r++) {
             g->y0s[r].assign(h / 2 + 2, 0);
             g->y1s[r].assign(h / 2 + 2, 0);
-            int k = grt_interleaved_stripes(h, r, n, 54, g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size());
+            int k = grt_balanced_stripes(h, r, n, 54, g->pending_cost.empty() ? nullptr : g->pending_cost.data(), (int)g->pending_cost.size(), g->y0s[r].data(),
+                                         g->y1s[r].data(), (int)g->y0s[r].size());
             if (k < 0) return k;
             g->y0s[r].resize(k);
             g->y1s[r].resize(k);
@@ -1751,12 +1875,35 @@ int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
         int rc = grt_comm_connect_local(g->ctx.data(), n);
         if (rc < 0) return rc;
         g->w = w; g->h = h; g->format = format; g->seq = 0; g->connected = true;
+        g->pending_cost.clear();
     }
     for (int r = n - 1; r >= 0; r--) {       // the owner last: its stream then waits for stores that are already queued
         int rc = grt_comm_render(g->ctx[r], g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size(), g->seq, r == 0 ? host_out : nullptr);
         if (rc < 0) return rc;
     }
     g->seq++;
+    return GRT_OK;
+}
+// Re-deal the stripes by the cost profile of the frame as it is now (metric, features and camera of rank 0's context): rank 0
+// measures every stripe, the assignment takes effect with the next grt_group_render.  Waits for the frames in flight.
+int grt_group_rebalance(grt_group* g, int w, int h) {
+    if (!g) { g_err = "null group"; return GRT_E_INVALID; }
+    const int n = (int)g->ctx.size();
+    if (n == 1) return GRT_OK;
+    int rc = grt_group_synchronize(g);
+    if (rc < 0) return rc;
+    std::vector<double> cost(h + 4);
+    const int k = grt_measure_stripe_costs(g->ctx[0], w, h, 54, cost.data(), (int)cost.size());
+    if (k < 0) return k;
+    if (!g->connected || w != g->w || h != g->h) { g->pending_cost.assign(cost.begin(), cost.begin() + k); return GRT_OK; }   // applied when the communicator is built
+    for (int r = 0; r < n; r++) {
+        g->y0s[r].assign(h / 2 + 2, 0);
+        g->y1s[r].assign(h / 2 + 2, 0);
+        int m = grt_balanced_stripes(h, r, n, 54, cost.data(), k, g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size());
+        if (m < 0) return m;
+        g->y0s[r].resize(m);
+        g->y1s[r].resize(m);
+    }
     return GRT_OK;
 }
 void* grt_group_frame(grt_group* g) { return (g && g->connected && g->seq > 0) ? grt_comm_frame(g->ctx[0], g->seq - 1) : nullptr; }

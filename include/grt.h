@@ -260,6 +260,20 @@ void* grt_comm_frame(grt_ctx*, unsigned seq);
  * evenly.  Writes up to max_stripes (y0, y1) pairs in ascending order, returns the count. */
 int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, int* y0s, int* y1s, int max_stripes);
 
+/* Load balancing of the stripes by measured cost (sort-first rendering with feedback from a frame already rendered: a camera moves
+ * little from one frame to the next, so the cost profile of the last frame predicts the next one).
+ * grt_measure_stripe_costs renders every HALF stripe of the frame by itself on this context (with its halo, statistics read back)
+ * and writes its trial ray-steps: cost_out[2 i] and cost_out[2 i + 1] are the upper and the lower half of stripe i.  A few
+ * milliseconds per half, meant for set-up time and for an occasional refresh; returns the number of costs written (2 x stripes).
+ * The result is a deterministic function of the bound program, the features and the camera: every rank that calls it gets the same
+ * numbers, or one rank measures and the host distributes them.
+ * grt_balanced_stripes deals the stripes to the ranks by longest-processing-time-first - a stripe heavier than 3/10 of a rank's
+ * fair share as its two halves - followed by pairwise exchanges that lower the heaviest rank, keeps the number of pieces per rank
+ * nearly equal, merges neighbouring pieces of one rank and returns this rank's stripes in ascending order.  With cost == NULL it is
+ * grt_interleaved_stripes. */
+int grt_measure_stripe_costs(grt_ctx*, int width, int height, int stripe_rows, double* cost_out, int max_costs);
+int grt_balanced_stripes(int height, int rank, int world, int stripe_rows, const double* cost, int n_cost, int* y0s, int* y1s, int max_stripes);
+
 /* A group: the contexts of several devices of one box driven as one renderer from one thread - what SURVEY.md 8(b2) writes as
  * grt_create(const int* devices, int ndev).  Rank 0 = devices[0] owns the assembled frame.  The setters broadcast to every context;
  * grt_group_render queues ONE frame on all devices (interleaved stripes of grt_interleaved_stripes with 54 rows, peer stores into
@@ -277,6 +291,9 @@ int grt_group_set_background(grt_group*, const uint8_t* rgba, int width, int hei
 int grt_group_set_camera(grt_group*, const float pos_txyz[4], const float quat_xyzw[4], int flip_r);
 int grt_group_set_frames_in_flight(grt_group*, int n);
 int grt_group_render(grt_group*, int width, int height, int format, void* host_out);
+/* Re-deal the stripes by measured cost (grt_measure_stripe_costs on devices[0], grt_balanced_stripes): call it after the metric, the
+ * features and the camera are set, and again whenever the view has changed much.  Waits for the frames in flight. */
+int grt_group_rebalance(grt_group*, int width, int height);
 void* grt_group_frame(grt_group*);          /* device pointer (on devices[0]) of the most recently queued frame's buffer */
 int grt_group_synchronize(grt_group*);
 

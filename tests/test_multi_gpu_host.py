@@ -82,3 +82,42 @@ def test_communicator_calls_fail_loudly_without_a_context(grt):
     assert L.grt_comm_init(None, 0, 2, 64, 64, 1, 2, None) < 0
     assert L.grt_comm_render(None, None, None, 0, 0, None) < 0
     assert L.grt_comm_frame(None, 0) is None
+
+
+def test_balanced_stripes_deal_by_cost():
+    """grt_balanced_stripes: the ranks' stripes tile the frame exactly once, the heaviest rank carries far less than with plain
+    interleaving (stripes that dominate a rank's share are dealt as halves), the same input gives the same answer on every rank, a
+    missing cost vector falls back to the interleaved pattern."""
+    import ctypes as C
+
+    import numpy as np
+
+    import geodesic_raytracing_b200 as grt
+    h, rows = 2160, 54
+    n = h // rows
+    y = (np.arange(2 * n) + 0.5) / (2 * n)                     # half stripes
+    # a ring-like profile: cheap sky, two narrow expensive bands where the rows are tangent to the shadow's edge, cheap culled centre
+    cost = 0.5 + 2.5 * np.exp(-((y - 0.36) / 0.03) ** 2) + 2.5 * np.exp(-((y - 0.64) / 0.03) ** 2)    # heaviest stripe: 0.7 of a fair share of 8
+    row_cost = np.repeat(cost / 27.0, 27)[:h]                   # per row, for scoring any partition
+    for world in (2, 4, 8):
+        owned = [grt.balanced_stripes(h, r, world, cost.tolist(), rows) for r in range(world)]
+        covered = np.zeros(h, int)
+        for o in owned:
+            assert o == sorted(o)
+            for y0, y1 in o:
+                assert y0 % 2 == 0 and y1 % 2 == 0 and y1 > y0
+                covered[y0:y1] += 1
+        assert (covered == 1).all()
+        load = [sum(row_cost[y0:y1].sum() for y0, y1 in o) for o in owned]
+        plain = [sum(row_cost[y0:y1].sum() for y0, y1 in grt.interleaved_stripes(h, r, world, rows)) for r in range(world)]
+        assert max(load) / np.mean(load) < 1.06, (world, load)
+        if world == 8:
+            assert max(load) < 0.85 * max(plain)
+        assert owned == [grt.balanced_stripes(h, r, world, cost.tolist(), rows) for r in range(world)]
+    L = grt.lib()
+    y0, y1 = (C.c_int * 64)(), (C.c_int * 64)()
+    k = L.grt_balanced_stripes(h, 3, 8, rows, None, 0, y0, y1, 64)
+    assert [(y0[i], y1[i]) for i in range(k)] == grt.interleaved_stripes(h, 3, 8, rows)
+    bad = (C.c_double * 3)(1.0, 2.0, 3.0)
+    assert L.grt_balanced_stripes(h, 0, 8, rows, bad, 3, y0, y1, 64) < 0          # cost vector of another frame shape
+    assert grt.balanced_stripes(100, 0, 1, [5.0, 1.0, 2.0, 2.0], rows) == [(0, 100)]
