@@ -288,7 +288,7 @@ std::vector<char> compile_cubin(const std::string& src, bool fast_math, const st
     }
     auto with_tier = [&](int n) { return "// GRT_TIER_FIXED\n#define GRT_INTEGRATE_MIN_BLOCKS " + std::to_string(n) + "\n" + src; };
     char hex[24];
-    snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(src + (fast_math ? "f" : "p"), 14695981039346656037ull));
+    snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(src + (fast_math ? "f" : "p") + "|rule:0.7", 14695981039346656037ull));   // the rule is part of the key: a remembered choice made under another rule is not reused
     const std::string tier_path = cache_dir() + "/" + name + "_" + hex + ".tier";
     {
         std::ifstream f(tier_path);
