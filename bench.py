@@ -54,8 +54,7 @@ _DEFAULT_KNOBS = {1: (4, 3)}.get(_WORLD, (12, 1))
 FRAMES_IN_FLIGHT = int(os.environ.get("GRT_BENCH_FRAMES_IN_FLIGHT", str(_DEFAULT_KNOBS[0])))
 BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS[1])))
 # 1: stripes dealt by measured cost (grt_balanced_stripes).  Off by default: at 8 GPUs the heaviest rank ends where it was (one-GPU
-# emulation of all eight ranks, profiles/round2_scaling.md) - every rank re-traces the prepass rows its stripes need, a rank's prepass
-# work depends on where its stripes lie, and that tenth of the work is not additive over stripes
+# emulation of all eight ranks, profiles/round2_scaling.md) - the predicted loads are equal to 3 %, the real ones stay 12 % apart
 BALANCE = os.environ.get("GRT_BENCH_BALANCE", "0") != "0"
 COMM_FRAMES = 16             # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
 BYTES_PER_RAY = 96           # 56 B read + 40 B written per ray by the integration stage, 0 B per step
