@@ -427,6 +427,33 @@ def test_scheduling_knobs_do_not_change_results(gpu_ctx, oracles, background):
     gpu_ctx.set_tuning(3, 0)
 
 
+@pytest.mark.parametrize("name", ["schwarzschild", "kerr_schild", "alcubierre"])
+def test_precise_program_matches_oracle(gpu_ctx, oracles, background, name):
+    """grt_set_fast_math(0): the program that keeps the reference's operation order in the loop (IEEE division and square root,
+    step control and Verlet update as in cl.cl:3273-3456) - the same bars as the fast program."""
+    metric, orc = oracles(name)
+    base = bind(gpu_ctx, metric, background)
+    try:
+        gpu_ctx.set_fast_math(False)
+        gpu_ctx.set_metric(metric)
+        w, h = 160, 96
+        img, st = gpu_ctx.render(w, h)
+        ref = orc.frame(w, h, oracle_features(orc, base), camera_pos=camera_of(metric), background=background, use_prepass=base["use_prepass"], max_probes=base["max_probes"])
+        rd = gpu_ctx.read_render_data(w, h).reshape(h, w)
+        assert (rd["terminated"] == ref["rdata"]["terminated"]).mean() >= 0.995
+        assert (np.abs(img[..., :3] - ref["image"][..., :3]).max(axis=-1) <= 2.0 / 255.0).mean() >= 0.99
+        assert abs(int(st.trial_steps) - ref["trial_steps"]) <= 0.03 * ref["trial_steps"] + 64      # the bar of compare_frame with adaptive sampling
+        assert int(st.accepted_steps) <= int(st.trial_steps) and int(st.rays_finished) > 0
+        # scheduling does not change the precise program's results either
+        gpu_ctx.set_tuning(1, 0)
+        img1, st1 = gpu_ctx.render(w, h)
+        assert np.array_equal(img, img1) and int(st1.trial_steps) == int(st.trial_steps) and int(st1.accepted_steps) == int(st.accepted_steps)
+    finally:
+        gpu_ctx.set_tuning(3, 0)
+        gpu_ctx.set_fast_math(True)
+        gpu_ctx.set_metric(metric)
+
+
 def test_feature_changes_take_effect(gpu_ctx, oracles, background):
     metric, orc = oracles("schwarzschild_fast")
     for feats in [dict(universe_size=12.0), dict(field_of_view=60.0), dict(max_precision_radius=6.0), dict(reparameterisation=1), dict(max_probes=2),
