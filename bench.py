@@ -56,6 +56,11 @@ BLOCKS_PER_SM = int(os.environ.get("GRT_BENCH_BLOCKS_PER_SM", str(_DEFAULT_KNOBS
 # 1: stripes dealt by measured cost (grt_balanced_stripes).  Off by default: at 8 GPUs the heaviest rank ends where it was (one-GPU
 # emulation of all eight ranks, profiles/round2_scaling.md) - the predicted loads are equal to 3 %, the real ones stay 12 % apart
 BALANCE = os.environ.get("GRT_BENCH_BALANCE", "0") != "0"
+# how a frame is shared out for N > 1: "interleaved" 54-row stripes, "balanced" (the same stripes dealt by measured cost) or "contiguous"
+# (one block of rows per rank with boundaries at equal measured cost: one halo per rank instead of one per stripe)
+PARTITION = os.environ.get("GRT_BENCH_PARTITION", "balanced" if BALANCE else "contiguous")      # measured at 8 GPUs: 3.42 ms per frame against 3.86 interleaved
+REFINE_ROUNDS = int(os.environ.get("GRT_BENCH_REFINE_ROUNDS", "3"))
+REFINE_BY = os.environ.get("GRT_BENCH_REFINE_BY", "ms")
 COMM_FRAMES = 16             # frame buffers the owner rotates through (>= the largest frames-in-flight setting)
 BYTES_PER_RAY = 96           # 56 B read + 40 B written per ray by the integration stage, 0 B per step
 ISSUE_SLOTS_PER_CLOCK = 148 * 4   # one warp instruction per scheduler and clock
@@ -88,7 +93,10 @@ def workload_config(cfg_id, n_gpus):
                 + (f", camera on a geodesic (speed {cfg['geodesic']['speed']}, proper time {cfg['geodesic']['tau']})" if "geodesic" in cfg else ""),
         "background": "synthetic 4096x2048 RGBA8 (the reference's nasa.png is not redistributable)",
         "out_format": "rgba8 (sRGB, the reference's screenshot encoding)",
-        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, {STRIPE_ROWS}-row stripes + halo dealt to the ranks " + ("by measured cost, longest first (grt_balanced_stripes; profile measured during set-up)" if BALANCE else "interleaved")
+        "parallelism": "1 GPU" if n_gpus == 1 else f"{n_gpus} GPUs, " + {
+            "interleaved": f"interleaved {STRIPE_ROWS}-row stripes + halo",
+            "balanced": f"{STRIPE_ROWS}-row stripes + halo dealt to the ranks by measured cost, longest first (grt_balanced_stripes; profile measured during set-up)",
+            "contiguous": f"one contiguous block of rows per rank, boundaries at equal measured cost (grt_contiguous_bounds from a stripe-cost profile + {REFINE_ROUNDS} rounds of grt_refine_bounds feedback from the ranks' measured {'times' if REFINE_BY == 'ms' else 'ray-steps'}, all during set-up, untimed)"}[PARTITION]
                        + ", partial prepass per rank, peer stores into rank 0's frame (grt_comm_*), no collective kernel",
         "l2": "inputs larger than L2: every frame reads and writes its slot's ray planes, work lists and shading records (> 260 MB per frame at 4K, 126 MB L2) and the frames in flight use different slots; no explicit flush",
         "pipelining": f"frames are queued back to back, {FRAMES_IN_FLIGHT} in flight on the context's frame slots (the reference keeps two render_state objects in flight, main.cpp:1463-1469); fps_at_2_in_flight and fps_latency (one frame at a time) are reported next to it",
@@ -268,7 +276,25 @@ class Job:
         part_world, part_rank = (emu_world, int(os.environ.get("GRT_BENCH_EMULATE_RANK", "0"))) if emu_world else (self.world, self.rank)
         # (emulation, diagnostic only: one GPU renders the stripes one rank of an N-GPU job would own - the per-rank pipeline without the delivery)
         self.stripe_costs = None
-        if part_world > 1 and BALANCE:
+        self.partition = "interleaved"
+        if part_world > 1 and PARTITION == "contiguous":
+            # one block of rows per rank, boundaries at equal measured cost, then two rounds of feedback from what the blocks really cost
+            self.partition = "contiguous"
+            self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
+            bounds = grt.contiguous_bounds(self.h, part_world, self.stripe_costs, STRIPE_ROWS)
+            self.block_costs = []
+            for _ in range(REFINE_ROUNDS + 1):
+                # the feedback signal: ray-steps of every block (REFINE_BY=steps), or what matters in the end - the time of every rank's own
+                # pipeline over a dozen frames without delivery (REFINE_BY=ms: equal ray-steps are not equal times, the ranks that hold the
+                # shadow's edge carry the long rays)
+                measured = self.block_ms_of(bounds, part_world, part_rank, bool(emu_world)) if REFINE_BY == "ms" else [m / 1e6 for m in self.block_costs_of(bounds, part_world, part_rank, bool(emu_world))]
+                self.block_costs.append([round(m, 2) for m in measured])
+                if len(self.block_costs) <= REFINE_ROUNDS:
+                    bounds = grt.refine_bounds(self.h, bounds, measured, self.stripe_costs, STRIPE_ROWS)
+            self.bounds = bounds
+            self.stripes = [(bounds[part_rank], bounds[part_rank + 1])]
+        elif part_world > 1 and PARTITION == "balanced":
+            self.partition = "balanced"
             self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
             self.stripes = grt.balanced_stripes(self.h, part_rank, part_world, self.stripe_costs, STRIPE_ROWS)
         else:
@@ -285,6 +311,48 @@ class Job:
         ctx.comm_connect(exchange_handles(handle, self.rank, self.world, self.device, self.dist))
         self.seq = 0
         self.host_out = [torch.empty((self.h, self.w, 4), dtype=torch.uint8).pin_memory() for _ in range(COMM_FRAMES)] if self.rank == 0 else None
+
+    def block_costs_of(self, bounds, world, rank, emulated):
+        """Trial ray-steps of every rank's block [bounds[r], bounds[r + 1]) rendered with its halo: each rank renders its own and the
+        numbers are all-gathered (emulation on one GPU: this process renders all of them)."""
+        torch = self.torch
+        def cost(r):
+            rows = bounds[r + 1] - bounds[r]
+            scratch = torch.empty((rows, self.w, 4), dtype=torch.uint8, device=self.device)
+            _, st = self.ctx.render(self.w, self.h, grt.GRT_FORMAT_RGBA8, out=scratch, stats=True, stripes=[(bounds[r], bounds[r + 1])])
+            return float(st.trial_steps)
+        if emulated or self.world == 1:
+            return [cost(r) for r in range(world)]
+        mine = torch.tensor([cost(rank)], dtype=torch.float64, device=self.device)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        self.dist.all_gather(parts, mine)
+        return [float(p.item()) for p in parts]
+
+    def block_ms_of(self, bounds, world, rank, emulated, frames=12):
+        """ms per frame of every rank's own pipeline on its block [bounds[r], bounds[r + 1]): `frames` frames queued back to back into
+        local buffers (no delivery, so no rank waits for another), CUDA events; each rank times its own and the numbers are all-gathered
+        (emulation on one GPU: this process times all of them)."""
+        torch = self.torch
+        def ms(r):
+            stripes = [(bounds[r], bounds[r + 1])]
+            outs = [torch.empty((bounds[r + 1] - bounds[r], self.w, 4), dtype=torch.uint8, device=self.device) for _ in range(FRAMES_IN_FLIGHT)]
+            for k in range(FRAMES_IN_FLIGHT):                       # every slot has its buffers for this geometry
+                self.ctx.render(self.w, self.h, grt.GRT_FORMAT_RGBA8, out=outs[k], stats=False, stripes=stripes)
+            self.ctx.synchronize(); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+            ends = []
+            for k in range(frames):
+                self.ctx.render(self.w, self.h, grt.GRT_FORMAT_RGBA8, out=outs[k % FRAMES_IN_FLIGHT], stats=False, stripes=stripes)
+                if k >= frames - FRAMES_IN_FLIGHT:
+                    e = torch.cuda.Event(enable_timing=True); e.record(torch.cuda.ExternalStream(self.ctx.stream, device=self.device)); ends.append(e)
+            self.ctx.synchronize(); torch.cuda.synchronize()
+            return max(e0.elapsed_time(e) for e in ends) / frames
+        if emulated or self.world == 1:
+            return [ms(r) for r in range(world)]
+        mine = torch.tensor([ms(rank)], dtype=torch.float64, device=self.device)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        self.dist.all_gather(parts, mine)
+        return [float(p.item()) for p in parts]
 
     def release(self):
         """Every rank unmaps the others' regions, then - behind a barrier - frees its own."""
@@ -444,7 +512,8 @@ def run_ours(args):
             "config": workload_config(args.config, world),
             "frame": {"ray_steps": frame_steps, "rays_integrated_rank0": int(st.rays_integrated), "extra_rays_rank0": int(st.extra_rays),
                       "rank0_stage_ms_one_frame_alone": stage_log, "rank0_frame_alone_ms": float(np.median(lat)), "sum_ranks_ray_steps": float(steps_all.item()),
-                      "timed_region_ms_by_rank": rank_ms, "stripes_rank0": job.stripes, "stripe_costs_mray_steps": [round(c / 1e6, 2) for c in job.stripe_costs] if job.stripe_costs else None, "host_ms_per_submit_rank0": 1e3 * job.submit_s / max(1, job.submits)},
+                      "timed_region_ms_by_rank": rank_ms, "stripes_rank0": job.stripes, "partition": job.partition, "bounds": getattr(job, "bounds", None), "block_costs_by_round": getattr(job, "block_costs", None), "block_cost_unit": ("ms per frame of the rank's own pipeline" if REFINE_BY == "ms" else "M ray-steps"),
+                      "stripe_costs_mray_steps": [round(c / 1e6, 2) for c in job.stripe_costs] if job.stripe_costs else None, "host_ms_per_submit_rank0": 1e3 * job.submit_s / max(1, job.submits)},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
                          "traffic": facts.get("mean_dram_bytes_per_launch"), "peak_kind": peak_kind,
                          "kernel": "k_integrate", "algorithmic_bytes_per_launch": algo_bytes_per_launch, "rays_per_launch": rays_per_launch,

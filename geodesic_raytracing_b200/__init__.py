@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
         "grt_interleaved_stripes": (ci, [ci, ci, ci, ci, pi, pi, ci]),
         "grt_measure_stripe_costs": (ci, [vp, ci, ci, ci, C.POINTER(C.c_double), ci]),
         "grt_balanced_stripes": (ci, [ci, ci, ci, ci, C.POINTER(C.c_double), ci, pi, pi, ci]),
+        "grt_contiguous_bounds": (ci, [ci, ci, ci, C.POINTER(C.c_double), ci, pi]),
+        "grt_refine_bounds": (ci, [ci, ci, ci, C.POINTER(C.c_double), ci, pi, C.POINTER(C.c_double), pi]),
         "grt_group_create": (vp, [pi, ci]), "grt_group_destroy": (None, [vp]), "grt_group_size": (ci, [vp]), "grt_group_ctx": (vp, [vp, ci]),
         "grt_group_set_metric": (ci, [vp, vp, ci]), "grt_group_update_params": (ci, [vp]), "grt_group_set_features": (ci, [vp, C.POINTER(Features)]),
         "grt_group_set_background": (ci, [vp, vp, ci, ci, ci]), "grt_group_set_camera": (ci, [vp, pf, pf, ci]), "grt_group_set_frames_in_flight": (ci, [vp, ci]),
@@ -614,6 +616,33 @@ def balanced_stripes(height: int, rank: int, world: int, costs, stripe_rows: int
     cost = (C.c_double * len(costs))(*[float(x) for x in costs])
     n = _check(lib().grt_balanced_stripes(height, rank, world, stripe_rows, cost, len(costs), y0, y1, cap))
     return [(y0[i], y1[i]) for i in range(n)]
+
+
+def contiguous_bounds(height: int, world: int, costs=None, stripe_rows: int = 54) -> List[int]:
+    """world + 1 row boundaries of equal-cost contiguous blocks (grt_contiguous_bounds); `costs` from Context.measure_stripe_costs
+    or None for equal heights.  Rank r renders rows [bounds[r], bounds[r + 1])."""
+    out = (C.c_int * (world + 1))()
+    if costs is None:
+        _check(lib().grt_contiguous_bounds(height, world, stripe_rows, None, 0, out))
+    else:
+        cost = (C.c_double * len(costs))(*[float(x) for x in costs])
+        _check(lib().grt_contiguous_bounds(height, world, stripe_rows, cost, len(costs), out))
+    return list(out)
+
+
+def refine_bounds(height: int, bounds: List[int], measured, costs=None, stripe_rows: int = 54) -> List[int]:
+    """Boundaries moved by the measured cost of every rank's block (grt_refine_bounds); `costs`: the stripe-cost profile the
+    bounds came from (its shape is kept inside a block)."""
+    world = len(bounds) - 1
+    b = (C.c_int * (world + 1))(*bounds)
+    m = (C.c_double * world)(*[float(x) for x in measured])
+    out = (C.c_int * (world + 1))()
+    if costs is None:
+        _check(lib().grt_refine_bounds(height, world, stripe_rows, None, 0, b, m, out))
+    else:
+        cost = (C.c_double * len(costs))(*[float(x) for x in costs])
+        _check(lib().grt_refine_bounds(height, world, stripe_rows, cost, len(costs), b, m, out))
+    return list(out)
 
 
 def save_png(path: str, rgba: np.ndarray) -> None:

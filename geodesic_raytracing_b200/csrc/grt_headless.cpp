@@ -9,7 +9,7 @@
 // on device 0 (grt_group_*: one context per device, peer stores into device 0's frame) - the single-context frame loop of
 // main.cpp:1069-1095 over several GPUs.  The window, ImGui, input and Steam parts of main.cpp are out of scope.
 //
-//   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K] [-gpus N | -devices 0,1,...] [-balance]
+//   grt_headless -content <folder> -bench <metric name> [-size W H] [-frames N] [-inflight K] [-gpus N | -devices 0,1,...] [-no-balance]
 //                [-param name value]... [-static] [-no-adaptive] [-redshift] [-geodesic tau] [-background file.png|file.ppm]
 //                [-settings settings.json] [-save-settings settings.json] [-screenshot] [-out frame.png|frame.ppm]
 #include <algorithm>
@@ -130,7 +130,7 @@ void write_ppm(const char* path, const std::vector<uint8_t>& rgba, int w, int h)
 int main(int argc, char** argv) {
     std::string content_dir, metric_name = "kerr_schild", out_path, background_path, settings_path = "settings.json", save_settings_path;
     int width = 0, height = 0, frames = 8, inflight = 2, gpus = 1;
-    bool is_static = false, adaptive = true, redshift = false, print_frametime = false, on_geodesic = false, screenshot = false, adaptive_given = false, balance = false;
+    bool is_static = false, adaptive = true, redshift = false, print_frametime = false, on_geodesic = false, screenshot = false, adaptive_given = false, balance = true;
     float geodesic_tau = 0.0f;
     std::vector<std::pair<std::string, float>> params;
     std::vector<int> devices;
@@ -144,7 +144,8 @@ int main(int argc, char** argv) {
         else if (a == "-frames") { frames = atoi(next()); i++; }
         else if (a == "-inflight") { inflight = atoi(next()); i++; }
         else if (a == "-gpus") { gpus = atoi(next()); i++; }
-        else if (a == "-balance") balance = true;                                             // stripes dealt by measured cost (grt_group_rebalance)
+        else if (a == "-balance") balance = true;                                             // the default: rows shared out by measured cost (grt_group_rebalance)
+        else if (a == "-no-balance") balance = false;                                         // plain interleaved stripes
         else if (a == "-devices") {                                                          // explicit device list, e.g. 0,1,2,3 (a device may repeat: ranks then share it)
             devices.clear();
             for (const char* q = next(); *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
@@ -227,7 +228,7 @@ int main(int argc, char** argv) {
         printf("Camera on its geodesic at proper time %g (%d path points)\n", geodesic_tau, n);
     }
     check(grt_group_set_frames_in_flight(group, inflight), "frames in flight");
-    if (gpus > 1 && balance) check(grt_group_rebalance(group, width, height), "stripe costs");   // -balance: the stripes of this view dealt by measured cost
+    if (gpus > 1 && balance) check(grt_group_rebalance(group, width, height), "stripe costs");   // one block of rows per device, boundaries at equal measured cost
 
     // one synchronous frame with statistics on device 0 (the whole frame), then `frames` frames queued back to back
     std::vector<uint8_t> host((size_t)width * height * 4);

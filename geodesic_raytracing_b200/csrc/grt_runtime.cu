@@ -1767,6 +1767,107 @@ int grt_balanced_stripes(int height, int rank, int world, int stripe_rows, const
     return k;
 }
 
+// Contiguous blocks of rows with equal cost.  `density` is a piecewise-constant cost per row: piece k covers rows [edge[k], edge[k + 1])
+// and costs cost[k] in all.  Boundaries go where the cumulative cost crosses r / world of the total, rounded to even rows, every
+// block at least two rows tall.
+namespace {
+void equal_cost_bounds(int height, int world, const std::vector<int>& edge, const std::vector<double>& cost, int* bounds) {
+    const int pieces = (int)cost.size();
+    double total = 0.0;
+    for (double c : cost) total += std::max(0.0, c);
+    bounds[0] = 0;
+    bounds[world] = height;
+    int k = 0;
+    double before = 0.0;       // cost of the pieces in front of piece k
+    for (int r = 1; r < world; r++) {
+        const double want = total * r / world;
+        while (k < pieces - 1 && before + std::max(0.0, cost[k]) < want) before += std::max(0.0, cost[k++]);
+        const double ck = std::max(0.0, cost[k]);
+        const double frac = ck > 0.0 ? std::min(1.0, std::max(0.0, (want - before) / ck)) : 0.0;
+        int y = (int)std::lround(edge[k] + frac * (edge[k + 1] - edge[k]));
+        y &= ~1;
+        y = std::max(y, bounds[r - 1] + 2);
+        y = std::min(y, height - 2 * (world - r) - (height & 1));
+        bounds[r] = y;
+    }
+}
+}  // namespace
+
+int grt_contiguous_bounds(int height, int world, int stripe_rows, const double* cost, int n_cost, int* bounds_out) {
+    if (height < 2 * world || world < 1 || !bounds_out) { g_err = "bad partition request"; return GRT_E_INVALID; }
+    stripe_rows = std::max(2, stripe_rows - (stripe_rows & 1));
+    const int n = (height + stripe_rows - 1) / stripe_rows;
+    std::vector<int> edge;
+    std::vector<double> c;
+    if (!cost) {                                 // no profile: equal heights
+        edge = {0, height};
+        c = {1.0};
+    } else {
+        if (n_cost != 2 * n) { g_err = "stripe cost vector does not match the stripe count of this height (two halves per stripe)"; return GRT_E_INVALID; }
+        for (int i = 0; i < n; i++) {
+            const StripeRows r = stripe_rows_of(i, stripe_rows, height);
+            edge.push_back(r.y0);
+            c.push_back(cost[2 * i]);
+            if (r.mid < r.y1) { edge.push_back(r.mid); c.push_back(cost[2 * i + 1]); }
+        }
+        edge.push_back(height);
+    }
+    equal_cost_bounds(height, world, edge, c, bounds_out);
+    return world + 1;
+}
+
+int grt_refine_bounds(int height, int world, int stripe_rows, const double* cost, int n_cost, const int* bounds, const double* measured, int* bounds_out) {
+    if (height < 2 * world || world < 1 || !bounds || !measured || !bounds_out) { g_err = "bad partition request"; return GRT_E_INVALID; }
+    if (bounds[0] != 0 || bounds[world] != height) { g_err = "bounds must run from 0 to the frame height"; return GRT_E_INVALID; }
+    for (int r = 0; r < world; r++)
+        if (bounds[r + 1] <= bounds[r]) { g_err = "bounds must ascend"; return GRT_E_INVALID; }
+    // the profile's pieces (its shape inside a block: the rows tangent to the shadow's edge cost ten times the sky rows) ...
+    std::vector<int> pe;
+    std::vector<double> pc;
+    if (cost) {
+        stripe_rows = std::max(2, stripe_rows - (stripe_rows & 1));
+        const int n = (height + stripe_rows - 1) / stripe_rows;
+        if (n_cost != 2 * n) { g_err = "stripe cost vector does not match the stripe count of this height (two halves per stripe)"; return GRT_E_INVALID; }
+        for (int i = 0; i < n; i++) {
+            const StripeRows r = stripe_rows_of(i, stripe_rows, height);
+            pe.push_back(r.y0);
+            pc.push_back(std::max(0.0, cost[2 * i]));
+            if (r.mid < r.y1) { pe.push_back(r.mid); pc.push_back(std::max(0.0, cost[2 * i + 1])); }
+        }
+        pe.push_back(height);
+    } else {
+        pe = {0, height};
+        pc = {1.0};
+    }
+    // ... cut at the block boundaries, and every block's pieces scaled so that they add up to what the block really cost
+    std::vector<int> edge;
+    std::vector<double> c;
+    std::vector<int> block_of;
+    std::vector<double> predicted(world, 0.0);
+    int k = 0;
+    for (int r = 0; r < world; r++) {
+        int y = bounds[r];
+        while (y < bounds[r + 1]) {
+            while (pe[k + 1] <= y) k++;
+            const int y_end = std::min(bounds[r + 1], pe[k + 1]);
+            const double part = pc[k] * (double)(y_end - y) / (double)(pe[k + 1] - pe[k]);
+            edge.push_back(y);
+            c.push_back(part);
+            block_of.push_back(r);
+            predicted[r] += part;
+            y = y_end;
+        }
+    }
+    edge.push_back(height);
+    for (size_t i = 0; i < c.size(); i++) {
+        const int r = block_of[i];
+        const double rows = (double)(edge[i + 1] - edge[i]), block_rows = (double)(bounds[r + 1] - bounds[r]);
+        c[i] = predicted[r] > 0.0 ? c[i] * std::max(0.0, measured[r]) / predicted[r] : std::max(0.0, measured[r]) * rows / block_rows;
+    }
+    equal_cost_bounds(height, world, edge, c, bounds_out);
+    return world + 1;
+}
+
 void* grt_comm_frame(grt_ctx* c, unsigned seq) {
     if (!c || !c->comm.active || c->comm.rank != 0) { g_err = "only the owner (rank 0) holds the frames"; return nullptr; }
     return c->comm.base[0] + kCommFrames + (size_t)(seq % (unsigned)c->comm.n_frames) * c->comm.frame_bytes;
@@ -1808,7 +1909,7 @@ struct grt_group {
     int w = 0, h = 0, format = -1, frames = 2;
     unsigned seq = 0;
     bool connected = false;
-    std::vector<double> pending_cost;      // grt_group_rebalance before the first frame of a shape: used when the communicator is built
+    std::vector<int> pending_bounds;       // grt_group_rebalance: the contiguous blocks (world + 1 boundaries) for a frame of height pending_bounds.back()
 };
 
 namespace {
@@ -1864,8 +1965,14 @@ int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
         for (int r = 0; r < n; r++) {
             g->y0s[r].assign(h / 2 + 2, 0);
             g->y1s[r].assign(h / 2 + 2, 0);
-            int k = grt_balanced_stripes(h, r, n, 54, g->pending_cost.empty() ? nullptr : g->pending_cost.data(), (int)g->pending_cost.size(), g->y0s[r].data(),
-                                         g->y1s[r].data(), (int)g->y0s[r].size());
+            int k;
+            if ((int)g->pending_bounds.size() == n + 1 && g->pending_bounds.back() == h) {       // shared out by cost (grt_group_rebalance)
+                g->y0s[r][0] = g->pending_bounds[r];
+                g->y1s[r][0] = g->pending_bounds[r + 1];
+                k = 1;
+            } else {
+                k = grt_interleaved_stripes(h, r, n, 54, g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size());
+            }
             if (k < 0) return k;
             g->y0s[r].resize(k);
             g->y1s[r].resize(k);
@@ -1875,7 +1982,6 @@ int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
         int rc = grt_comm_connect_local(g->ctx.data(), n);
         if (rc < 0) return rc;
         g->w = w; g->h = h; g->format = format; g->seq = 0; g->connected = true;
-        g->pending_cost.clear();
     }
     for (int r = n - 1; r >= 0; r--) {       // the owner last: its stream then waits for stores that are already queued
         int rc = grt_comm_render(g->ctx[r], g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size(), g->seq, r == 0 ? host_out : nullptr);
@@ -1884,26 +1990,46 @@ int grt_group_render(grt_group* g, int w, int h, int format, void* host_out) {
     g->seq++;
     return GRT_OK;
 }
-// Re-deal the stripes by the cost profile of the frame as it is now (metric, features and camera of rank 0's context): rank 0
-// measures every stripe, the assignment takes effect with the next grt_group_render.  Waits for the frames in flight.
+// Share the frame out again by what it costs as it is now (metric, features and camera as set): rank 0 measures the stripe-cost profile,
+// every rank gets one contiguous block of rows with boundaries at equal cost, and two rounds of feedback move the boundaries by what
+// every context's block really cost (its trial ray-steps).  Takes effect with the next grt_group_render.  Waits for the frames in flight.
 int grt_group_rebalance(grt_group* g, int w, int h) {
     if (!g) { g_err = "null group"; return GRT_E_INVALID; }
     const int n = (int)g->ctx.size();
     if (n == 1) return GRT_OK;
+    if (h < 2 * n) { g_err = "frame too short to share out"; return GRT_E_INVALID; }
     int rc = grt_group_synchronize(g);
     if (rc < 0) return rc;
     std::vector<double> cost(h + 4);
     const int k = grt_measure_stripe_costs(g->ctx[0], w, h, 54, cost.data(), (int)cost.size());
     if (k < 0) return k;
-    if (!g->connected || w != g->w || h != g->h) { g->pending_cost.assign(cost.begin(), cost.begin() + k); return GRT_OK; }   // applied when the communicator is built
-    for (int r = 0; r < n; r++) {
-        g->y0s[r].assign(h / 2 + 2, 0);
-        g->y1s[r].assign(h / 2 + 2, 0);
-        int m = grt_balanced_stripes(h, r, n, 54, cost.data(), k, g->y0s[r].data(), g->y1s[r].data(), (int)g->y0s[r].size());
-        if (m < 0) return m;
-        g->y0s[r].resize(m);
-        g->y1s[r].resize(m);
+    std::vector<int> bounds(n + 1), next(n + 1);
+    rc = grt_contiguous_bounds(h, n, 54, cost.data(), k, bounds.data());
+    if (rc < 0) return rc;
+    for (int round = 0; round < 2; round++) {
+        std::vector<double> measured(n, 0.0);
+        for (int r = 0; r < n; r++) {
+            grt_ctx* c = g->ctx[r];
+            DevBuf scratch;
+            rc = guard([&] {
+                bind(c);
+                scratch.ensure((size_t)(bounds[r + 1] - bounds[r]) * (size_t)w * 4);
+                return GRT_OK;
+            });
+            if (rc < 0) return rc;
+            grt_stats st{};
+            rc = grt_render_stripes(c, w, h, &bounds[r], &bounds[r + 1], 1, scratch.p, GRT_FORMAT_RGBA8, GRT_OUT_DEVICE, &st);
+            scratch.release();
+            if (rc < 0) return rc;
+            measured[r] = (double)st.trial_steps;
+        }
+        rc = grt_refine_bounds(h, n, 54, cost.data(), k, bounds.data(), measured.data(), next.data());
+        if (rc < 0) return rc;
+        bounds = next;
     }
+    g->pending_bounds = bounds;
+    if (g->connected && w == g->w && h == g->h)
+        for (int r = 0; r < n; r++) { g->y0s[r] = {bounds[r]}; g->y1s[r] = {bounds[r + 1]}; }
     return GRT_OK;
 }
 void* grt_group_frame(grt_group* g) { return (g && g->connected && g->seq > 0) ? grt_comm_frame(g->ctx[0], g->seq - 1) : nullptr; }

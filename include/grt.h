@@ -273,6 +273,16 @@ int grt_interleaved_stripes(int height, int rank, int world, int stripe_rows, in
  * grt_interleaved_stripes. */
 int grt_measure_stripe_costs(grt_ctx*, int width, int height, int stripe_rows, double* cost_out, int max_costs);
 int grt_balanced_stripes(int height, int rank, int world, int stripe_rows, const double* cost, int n_cost, int* y0s, int* y1s, int max_stripes);
+/* The other way to share a frame out: ONE contiguous block of rows per rank (rank r renders rows [bounds[r], bounds[r + 1])), tall where
+ * the rows are cheap and short where they are expensive.  A rank then pays one halo and one run of prepass rows instead of one per
+ * stripe (at 8 GPUs the 54-row stripes cost 8 % more ray-steps than the frame holds).  grt_contiguous_bounds places the world + 1
+ * boundaries at equal cumulative cost of a profile from grt_measure_stripe_costs (cost == NULL: equal heights); grt_refine_bounds moves
+ * them by what every rank's block really cost in a frame rendered with them (the trial_steps of its grt_stats): the profile keeps its
+ * shape inside a block and is scaled block by block to the measured totals (cost == NULL: uniform inside a block) - feedback an
+ * interactive host applies every few frames; two rounds bring the ranks of the headline frame within a few percent.  Boundaries are
+ * even, every block is at least two rows tall; both are pure functions of their arguments, so every rank computes the same partition. */
+int grt_contiguous_bounds(int height, int world, int stripe_rows, const double* cost, int n_cost, int* bounds_out /* world + 1 */);
+int grt_refine_bounds(int height, int world, int stripe_rows, const double* cost, int n_cost, const int* bounds, const double* measured_cost_per_rank, int* bounds_out /* world + 1 */);
 
 /* A group: the contexts of several devices of one box driven as one renderer from one thread - what SURVEY.md 8(b2) writes as
  * grt_create(const int* devices, int ndev).  Rank 0 = devices[0] owns the assembled frame.  The setters broadcast to every context;
@@ -291,8 +301,10 @@ int grt_group_set_background(grt_group*, const uint8_t* rgba, int width, int hei
 int grt_group_set_camera(grt_group*, const float pos_txyz[4], const float quat_xyzw[4], int flip_r);
 int grt_group_set_frames_in_flight(grt_group*, int n);
 int grt_group_render(grt_group*, int width, int height, int format, void* host_out);
-/* Re-deal the stripes by measured cost (grt_measure_stripe_costs on devices[0], grt_balanced_stripes): call it after the metric, the
- * features and the camera are set, and again whenever the view has changed much.  Waits for the frames in flight. */
+/* Share the frame out by measured cost: one contiguous block of rows per device (grt_measure_stripe_costs on devices[0],
+ * grt_contiguous_bounds, two rounds of grt_refine_bounds with every device's own ray-steps).  Call it after the metric, the features
+ * and the camera are set, and again whenever the view has changed much; without it grt_group_render uses the interleaved stripes.
+ * Waits for the frames in flight. */
 int grt_group_rebalance(grt_group*, int width, int height);
 void* grt_group_frame(grt_group*);          /* device pointer (on devices[0]) of the most recently queued frame's buffer */
 int grt_group_synchronize(grt_group*);

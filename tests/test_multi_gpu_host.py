@@ -121,3 +121,42 @@ def test_balanced_stripes_deal_by_cost():
     bad = (C.c_double * 3)(1.0, 2.0, 3.0)
     assert L.grt_balanced_stripes(h, 0, 8, rows, bad, 3, y0, y1, 64) < 0          # cost vector of another frame shape
     assert grt.balanced_stripes(100, 0, 1, [5.0, 1.0, 2.0, 2.0], rows) == [(0, 100)]
+
+
+def test_contiguous_bounds_and_feedback():
+    """grt_contiguous_bounds / grt_refine_bounds: even, ascending boundaries from 0 to the height; equal-cost blocks for a peaked
+    profile; the feedback rounds bring the real loads of a finer-grained truth within a few percent; bad input is refused."""
+    import ctypes as C
+
+    import numpy as np
+
+    import geodesic_raytracing_b200 as grt
+    h, rows = 2160, 54
+    n = h // rows
+    yy = (np.arange(h) + 0.5) / h
+    row = 0.5 + 4.0 * np.exp(-((yy - 0.36) / 0.015) ** 2) + 4.0 * np.exp(-((yy - 0.64) / 0.015) ** 2)       # true cost per row, sharper than the profile resolves
+    halves = [(i * rows + (0 if k == 0 else 26), i * rows + (26 if k == 0 else rows)) for i in range(n) for k in (0, 1)]
+    profile = [row[a:b].sum() for a, b in halves]
+    assert grt.contiguous_bounds(h, 8) == [270 * r for r in range(9)]
+    for world in (2, 3, 4, 8):
+        b = grt.contiguous_bounds(h, world, profile, rows)
+        for _ in range(3):
+            assert b[0] == 0 and b[-1] == h and all(x % 2 == 0 for x in b) and all(b[r + 1] - b[r] >= 2 for r in range(world))
+            load = [row[b[r]:b[r + 1]].sum() for r in range(world)]
+            b = grt.refine_bounds(h, b, load, profile, rows)
+        load = [row[b[r]:b[r + 1]].sum() for r in range(world)]
+        assert max(load) / np.mean(load) < 1.05, (world, b, load)
+    # a degenerate profile (all the cost in one half stripe) still gives every rank two rows
+    spike = [0.0] * (2 * n)
+    spike[40] = 1.0
+    b = grt.contiguous_bounds(h, 8, spike, rows)
+    assert b[0] == 0 and b[-1] == h and all(b[r + 1] - b[r] >= 2 for r in range(8))
+    L = grt.lib()
+    out = (C.c_int * 9)()
+    bad = (C.c_double * 3)(1.0, 2.0, 3.0)
+    assert L.grt_contiguous_bounds(h, 8, rows, bad, 3, out) < 0
+    assert L.grt_contiguous_bounds(10, 8, rows, None, 0, out) < 0                     # fewer than two rows per rank
+    desc = (C.c_int * 3)(0, 1200, 1000)
+    m = (C.c_double * 2)(1.0, 1.0)
+    assert L.grt_refine_bounds(h, 2, rows, None, 0, desc, m, out) < 0
+    assert grt.refine_bounds(h, [0, 1000, h], [3.0, 1.0])[1] < 1000                    # without a profile: uniform inside a block

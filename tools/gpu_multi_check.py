@@ -47,6 +47,20 @@ def main():
                 mine[y0:y1] += 1
             dist.all_reduce(mine)
             ok &= bool((mine == 1).all().item())          # the ranks' stripes tile the frame exactly once
+        elif world <= 4:
+            # one contiguous block per rank with boundaries at equal measured cost, moved once by the blocks' real cost
+            ctx.set_camera(cams[0])
+            costs = ctx.measure_stripe_costs(w, h, 18)
+            bounds = grt.contiguous_bounds(h, world, costs, 18)
+            scratch = torch.empty((h, w, 4), dtype=torch.uint8, device=device)
+            _, st = ctx.render(w, h, grt.GRT_FORMAT_RGBA8, out=scratch, stats=True, stripes=[(bounds[rank], bounds[rank + 1])])
+            mine = torch.tensor([float(st.trial_steps)], dtype=torch.float64, device=device)
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            bounds = grt.refine_bounds(h, bounds, [float(p.item()) for p in parts], costs, 18)
+            stripes = [(bounds[rank], bounds[rank + 1])]
+            if rank == 0:
+                print(f"{name} world {world}: contiguous bounds {bounds}", flush=True)
         else:
             stripes = grt.interleaved_stripes(h, rank, world, 18)
         host = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in cams] if rank == 0 else None

@@ -8,5 +8,5 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/${T}_bench_n$N.json").read().strip().splitlines()[-1])
-print("N=$N", {k:round(d[k],2) for k in ("value","ms_per_step","fps","fps_at_2_in_flight","fps_latency")}, "e2e fps", round(d["e2e"]["fps"],1), "by rank", [round(x,1) for x in d["frame"]["timed_region_ms_by_rank"]], "cfg5 fps", d.get("config5",{}).get("fps"))
+print("N=$N", {k:round(d[k],2) for k in ("value","ms_per_step","fps","fps_at_2_in_flight","fps_latency")}, "e2e fps", round(d["e2e"]["fps"],1), "by rank", [round(x,1) for x in d["frame"]["timed_region_ms_by_rank"]], "cfg5 fps", d.get("config5",{}).get("fps"), d["frame"].get("partition"), d["frame"].get("bounds"), d["frame"].get("block_costs_by_round"))
 PY
