@@ -246,8 +246,9 @@ class Job:
         self.ctx = None
         self.submit_s, self.submits = 0.0, 0
 
-    def bind(self, cfg_id):
+    def bind(self, cfg_id, partition=None):
         """A fresh context for one BASELINE config: metric, features, camera, background, communicator."""
+        partition = partition or PARTITION
         torch = self.torch
         cfg = CONFIGS[cfg_id]
         if self.ctx is not None:
@@ -277,7 +278,7 @@ class Job:
         # (emulation, diagnostic only: one GPU renders the stripes one rank of an N-GPU job would own - the per-rank pipeline without the delivery)
         self.stripe_costs = None
         self.partition = "interleaved"
-        if part_world > 1 and PARTITION == "contiguous":
+        if part_world > 1 and partition == "contiguous":
             # one block of rows per rank, boundaries at equal measured cost, then two rounds of feedback from what the blocks really cost
             self.partition = "contiguous"
             self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
@@ -293,7 +294,7 @@ class Job:
                     bounds = grt.refine_bounds(self.h, bounds, measured, self.stripe_costs, STRIPE_ROWS)
             self.bounds = bounds
             self.stripes = [(bounds[part_rank], bounds[part_rank + 1])]
-        elif part_world > 1 and PARTITION == "balanced":
+        elif part_world > 1 and partition == "balanced":
             self.partition = "balanced"
             self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
             self.stripes = grt.balanced_stripes(self.h, part_rank, part_world, self.stripe_costs, STRIPE_ROWS)
@@ -555,7 +556,7 @@ def run_ours(args):
             side["full_sampling"] = {"error": str(exc)}
         try:
             # BASELINE config 5 on the same GPUs: double_unequal_kerr 3840x2160, row-tiled (register-bound kernel: 167 registers, 3 blocks/SM)
-            job.bind(5)
+            job.bind(5, partition="interleaved")      # no horizon, flat cost profile: the plain stripes (and no set-up collectives inside a side measurement)
             ms5 = job.measure(8, 2, FRAMES_IN_FLIGHT)
             ms5_1 = job.measure(4, 1, 1)
             if rank == 0:
