@@ -1,5 +1,5 @@
-"""Host-side logic of the multi-GPU path on CPU: the stripe partition (computed in libgrt) and the world_size-2
-exchange of the communicator handles (gloo).  The delivery itself - peer stores into the owner's frame - is tested with -m gpu."""
+"""Host-side logic of the multi-GPU path on CPU: the partitions of a frame (computed in libgrt), the world_size-2
+exchange of the communicator handles and the feedback loop of the contiguous partition (gloo).  The delivery itself - peer stores into the owner's frame - is tested with -m gpu."""
 import os
 import socket
 
@@ -48,7 +48,23 @@ def _worker(rank, world, port, q):
     stripes = bench.grt.interleaved_stripes(2160, rank, world, bench.STRIPE_ROWS)
     rows = torch.tensor([sum(b - a for a, b in stripes)], dtype=torch.int64)
     dist.all_reduce(rows)
-    q.put((rank, got == want, int(rows.item())))
+    # the feedback loop of the contiguous partition as bench.py runs it: every rank "measures" its own block (here: a synthetic cost per
+    # row), the numbers are all-gathered, and every rank must arrive at the same boundaries
+    yy = (np.arange(2160) + 0.5) / 2160
+    row = 0.5 + 4.0 * np.exp(-((yy - 0.36) / 0.02) ** 2) + 4.0 * np.exp(-((yy - 0.64) / 0.02) ** 2) + (0.3 if world == 2 else 0.0) * yy
+    halves = [(i * 54 + (0 if k == 0 else 26), i * 54 + (26 if k == 0 else 54)) for i in range(40) for k in (0, 1)]
+    profile = [float(row[a:b].sum()) for a, b in halves]
+    bounds = bench.grt.contiguous_bounds(2160, world, profile, 54)
+    for _ in range(3):
+        mine = torch.tensor([float(row[bounds[rank]:bounds[rank + 1]].sum())], dtype=torch.float64)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        bounds = bench.grt.refine_bounds(2160, bounds, [float(p.item()) for p in parts], profile, 54)
+    loads = [float(row[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
+    all_bounds = [None] * world
+    dist.all_gather_object(all_bounds, bounds)
+    balanced = all(b == bounds for b in all_bounds) and max(loads) / (sum(loads) / world) < 1.03
+    q.put((rank, got == want and balanced, int(rows.item())))
     dist.destroy_process_group()
 
 
