@@ -284,14 +284,17 @@ class Job:
             self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
             bounds = grt.contiguous_bounds(self.h, part_world, self.stripe_costs, STRIPE_ROWS)
             self.block_costs = []
+            tried = []
             for _ in range(REFINE_ROUNDS + 1):
                 # the feedback signal: ray-steps of every block (REFINE_BY=steps), or what matters in the end - the time of every rank's own
                 # pipeline over a dozen frames without delivery (REFINE_BY=ms: equal ray-steps are not equal times, the ranks that hold the
                 # shadow's edge carry the long rays)
                 measured = self.block_ms_of(bounds, part_world, part_rank, bool(emu_world)) if REFINE_BY == "ms" else [m / 1e6 for m in self.block_costs_of(bounds, part_world, part_rank, bool(emu_world))]
                 self.block_costs.append([round(m, 2) for m in measured])
+                tried.append((max(measured), list(bounds)))
                 if len(self.block_costs) <= REFINE_ROUNDS:
                     bounds = grt.refine_bounds(self.h, bounds, measured, self.stripe_costs, STRIPE_ROWS)
+            bounds = min(tried, key=lambda t: t[0])[1]          # every candidate was measured (the same numbers on every rank): keep the one whose slowest rank is fastest
             self.bounds = bounds
             self.stripes = [(bounds[part_rank], bounds[part_rank + 1])]
         elif part_world > 1 and partition == "balanced":
