@@ -194,7 +194,9 @@ enum class K {
     Spread,      // ...expr in a call, an array literal or an object literal
     Switch,      // kids[0] discriminant, then Case nodes
     Case,        // kids[0] test (Empty for `default`), then the statements
-    Class        // s = name, kids[0] = parent expression or Empty, members in `members`
+    Class,       // s = name, kids[0] = parent expression or Empty, members in `members`
+    Labeled,     // s = label, kids[0] = the statement
+    ObjectRest   // kids[0] = source object, s = excluded keys joined by '\x1f': the `...rest` of an object pattern
 };
 
 struct Node;
@@ -222,7 +224,7 @@ struct Node {
     bool flag = false;      // Update: prefix; Literal: bool value
     std::vector<NodeP> kids;
     std::unique_ptr<FuncDef> fn;
-    struct ClassMember { std::string name; std::unique_ptr<FuncDef> fn; bool is_static = false; char accessor = 0; };   // accessor: 'g' getter, 's' setter
+    struct ClassMember { std::string name; std::unique_ptr<FuncDef> fn; bool is_static = false; char accessor = 0; NodeP init; bool is_field = false; };   // accessor: 'g' getter, 's' setter; field: `init` (may be null)
     std::vector<ClassMember> members;       // Class
     Node(K kind, int ln) : k(kind), line(ln) {}
 };
@@ -369,10 +371,20 @@ struct Parser {
             }
             expect_punct("]");
         } else if (eat_punct("{")) {
+            std::string taken;
             while (!is_punct("}")) {
-                if (is_punct("...")) fail("rest properties in object patterns are not supported by the metric script interpreter");
+                if (eat_punct("...")) {                    // {a, ...rest}: what is left of the source
+                    auto d = ident_node(ident_name());
+                    auto r = mk(K::ObjectRest);
+                    r->s = taken;
+                    r->kids.push_back(ident_node(src));
+                    d->kids.push_back(std::move(r));
+                    decls.push_back(std::move(d));
+                    break;
+                }
                 const bool was_ident = t[p].type == Tok::Ident;
                 std::string key = property_name();
+                taken += key + '\x1f';
                 auto access = [&, key]() { auto m = mk(K::Member); m->s = key; m->kids.push_back(ident_node(src)); return NodeP(std::move(m)); };
                 if (eat_punct(":")) bind_target(access);
                 else {
@@ -570,8 +582,13 @@ struct Parser {
             eat_punct(";");
             return n;
         }
-        if (is_kw("break")) { auto n = mk(K::Break); p++; consume_semicolon(); return n; }
-        if (is_kw("continue")) { auto n = mk(K::Continue); p++; consume_semicolon(); return n; }
+        if (is_kw("break") || is_kw("continue")) {
+            auto n = mk(is_kw("break") ? K::Break : K::Continue);
+            p++;
+            if (t[p].type == Tok::Ident && !t[p].nl_before) n->s = t[p++].text;       // break label; / continue label;
+            consume_semicolon();
+            return n;
+        }
         if (is_kw("throw")) {
             auto n = mk(K::Throw);
             p++;
@@ -625,8 +642,13 @@ struct Parser {
         }
         if (t[p].type == Tok::Ident && (t[p].text == "async" || t[p].text == "yield" || t[p].text == "await") && t[p + 1].type != Tok::Punct)
             fail("'" + t[p].text + "' is not supported by the metric script interpreter");
-        if (t[p].type == Tok::Ident && t[p + 1].type == Tok::Punct && t[p + 1].text == ":")
-            fail("labelled statements are not supported by the metric script interpreter");
+        if (t[p].type == Tok::Ident && t[p + 1].type == Tok::Punct && t[p + 1].text == ":") {
+            auto n = mk(K::Labeled);
+            n->s = t[p].text;
+            p += 2;
+            n->kids.push_back(statement());
+            return n;
+        }
         auto e = mk(K::ExprStmt);
         e->kids.push_back(expression());
         consume_semicolon();
@@ -685,7 +707,8 @@ struct Parser {
         static const char* ops[] = {"=", "+=", "-=", "*=", "/=", "%=", "**=", "&=", "|=", "^=", "<<=", ">>=", ">>>="};
         for (const char* op : ops) {
             if (is_punct(op)) {
-                if (lhs->k != K::Ident && lhs->k != K::Member && lhs->k != K::Index) fail("invalid assignment target");
+                const bool pattern = (lhs->k == K::ArrayLit || lhs->k == K::ObjectLit) && std::string(op) == "=";     // [a, b] = ...; ({a, b} = ...)
+                if (lhs->k != K::Ident && lhs->k != K::Member && lhs->k != K::Index && !pattern) fail("invalid assignment target");
                 auto n = mk(K::Assign);
                 n->s = op;
                 p++;
@@ -821,12 +844,85 @@ struct Parser {
             if (t[p].type == Tok::Ident && (t[p].text == "get" || t[p].text == "set") && !(t[p + 1].type == Tok::Punct && t[p + 1].text == "(")) { m.accessor = t[p].text[0]; p++; }
             if (is_punct("*") || is_punct("[") || is_punct("#")) fail("generator, computed and private class members are not supported by the metric script interpreter");
             m.name = property_name();
-            if (!is_punct("(")) fail("class fields are not supported by the metric script interpreter (assign them in the constructor)");
+            if (!is_punct("(")) {                          // a field: `x = expr;`, `x;`, `static y = expr;`
+                if (m.accessor) fail("expected '(' after an accessor name");
+                m.is_field = true;
+                if (eat_punct("=")) m.init = assignment();
+                consume_semicolon();
+                c->members.push_back(std::move(m));
+                continue;
+            }
             m.fn = function_rest(m.name);
             c->members.push_back(std::move(m));
         }
         expect_punct("}");
+        lower_instance_fields(*c);
         return c;
+    }
+
+    // Instance fields become assignments `this.name = init;` in the constructor: at the top of a base class's constructor, right
+    // behind the top-level `super(...)` statement of a derived class's (where JavaScript runs them); a class without a constructor
+    // gets the default one.  (An initialiser therefore sees the constructor's parameters, which JavaScript's does not - a script
+    // that shadows an outer name by a constructor parameter AND reads that name in a field initialiser would differ.)  Static
+    // fields stay members: the evaluator sets them when the class is created.
+    void lower_instance_fields(Node& c) {
+        std::vector<NodeP> inits;
+        for (auto it = c.members.begin(); it != c.members.end();) {
+            if (!it->is_field || it->is_static) { ++it; continue; }
+            auto target = mk(K::Member);
+            target->s = it->name;
+            target->kids.push_back(mk(K::This));
+            auto asg = mk(K::Assign);
+            asg->s = "=";
+            asg->kids.push_back(std::move(target));
+            if (it->init) asg->kids.push_back(std::move(it->init));
+            else { auto u = mk(K::Literal); u->s = "undefined"; asg->kids.push_back(std::move(u)); }
+            auto st = mk(K::ExprStmt);
+            st->kids.push_back(std::move(asg));
+            inits.push_back(std::move(st));
+            it = c.members.erase(it);
+        }
+        if (inits.empty()) return;
+        const bool derived = c.kids[0]->k != K::Empty;
+        FuncDef* ctor = nullptr;
+        for (auto& m : c.members)
+            if (m.name == "constructor" && !m.is_static && !m.accessor && !m.is_field) ctor = m.fn.get();
+        if (!ctor) {
+            Node::ClassMember m;
+            m.name = "constructor";
+            m.fn = std::make_unique<FuncDef>();
+            m.fn->name = "constructor";
+            m.fn->source = name;
+            m.fn->body = mk(K::Block);
+            if (derived) {                                   // constructor(...args) { super(...args); }
+                m.fn->rest = "args";
+                auto call = mk(K::Call);
+                auto callee = mk(K::Ident);
+                callee->s = "super";
+                call->kids.push_back(std::move(callee));
+                auto sp = mk(K::Spread);
+                auto a = mk(K::Ident);
+                a->s = "args";
+                sp->kids.push_back(std::move(a));
+                call->kids.push_back(std::move(sp));
+                auto st = mk(K::ExprStmt);
+                st->kids.push_back(std::move(call));
+                m.fn->body->kids.push_back(std::move(st));
+            }
+            ctor = m.fn.get();
+            c.members.push_back(std::move(m));
+        }
+        auto& body = ctor->body->kids;
+        size_t at = 0;
+        if (derived) {
+            at = body.size() + 1;
+            for (size_t i = 0; i < body.size(); i++) {
+                const Node* st = body[i].get();
+                if (st->k == K::ExprStmt && st->kids[0]->k == K::Call && st->kids[0]->kids[0]->k == K::Ident && st->kids[0]->kids[0]->s == "super") { at = i + 1; break; }
+            }
+            if (at > body.size()) fail("class fields of a derived class need super(...) as a top-level statement of its constructor");
+        }
+        for (size_t i = 0; i < inits.size(); i++) body.insert(body.begin() + (long)(at + i), std::move(inits[i]));
     }
 
     NodeP call_member() {
@@ -924,10 +1020,40 @@ struct Parser {
                     if (!eat_punct(",")) break;
                     continue;
                 }
-                if (is_punct("[")) fail("computed property names are not supported by the metric script interpreter");
+                if (eat_punct("[")) {                     // {[expr]: value} and {[expr](..) {..}}: the key node is the expression itself
+                    NodeP key = assignment();
+                    expect_punct("]");
+                    if (key->k == K::Str) { auto wrap = mk(K::Comma); wrap->kids.push_back(std::move(key)); key = std::move(wrap); }   // a Str node is a literal key: keep a computed one apart
+                    if (is_punct("(")) {
+                        auto fnode = mk(K::Func);
+                        fnode->fn = function_rest("");
+                        o->kids.push_back(std::move(key));
+                        o->kids.push_back(std::move(fnode));
+                    } else {
+                        expect_punct(":");
+                        o->kids.push_back(std::move(key));
+                        o->kids.push_back(assignment());
+                    }
+                    if (!eat_punct(",")) break;
+                    continue;
+                }
                 auto key = mk(K::Str);
                 bool was_ident = t[p].type == Tok::Ident;
                 key->s = property_name();
+                if (was_ident && is_punct("=")) {          // {x = 1}: only meaningful as an assignment pattern ({x = 1} = obj)
+                    auto id = mk(K::Ident);
+                    id->s = key->s;
+                    auto dflt = mk(K::Assign);
+                    dflt->s = "=";
+                    dflt->flag = true;                     // a shorthand default, not an assignment expression
+                    p++;
+                    dflt->kids.push_back(std::move(id));
+                    dflt->kids.push_back(assignment());
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(std::move(dflt));
+                    if (!eat_punct(",")) break;
+                    continue;
+                }
                 if (is_punct("(")) {  // method shorthand
                     auto fnode = mk(K::Func);
                     fnode->fn = function_rest(key->s);
@@ -1045,11 +1171,76 @@ struct Evaluator {
     bool loose_equal(const Value& a, const Value& b);
     bool strict_equal(const Value& a, const Value& b);
 
+    // break / continue with a label: `jump_label` names the target while the completion travels outwards; a loop learns the labels it
+    // carries from the Labeled node that runs it
+    std::string jump_label;
+    std::vector<std::string> loop_labels;
+    std::vector<std::string> take_loop_labels() { std::vector<std::string> l; l.swap(loop_labels); return l; }
+    // what a loop does with its body's completion: true = stop iterating (the caller breaks out normally when it was this loop's own
+    // break, otherwise hands the completion on); false = next iteration (normal completion, or a continue meant for this loop)
+    bool leaves_loop(Comp c, const std::vector<std::string>& mine) {
+        const bool own = jump_label.empty() || std::find(mine.begin(), mine.end(), jump_label) != mine.end();
+        if (c == Comp::Normal) return false;
+        if (c == Comp::Return) return true;
+        if (own) {
+            jump_label.clear();
+            return c == Comp::Break;          // own continue: keep going
+        }
+        return true;                          // a break / continue for an outer statement: out of this loop, label kept
+    }
     Value eval(const Node* n, EnvP& env);
     Comp exec(const Node* n, EnvP& env);
     Comp exec_block(const std::vector<NodeP>& body, EnvP& env);
     Value call_function(const Node* n, const Value& fn, const Value& self, std::vector<Value>& args);
     void assign_to(const Node* target, EnvP& env, const Value& v);
+    // assignment pattern: an array or object literal on the left of '=' (elements: targets, nested patterns, `target = default`,
+    // holes, a trailing `...rest`)
+    void destructure_assign(const Node* pat, EnvP& env, const Value& v) {
+        auto put = [&](const Node* el, Value item) {
+            const Node* target = el;
+            if (el->k == K::Assign && el->s == "=") {                    // default value
+                target = el->kids[0].get();
+                if (item.is_undefined()) item = eval(el->kids[1].get(), env);
+            }
+            if (target->k == K::ArrayLit || target->k == K::ObjectLit) destructure_assign(target, env, item);
+            else if (target->k == K::Ident || target->k == K::Member || target->k == K::Index) assign_to(target, env, item);
+            else fail(target, "SyntaxError: invalid destructuring assignment target");
+        };
+        if (v.type == Value::Undefined || v.type == Value::Null) fail(pat, "TypeError: cannot destructure 'undefined' or 'null'");
+        if (pat->k == K::ArrayLit) {
+            std::vector<Value> items;
+            if (v.type == Value::Obj && v.obj->kind == Object::Array) items = v.obj->arr;
+            else if (v.type == Value::String) for (char ch : v.str) items.push_back(Value(std::string(1, ch)));
+            else fail(pat, "TypeError: array destructuring needs an array");
+            for (size_t i = 0; i < pat->kids.size(); i++) {
+                const Node* el = pat->kids[i].get();
+                if (el->k == K::Literal && el->s == "hole") continue;
+                if (el->k == K::Spread) {
+                    std::vector<Value> rest(items.begin() + (long)std::min(i, items.size()), items.end());
+                    put(el->kids[0].get(), Value(Interp::make_array(rest)));
+                    break;
+                }
+                put(el, i < items.size() ? items[i] : Value());
+            }
+            return;
+        }
+        std::string taken;
+        for (size_t i = 0; i + 1 < pat->kids.size(); i += 2) {
+            const Node* key = pat->kids[i].get();
+            const Node* el = pat->kids[i + 1].get();
+            if (key->k == K::Str && key->s == "..." && el->k != K::Str) {       // {...rest}
+                auto o = Interp::make_object();
+                if (v.type == Value::Obj)
+                    for (auto& kv : v.obj->props)
+                        if (taken.find('\x1f' + kv.first + '\x1f') == std::string::npos) o->props[kv.first] = kv.second;
+                put(el, Value(o));
+                break;
+            }
+            const std::string name = key->k == K::Str ? key->s : key_of(eval(key, env));
+            taken += '\x1f' + name + '\x1f';
+            put(el, get_prop(pat, v, name));
+        }
+    }
 
     // one argument / array element: `...expr` contributes every element of the array it evaluates to
     void push_arg(const Node* k, EnvP& env, std::vector<Value>& out) {
@@ -1088,6 +1279,7 @@ struct Evaluator {
             cenv->vars["super"] = Value(sup);
         }
         for (auto& m : n->members) {
+            if (m.is_field) continue;                     // static fields: below, once the class is complete (instance fields were lowered by the parser)
             if (m.name == "constructor" && !m.is_static && !m.accessor) { ctor_def = m.fn.get(); continue; }
             auto f = std::make_shared<Object>();
             f->kind = Object::Function;
@@ -1105,6 +1297,12 @@ struct Evaluator {
         ctor->props["prototype"] = Value(proto);
         Value cv(ctor);
         if (!n->s.empty()) cenv->vars[n->s] = cv;
+        for (auto& m : n->members) {                      // static x = expr;  (`this` is the class)
+            if (!m.is_field) continue;
+            EnvP fenv = new_env(cenv, false);
+            fenv->this_val = cv;
+            ctor->props[m.name] = m.init ? eval(m.init.get(), fenv) : Value();
+        }
         return cv;
     }
 };
@@ -1407,6 +1605,12 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
         case K::ObjectLit: {
             auto o = Interp::make_object();
             for (size_t i = 0; i + 1 < n->kids.size(); i += 2) {
+                if (n->kids[i]->k != K::Str) {                                      // {[expr]: value}: the key is evaluated first
+                    const std::string key = key_of(eval(n->kids[i].get(), env));
+                    o->props[key] = eval(n->kids[i + 1].get(), env);
+                    continue;
+                }
+                if (n->kids[i + 1]->k == K::Assign && n->kids[i + 1]->flag) fail(n->kids[i + 1].get(), "SyntaxError: invalid shorthand property initializer");
                 Value v = eval(n->kids[i + 1].get(), env);
                 if (n->kids[i]->s == "..." && n->kids[i + 1]->k != K::Str) {      // {...base}
                     if (v.type == Value::Obj) {
@@ -1514,8 +1718,23 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             if (n->s == "||") return Interp::to_boolean(a) ? a : eval(n->kids[1].get(), env);
             return (a.type == Value::Undefined || a.type == Value::Null) ? eval(n->kids[1].get(), env) : a;
         }
+        case K::ObjectRest: {
+            Value src = eval(n->kids[0].get(), env);
+            auto o = Interp::make_object();
+            if (src.type == Value::Obj) {
+                const std::string skip = '\x1f' + n->s;         // "\x1fa\x1fb\x1f"
+                for (auto& kv : src.obj->props)
+                    if (skip.find('\x1f' + kv.first + '\x1f') == std::string::npos && kv.first.compare(0, 5, "$get$") != 0 && kv.first.compare(0, 5, "$set$") != 0) o->props[kv.first] = kv.second;
+            }
+            return Value(o);
+        }
         case K::Assign: {
             const Node* target = n->kids[0].get();
+            if (n->s == "=" && (target->k == K::ArrayLit || target->k == K::ObjectLit)) {      // [a, b] = value;  ({a, b: [c]} = value)
+                Value v = eval(n->kids[1].get(), env);
+                destructure_assign(target, env, v);
+                return v;
+            }
             if (n->s == "=") {
                 // evaluate target object before the value, as JavaScript does
                 if (target->k == K::Ident) {
@@ -1590,7 +1809,7 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
                 const Node* c = n->kids[i].get();
                 for (size_t k = 1; k < c->kids.size(); k++) {
                     Comp r = exec(c->kids[k].get(), inner);
-                    if (r == Comp::Break) return Comp::Normal;
+                    if (r == Comp::Break && jump_label.empty()) return Comp::Normal;
                     if (r != Comp::Normal) return r;
                 }
             }
@@ -1611,18 +1830,19 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
             return exec_block(n->kids, inner);
         }
         case K::For: {
+            const std::vector<std::string> mine = take_loop_labels();
             EnvP loop = new_env(env, false);
             exec(n->kids[0].get(), loop);
             while (true) {
                 if (n->kids[1]->k != K::Empty && !Interp::to_boolean(eval(n->kids[1].get(), loop))) break;
                 Comp c = exec(n->kids[3].get(), loop);
-                if (c == Comp::Break) break;
-                if (c == Comp::Return) return c;
+                if (leaves_loop(c, mine)) { if (c == Comp::Break && jump_label.empty()) break; return c; }
                 if (n->kids[2]->k != K::Empty) eval(n->kids[2].get(), loop);
             }
             return Comp::Normal;
         }
         case K::ForIn: case K::ForOf: {
+            const std::vector<std::string> mine = take_loop_labels();
             Value it = eval(n->kids[0].get(), env);
             std::vector<Value> items;
             if (it.type == Value::Obj) {
@@ -1639,27 +1859,38 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
                 if (n->flag && n->num != 0) loop->vars[n->s] = item;
                 else set_var(n, loop, n->s, item);
                 Comp c = exec(n->kids[1].get(), loop);
-                if (c == Comp::Break) break;
-                if (c == Comp::Return) return c;
+                if (leaves_loop(c, mine)) { if (c == Comp::Break && jump_label.empty()) break; return c; }
             }
             return Comp::Normal;
         }
-        case K::While:
+        case K::While: {
+            const std::vector<std::string> mine = take_loop_labels();
             while (Interp::to_boolean(eval(n->kids[0].get(), env))) {
                 Comp c = exec(n->kids[1].get(), env);
-                if (c == Comp::Break) break;
-                if (c == Comp::Return) return c;
+                if (leaves_loop(c, mine)) { if (c == Comp::Break && jump_label.empty()) break; return c; }
             }
             return Comp::Normal;
-        case K::DoWhile:
+        }
+        case K::DoWhile: {
+            const std::vector<std::string> mine = take_loop_labels();
             do {
                 Comp c = exec(n->kids[0].get(), env);
-                if (c == Comp::Break) break;
-                if (c == Comp::Return) return c;
+                if (leaves_loop(c, mine)) { if (c == Comp::Break && jump_label.empty()) break; return c; }
             } while (Interp::to_boolean(eval(n->kids[1].get(), env)));
             return Comp::Normal;
-        case K::Break: return Comp::Break;
-        case K::Continue: return Comp::Continue;
+        }
+        case K::Break: jump_label = n->s; return Comp::Break;
+        case K::Continue: jump_label = n->s; return Comp::Continue;
+        case K::Labeled: {
+            const Node* st = n->kids[0].get();
+            std::vector<std::string> labels = {n->s};
+            while (st->k == K::Labeled) { labels.push_back(st->s); st = st->kids[0].get(); }      // a: b: for (...)
+            if (st->k == K::For || st->k == K::ForIn || st->k == K::ForOf || st->k == K::While || st->k == K::DoWhile) loop_labels = labels;    // a loop owns its labels (continue label)
+            Comp c = exec(st, env);
+            loop_labels.clear();
+            if (c == Comp::Break && std::find(labels.begin(), labels.end(), jump_label) != labels.end()) { jump_label.clear(); return Comp::Normal; }
+            return c;
+        }
         case K::Throw: throw Thrown{eval(n->kids[0].get(), env)};
         case K::Try: {
             Comp c = Comp::Normal;

@@ -173,6 +173,60 @@ b`;
         const Twice = make(2), Thrice = make(3);
         function f(t, x, y, z) { return [-1, new Twice(x).times(), new Thrice(y).times(), (typeof Twice === "function" ? 1 : 0) + 0 * z]; }
         f""", [-1, 3.0, 2.1, 1]),
+    "computed property names": ("""
+        function f(t, x, y, z) {
+            const k = "ab", i = 2;
+            const o = {[k]: x, ["c" + i]: y, [i * 2]: 7, [`m${i}`](v) { return v * 3; }, plain: 1};
+            return [-1, o.ab + o.c2, o[4] + o.plain + 0 * y, o.m2(z)];
+        }
+        f""", [-1, 1.5 + 0.7, 8, 1.2]),
+    "class fields": ("""
+        class Base { scale = 2; offset; static count = 3; static twice = this.count * 2; constructor(v) { this.v = v * this.scale; } }
+        class Child extends Base { extra = this.v + 1; constructor(v) { super(v); this.sum = this.extra + this.scale; } }
+        class Quiet extends Base { tag = 5; }
+        class Bare { w = 4; }
+        function f(t, x, y, z) {
+            const c = new Child(x), q = new Quiet(y), b = new Bare();
+            return [-1, c.v, c.sum, q.tag + q.v + b.w + Base.count + Base.twice + (c.offset === undefined ? 1 : 0) + 0 * z];
+        }
+        f""", [-1, 3.0, 3.0 + 1 + 2, 5 + 1.4 + 4 + 3 + 6 + 1]),
+    "labelled statements": ("""
+        function f(t, x, y, z) {
+            let hits = 0, rows = 0;
+            outer: for (let i = 0; i < 4; i++) {
+                rows++;
+                for (let j = 0; j < 4; j++) {
+                    if (j == 2) continue outer;
+                    if (i == 3) break outer;
+                    hits++;
+                }
+            }
+            let w = 0;
+            blk: { w = 1; if (w > 0) break blk; w = 100; }
+            let n = 0, k = 0;
+            scan: while (true) { k++; switch (k) { case 3: break scan; default: n += k; } }
+            return [-1, hits + 0 * x, rows + w + 0 * y, n + k + 0 * z];
+        }
+        f""", [-1, 6, 5, 6]),
+    "destructuring assignment": ("""
+        function f(t, x, y, z) {
+            let a = x, b = y, c, d, rest, o = {}, arr = [0, 0];
+            [a, b] = [b, a];
+            ({c, d = 7, ...rest} = {c: 2, e: 5, g: 6});
+            [o.p, arr[1], [c] = [9]] = [3, 4];
+            const r = ([a, b] = [a + 1, b + 1]);
+            let m, n2;
+            ({m, q: {n2}} = {m: 1, q: {n2: 2}});
+            return [-1, a, b + d + rest.e + rest.g + r.length, o.p + arr[1] + c + m + n2 + 0 * z];
+        }
+        f""", [-1, 0.7 + 1, 1.5 + 1 + 7 + 5 + 6 + 2, 3 + 4 + 9 + 1 + 2]),
+    "object rest in declarations": ("""
+        function pick({keep, ...others}) { return keep + Object.keys(others).length; }
+        function f(t, x, y, z) {
+            const {a, b: {c, ...inner}, ...outer} = {a: x, b: {c: 1, d: 2, e: 3}, f: 4, g: 5};
+            return [-1, a + c, inner.d + inner.e + outer.f + outer.g + 0 * y, pick({keep: z, u: 1, v: 2})];
+        }
+        f""", [-1, 2.5, 14, 2.4]),
 }
 
 
@@ -196,11 +250,10 @@ def test_modern_javascript_constructs(grt, oracle_mod, have_reference, tmp_path,
 REFUSED = {
     "generator function": ("function* gen() { yield 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "generator"),
     "async function": ("async function g() { return 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "async"),
-    "class field": ("class A { n = 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "class fields"),
     "tagged template": ("function tag(s) { return 1; }\nfunction f(t,x,y,z){ return [-1, tag`a`, 1, 1]; }\nf", "tagged template"),
-    "labelled statement": ("function f(t,x,y,z){ outer: for (var i = 0; i < 2; i++) {} return [-1,1,1,1]; }\nf", "labelled"),
-    "computed property name": ("function f(t,x,y,z){ var k = 'a'; var o = {[k]: 1}; return [-1,1,1,1]; }\nf", "computed property"),
-    "destructuring assignment": ("function f(t,x,y,z){ var a, b; [a, b] = [1, 2]; return [-1,a,b,1]; }\nf", "assignment target"),
+    "private class member": ("class A { #n = 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "unexpected character '#'"),
+    "shorthand default outside a pattern": ("function f(t,x,y,z){ var o = {q = 1}; return [-1,1,1,1]; }\nf", "shorthand property"),
+    "field of a derived class without a top-level super": ("class A {}\nclass B extends A { n = 1; constructor() { if (true) { super(); } } }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "top-level statement"),
     "class called without new": ("class A {}\nfunction f(t,x,y,z){ A(); return [-1,1,1,1]; }\nf", "'new'"),
 }
 

@@ -70,6 +70,10 @@ class Gen:
             f"const tag = `n${{{n}}}`; let r; switch (tag) {{ case 'n2': r = {a}; break; case 'n3': r = {b}; break; default: r = {c}; }} const tbl = {{n2: 2, n3: 3, n4: 4}}; return r * tbl[tag] + `${{1}}${{2}}` * 1;",
             f"class Acc {{ constructor(s) {{ this.s = s; }} add(v) {{ this.s = this.s + v; return this; }} get doubled() {{ return this.s * 2; }} static of(v) {{ return new Acc(v); }} }} "
             f"class Neg extends Acc {{ add(v) {{ return super.add(-v); }} }} return Acc.of({a}).add({b}).doubled + new Neg({c}).add({b}).s;",
+            # computed keys, class fields, labels, destructuring assignment, object rest
+            f"const key = 'k' + {n}; const o = {{[key]: {a}, ['w' + 1]: {b}, [{n} * 2]: {c}}}; let p, q, others; ({{[key]: p, ...others}} = o); [p, q] = [others.w1, p]; return p * 2 + q + others[{n} * 2];",
+            f"class Cell {{ gain = {n}; bias = {c}; static made = 1; constructor(v) {{ this.v = v * this.gain + this.bias; }} }} class Wide extends Cell {{ extra = this.v * 0.5; }} return new Cell({a}).v + new Wide({b}).extra + Cell.made;",
+            f"let acc = {c}; outer: for (let i = 0; i < {n}; i++) {{ for (let j = 0; j < 3; j++) {{ if (j == 1) continue outer; if (i == {n} - 1) break outer; acc = acc + {a} * (i + 1); }} }} done: {{ acc = acc * 0.5; if (acc !== 0) break done; acc = 0; }} return acc + {b};",
         ]
         body = bodies[self.force_body] if self.force_body is not None else self.pick(bodies)
         return f"(function() {{ {body} }})()"
@@ -133,9 +137,9 @@ def test_random_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_
     except FileNotFoundError:
         pytest.skip("reference not mounted")
     checked = 0
-    for k in range(12):
+    for k in range(13):
         seed = 1000 * block + k
-        js = Gen(seed, force_body=(k % 10) if block % 2 else None).script()
+        js = Gen(seed, force_body=(k % 13) if block % 2 else None).script()
         assert block % 2 == 0 or "(function() {" in js
         folder = write_folder(tmp_path / f"s{seed}", js)
         path = os.path.join(folder, "probe.js")
@@ -153,7 +157,7 @@ def test_random_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_
                 scale = max(1.0, np.abs(want[ok]).max()) if ok.any() else 1.0
                 assert not ok.any() or np.abs(got[ok] - want[ok]).max() <= 1e-9 * scale, (what, seed, np.abs(got[ok] - want[ok]).max(), js)
             checked += 1
-    assert checked == 24
+    assert checked == 26
 
 
 def complex_script(seed):
