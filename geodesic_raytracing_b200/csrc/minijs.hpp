@@ -16,6 +16,7 @@
 // reference obtains the metric function (/root/reference/js_interop.cpp:738-742).
 #pragma once
 #include <functional>
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -59,9 +60,85 @@ struct FuncDef;  // AST
 struct Env;
 using EnvP = std::shared_ptr<Env>;
 
+// The own properties of an object in JavaScript's enumeration order: integer-like keys ascending, then the other keys in the order they
+// were created (for-in, Object.keys, spread and object rest see this order; the reference's QuickJS does the same).  The interface is
+// the part of std::map the interpreter uses.  Objects are small: lookups go through a hash index, the order is rebuilt lazily.
+class PropMap {
+public:
+    using value_type = std::pair<std::string, Value>;
+    template <class Map, class Ref>
+    class Iter {
+    public:
+        Iter(Map* m, size_t pos) : m_(m), pos_(pos) {}
+        Ref& operator*() const { return m_->items_[m_->order_[pos_]]; }
+        Ref* operator->() const { return &m_->items_[m_->order_[pos_]]; }
+        Iter& operator++() { ++pos_; return *this; }
+        bool operator==(const Iter& o) const { return pos_ == o.pos_; }
+        bool operator!=(const Iter& o) const { return pos_ != o.pos_; }
+    private:
+        Map* m_;
+        size_t pos_;
+    };
+    using iterator = Iter<PropMap, value_type>;
+    using const_iterator = Iter<const PropMap, const value_type>;
+
+    Value& operator[](const std::string& key) {
+        auto it = index_.find(key);
+        if (it != index_.end()) return items_[it->second].second;
+        index_.emplace(key, items_.size());
+        items_.emplace_back(key, Value());
+        dirty_ = true;
+        return items_.back().second;
+    }
+    iterator find(const std::string& key) { return iterator(this, position(key)); }
+    const_iterator find(const std::string& key) const { return const_iterator(this, position(key)); }
+    size_t count(const std::string& key) const { return index_.count(key); }
+    size_t size() const { return items_.size(); }
+    bool empty() const { return items_.empty(); }
+    void clear() { items_.clear(); index_.clear(); order_.clear(); dirty_ = false; }
+    iterator begin() { sort(); return iterator(this, 0); }
+    iterator end() { return iterator(this, items_.size()); }
+    const_iterator begin() const { sort(); return const_iterator(this, 0); }
+    const_iterator end() const { return const_iterator(this, items_.size()); }
+
+private:
+    static bool array_index(const std::string& k, unsigned long long& out) {
+        if (k.empty() || k.size() > 10 || (k.size() > 1 && k[0] == '0')) return false;
+        out = 0;
+        for (char c : k) { if (c < '0' || c > '9') return false; out = out * 10 + (unsigned long long)(c - '0'); }
+        return out < 4294967295ull;
+    }
+    void sort() const {
+        if (!dirty_ && order_.size() == items_.size()) return;
+        std::vector<std::pair<unsigned long long, size_t>> ints;
+        std::vector<size_t> rest;
+        for (size_t i = 0; i < items_.size(); i++) {
+            unsigned long long v;
+            if (array_index(items_[i].first, v)) ints.emplace_back(v, i); else rest.push_back(i);
+        }
+        std::sort(ints.begin(), ints.end());
+        order_.clear();
+        for (auto& p : ints) order_.push_back(p.second);
+        order_.insert(order_.end(), rest.begin(), rest.end());
+        dirty_ = false;
+    }
+    size_t position(const std::string& key) const {
+        auto it = index_.find(key);
+        if (it == index_.end()) return items_.size();
+        sort();
+        for (size_t i = 0; i < order_.size(); i++) if (order_[i] == it->second) return i;
+        return items_.size();
+    }
+    std::vector<value_type> items_;                       // creation order
+    std::unordered_map<std::string, size_t> index_;
+    mutable std::vector<size_t> order_;                   // enumeration order: indices into items_
+    mutable bool dirty_ = false;
+    template <class, class> friend class Iter;
+};
+
 struct Object {
     enum Kind { Plain, Array, Function, Native, Host } kind = Plain;
-    std::map<std::string, Value> props;
+    PropMap props;
     std::vector<Value> arr;                 // Array
     const FuncDef* def = nullptr;           // Function
     EnvP env;                               // Function closure

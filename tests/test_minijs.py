@@ -173,6 +173,18 @@ b`;
         const Twice = make(2), Thrice = make(3);
         function f(t, x, y, z) { return [-1, new Twice(x).times(), new Thrice(y).times(), (typeof Twice === "function" ? 1 : 0) + 0 * z]; }
         f""", [-1, 3.0, 2.1, 1]),
+    "property enumeration order": ("""
+        function f(t, x, y, z) {
+            const o = {r: 1, theta: 2, phi: 3, 10: 4, 2: 5};
+            o.alpha = 6;
+            let code = 0, m = 1;
+            for (const k in o) { code += m * o[k]; m *= 10; }
+            let code2 = 0; m = 1;
+            for (const k of Object.keys({...o, beta: 7})) { code2 += m * (o[k] === undefined ? 7 : o[k]); m *= 10; }
+            const {theta, ...others} = o;
+            return [-1, code + 0 * x, code2 + 0 * y, Object.keys(others).join("") === "210rphialpha" ? 1 : 0];
+        }
+        f""", [-1, 632145, 7632145, 1]),
     "computed property names": ("""
         function f(t, x, y, z) {
             const k = "ab", i = 2;
