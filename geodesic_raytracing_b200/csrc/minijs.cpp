@@ -1164,6 +1164,8 @@ struct Evaluator {
     Value get_prop(const Node* n, const Value& objv, const std::string& key);
     void set_prop(const Node* n, const Value& objv, const std::string& key, const Value& v);
     Value array_method(const Node* n, const ObjP& a, const std::string& key);
+    Value string_method(const std::string& str, const std::string& key);
+    Value number_method(double num, const std::string& key);
 
     // ---- operators ----
     bool is_host(const Value& v) { return v.type == Value::Obj && v.obj->kind == Object::Host; }
@@ -1360,6 +1362,128 @@ Value Evaluator::array_method(const Node* n, const ObjP& a, const std::string& k
         for (size_t i = 0; i < s->arr.size(); i++) { if (i) out += sep; out += ip.to_string(s->arr[i]); }
         return Value(out);
     });
+    if (key == "reverse") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>&) {
+        auto s = self();
+        std::reverse(s->arr.begin(), s->arr.end());
+        return Value(s);
+    });
+    if (key == "shift") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>&) {
+        auto s = self();
+        if (s->arr.empty()) return Value();
+        Value v = s->arr.front();
+        s->arr.erase(s->arr.begin());
+        return v;
+    });
+    if (key == "unshift") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        s->arr.insert(s->arr.begin(), args.begin(), args.end());
+        return Value((double)s->arr.size());
+    });
+    if (key == "splice") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        const long len = (long)s->arr.size();
+        long b = args.size() > 0 ? (long)Interp::to_number(args[0]) : 0;
+        if (b < 0) b = std::max(0L, len + b);
+        b = std::min(b, len);
+        long cnt = args.size() > 1 ? (long)Interp::to_number(args[1]) : len - b;
+        cnt = std::max(0L, std::min(cnt, len - b));
+        if (args.empty()) cnt = 0;
+        std::vector<Value> removed(s->arr.begin() + b, s->arr.begin() + b + cnt);
+        s->arr.erase(s->arr.begin() + b, s->arr.begin() + b + cnt);
+        if (args.size() > 2) s->arr.insert(s->arr.begin() + b, args.begin() + 2, args.end());
+        return Value(Interp::make_array(removed));
+    });
+    if (key == "includes" || key == "lastIndexOf") return Interp::make_native([self, this, key](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        const Value want = args.empty() ? Value() : args[0];
+        for (size_t k = s->arr.size(); k-- > 0;) {
+            const bool same = strict_equal(s->arr[k], want) || (key == "includes" && want.type == Value::Number && std::isnan(want.num) && s->arr[k].type == Value::Number && std::isnan(s->arr[k].num));
+            if (same) return key == "includes" ? Value(true) : Value((double)k);
+        }
+        return key == "includes" ? Value(false) : Value(-1.0);
+    });
+    if (key == "at") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        long i = args.empty() ? 0 : (long)Interp::to_number(args[0]);
+        if (i < 0) i += (long)s->arr.size();
+        return i >= 0 && i < (long)s->arr.size() ? s->arr[(size_t)i] : Value();
+    });
+    if (key == "find" || key == "findIndex" || key == "findLast" || key == "findLastIndex") return Interp::make_native([self, key](Interp& ip, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        if (args.empty()) throw JsError("TypeError: callback required");
+        const bool last = key == "findLast" || key == "findLastIndex", want_index = key == "findIndex" || key == "findLastIndex";
+        const long n = (long)s->arr.size();
+        for (long k = last ? n - 1 : 0; last ? k >= 0 : k < n; k += last ? -1 : 1)
+            if (Interp::to_boolean(ip.call(args[0], Value(), {s->arr[(size_t)k], Value((double)k), Value(s)}))) return want_index ? Value((double)k) : s->arr[(size_t)k];
+        return want_index ? Value(-1.0) : Value();
+    });
+    if (key == "flat") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        const double depth = args.empty() || args[0].is_undefined() ? 1.0 : Interp::to_number(args[0]);
+        std::vector<Value> out;
+        std::function<void(const std::vector<Value>&, double)> go = [&](const std::vector<Value>& xs, double d) {
+            for (auto& v : xs) {
+                if (v.type == Value::Obj && v.obj->kind == Object::Array && d >= 1) go(v.obj->arr, d - 1);
+                else out.push_back(v);
+            }
+        };
+        go(s->arr, depth);
+        return Value(Interp::make_array(out));
+    });
+    if (key == "flatMap") return Interp::make_native([self](Interp& ip, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        if (args.empty()) throw JsError("TypeError: callback required");
+        std::vector<Value> out;
+        for (size_t i = 0; i < s->arr.size(); i++) {
+            Value r = ip.call(args[0], Value(), {s->arr[i], Value((double)i), Value(s)});
+            if (r.type == Value::Obj && r.obj->kind == Object::Array) out.insert(out.end(), r.obj->arr.begin(), r.obj->arr.end());
+            else out.push_back(r);
+        }
+        return Value(Interp::make_array(out));
+    });
+    if (key == "reduceRight") return Interp::make_native([self](Interp& ip, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        if (args.empty()) throw JsError("TypeError: callback required");
+        long i = (long)s->arr.size() - 1;
+        Value acc;
+        if (args.size() > 1) acc = args[1];
+        else { if (i < 0) throw JsError("TypeError: reduce of empty array"); acc = s->arr[(size_t)i--]; }
+        for (; i >= 0; i--) acc = ip.call(args[0], Value(), {acc, s->arr[(size_t)i], Value((double)i), Value(s)});
+        return acc;
+    });
+    // sort: stable; without a comparator by the elements' strings (10 < 9), undefined last - as JavaScript does
+    if (key == "sort") return Interp::make_native([self](Interp& ip, const Value&, std::vector<Value>& args) {
+        auto s = self();
+        const bool has_cmp = !args.empty() && !args[0].is_undefined();
+        Value cmp = has_cmp ? args[0] : Value();
+        std::vector<Value> defined, undefined;
+        for (auto& v : s->arr) (v.is_undefined() ? undefined : defined).push_back(v);
+        std::vector<std::string> keys;
+        if (!has_cmp) for (auto& v : defined) keys.push_back(ip.to_string(v));
+        std::vector<size_t> order(defined.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            if (!has_cmp) return keys[a] < keys[b];
+            const double r = Interp::to_number(ip.call(cmp, Value(), {defined[a], defined[b]}));
+            return r < 0;
+        });
+        std::vector<Value> out;
+        for (size_t i : order) out.push_back(defined[i]);
+        out.insert(out.end(), undefined.begin(), undefined.end());
+        s->arr = out;
+        return Value(s);
+    });
+    if (key == "keys" || key == "values" || key == "entries") return Interp::make_native([self, key](Interp&, const Value&, std::vector<Value>&) {
+        // no iterator protocol in this interpreter: the sequence itself, as an array (for-of and spread take it)
+        auto s = self();
+        std::vector<Value> out;
+        for (size_t i = 0; i < s->arr.size(); i++) {
+            if (key == "keys") out.push_back(Value((double)i));
+            else if (key == "values") out.push_back(s->arr[i]);
+            else out.push_back(Value(Interp::make_array({Value((double)i), s->arr[i]})));
+        }
+        return Value(Interp::make_array(out));
+    });
     if (key == "map" || key == "forEach" || key == "filter" || key == "reduce" || key == "some" || key == "every")
         return Interp::make_native([self, key](Interp& ip, const Value&, std::vector<Value>& args) {
             auto s = self();
@@ -1389,6 +1513,129 @@ Value Evaluator::array_method(const Node* n, const ObjP& a, const std::string& k
     return Value();
 }
 
+// Methods of string values (ASCII semantics: metric scripts build names and labels, not text)
+Value Evaluator::string_method(const std::string& str, const std::string& key) {
+    auto arg_str = [](Interp& ip, std::vector<Value>& a, size_t i) { return i < a.size() ? ip.to_string(a[i]) : std::string("undefined"); };
+    auto clamp_index = [](double d, long len) { long i = std::isnan(d) ? 0 : (long)std::max(-1e15, std::min(1e15, d)); if (i < 0) i = std::max(0L, len + i); return std::min(i, len); };
+    const std::string s = str;
+    if (key == "charAt") return Value(Interp::make_native([s](Interp&, const Value&, std::vector<Value>& a) { long i = a.empty() ? 0 : (long)Interp::to_number(a[0]); return Value(i >= 0 && i < (long)s.size() ? std::string(1, s[(size_t)i]) : std::string()); }));
+    if (key == "charCodeAt") return Value(Interp::make_native([s](Interp&, const Value&, std::vector<Value>& a) { long i = a.empty() ? 0 : (long)Interp::to_number(a[0]); return Value(i >= 0 && i < (long)s.size() ? (double)(unsigned char)s[(size_t)i] : NAN); }));
+    if (key == "at") return Value(Interp::make_native([s](Interp&, const Value&, std::vector<Value>& a) { long i = a.empty() ? 0 : (long)Interp::to_number(a[0]); if (i < 0) i += (long)s.size(); return i >= 0 && i < (long)s.size() ? Value(std::string(1, s[(size_t)i])) : Value(); }));
+    if (key == "indexOf" || key == "lastIndexOf" || key == "includes" || key == "startsWith" || key == "endsWith")
+        return Value(Interp::make_native([s, key, arg_str](Interp& ip, const Value&, std::vector<Value>& a) {
+            const std::string what = arg_str(ip, a, 0);
+            if (key == "startsWith") return Value(s.compare(0, what.size(), what) == 0);
+            if (key == "endsWith") return Value(s.size() >= what.size() && s.compare(s.size() - what.size(), what.size(), what) == 0);
+            const size_t at = key == "lastIndexOf" ? s.rfind(what) : s.find(what, a.size() > 1 ? (size_t)std::max(0.0, Interp::to_number(a[1])) : 0);
+            if (key == "includes") return Value(at != std::string::npos);
+            return Value(at == std::string::npos ? -1.0 : (double)at);
+        }));
+    if (key == "slice" || key == "substring" || key == "substr")
+        return Value(Interp::make_native([s, key, clamp_index](Interp&, const Value&, std::vector<Value>& a) {
+            const long len = (long)s.size();
+            const double d0 = a.empty() ? 0.0 : Interp::to_number(a[0]), d1 = a.size() > 1 && !a[1].is_undefined() ? Interp::to_number(a[1]) : (double)len;
+            long b, e;
+            if (key == "slice") { b = clamp_index(d0, len); e = clamp_index(d1, len); }
+            else if (key == "substr") { b = clamp_index(d0, len); e = a.size() > 1 && !a[1].is_undefined() ? std::min(len, b + std::max(0L, (long)d1)) : len; }
+            else { b = std::min(len, std::max(0L, std::isnan(d0) ? 0L : (long)d0)); e = std::min(len, std::max(0L, std::isnan(d1) ? 0L : (long)d1)); if (b > e) std::swap(b, e); }
+            return Value(e > b ? s.substr((size_t)b, (size_t)(e - b)) : std::string());
+        }));
+    if (key == "toUpperCase" || key == "toLowerCase")
+        return Value(Interp::make_native([s, key](Interp&, const Value&, std::vector<Value>&) { std::string o = s; for (auto& c : o) c = (char)(key == "toUpperCase" ? toupper((unsigned char)c) : tolower((unsigned char)c)); return Value(o); }));
+    if (key == "trim" || key == "trimStart" || key == "trimEnd")
+        return Value(Interp::make_native([s, key](Interp&, const Value&, std::vector<Value>&) {
+            size_t b = 0, e = s.size();
+            if (key != "trimEnd") while (b < e && isspace((unsigned char)s[b])) b++;
+            if (key != "trimStart") while (e > b && isspace((unsigned char)s[e - 1])) e--;
+            return Value(s.substr(b, e - b));
+        }));
+    if (key == "repeat") return Value(Interp::make_native([s](Interp&, const Value&, std::vector<Value>& a) {
+        const double n = a.empty() ? 0 : Interp::to_number(a[0]);
+        if (n < 0 || n * (double)s.size() > 1e7) throw JsError("RangeError: invalid count value");
+        std::string o;
+        for (long i = 0; i < (long)n; i++) o += s;
+        return Value(o);
+    }));
+    if (key == "padStart" || key == "padEnd") return Value(Interp::make_native([s, key](Interp& ip, const Value&, std::vector<Value>& a) {
+        const long want = a.empty() ? 0 : (long)Interp::to_number(a[0]);
+        const std::string fill = a.size() > 1 && !a[1].is_undefined() ? ip.to_string(a[1]) : " ";
+        if (want <= (long)s.size() || fill.empty() || want > 10000000) return Value(s);
+        std::string pad;
+        while ((long)(pad.size() + s.size()) < want) pad += fill;
+        pad.resize((size_t)want - s.size());
+        return Value(key == "padStart" ? pad + s : s + pad);
+    }));
+    if (key == "concat") return Value(Interp::make_native([s](Interp& ip, const Value&, std::vector<Value>& a) { std::string o = s; for (auto& v : a) o += ip.to_string(v); return Value(o); }));
+    if (key == "split") return Value(Interp::make_native([s](Interp& ip, const Value&, std::vector<Value>& a) {
+        std::vector<Value> out;
+        if (a.empty() || a[0].is_undefined()) return Value(Interp::make_array({Value(s)}));
+        const std::string sep = ip.to_string(a[0]);
+        if (sep.empty()) { for (char c : s) out.push_back(Value(std::string(1, c))); return Value(Interp::make_array(out)); }
+        size_t from = 0;
+        for (;;) {
+            const size_t at = s.find(sep, from);
+            out.push_back(Value(s.substr(from, at == std::string::npos ? std::string::npos : at - from)));
+            if (at == std::string::npos) break;
+            from = at + sep.size();
+        }
+        return Value(Interp::make_array(out));
+    }));
+    if (key == "replace" || key == "replaceAll") return Value(Interp::make_native([s, key](Interp& ip, const Value&, std::vector<Value>& a) {
+        // string patterns only (there are no regular expressions in this interpreter)
+        const std::string what = a.empty() ? "undefined" : ip.to_string(a[0]), with = a.size() > 1 ? ip.to_string(a[1]) : "undefined";
+        std::string o = s;
+        size_t from = 0;
+        while (!what.empty()) {
+            const size_t at = o.find(what, from);
+            if (at == std::string::npos) break;
+            o.replace(at, what.size(), with);
+            from = at + with.size();
+            if (key == "replace") break;
+        }
+        return Value(o);
+    }));
+    if (key == "toString" || key == "valueOf") return Value(Interp::make_native([s](Interp&, const Value&, std::vector<Value>&) { return Value(s); }));
+    return Value();
+}
+
+// Methods of number values
+Value Evaluator::number_method(double num, const std::string& key) {
+    if (key == "toFixed") return Value(Interp::make_native([num](Interp& ip, const Value&, std::vector<Value>& a) {
+        const int digits = a.empty() ? 0 : (int)Interp::to_number(a[0]);
+        if (digits < 0 || digits > 100) throw JsError("RangeError: toFixed() digits argument must be between 0 and 100");
+        if (!std::isfinite(num) || std::fabs(num) >= 1e21) return Value(ip.to_string(Value(num)));
+        char buf[160];
+        snprintf(buf, sizeof buf, "%.*f", digits, num);
+        return Value(std::string(buf));
+    }));
+    if (key == "toPrecision") return Value(Interp::make_native([num](Interp& ip, const Value&, std::vector<Value>& a) {
+        if (a.empty() || a[0].is_undefined() || !std::isfinite(num)) return Value(ip.to_string(Value(num)));
+        const int p = (int)Interp::to_number(a[0]);
+        if (p < 1 || p > 100) throw JsError("RangeError: toPrecision() argument must be between 1 and 100");
+        char buf[160];
+        snprintf(buf, sizeof buf, "%.*e", p - 1, num);
+        const int e = atoi(strchr(buf, 'e') + 1);
+        if (e < -6 || e >= p) {                                        // exponential form, "e+N" without zero padding
+            std::string m(buf, strchr(buf, 'e'));
+            return Value(m + "e" + (e >= 0 ? "+" : "-") + std::to_string(std::abs(e)));
+        }
+        snprintf(buf, sizeof buf, "%.*f", std::max(0, p - 1 - e), num);
+        return Value(std::string(buf));
+    }));
+    if (key == "toString") return Value(Interp::make_native([num](Interp& ip, const Value&, std::vector<Value>& a) {
+        const int radix = a.empty() || a[0].is_undefined() ? 10 : (int)Interp::to_number(a[0]);
+        if (radix == 10 || !std::isfinite(num) || num != std::floor(num)) return Value(ip.to_string(Value(num)));
+        if (radix < 2 || radix > 36) throw JsError("RangeError: toString() radix must be between 2 and 36");
+        std::string o;
+        double v = std::fabs(num);
+        if (v == 0) o = "0";
+        while (v >= 1) { const int d = (int)std::fmod(v, radix); o.insert(o.begin(), (char)(d < 10 ? '0' + d : 'a' + d - 10)); v = std::floor(v / radix); }
+        return Value(num < 0 ? "-" + o : o);
+    }));
+    if (key == "valueOf") return Value(Interp::make_native([num](Interp&, const Value&, std::vector<Value>&) { return Value(num); }));
+    return Value();
+}
+
 Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& key) {
     if (objv.type == Value::Undefined || objv.type == Value::Null)
         fail(n, "TypeError: cannot read property '" + key + "' of " + (objv.type == Value::Null ? "null" : "undefined"));
@@ -1396,8 +1643,9 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
         if (key == "length") return Value((double)objv.str.size());
         size_t idx;
         if (array_index(key, idx) && idx < objv.str.size()) return Value(std::string(1, objv.str[idx]));
-        return Value();
+        return string_method(objv.str, key);
     }
+    if (objv.type == Value::Number) return number_method(objv.num, key);
     if (objv.type != Value::Obj) return Value();
     const ObjP& o = objv.obj;
     if (o->get_hook) {
@@ -1518,6 +1766,9 @@ Value Evaluator::binary_op(const Node* n, const std::string& op, const Value& a,
         if (a.type != Value::Obj) return Value(false);
         for (const Object* c = a.obj->klass.get(); c; c = c->klass.get())
             if (c == b.obj.get()) return Value(true);
+        if (b.obj.get() == in.builtin_array.get()) return Value(a.obj->kind == Object::Array);
+        if (b.obj.get() == in.builtin_object.get()) return Value(true);
+        if (b.obj.get() == in.builtin_function.get()) return Value(a.obj->kind == Object::Function || a.obj->kind == Object::Native);
         return Value(false);
     }
     double x = Interp::to_number(a), y = Interp::to_number(b);
@@ -1670,6 +1921,17 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             return r.type == Value::Obj ? r : self;
         }
         case K::Unary: {
+            if (n->s == "delete" && (n->kids[0]->k == K::Member || n->kids[0]->k == K::Index)) {       // delete o.k / delete o[k] / delete a[i]
+                const Node* target = n->kids[0].get();
+                Value o = eval(target->kids[0].get(), env);
+                const std::string key = target->k == K::Member ? target->s : key_of(eval(target->kids[1].get(), env));
+                if (o.type == Value::Obj) {
+                    size_t idx;
+                    if (o.obj->kind == Object::Array && array_index(key, idx)) { if (idx < o.obj->arr.size()) o.obj->arr[idx] = Value(); }   // a hole reads as undefined
+                    else o.obj->props.erase(key);
+                }
+                return Value(true);
+            }
             if (n->s == "typeof") {
                 Value v;
                 if (n->kids[0]->k == K::Ident && !lookup_env(env.get(), n->kids[0]->s) && !in.global_getters.count(n->kids[0]->s)) return Value("undefined");
@@ -1685,7 +1947,7 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             }
             Value v = eval(n->kids[0].get(), env);
             if (n->s == "void") return Value();
-            if (n->s == "delete") return Value(true);
+            if (n->s == "delete") return Value(true);      // (a delete of a property is handled before the operand is evaluated, below)
             if (n->s == "!") return Value(!Interp::to_boolean(v));
             if (is_host(v)) {
                 if (!in.host_operator) fail(n, "TypeError: no operator overloads installed");
@@ -1833,10 +2095,19 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
             const std::vector<std::string> mine = take_loop_labels();
             EnvP loop = new_env(env, false);
             exec(n->kids[0].get(), loop);
+            // for (let i ...): every iteration has its own binding of the loop variables - a closure made in the body keeps the value of
+            // ITS iteration (the copy is taken after the body and before the update expression, as JavaScript does)
+            const bool per_iteration = n->kids[0]->k == K::VarDecl && n->kids[0]->s != "var";
             while (true) {
                 if (n->kids[1]->k != K::Empty && !Interp::to_boolean(eval(n->kids[1].get(), loop))) break;
                 Comp c = exec(n->kids[3].get(), loop);
                 if (leaves_loop(c, mine)) { if (c == Comp::Break && jump_label.empty()) break; return c; }
+                if (per_iteration) {
+                    EnvP next = new_env(env, false);
+                    next->vars = loop->vars;
+                    next->is_const = loop->is_const;
+                    loop = next;
+                }
                 if (n->kids[2]->k != K::Empty) eval(n->kids[2].get(), loop);
             }
             return Comp::Normal;
@@ -1905,9 +2176,7 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
             } catch (JsError& e) {
                 if (n->kids[1]->k == K::Empty) { run_finally(); throw; }
                 EnvP h = new_env(env, false);
-                auto eo = Interp::make_object();
-                eo->props["message"] = Value(std::string(e.what()));
-                if (!n->s.empty()) h->vars[n->s] = Value(eo);
+                if (!n->s.empty()) h->vars[n->s] = in.make_error_object(e.what());
                 c = exec(n->kids[1].get(), h);
             }
             run_finally();
@@ -1981,17 +2250,29 @@ std::string Interp::to_string(const Value& v) {
         case Value::Number: {
             if (std::isnan(v.num)) return "NaN";
             if (std::isinf(v.num)) return v.num > 0 ? "Infinity" : "-Infinity";
+            if (v.num == 0) return "0";
+            // Number::toString: the shortest digit string that reads back as the same double, laid out as ECMAScript does
+            // (plain decimals for 1e-7 <= |x| < 1e21, otherwise d.ddde+N)
             char buf[40];
-            if (v.num == std::floor(v.num) && std::fabs(v.num) < 1e21) snprintf(buf, sizeof buf, "%.0f", v.num);
-            else snprintf(buf, sizeof buf, "%.17g", v.num);
-            // shortest round-trip
-            if (!(v.num == std::floor(v.num))) {
-                for (int prec = 1; prec <= 17; prec++) {
-                    snprintf(buf, sizeof buf, "%.*g", prec, v.num);
-                    if (strtod(buf, nullptr) == v.num) break;
-                }
+            int prec = 1;
+            for (; prec <= 17; prec++) {
+                snprintf(buf, sizeof buf, "%.*e", prec - 1, std::fabs(v.num));
+                if (strtod(buf, nullptr) == std::fabs(v.num)) break;
             }
-            return buf;
+            std::string digits;
+            for (const char* c = buf; *c && *c != 'e'; c++) if (*c != '.') digits += *c;
+            const int exp10 = atoi(strchr(buf, 'e') + 1);        // value = 0.d1d2... x 10^(exp10 + 1)
+            const int n = exp10 + 1, k = (int)digits.size();
+            std::string out = v.num < 0 ? "-" : "";
+            if (k <= n && n <= 21) out += digits + std::string((size_t)(n - k), '0');
+            else if (0 < n && n <= 21) out += digits.substr(0, (size_t)n) + "." + digits.substr((size_t)n);
+            else if (-6 < n && n <= 0) out += "0." + std::string((size_t)(-n), '0') + digits;
+            else {
+                out += digits.substr(0, 1);
+                if (k > 1) out += "." + digits.substr(1);
+                out += std::string("e") + (n - 1 >= 0 ? "+" : "-") + std::to_string(std::abs(n - 1));
+            }
+            return out;
         }
         case Value::String: return v.str;
         case Value::Obj:
@@ -2041,9 +2322,56 @@ Interp::Interp() {
     globals->vars["Infinity"] = Value(INFINITY);
     globals->vars["isNaN"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::isnan(a.empty() ? NAN : to_number(a[0]))); }));
     globals->vars["isFinite"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value((bool)std::isfinite(a.empty() ? NAN : to_number(a[0]))); }));
-    globals->vars["parseFloat"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? NAN : strtod(ip.to_string(a[0]).c_str(), nullptr)); }));
-    globals->vars["parseInt"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? NAN : std::trunc(strtod(ip.to_string(a[0]).c_str(), nullptr))); }));
-    globals->vars["Number"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(a.empty() ? 0.0 : to_number(a[0])); }));
+    auto parse_float = make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        if (a.empty()) return Value(NAN);
+        const std::string s = ip.to_string(a[0]);
+        size_t b = s.find_first_not_of(" \t\n\r");
+        if (b == std::string::npos) return Value(NAN);
+        if (s.compare(b, 2, "0x") == 0 || s.compare(b, 2, "0X") == 0) return Value(0.0);      // parseFloat reads the leading zero only
+        char* end = nullptr;
+        const double v = strtod(s.c_str() + b, &end);
+        return Value(end == s.c_str() + b ? NAN : v);
+    });
+    auto parse_int = make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        if (a.empty()) return Value(NAN);
+        std::string s = ip.to_string(a[0]);
+        size_t b = s.find_first_not_of(" \t\n\r");
+        if (b == std::string::npos) return Value(NAN);
+        bool neg = false;
+        if (s[b] == '+' || s[b] == '-') { neg = s[b] == '-'; b++; }
+        int radix = a.size() > 1 && !a[1].is_undefined() ? (int)to_number(a[1]) : 0;
+        if ((radix == 0 || radix == 16) && (s.compare(b, 2, "0x") == 0 || s.compare(b, 2, "0X") == 0)) { radix = 16; b += 2; }
+        if (radix == 0) radix = 10;
+        if (radix < 2 || radix > 36) return Value(NAN);
+        double v = 0;
+        bool any = false;
+        for (; b < s.size(); b++) {
+            const char c = s[b];
+            const int d = c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'z' ? c - 'a' + 10 : (c >= 'A' && c <= 'Z' ? c - 'A' + 10 : 99));
+            if (d >= radix) break;
+            v = v * radix + d;
+            any = true;
+        }
+        return Value(any ? (neg ? -v : v) : NAN);
+    });
+    globals->vars["parseFloat"] = Value(parse_float);
+    globals->vars["parseInt"] = Value(parse_int);
+    auto number_ctor = make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(a.empty() ? 0.0 : to_number(a[0])); });
+    number_ctor->props["isFinite"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Number && std::isfinite(a[0].num)); }));
+    number_ctor->props["isNaN"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Number && std::isnan(a[0].num)); }));
+    number_ctor->props["isInteger"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Number && std::isfinite(a[0].num) && a[0].num == std::floor(a[0].num)); }));
+    number_ctor->props["isSafeInteger"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Number && std::isfinite(a[0].num) && a[0].num == std::floor(a[0].num) && std::fabs(a[0].num) <= 9007199254740991.0); }));
+    number_ctor->props["parseFloat"] = Value(parse_float);
+    number_ctor->props["parseInt"] = Value(parse_int);
+    number_ctor->props["EPSILON"] = Value(2.220446049250313e-16);
+    number_ctor->props["MAX_SAFE_INTEGER"] = Value(9007199254740991.0);
+    number_ctor->props["MIN_SAFE_INTEGER"] = Value(-9007199254740991.0);
+    number_ctor->props["MAX_VALUE"] = Value(1.7976931348623157e308);
+    number_ctor->props["MIN_VALUE"] = Value(5e-324);
+    number_ctor->props["POSITIVE_INFINITY"] = Value(INFINITY);
+    number_ctor->props["NEGATIVE_INFINITY"] = Value(-INFINITY);
+    number_ctor->props["NaN"] = Value(NAN);
+    globals->vars["Number"] = Value(number_ctor);
     globals->vars["String"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? std::string() : ip.to_string(a[0])); }));
     globals->vars["Boolean"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && to_boolean(a[0])); }));
     auto array_ctor = make_native([](Interp&, const Value&, std::vector<Value>& a) {
@@ -2054,7 +2382,27 @@ Interp::Interp() {
         return Value(make_array(a));
     });
     array_ctor->props["isArray"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && a[0].type == Value::Obj && a[0].obj->kind == Object::Array); }));
+    array_ctor->props["of"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(make_array(a)); }));
+    // Array.from(array | string | {length: n} [, (v, i) => ...])
+    array_ctor->props["from"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        std::vector<Value> items;
+        if (!a.empty() && a[0].type == Value::String) for (char c : a[0].str) items.push_back(Value(std::string(1, c)));
+        else if (!a.empty() && a[0].type == Value::Obj && a[0].obj->kind == Object::Array) items = a[0].obj->arr;
+        else if (!a.empty() && a[0].type == Value::Obj) {
+            auto len = a[0].obj->props.find("length");
+            const double n = len == a[0].obj->props.end() ? 0.0 : to_number(len->second);
+            if (n > 1e7) throw JsError("RangeError: invalid array length");
+            for (size_t i = 0; n > 0 && i < (size_t)n; i++) {
+                auto it = a[0].obj->props.find(std::to_string(i));
+                items.push_back(it == a[0].obj->props.end() ? Value() : it->second);
+            }
+        }
+        if (a.size() > 1 && !a[1].is_undefined())
+            for (size_t i = 0; i < items.size(); i++) items[i] = ip.call(a[1], Value(), {items[i], Value((double)i)});
+        return Value(make_array(items));
+    }));
     globals->vars["Array"] = Value(array_ctor);
+    builtin_array = array_ctor;
     auto object_ctor = make_native([](Interp&, const Value&, std::vector<Value>&) { return Value(make_object()); });
     object_ctor->props["keys"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
         std::vector<Value> keys;
@@ -2064,7 +2412,69 @@ Interp::Interp() {
         }
         return Value(make_array(keys));
     }));
+    auto own_keys = [](const Value& v) {
+        std::vector<std::string> keys;
+        if (v.type == Value::Obj) {
+            if (v.obj->kind == Object::Array) for (size_t i = 0; i < v.obj->arr.size(); i++) keys.push_back(std::to_string(i));
+            for (auto& kv : v.obj->props) if (kv.first.compare(0, 5, "$get$") != 0 && kv.first.compare(0, 5, "$set$") != 0) keys.push_back(kv.first);
+        }
+        return keys;
+    };
+    auto own_value = [](const Value& v, const std::string& k) {
+        size_t idx = 0;
+        bool is_index = !k.empty() && k.find_first_not_of("0123456789") == std::string::npos;
+        if (is_index) idx = (size_t)strtoull(k.c_str(), nullptr, 10);
+        if (v.obj->kind == Object::Array && is_index) return idx < v.obj->arr.size() ? v.obj->arr[idx] : Value();
+        auto it = v.obj->props.find(k);
+        return it == v.obj->props.end() ? Value() : it->second;
+    };
+    object_ctor->props["values"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+        std::vector<Value> out;
+        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(own_value(a[0], k));
+        return Value(make_array(out));
+    }));
+    object_ctor->props["entries"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+        std::vector<Value> out;
+        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(Value(make_array({Value(k), own_value(a[0], k)})));
+        return Value(make_array(out));
+    }));
+    object_ctor->props["fromEntries"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        auto o = make_object();
+        if (!a.empty() && a[0].type == Value::Obj && a[0].obj->kind == Object::Array)
+            for (auto& e : a[0].obj->arr)
+                if (e.type == Value::Obj && e.obj->kind == Object::Array && e.obj->arr.size() >= 2) o->props[ip.to_string(e.obj->arr[0])] = e.obj->arr[1];
+        return Value(o);
+    }));
+    object_ctor->props["assign"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+        if (a.empty() || a[0].type != Value::Obj) throw JsError("TypeError: Object.assign needs an object");
+        for (size_t i = 1; i < a.size(); i++)
+            if (a[i].type == Value::Obj) for (auto& k : own_keys(a[i])) a[0].obj->props[k] = own_value(a[i], k);
+        return a[0];
+    }));
+    for (const char* same : {"freeze", "seal", "preventExtensions"})      // no property attributes in this interpreter: the object is handed back
+        object_ctor->props[same] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return a.empty() ? Value() : a[0]; }));
     globals->vars["Object"] = Value(object_ctor);
+    builtin_object = object_ctor;
+    builtin_function = make_native([](Interp&, const Value&, std::vector<Value>&) -> Value { throw JsError("EvalError: the Function constructor is not available to metric scripts"); });
+    globals->vars["Function"] = Value(builtin_function);
+    // Error and its kinds: `new TypeError(msg)` -> {message, name}, `e instanceof Error`; errors the interpreter raises itself are
+    // caught as objects of the matching kind (make_error_object)
+    for (const char* kind : {"Error", "TypeError", "RangeError", "ReferenceError", "SyntaxError", "EvalError"}) {
+        const std::string name = kind;
+        auto ctor = std::make_shared<Object>();
+        ctor->kind = Object::Native;
+        std::weak_ptr<Object> self = ctor;
+        ctor->native = [name, self](Interp& ip, const Value&, std::vector<Value>& a) {
+            auto e = make_object();
+            e->klass = self.lock();
+            e->props["message"] = Value(a.empty() || a[0].is_undefined() ? std::string() : ip.to_string(a[0]));
+            e->props["name"] = Value(name);
+            return Value(e);
+        };
+        if (name != "Error") ctor->klass = error_types["Error"];
+        error_types[name] = ctor;
+        globals->vars[name] = Value(ctor);
+    }
     auto console = make_object();
     auto logfn = make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
         std::string line;
@@ -2091,6 +2501,19 @@ Interp::~Interp() {
             if (kv.second.type == Value::Obj && kv.second.obj->env) clear(kv.second.obj->env.get());
     };
     clear(globals.get());
+}
+
+Value Interp::make_error_object(const std::string& what) {
+    auto e = make_object();
+    std::string kind = "Error";
+    for (auto& kv : error_types) {
+        const size_t at = what.find(kv.first + ": ");
+        if (kv.first != "Error" && at != std::string::npos) { kind = kv.first; break; }
+    }
+    e->klass = error_types[kind];
+    e->props["message"] = Value(what);
+    e->props["name"] = Value(kind);
+    return Value(e);
 }
 
 void Interp::set_global(const std::string& name, const Value& v) { globals->vars[name] = v; }

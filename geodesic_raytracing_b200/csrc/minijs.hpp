@@ -96,6 +96,16 @@ public:
     size_t size() const { return items_.size(); }
     bool empty() const { return items_.empty(); }
     void clear() { items_.clear(); index_.clear(); order_.clear(); dirty_ = false; }
+    bool erase(const std::string& key) {
+        auto it = index_.find(key);
+        if (it == index_.end()) return false;
+        const size_t at = it->second;
+        items_.erase(items_.begin() + (long)at);
+        index_.erase(it);
+        for (auto& kv : index_) if (kv.second > at) kv.second--;
+        dirty_ = true;
+        return true;
+    }
     iterator begin() { sort(); return iterator(this, 0); }
     iterator end() { return iterator(this, items_.size()); }
     const_iterator begin() const { sort(); return const_iterator(this, 0); }
@@ -190,6 +200,10 @@ struct Interp {
     std::string to_string(const Value& v);
 
     EnvP globals;
+    ObjP builtin_array, builtin_object, builtin_function;      // the constructors `instanceof` knows without a class chain
+    std::map<std::string, ObjP> error_types;                  // Error, TypeError, RangeError, ReferenceError, SyntaxError
+    // the object a `catch` binds for an error raised by the interpreter itself ("... TypeError: cannot read ..."): message, name, class
+    Value make_error_object(const std::string& what);
     std::vector<std::unique_ptr<Program>> programs;  // keep ASTs alive for closures
     std::unordered_map<std::string, std::function<Value(Interp&)>> global_getters;
     int call_depth = 0;
