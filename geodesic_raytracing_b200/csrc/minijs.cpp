@@ -28,6 +28,47 @@ static const std::set<std::string> kKeywords = {
     "throw", "try", "catch", "finally", "void", "delete", "instanceof", "class", "switch",
     "case", "default"};
 
+// one escape sequence after a backslash at src[pos] (pos is advanced): appends the character(s); code points above 0x7f as UTF-8
+static void read_escape(const std::string& src, size_t& pos, std::string& out, int& line) {
+    auto hex = [&](size_t count, unsigned& v) {
+        v = 0;
+        if (pos + count > src.size()) return false;
+        for (size_t i = 0; i < count; i++) { if (!isxdigit((unsigned char)src[pos + i])) return false; v = v * 16 + (unsigned)(isdigit((unsigned char)src[pos + i]) ? src[pos + i] - '0' : tolower((unsigned char)src[pos + i]) - 'a' + 10); }
+        pos += count;
+        return true;
+    };
+    auto utf8 = [&](unsigned cp) {
+        if (cp < 0x80) out += (char)cp;
+        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+        else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+        else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+    };
+    const char e = src[pos++];
+    unsigned v = 0;
+    switch (e) {
+        case 'n': out += '\n'; break;
+        case 't': out += '\t'; break;
+        case 'r': out += '\r'; break;
+        case 'b': out += '\b'; break;
+        case 'f': out += '\f'; break;
+        case 'v': out += '\v'; break;
+        case '0': out += '\0'; break;
+        case '\n': line++; break;                                   // line continuation
+        case 'x': if (hex(2, v)) utf8(v); else out += 'x'; break;
+        case 'u':
+            if (pos < src.size() && src[pos] == '{') {
+                size_t close = src.find('}', pos);
+                unsigned cp = 0;
+                bool ok = close != std::string::npos && close > pos + 1;
+                for (size_t i = pos + 1; ok && i < close; i++) { if (!isxdigit((unsigned char)src[i])) ok = false; else cp = cp * 16 + (unsigned)(isdigit((unsigned char)src[i]) ? src[i] - '0' : tolower((unsigned char)src[i]) - 'a' + 10); }
+                if (ok) { utf8(cp); pos = close + 1; } else out += 'u';
+            } else if (hex(4, v)) utf8(v);
+            else out += 'u';
+            break;
+        default: out += e;
+    }
+}
+
 struct Lexer {
     const std::string& src;
     std::string name;
@@ -74,14 +115,41 @@ struct Lexer {
             if (pos >= src.size()) { t.type = Tok::End; toks.push_back(t); return; }
             char c = src[pos];
             if (isdigit((unsigned char)c) || (c == '.' && pos + 1 < src.size() && isdigit((unsigned char)src[pos + 1]))) {
-                if (c == '0' && pos + 1 < src.size() && (src[pos + 1] == 'x' || src[pos + 1] == 'X')) {
-                    char* end;
-                    t.num = (double)strtoull(src.c_str() + pos, &end, 16);
-                    pos = end - src.c_str();
+                const char kind = c == '0' && pos + 1 < src.size() ? (char)tolower((unsigned char)src[pos + 1]) : 0;
+                if (kind == 'x' || kind == 'o' || kind == 'b') {              // 0x1f  0o17  0b101, with numeric separators
+                    const int radix = kind == 'x' ? 16 : (kind == 'o' ? 8 : 2);
+                    pos += 2;
+                    double v = 0;
+                    bool any = false;
+                    for (; pos < src.size(); pos++) {
+                        const char d = src[pos];
+                        if (d == '_' && any) continue;
+                        const int digit = isdigit((unsigned char)d) ? d - '0' : (isalpha((unsigned char)d) ? tolower((unsigned char)d) - 'a' + 10 : 99);
+                        if (digit >= radix) break;
+                        v = v * radix + digit;
+                        any = true;
+                    }
+                    if (!any) fail("missing digits after the numeric prefix");
+                    t.num = v;
                 } else {
-                    char* end;
-                    t.num = strtod(src.c_str() + pos, &end);
-                    pos = end - src.c_str();
+                    // decimal: the text with its numeric separators removed (1_000.5e1_0)
+                    std::string text;
+                    size_t q = pos;
+                    bool seen_e = false, seen_dot = false;
+                    for (; q < src.size(); q++) {
+                        const char d = src[q];
+                        if (isdigit((unsigned char)d)) text += d;
+                        else if (d == '_' && !text.empty() && isdigit((unsigned char)text.back()) && q + 1 < src.size() && isdigit((unsigned char)src[q + 1])) continue;
+                        else if (d == '.' && !seen_dot && !seen_e) { seen_dot = true; text += d; }
+                        else if ((d == 'e' || d == 'E') && !seen_e && !text.empty() && q + 1 < src.size() &&
+                                 (isdigit((unsigned char)src[q + 1]) || ((src[q + 1] == '+' || src[q + 1] == '-') && q + 2 < src.size() && isdigit((unsigned char)src[q + 2])))) {
+                            seen_e = true;
+                            text += d;
+                            if (src[q + 1] == '+' || src[q + 1] == '-') text += src[++q];
+                        } else break;
+                    }
+                    t.num = strtod(text.c_str(), nullptr);
+                    pos = q;
                     if (pos < src.size() && src[pos] == 'n') pos++;  // BigInt suffix: treat as number
                 }
                 t.type = Tok::Num;
@@ -110,8 +178,7 @@ struct Lexer {
                     char ch = src[pos++];
                     if (ch == '`') break;
                     if (ch == '\\' && pos < src.size()) {
-                        char e = src[pos++];
-                        switch (e) { case 'n': piece += '\n'; break; case 't': piece += '\t'; break; case 'r': piece += '\r'; break; case '\n': line++; break; default: piece += e; }
+                        read_escape(src, pos, piece, line);
                     } else if (ch == '$' && pos < src.size() && src[pos] == '{') {
                         pos++;
                         size_t start = pos;
@@ -148,17 +215,8 @@ struct Lexer {
                 while (pos < src.size() && src[pos] != q) {
                     char ch = src[pos++];
                     if (ch == '\n') { if (q != '`') fail("unterminated string"); line++; }
-                    if (ch == '\\' && pos < src.size()) {
-                        char e = src[pos++];
-                        switch (e) {
-                            case 'n': out += '\n'; break;
-                            case 't': out += '\t'; break;
-                            case 'r': out += '\r'; break;
-                            case '0': out += '\0'; break;
-                            case '\n': line++; break;
-                            default: out += e;
-                        }
-                    } else out += ch;
+                    if (ch == '\\' && pos < src.size()) read_escape(src, pos, out, line);
+                    else out += ch;
                 }
                 if (pos >= src.size()) fail("unterminated string");
                 pos++;
@@ -194,6 +252,7 @@ enum class K {
     Spread,      // ...expr in a call, an array literal or an object literal
     Switch,      // kids[0] discriminant, then Case nodes
     Case,        // kids[0] test (Empty for `default`), then the statements
+    OptChain,    // kids[0] = a member / index / call chain with at least one `?.` link (flag on the link): undefined once a link's base is null or undefined
     Class,       // s = name, kids[0] = parent expression or Empty, members in `members`
     Labeled,     // s = label, kids[0] = the statement
     ObjectRest   // kids[0] = source object, s = excluded keys joined by '\x1f': the `...rest` of an object pattern
@@ -944,7 +1003,34 @@ struct Parser {
             if (is_punct("(")) arguments(*n);
             e = std::move(n);
         } else e = primary();
+        bool optional_chain = false;
         while (true) {
+            if (is_punct("?") && t[p + 1].type == Tok::Punct && t[p + 1].text == ".") {      // a?.b   a?.[k]   a?.(args)
+                p += 2;
+                optional_chain = true;
+                if (is_punct("[")) {
+                    auto m = mk(K::Index);
+                    p++;
+                    m->flag = true;
+                    m->kids.push_back(std::move(e));
+                    m->kids.push_back(expression());
+                    expect_punct("]");
+                    e = std::move(m);
+                } else if (is_punct("(")) {
+                    auto c = mk(K::Call);
+                    c->flag = true;
+                    c->kids.push_back(std::move(e));
+                    arguments(*c);
+                    e = std::move(c);
+                } else {
+                    auto m = mk(K::Member);
+                    m->flag = true;
+                    m->s = property_name();
+                    m->kids.push_back(std::move(e));
+                    e = std::move(m);
+                }
+                continue;
+            }
             if (is_punct(".")) {
                 auto m = mk(K::Member);
                 p++;
@@ -964,6 +1050,11 @@ struct Parser {
                 arguments(*c);
                 e = std::move(c);
             } else break;
+        }
+        if (optional_chain) {
+            auto w = mk(K::OptChain);
+            w->kids.push_back(std::move(e));
+            e = std::move(w);
         }
         return e;
     }
@@ -1034,6 +1125,20 @@ struct Parser {
                         o->kids.push_back(std::move(key));
                         o->kids.push_back(assignment());
                     }
+                    if (!eat_punct(",")) break;
+                    continue;
+                }
+                if (t[p].type == Tok::Ident && (t[p].text == "get" || t[p].text == "set") &&
+                    !(t[p + 1].type == Tok::Punct && (t[p + 1].text == "(" || t[p + 1].text == ":" || t[p + 1].text == "," || t[p + 1].text == "}" || t[p + 1].text == "="))) {
+                    // {get v() {...}, set v(x) {...}}: stored like a class's accessors, under "$get$v" / "$set$v"
+                    const char which = t[p].text[0];
+                    p++;
+                    auto key = mk(K::Str);
+                    key->s = std::string(which == 'g' ? "$get$" : "$set$") + property_name();
+                    auto fnode = mk(K::Func);
+                    fnode->fn = function_rest(key->s.substr(5));
+                    o->kids.push_back(std::move(key));
+                    o->kids.push_back(std::move(fnode));
                     if (!eat_punct(",")) break;
                     continue;
                 }
@@ -1165,6 +1270,18 @@ struct Evaluator {
     void set_prop(const Node* n, const Value& objv, const std::string& key, const Value& v);
     Value array_method(const Node* n, const ObjP& a, const std::string& key);
     Value string_method(const std::string& str, const std::string& key);
+    // valueOf(), then toString(), of a plain object or class instance that defines them; anything else comes back unchanged
+    Value to_primitive(const Node* n, const Value& v) {
+        if (v.type != Value::Obj || v.obj->kind != Object::Plain) return v;
+        for (const char* name : {"valueOf", "toString"}) {
+            auto it = v.obj->props.find(name);
+            if (it == v.obj->props.end() || it->second.type != Value::Obj || (it->second.obj->kind != Object::Function && it->second.obj->kind != Object::Native)) continue;
+            std::vector<Value> none;
+            Value r = call_function(n, it->second, v, none);
+            if (r.type != Value::Obj) return r;
+        }
+        return v;
+    }
     Value number_method(double num, const std::string& key);
 
     // ---- operators ----
@@ -1175,6 +1292,7 @@ struct Evaluator {
 
     // break / continue with a label: `jump_label` names the target while the completion travels outwards; a loop learns the labels it
     // carries from the Labeled node that runs it
+    bool chain_short = false;        // an optional chain met a null / undefined base: the links above it yield undefined (K::OptChain resets it)
     std::string jump_label;
     std::vector<std::string> loop_labels;
     std::vector<std::string> take_loop_labels() { std::vector<std::string> l; l.swap(loop_labels); return l; }
@@ -1259,7 +1377,8 @@ struct Evaluator {
         Value parent;
         if (n->kids[0]->k != K::Empty) {
             parent = eval(n->kids[0].get(), env);
-            if (parent.type != Value::Obj || parent.obj->kind != Object::Function) fail(n, "TypeError: class extends value is not a constructor");
+            const bool native_error = parent.type == Value::Obj && parent.obj->kind == Object::Native && [&] { for (auto& kv : in.error_types) if (kv.second == parent.obj) return true; return false; }();
+            if (parent.type != Value::Obj || (parent.obj->kind != Object::Function && !native_error)) fail(n, "TypeError: class extends value is not a constructor");
         }
         EnvP cenv = new_env(env, false);        // `super` and the class's own name are visible to its methods
         auto proto = Interp::make_object();
@@ -1359,7 +1478,7 @@ Value Evaluator::array_method(const Node* n, const ObjP& a, const std::string& k
         auto s = self();
         std::string sep = args.empty() ? "," : ip.to_string(args[0]);
         std::string out;
-        for (size_t i = 0; i < s->arr.size(); i++) { if (i) out += sep; out += ip.to_string(s->arr[i]); }
+        for (size_t i = 0; i < s->arr.size(); i++) { if (i) out += sep; if (s->arr[i].type != Value::Undefined && s->arr[i].type != Value::Null) out += ip.to_string(s->arr[i]); }
         return Value(out);
     });
     if (key == "reverse") return Interp::make_native([self](Interp&, const Value&, std::vector<Value>&) {
@@ -1662,6 +1781,10 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
     }
     auto it = o->props.find(key);
     if (it != o->props.end()) return it->second;
+    if (o->kind == Object::Plain) {                         // an accessor written in the object literal
+        auto g = o->props.find("$get$" + key);
+        if (g != o->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
+    }
     for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a getter of the instance's class (or a parent's)
         auto pr = c->props.find("prototype");
         if (pr == c->props.end() || pr->second.type != Value::Obj) break;
@@ -1680,6 +1803,36 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
             return ip.call(fn, self, rest);
         }));
     }
+    if ((o->kind == Object::Function || o->kind == Object::Native) && key == "apply") {
+        Value fn = objv;
+        return Value(Interp::make_native([fn](Interp& ip, const Value&, std::vector<Value>& args) {
+            Value self = args.empty() ? Value() : args[0];
+            std::vector<Value> rest;
+            if (args.size() > 1 && args[1].type == Value::Obj && args[1].obj->kind == Object::Array) rest = args[1].obj->arr;
+            return ip.call(fn, self, rest);
+        }));
+    }
+    if ((o->kind == Object::Function || o->kind == Object::Native) && key == "bind") {
+        Value fn = objv;
+        return Value(Interp::make_native([fn](Interp&, const Value&, std::vector<Value>& args) {
+            Value self = args.empty() ? Value() : args[0];
+            std::vector<Value> bound(args.size() > 1 ? args.begin() + 1 : args.end(), args.end());
+            return Value(Interp::make_native([fn, self, bound](Interp& ip, const Value&, std::vector<Value>& more) {
+                std::vector<Value> all = bound;
+                all.insert(all.end(), more.begin(), more.end());
+                return ip.call(fn, self, all);
+            }));
+        }));
+    }
+    if (key == "hasOwnProperty") {                            // o.hasOwnProperty(k); also reached through Object.prototype.hasOwnProperty.call(o, k)
+        return Value(Interp::make_native([](Interp& ip, const Value& self, std::vector<Value>& args) {
+            if (self.type != Value::Obj) return Value(false);
+            const std::string k = args.empty() ? "undefined" : ip.to_string(args[0]);
+            for (auto& own : Interp::own_keys(self)) if (own == k) return Value(true);
+            return Value(false);
+        }));
+    }
+    if (o.get() == in.builtin_object.get() && key == "prototype") return Value(Interp::make_object());    // Object.prototype.hasOwnProperty.call(...)
     return Value();
 }
 
@@ -1701,6 +1854,15 @@ void Evaluator::set_prop(const Node* n, const Value& objv, const std::string& ke
             o->arr[idx] = v;
             return;
         }
+    }
+    if (o->kind == Object::Function && o->is_class) {               // static set name(v) {...}
+        auto st = o->props.find("$set$" + key);
+        if (st != o->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
+    }
+    if (o->kind == Object::Plain && !o->props.count(key)) {       // an accessor written in the object literal
+        auto st = o->props.find("$set$" + key);
+        if (st != o->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
+        if (o->props.count("$get$" + key)) return;                 // getter only: the assignment is ignored (sloppy mode)
     }
     for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a setter of the instance's class (or a parent's)
         auto pr = c->props.find("prototype");
@@ -1738,6 +1900,13 @@ Value Evaluator::binary_op(const Node* n, const std::string& op, const Value& a,
         if (op == "!==") return Value(!strict_equal(a, b));
         if (!in.host_operator) fail(n, "TypeError: no operator overloads installed");
         return in.host_operator(in, op, a, b);
+    }
+    if (op != "===" && op != "!==" && op != "==" && op != "!=" && op != "in" && op != "instanceof") {
+        // an object with its own valueOf / toString takes part as that primitive
+        Value pa = to_primitive(n, a), pb = to_primitive(n, b);
+        if (pa.type != Value::Obj || pb.type != Value::Obj) {
+            if ((a.type == Value::Obj && pa.type != Value::Obj) || (b.type == Value::Obj && pb.type != Value::Obj)) return binary_op(n, op, pa, pb);
+        }
     }
     if (op == "+") {
         bool as = a.type == Value::String || (a.type == Value::Obj), bs = b.type == Value::String || (b.type == Value::Obj);
@@ -1877,9 +2046,28 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
         case K::Spread: fail(n, "SyntaxError: '...' is only valid in a call, an array literal or an object literal");
         case K::Class: return make_class(n, env);
         case K::Func: return make_closure(n->fn.get(), env);
-        case K::Member: return get_prop(n, eval(n->kids[0].get(), env), n->s);
+        case K::OptChain: {
+            const bool outer = chain_short;
+            chain_short = false;
+            Value v = eval(n->kids[0].get(), env);
+            if (chain_short) v = Value();
+            chain_short = outer;
+            return v;
+        }
+        case K::Member: {
+            Value o = eval(n->kids[0].get(), env);
+            if (chain_short) return Value();
+            if (n->kids[0]->k == K::Ident && n->kids[0]->s == "super" && o.type == Value::Obj) {
+                auto g = o.obj->props.find("$get$" + n->s);
+                if (g != o.obj->props.end()) { std::vector<Value> none; return call_function(n, g->second, env->this_val, none); }
+            }
+            if (n->flag && (o.type == Value::Undefined || o.type == Value::Null)) { chain_short = true; return Value(); }
+            return get_prop(n, o, n->s);
+        }
         case K::Index: {
             Value o = eval(n->kids[0].get(), env);
+            if (chain_short) return Value();
+            if (n->flag && (o.type == Value::Undefined || o.type == Value::Null)) { chain_short = true; return Value(); }
             Value k = eval(n->kids[1].get(), env);
             return get_prop(n, o, key_of(k));
         }
@@ -1888,18 +2076,33 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             Value self, fn;
             if (callee->k == K::Member) {
                 self = eval(callee->kids[0].get(), env);
+                if (chain_short) return Value();
+                if (callee->flag && (self.type == Value::Undefined || self.type == Value::Null)) { chain_short = true; return Value(); }
                 fn = get_prop(callee, self, callee->s);
+                if (n->flag && (fn.type == Value::Undefined || fn.type == Value::Null)) { chain_short = true; return Value(); }
                 if (fn.is_undefined()) fail(n, "TypeError: '" + callee->s + "' is not a function");
             } else if (callee->k == K::Index) {
                 self = eval(callee->kids[0].get(), env);
+                if (chain_short) return Value();
+                if (callee->flag && (self.type == Value::Undefined || self.type == Value::Null)) { chain_short = true; return Value(); }
                 fn = get_prop(callee, self, key_of(eval(callee->kids[1].get(), env)));
-            } else fn = eval(callee, env);
+                if (n->flag && (fn.type == Value::Undefined || fn.type == Value::Null)) { chain_short = true; return Value(); }
+            } else {
+                fn = eval(callee, env);
+                if (chain_short) return Value();
+                if (n->flag && (fn.type == Value::Undefined || fn.type == Value::Null)) { chain_short = true; return Value(); }
+            }
             // super(...) and super.method(...) run with the current `this`
             if ((callee->k == K::Ident && callee->s == "super") || (callee->k == K::Member && callee->kids[0]->k == K::Ident && callee->kids[0]->s == "super")) self = env->this_val;
             std::vector<Value> args;
             for (size_t i = 1; i < n->kids.size(); i++) push_arg(n->kids[i].get(), env, args);
             if (fn.type != Value::Obj) fail(n, "TypeError: " + (callee->k == K::Ident ? "'" + callee->s + "'" : std::string("expression")) + " is not a function");
             if (fn.obj->is_class && !(callee->k == K::Ident && callee->s == "super")) fail(n, "TypeError: class constructors must be invoked with 'new'");
+            if (callee->k == K::Ident && callee->s == "super" && fn.obj->kind == Object::Native && self.type == Value::Obj) {
+                Value made = call_function(n, fn, self, args);          // class MyErr extends Error: the native parent builds {message, name}
+                if (made.type == Value::Obj) for (auto& kv : made.obj->props) self.obj->props[kv.first] = kv.second;
+                return Value();
+            }
             return call_function(n, fn, self, args);
         }
         case K::New: {
@@ -2121,8 +2324,7 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
                     if (it.obj->kind != Object::Array) fail(n, "TypeError: for-of needs an array");
                     items = it.obj->arr;
                 } else {
-                    if (it.obj->kind == Object::Array) for (size_t i = 0; i < it.obj->arr.size(); i++) items.push_back(Value(std::to_string(i)));
-                    for (auto& kv : it.obj->props) items.push_back(Value(kv.first));
+                    for (auto& k : Interp::own_keys(it)) items.push_back(Value(k));
                 }
             }
             for (auto& item : items) {
@@ -2406,36 +2608,28 @@ Interp::Interp() {
     auto object_ctor = make_native([](Interp&, const Value&, std::vector<Value>&) { return Value(make_object()); });
     object_ctor->props["keys"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
         std::vector<Value> keys;
-        if (!a.empty() && a[0].type == Value::Obj) {
-            if (a[0].obj->kind == Object::Array) for (size_t i = 0; i < a[0].obj->arr.size(); i++) keys.push_back(Value(std::to_string(i)));
-            for (auto& kv : a[0].obj->props) keys.push_back(Value(kv.first));
-        }
+        if (!a.empty()) for (auto& k : Interp::own_keys(a[0])) keys.push_back(Value(k));
         return Value(make_array(keys));
     }));
-    auto own_keys = [](const Value& v) {
-        std::vector<std::string> keys;
-        if (v.type == Value::Obj) {
-            if (v.obj->kind == Object::Array) for (size_t i = 0; i < v.obj->arr.size(); i++) keys.push_back(std::to_string(i));
-            for (auto& kv : v.obj->props) if (kv.first.compare(0, 5, "$get$") != 0 && kv.first.compare(0, 5, "$set$") != 0) keys.push_back(kv.first);
-        }
-        return keys;
-    };
-    auto own_value = [](const Value& v, const std::string& k) {
+    auto own_keys = [](const Value& v) { return Interp::own_keys(v); };
+    auto own_value = [](Interp& ip, const Value& v, const std::string& k) {
         size_t idx = 0;
         bool is_index = !k.empty() && k.find_first_not_of("0123456789") == std::string::npos;
         if (is_index) idx = (size_t)strtoull(k.c_str(), nullptr, 10);
         if (v.obj->kind == Object::Array && is_index) return idx < v.obj->arr.size() ? v.obj->arr[idx] : Value();
         auto it = v.obj->props.find(k);
-        return it == v.obj->props.end() ? Value() : it->second;
+        if (it != v.obj->props.end()) return it->second;
+        auto g = v.obj->props.find("$get$" + k);                         // an accessor of the object literal: its value
+        return g == v.obj->props.end() ? Value() : ip.call(g->second, v, {});
     };
-    object_ctor->props["values"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+    object_ctor->props["values"] = Value(make_native([own_keys, own_value](Interp& ip, const Value&, std::vector<Value>& a) {
         std::vector<Value> out;
-        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(own_value(a[0], k));
+        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(own_value(ip, a[0], k));
         return Value(make_array(out));
     }));
-    object_ctor->props["entries"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+    object_ctor->props["entries"] = Value(make_native([own_keys, own_value](Interp& ip, const Value&, std::vector<Value>& a) {
         std::vector<Value> out;
-        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(Value(make_array({Value(k), own_value(a[0], k)})));
+        if (!a.empty()) for (auto& k : own_keys(a[0])) out.push_back(Value(make_array({Value(k), own_value(ip, a[0], k)})));
         return Value(make_array(out));
     }));
     object_ctor->props["fromEntries"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
@@ -2445,10 +2639,10 @@ Interp::Interp() {
                 if (e.type == Value::Obj && e.obj->kind == Object::Array && e.obj->arr.size() >= 2) o->props[ip.to_string(e.obj->arr[0])] = e.obj->arr[1];
         return Value(o);
     }));
-    object_ctor->props["assign"] = Value(make_native([own_keys, own_value](Interp&, const Value&, std::vector<Value>& a) {
+    object_ctor->props["assign"] = Value(make_native([own_keys, own_value](Interp& ip, const Value&, std::vector<Value>& a) {
         if (a.empty() || a[0].type != Value::Obj) throw JsError("TypeError: Object.assign needs an object");
         for (size_t i = 1; i < a.size(); i++)
-            if (a[i].type == Value::Obj) for (auto& k : own_keys(a[i])) a[0].obj->props[k] = own_value(a[i], k);
+            if (a[i].type == Value::Obj) for (auto& k : own_keys(a[i])) a[0].obj->props[k] = own_value(ip, a[i], k);
         return a[0];
     }));
     for (const char* same : {"freeze", "seal", "preventExtensions"})      // no property attributes in this interpreter: the object is handed back
@@ -2501,6 +2695,21 @@ Interp::~Interp() {
             if (kv.second.type == Value::Obj && kv.second.obj->env) clear(kv.second.obj->env.get());
     };
     clear(globals.get());
+}
+
+// Enumerable own property names in JavaScript's order; an accessor of an object literal ("$get$v" / "$set$v") counts once, as "v"
+std::vector<std::string> Interp::own_keys(const Value& v) {
+    std::vector<std::string> keys;
+    if (v.type != Value::Obj) return keys;
+    if (v.obj->kind == Object::Array) for (size_t i = 0; i < v.obj->arr.size(); i++) keys.push_back(std::to_string(i));
+    std::set<std::string> accessors;
+    for (auto& kv : v.obj->props) {
+        if (kv.first.compare(0, 5, "$get$") == 0 || kv.first.compare(0, 5, "$set$") == 0) {
+            const std::string name = kv.first.substr(5);
+            if (accessors.insert(name).second && !v.obj->props.count(name)) keys.push_back(name);
+        } else keys.push_back(kv.first);
+    }
+    return keys;
 }
 
 Value Interp::make_error_object(const std::string& what) {

@@ -204,6 +204,7 @@ struct Interp {
     std::map<std::string, ObjP> error_types;                  // Error, TypeError, RangeError, ReferenceError, SyntaxError
     // the object a `catch` binds for an error raised by the interpreter itself ("... TypeError: cannot read ..."): message, name, class
     Value make_error_object(const std::string& what);
+    static std::vector<std::string> own_keys(const Value& v);   // enumerable own property names, JavaScript's order
     std::vector<std::unique_ptr<Program>> programs;  // keep ASTs alive for closures
     std::unordered_map<std::string, std::function<Value(Interp&)>> global_getters;
     int call_depth = 0;

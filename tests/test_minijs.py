@@ -279,3 +279,28 @@ def test_unsupported_javascript_is_refused_loudly(grt, tmp_path, what):
         grt.Content(folder).load(os.path.join(folder, "probe.js"))
     msg = e.value.message
     assert needle in msg and "probe.js:" in msg, msg
+
+
+def _probes():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "script_engine_probes.json")))
+
+
+@pytest.mark.parametrize("what", sorted(_probes()))
+def test_probe_scripts_agree_with_quickjs(grt, oracle_mod, have_reference, tmp_path, what):
+    """Corners of JavaScript a metric script may rely on (tests/golden/make_script_engine_probes.py): the interpreter gives the metric
+    the reference's QuickJS gave when the table was recorded - and gives live, where the reference is mounted."""
+    body, want = _probes()[what]
+    js = "function f(t, x, y, z) {\n" + body + "\n}\nf"
+    pos = (0.3, 1.5, 0.7, 0.4)
+    folder = write_folder(tmp_path, js)
+    m = grt.Content(folder).load(os.path.join(folder, "probe.js"))
+    got = np.diag(np.asarray(m.eval_symbolic(pos)["g"]).reshape(4, 4))
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12), (what, got, want)
+    if have_reference:
+        try:
+            q = oracle_mod.QuickJSReference()
+        except FileNotFoundError:
+            return
+        qg, _, _, _ = q.metric(os.path.join(folder, "probe.js"), np.array(pos, np.float64))
+        assert np.allclose(got, np.diag(np.asarray(qg).reshape(4, 4)), rtol=1e-9, atol=1e-12), what
