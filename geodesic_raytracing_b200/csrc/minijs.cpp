@@ -1416,6 +1416,7 @@ struct Evaluator {
             ctor->env = parent.obj->def ? parent.obj->env : cenv;
         } else ctor->def = ctor_def ? ctor_def : &empty_ctor;
         ctor->props["prototype"] = Value(proto);
+        if (!n->s.empty() && !ctor->props.count("name")) ctor->props["name"] = Value(n->s);
         Value cv(ctor);
         if (!n->s.empty()) cenv->vars[n->s] = cv;
         for (auto& m : n->members) {                      // static x = expr;  (`this` is the class)
@@ -1795,6 +1796,12 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
         auto g = o->props.find("$get$" + key);
         if (g != o->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
     }
+    if (o->kind == Object::Function && o->def && key == "name") return Value(o->def->name);
+    if (o->kind == Object::Function && o->def && key == "length") {
+        size_t n_params = 0;
+        for (size_t i = 0; i < o->def->params.size() && !o->def->defaults[i]; i++) n_params++;       // parameters before the first default
+        return Value((double)n_params);
+    }
     if ((o->kind == Object::Function || o->kind == Object::Native) && key == "call") {
         Value fn = objv;
         return Value(Interp::make_native([fn](Interp& ip, const Value&, std::vector<Value>& args) {
@@ -2045,7 +2052,15 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
         }
         case K::Spread: fail(n, "SyntaxError: '...' is only valid in a call, an array literal or an object literal");
         case K::Class: return make_class(n, env);
-        case K::Func: return make_closure(n->fn.get(), env);
+        case K::Func: {
+            if (!n->fn->is_arrow && !n->fn->name.empty() && n->fn->name != "constructor") {      // const f = function fact(n) { ... fact(n - 1) ... }
+                EnvP named = new_env(env, false);
+                Value f = make_closure(n->fn.get(), named);
+                named->vars[n->fn->name] = f;
+                return f;
+            }
+            return make_closure(n->fn.get(), env);
+        }
         case K::OptChain: {
             const bool outer = chain_short;
             chain_short = false;
@@ -2504,7 +2519,18 @@ Interp::Interp() {
     M1("log2", std::log2); M1("log10", std::log10); M1("abs", std::fabs); M1("floor", std::floor); M1("ceil", std::ceil);
     M1("trunc", std::trunc); M1("sinh", std::sinh); M1("cosh", std::cosh); M1("tanh", std::tanh);
 #undef M1
-    math->props["round"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::floor((a.empty() ? NAN : to_number(a[0])) + 0.5)); }));
+    math->props["round"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        const double x = a.empty() ? NAN : to_number(a[0]);
+        if (!std::isfinite(x) || std::fabs(x) >= 4503599627370496.0) return Value(x);
+        const double r = std::floor(x + 0.5);                       // ties go up
+        return Value(r == 0 && (x < 0 || std::signbit(x)) ? -0.0 : r);
+    }));
+    math->props["fround"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value((double)(float)(a.empty() ? NAN : to_number(a[0]))); }));
+    math->props["expm1"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::expm1(a.empty() ? NAN : to_number(a[0]))); }));
+    math->props["log1p"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::log1p(a.empty() ? NAN : to_number(a[0]))); }));
+    math->props["asinh"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::asinh(a.empty() ? NAN : to_number(a[0]))); }));
+    math->props["acosh"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::acosh(a.empty() ? NAN : to_number(a[0]))); }));
+    math->props["atanh"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::atanh(a.empty() ? NAN : to_number(a[0]))); }));
     math->props["sign"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { double x = a.empty() ? NAN : to_number(a[0]); return Value(x > 0 ? 1.0 : (x < 0 ? -1.0 : x)); }));
     math->props["atan2"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::atan2(a.size() > 0 ? to_number(a[0]) : NAN, a.size() > 1 ? to_number(a[1]) : NAN)); }));
     math->props["pow"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(std::pow(a.size() > 0 ? to_number(a[0]) : NAN, a.size() > 1 ? to_number(a[1]) : NAN)); }));
@@ -2603,6 +2629,19 @@ Interp::Interp() {
             for (size_t i = 0; i < items.size(); i++) items[i] = ip.call(a[1], Value(), {items[i], Value((double)i)});
         return Value(make_array(items));
     }));
+    // Array.prototype.slice.call(arguments, 1) and friends: every array method, applied to the array handed over as `this`
+    auto array_proto = make_object();
+    array_proto->get_hook = [](Interp&, const std::string& key, Value& out) {
+        out = Value(make_native([key](Interp& ip, const Value& self, std::vector<Value>& args) {
+            if (self.type != Value::Obj || self.obj->kind != Object::Array) throw JsError("TypeError: Array.prototype." + key + " needs an array as 'this'");
+            Evaluator ev(ip, "<call>");
+            Value m = ev.get_prop(nullptr, self, key);
+            if (m.type != Value::Obj) throw JsError("TypeError: Array.prototype." + key + " is not a function");
+            return ip.call(m, self, args);
+        }));
+        return true;
+    };
+    array_ctor->props["prototype"] = Value(array_proto);
     globals->vars["Array"] = Value(array_ctor);
     builtin_array = array_ctor;
     auto object_ctor = make_native([](Interp&, const Value&, std::vector<Value>&) { return Value(make_object()); });

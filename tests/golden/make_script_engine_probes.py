@@ -64,6 +64,29 @@ CASES["toString valueOf coercion on objects"] = "const o={valueOf(){return 4;}, 
 CASES["label block and nested switch break"] = "let r=0; sw: switch(1){ case 1: for(let i=0;i<3;i++){ if(i==1) break sw; r++; } r=99; } return [-1, r+0*x, 1+0*y, 1+0*z];"
 CASES["getter setter static and computed class member absent"] = "class P{ static get ver(){ return 3; } static set ver(v){ P._v=v; } } P.ver=8; return [-1, P.ver+P._v+0*x, 1+0*y, 1+0*z];"
 CASES["exceptions rethrow custom"] = "class MyErr extends Error{ constructor(m){ super(m); this.code=7; } } let r=0; try { try { throw new MyErr('x'); } catch(e) { r=e.code+(e instanceof Error?10:0)+(e.message=='x'?100:0); throw e; } } catch(e2) { r+=1000; } return [-1, r+0*x, 1+0*y, 1+0*z];"
+CASES["block scoping and shadowing"] = "let a=1; { let a=2; { const a=3; var b=a; } b+=a; } return [-1, a+0*x, b+0*y, 1+0*z];"
+CASES["const reassign is an error"] = "const c=1; let r=0; try { c=2; } catch(e) { r=(e instanceof TypeError)?1:2; } return [-1, r+c+0*x, 1+0*y, 1+0*z];"
+CASES["tdz"] = "let r=0; try { r=q; let q=1; } catch(e) { r=(e instanceof ReferenceError)?5:6; } return [-1, r+0*x, 1+0*y, 1+0*z];"
+CASES["named function expression binding"] = "const f=function fact(n){ return n<=1?1:n*fact(n-1); }; return [-1, f(4)+0*x, (typeof fact=='undefined'?1:0)+0*y, 1+0*z];"
+CASES["arguments in arrow uses outer"] = "function outer(){ const g=()=>arguments[0]*2; return g(99); } return [-1, outer(4)+0*x, 1+0*y, 1+0*z];"
+CASES["slice.call arguments / Array.prototype"] = "function f2(){ const a=Array.prototype.slice.call(arguments,1); return a.length*10+a[0]; } return [-1, f2(1,2,3)+0*x, 1+0*y, 1+0*z];"
+CASES["for-of closures and for-in closures"] = "const fs=[]; for (const v of [1,2,3]) fs.push(()=>v); const gs=[]; for (const k in {a:1,b:2}) gs.push(()=>k); return [-1, fs[0]()+fs[2]()+0*x, (gs[0]()+gs[1]()).length+(gs[0]()=='a'?10:0)+0*y, 1+0*z];"
+CASES["typeof class and function props"] = "class A{} function g(){} g.tag=3; return [-1, (typeof A=='function'?1:0)+g.tag+0*x, g.name.length+A.name.length+0*y, g.length+((a,b)=>0).length+0*z];"
+CASES["catch without binding, nested try finally order"] = "let log=''; try { try { throw 1; } finally { log+='f'; } } catch { log+='c'; } finally { log+='F'; } return [-1, log.length+(log=='fcF'?10:0)+0*x, 1+0*y, 1+0*z];"
+CASES["throw non-error values"] = "let r=0; try { throw {code:4}; } catch(e) { r=e.code; } try { throw 'str'; } catch(e) { r+=e.length; } try { throw 7; } catch(e) { r+=e; } return [-1, r+0*x, 1+0*y, 1+0*z];"
+CASES["switch scoping and fallthrough with blocks"] = "function k(v){ let r=0; switch(v){ case 1: { let t=5; r+=t; } case 2: r+=1; break; case 3: r=9; } return r; } return [-1, k(1)+0*x, k(2)+k(3)+0*y, k(4)+1+0*z];"
+CASES["exponent assoc, unary minus, modulo sign"] = "return [-1, 2**3**2+0*x, (-2)**2+(-7%3)+(7%-3)+0*y, -(2**2)+0*z];"
+CASES["array length semantics"] = "const a=[1,2,3]; a.length=1; a[3]=9; const b=[]; b[2]=1; return [-1, a.length+0*x, b.length+(a[1]===undefined?10:0)+0*y, a.indexOf(9)+0*z];"
+CASES["number methods"] = "const n=255; return [-1, n.toString(16).length+(n.toString(2)=='11111111'?10:0)+0*x, (3.14159).toFixed(2)*100+0*y, (1234.5678).toPrecision(6)*1+(0.00001234).toPrecision(2).length+0*z];"
+CASES["Math.round ties and negative zero"] = "return [-1, Math.round(-0.5)+Math.round(-1.5)+Math.round(2.4999)+0*x, (1/Math.round(-0.2)<0?1:0)+0*y, Math.sign(-0)+Math.trunc(0.9)+Math.fround?1:0+0*z];"
+CASES["object spread order and override"] = "const a={x:1,y:2}; const b={...a, y:3, z:4}; const c={y:0, ...a}; return [-1, b.y+c.y+0*x, Object.keys(b).join('').length+(Object.keys(c)[0]=='y'?10:0)+0*y, b.z+0*z];"
+CASES["nested destructuring defaults with calls"] = "let calls=0; const d=()=>{calls++; return 5;}; const {a=d(), b:{c=d()}={}} = {a:1}; const [p=d(), q=d()] = [undefined, 2]; return [-1, a+c+0*x, p+q+0*y, calls+0*z];"
+CASES["closures mutate shared"] = "function mk(){ let v=0; return {inc:()=>++v, get:()=>v}; } const a=mk(), b=mk(); a.inc(); a.inc(); b.inc(); return [-1, a.get()+0*x, b.get()+0*y, 1+0*z];"
+CASES["sort stability and comparator"] = "const a=[{k:1,v:'a'},{k:0,v:'b'},{k:1,v:'c'},{k:0,v:'d'}]; a.sort((p,q)=>p.k-q.k); return [-1, (a.map(e=>e.v).join('')=='bdac'?1:0)+0*x, [3,20,100].sort()[0]+0*y, [3,20,100].sort((p,q)=>p-q)[2]+0*z];"
+CASES["getter this in static and inheritance of statics"] = "class A{ static base=2; static get twice(){ return this.base*2; } } class B extends A{ static base=5; } return [-1, A.twice+0*x, B.twice+0*y, 1+0*z];"
+CASES["in-place array methods return values"] = "const a=[1,2,3]; const r1=a.push(4); const r2=a.unshift(0); const r3=a.pop(); const r4=a.shift(); return [-1, r1*10+r2+0*x, r3*10+r4+0*y, a.length+0*z];"
+CASES["chained ternary with assignment and comma in for"] = "let s=0; for (let i=0,j=10; i<j; i+=2,j-=2) s+=i*j; return [-1, s+0*x, 1+0*y, 1+0*z];"
+CASES["string to number edge"] = "return [-1, (+'0x10')+(+'1e2')+(+'  7  ')+0*x, (isNaN(+'1_0')?1:0)+(isNaN(+'abc')?10:0)+(+[]===0?100:0)+0*y, (+[5])+(isNaN(+[1,2])?10:0)+0*z];"
 SKIP = {"in operator and hasOwnProperty", "array holes length and join", "toString valueOf coercion on objects", "nested functions this binding", "json", "Math.random absent / Date"}
 out = {}
 for name, body in CASES.items():
