@@ -2170,7 +2170,7 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             if (is_host(v)) {
                 if (!in.host_operator) fail(n, "TypeError: no operator overloads installed");
                 if (n->s == "-") return in.host_operator(in, "neg", v, Value());
-                if (n->s == "+") return in.host_operator(in, "pos", v, Value());
+                if (n->s == "+") fail(n, "TypeError: no overloaded operator pos");       // number.js overloads neg, not pos: the reference's engine refuses +x on a number object
                 fail(n, "TypeError: unsupported unary operator on number object");
             }
             if (n->s == "-") return Value(-Interp::to_number(v));

@@ -266,6 +266,7 @@ REFUSED = {
     "private class member": ("class A { #n = 1; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "unexpected character '#'"),
     "shorthand default outside a pattern": ("function f(t,x,y,z){ var o = {q = 1}; return [-1,1,1,1]; }\nf", "shorthand property"),
     "field of a derived class without a top-level super": ("class A {}\nclass B extends A { n = 1; constructor() { if (true) { super(); } } }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "top-level statement"),
+    "unary plus on a number object": ("function f(t,x,y,z){ return [-1, +x, 1, 1]; }\nf", "operator pos"),
     "class called without new": ("class A {}\nfunction f(t,x,y,z){ A(); return [-1,1,1,1]; }\nf", "'new'"),
 }
 
