@@ -1371,8 +1371,26 @@ struct Evaluator {
         out.insert(out.end(), v.obj->arr.begin(), v.obj->arr.end());
     }
 
+    // F.prototype of a function: made on first use for a plain function (ES5 constructors: F.prototype.m = function ...), the class's
+    // prototype object for a class
+    Value prototype_of_function(const ObjP& f) {
+        if (!f || f->kind != Object::Function) return Value();
+        auto it = f->props.find("prototype");
+        if (it != f->props.end()) return it->second;
+        if (f->is_arrow) return Value();
+        Value p(Interp::make_object());
+        f->props["prototype"] = p;
+        return p;
+    }
+    // the first object of o's prototype chain (o included) that has `key` as its own property; null if none
+    static const Object* holder_of(const Object* o, const std::string& key) {
+        for (int depth = 0; o && depth < 64; o = o->proto.get(), depth++)
+            if (o->props.count(key)) return o;
+        return nullptr;
+    }
+
     // class C [extends B] { ... } -> a constructor object: props["prototype"] holds the methods (getters / setters under "$get$name" /
-    // "$set$name"), static members are properties of the constructor, `klass` links to the parent class
+    // "$set$name") and chains to the parent's prototype, static members are properties of the constructor, which chains to the parent class
     Value make_class(const Node* n, EnvP& env) {
         Value parent;
         if (n->kids[0]->k != K::Empty) {
@@ -1387,16 +1405,17 @@ struct Evaluator {
         ctor->is_class = true;
         ctor->env = cenv;
         const FuncDef* ctor_def = nullptr;
+        proto->class_proto = true;
         if (parent.type == Value::Obj) {
             ctor->klass = parent.obj;
-            auto pp = parent.obj->props.find("prototype");
-            if (pp != parent.obj->props.end() && pp->second.type == Value::Obj) proto->props = pp->second.obj->props;     // inherited methods
-            for (auto& kv : parent.obj->props) if (kv.first != "prototype") ctor->props[kv.first] = kv.second;              // inherited statics
-            // `super`: callable (the parent constructor on the current `this`) and carrying the parent's methods
+            ctor->proto = parent.obj;                                                       // inherited statics
+            Value pp = prototype_of_function(parent.obj);
+            if (pp.type == Value::Obj) proto->proto = pp.obj;                               // inherited methods
+            // `super`: callable (the parent constructor on the current `this`); its properties are the parent's prototype's
             auto sup = std::make_shared<Object>(*parent.obj);
             sup->is_class = false;
             sup->props.clear();
-            if (pp != parent.obj->props.end() && pp->second.type == Value::Obj) sup->props = pp->second.obj->props;
+            sup->proto = pp.type == Value::Obj ? pp.obj : nullptr;
             cenv->vars["super"] = Value(sup);
         }
         for (auto& m : n->members) {
@@ -1415,6 +1434,7 @@ struct Evaluator {
             ctor->def = parent.obj->def ? parent.obj->def : &empty_ctor;
             ctor->env = parent.obj->def ? parent.obj->env : cenv;
         } else ctor->def = ctor_def ? ctor_def : &empty_ctor;
+        if (parent.type == Value::Obj && parent.obj->kind == Object::Native) proto->klass = parent.obj;      // class E extends Error: instances are Errors
         ctor->props["prototype"] = Value(proto);
         if (!n->s.empty() && !ctor->props.count("name")) ctor->props["name"] = Value(n->s);
         Value cv(ctor);
@@ -1780,21 +1800,14 @@ Value Evaluator::get_prop(const Node* n, const Value& objv, const std::string& k
         if (it != o->props.end()) return it->second;
         return array_method(n, o, key);
     }
-    auto it = o->props.find(key);
-    if (it != o->props.end()) return it->second;
-    if (o->kind == Object::Plain) {                         // an accessor written in the object literal
-        auto g = o->props.find("$get$" + key);
-        if (g != o->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
-    }
-    for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a getter of the instance's class (or a parent's)
-        auto pr = c->props.find("prototype");
-        if (pr == c->props.end() || pr->second.type != Value::Obj) break;
-        auto g = pr->second.obj->props.find("$get$" + key);
-        if (g != pr->second.obj->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
-    }
-    if (o->kind == Object::Function && o->is_class) {        // static getter
-        auto g = o->props.find("$get$" + key);
-        if (g != o->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
+    if (o->kind == Object::Function && key == "prototype") return prototype_of_function(o);
+    // own property, own accessor, then the same along the prototype chain (an instance's methods live on C.prototype, a class's
+    // inherited statics on its parent class)
+    for (const Object* c = o.get(); c; c = c->proto.get()) {
+        auto it = c->props.find(key);
+        if (it != c->props.end()) return it->second;
+        auto g = c->props.find("$get$" + key);
+        if (g != c->props.end()) { std::vector<Value> none; return call_function(n, g->second, objv, none); }
     }
     if (o->kind == Object::Function && o->def && key == "name") return Value(o->def->name);
     if (o->kind == Object::Function && o->def && key == "length") {
@@ -1862,20 +1875,15 @@ void Evaluator::set_prop(const Node* n, const Value& objv, const std::string& ke
             return;
         }
     }
-    if (o->kind == Object::Function && o->is_class) {               // static set name(v) {...}
-        auto st = o->props.find("$set$" + key);
-        if (st != o->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
-    }
-    if (o->kind == Object::Plain && !o->props.count(key)) {       // an accessor written in the object literal
-        auto st = o->props.find("$set$" + key);
-        if (st != o->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
-        if (o->props.count("$get$" + key)) return;                 // getter only: the assignment is ignored (sloppy mode)
-    }
-    for (const Object* c = o->klass.get(); c && o->kind == Object::Plain; c = c->klass.get()) {       // a setter of the instance's class (or a parent's)
-        auto pr = c->props.find("prototype");
-        if (pr == c->props.end() || pr->second.type != Value::Obj) break;
-        auto st = pr->second.obj->props.find("$set$" + key);
-        if (st != pr->second.obj->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
+    if (!o->props.count(key)) {
+        // a setter of the object itself (object literal, static), of its class or of a parent; a getter without a setter swallows the
+        // assignment (sloppy mode)
+        for (const Object* c = o.get(); c; c = c->proto.get()) {
+            auto st = c->props.find("$set$" + key);
+            if (st != c->props.end()) { std::vector<Value> arg{v}; call_function(n, st->second, objv, arg); return; }
+            if (c->props.count("$get$" + key)) return;
+            if (c != o.get() && c->props.count(key)) break;         // a plain inherited value: shadowed by an own property
+        }
     }
     o->props[key] = v;
 }
@@ -1935,13 +1943,21 @@ Value Evaluator::binary_op(const Node* n, const std::string& op, const Value& a,
         std::string k = key_of(a);
         size_t idx;
         if (b.obj->kind == Object::Array && array_index(k, idx)) return Value(idx < b.obj->arr.size());
-        return Value(b.obj->props.count(k) > 0);
+        return Value(holder_of(b.obj.get(), k) != nullptr || holder_of(b.obj.get(), "$get$" + k) != nullptr);
     }
     if (op == "instanceof") {
         if (b.type != Value::Obj || (b.obj->kind != Object::Function && b.obj->kind != Object::Native)) fail(n, "TypeError: right-hand side of 'instanceof' is not callable");
         if (a.type != Value::Obj) return Value(false);
-        for (const Object* c = a.obj->klass.get(); c; c = c->klass.get())
+        for (const Object* c = a.obj->klass.get(); c; c = c->klass.get())                  // error kinds
             if (c == b.obj.get()) return Value(true);
+        if (b.obj->kind == Object::Function) {
+            Value bp = prototype_of_function(b.obj);
+            for (const Object* c = a.obj->proto.get(); c && bp.type == Value::Obj; c = c->proto.get())
+                if (c == bp.obj.get()) return Value(true);
+        }
+        for (const Object* c = a.obj->proto.get(); c; c = c->proto.get())                   // class E extends Error: the chain reaches a native kind through the class
+            for (const Object* k = c->klass.get(); k; k = k->klass.get())
+                if (k == b.obj.get()) return Value(true);
         if (b.obj.get() == in.builtin_array.get()) return Value(a.obj->kind == Object::Array);
         if (b.obj.get() == in.builtin_object.get()) return Value(true);
         if (b.obj.get() == in.builtin_function.get()) return Value(a.obj->kind == Object::Function || a.obj->kind == Object::Native);
@@ -2073,8 +2089,10 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             Value o = eval(n->kids[0].get(), env);
             if (chain_short) return Value();
             if (n->kids[0]->k == K::Ident && n->kids[0]->s == "super" && o.type == Value::Obj) {
-                auto g = o.obj->props.find("$get$" + n->s);
-                if (g != o.obj->props.end()) { std::vector<Value> none; return call_function(n, g->second, env->this_val, none); }
+                if (const Object* h = holder_of(o.obj.get(), "$get$" + n->s)) {
+                    std::vector<Value> none;
+                    return call_function(n, h->props.find("$get$" + n->s)->second, env->this_val, none);
+                }
             }
             if (n->flag && (o.type == Value::Undefined || o.type == Value::Null)) { chain_short = true; return Value(); }
             return get_prop(n, o, n->s);
@@ -2127,13 +2145,9 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
             if (ctor.type != Value::Obj) fail(n, "TypeError: not a constructor");
             if (ctor.obj->kind == Object::Native) return ctor.obj->native(in, Value(), args);
             Value self(Interp::make_object());
-            if (ctor.obj->is_class) {
-                // no prototype chain in this interpreter: an instance carries its class (instanceof, getters) and gets the methods copied in
-                self.obj->klass = ctor.obj;
-                auto proto = ctor.obj->props.find("prototype");
-                if (proto != ctor.obj->props.end() && proto->second.type == Value::Obj)
-                    for (auto& kv : proto->second.obj->props)
-                        if (kv.first.compare(0, 5, "$get$") != 0 && kv.first.compare(0, 5, "$set$") != 0) self.obj->props[kv.first] = kv.second;
+            {
+                Value pr = prototype_of_function(ctor.obj);          // methods are found through the chain, the instance owns its fields only
+                if (pr.type == Value::Obj) self.obj->proto = pr.obj;
             }
             Value r = call_function(n, ctor, self, args);
             return r.type == Value::Obj ? r : self;
@@ -2684,6 +2698,35 @@ Interp::Interp() {
             if (a[i].type == Value::Obj) for (auto& k : own_keys(a[i])) a[0].obj->props[k] = own_value(ip, a[i], k);
         return a[0];
     }));
+    object_ctor->props["create"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        auto o = make_object();
+        if (!a.empty() && a[0].type == Value::Obj) o->proto = a[0].obj;
+        else if (a.empty() || a[0].type != Value::Null) throw JsError("TypeError: Object.create needs an object or null");
+        return Value(o);
+    }));
+    object_ctor->props["getPrototypeOf"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        if (a.empty() || a[0].type != Value::Obj || !a[0].obj->proto) return Value::null();
+        return Value(a[0].obj->proto);
+    }));
+    object_ctor->props["setPrototypeOf"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        if (a.size() < 2 || a[0].type != Value::Obj) throw JsError("TypeError: Object.setPrototypeOf needs an object");
+        for (const Object* c = a[1].type == Value::Obj ? a[1].obj.get() : nullptr; c; c = c->proto.get())
+            if (c == a[0].obj.get()) throw JsError("TypeError: cyclic prototype chain");
+        a[0].obj->proto = a[1].type == Value::Obj ? a[1].obj : nullptr;
+        return a[0];
+    }));
+    // Object.defineProperty(o, key, {value} | {get, set}): attributes (enumerable, writable, configurable) are not modelled
+    object_ctor->props["defineProperty"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        if (a.size() < 3 || a[0].type != Value::Obj || a[2].type != Value::Obj) throw JsError("TypeError: Object.defineProperty needs an object, a key and a descriptor");
+        const std::string key = ip.to_string(a[1]);
+        auto& d = a[2].obj->props;
+        if (d.count("get") || d.count("set")) {
+            if (d.count("get") && d["get"].type == Value::Obj) a[0].obj->props["$get$" + key] = d["get"];
+            if (d.count("set") && d["set"].type == Value::Obj) a[0].obj->props["$set$" + key] = d["set"];
+        } else a[0].obj->props[key] = d.count("value") ? d["value"] : Value();
+        if (d.count("enumerable") && to_boolean(d["enumerable"])) a[0].obj->hidden.erase(key); else a[0].obj->hidden.insert(key);
+        return a[0];
+    }));
     for (const char* same : {"freeze", "seal", "preventExtensions"})      // no property attributes in this interpreter: the object is handed back
         object_ctor->props[same] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return a.empty() ? Value() : a[0]; }));
     globals->vars["Object"] = Value(object_ctor);
@@ -2745,8 +2788,8 @@ std::vector<std::string> Interp::own_keys(const Value& v) {
     for (auto& kv : v.obj->props) {
         if (kv.first.compare(0, 5, "$get$") == 0 || kv.first.compare(0, 5, "$set$") == 0) {
             const std::string name = kv.first.substr(5);
-            if (accessors.insert(name).second && !v.obj->props.count(name)) keys.push_back(name);
-        } else keys.push_back(kv.first);
+            if (accessors.insert(name).second && !v.obj->props.count(name) && !v.obj->hidden.count(name)) keys.push_back(name);
+        } else if (!v.obj->hidden.count(kv.first)) keys.push_back(kv.first);
     }
     return keys;
 }

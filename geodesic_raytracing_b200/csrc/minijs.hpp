@@ -20,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <stdexcept>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -157,7 +158,10 @@ struct Object {
     NativeFn native;                        // Native
     int host_tag = 0;                       // Host: type tag chosen by the embedder
     std::shared_ptr<void> host;             // Host payload
-    ObjP klass;                             // instance: the class (constructor object) that built it; class: its parent class
+    ObjP klass;                             // an error object: its kind (a native constructor); a class / error kind: its parent
+    ObjP proto;                             // the prototype: where a property that is not the object's own is looked up (instances -> C.prototype -> B.prototype ...; a class -> its parent class, for statics)
+    bool class_proto = false;               // a prototype object made by `class`: its members do not show in for-in
+    std::set<std::string> hidden;           // own properties that do not enumerate (Object.defineProperty without enumerable: true)
     bool is_class = false;                  // a constructor made by `class`: props["prototype"] holds its methods
     // property hooks for Host objects (return true when handled)
     std::function<bool(Interp&, const std::string&, Value&)> get_hook;

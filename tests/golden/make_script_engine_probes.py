@@ -99,6 +99,13 @@ CASES["functions returning functions of number objects"] = "const lin=(m,c)=>(v)
 CASES["division and chained ops order"] = "return [-1, x/y/z, x-y-z+1, x/(y/z)];"
 CASES["pin and cfg"] = "const a=$cfg.mass; $cfg.mass.$default=2; const r=$pin(x*x+y*y); return [-1, r*a, r/(a+1), $pin(r)+0*z];"
 CASES["unary minus on number objects"] = "return [-1, -x, y+(-(-z)), 1+0*z];"
+CASES["instance keys exclude methods"] = "class V{ constructor(){ this.a=1; this.b=2; } norm(){ return 3; } get g(){ return 4; } } const v=new V(); let n=0; for (const k in v) n++; const c={...v}; return [-1, Object.keys(v).length+0*x, n+0*y, Object.keys(c).length+(typeof c.norm=='undefined'?10:0)+0*z];"
+CASES["method override on instance and hasOwnProperty"] = "class V{ m(){ return 1; } } const v=new V(); const own0=v.hasOwnProperty('m'); v.m=()=>2; return [-1, v.m()+0*x, (own0?1:0)+(v.hasOwnProperty('m')?10:0)+0*y, new V().m()+0*z];"
+CASES["prototype method added later"] = "class V{} V.prototype.twice=function(){ return this.k*2; }; const v=new V(); v.k=4; return [-1, v.twice()+0*x, 1+0*y, 1+0*z];"
+CASES["function constructor with prototype (ES5 classes)"] = "function P(a){ this.a=a; } P.prototype.get=function(){ return this.a+1; }; const p=new P(4); return [-1, p.get()+0*x, (p instanceof P?1:0)+0*y, Object.keys(p).length+0*z];"
+CASES["Object.create and getPrototypeOf"] = "const base={hi(){ return 7; }}; const o=Object.create(base); o.own=1; return [-1, o.hi()+0*x, Object.keys(o).length+0*y, (Object.getPrototypeOf(o)===base?1:0)+0*z];"
+CASES["JSON-free deep copy via spread and map"] = "const a=[{v:1},{v:2}]; const b=a.map(e=>({...e})); b[0].v=9; return [-1, a[0].v+0*x, b[0].v+0*y, 1+0*z];"
+CASES["getter on instance via defineProperty"] = "const o={}; Object.defineProperty(o,'v',{get(){ return 5; }, enumerable:false}); Object.defineProperty(o,'w',{value:6}); return [-1, o.v+0*x, o.w+0*y, Object.keys(o).length+1+0*z];"
 SKIP = {"in operator and hasOwnProperty", "array holes length and join", "toString valueOf coercion on objects", "nested functions this binding", "json", "Math.random absent / Date"}
 out = {}
 for name, body in CASES.items():
