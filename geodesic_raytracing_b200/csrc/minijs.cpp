@@ -492,6 +492,13 @@ struct Parser {
         expect_punct("(");
         parameters(*f);
         f->body = block();
+        // `let` / `const` at the top of the body must not redeclare a parameter (the reference's engine refuses the script)
+        for (auto& st : f->body->kids) {
+            if (st->k != K::VarDecl || st->s == "var") continue;
+            for (auto& d : st->kids)
+                if (std::find(f->params.begin(), f->params.end(), d->s) != f->params.end() || (!f->rest.empty() && d->s == f->rest))
+                    throw JsError(name + ":" + std::to_string(st->line) + ": SyntaxError: invalid redefinition of parameter name '" + d->s + "'");
+        }
         collect_hoisted(f->body.get(), *f, true);
         return f;
     }
@@ -1366,9 +1373,9 @@ struct Evaluator {
     void push_arg(const Node* k, EnvP& env, std::vector<Value>& out) {
         if (k->k != K::Spread) { out.push_back(eval(k, env)); return; }
         Value v = eval(k->kids[0].get(), env);
-        if (v.type == Value::String) { for (char c : v.str) out.push_back(Value(std::string(1, c))); return; }
-        if (v.type != Value::Obj || v.obj->kind != Object::Array) fail(k, "TypeError: spread needs an array");
-        out.insert(out.end(), v.obj->arr.begin(), v.obj->arr.end());
+        std::vector<Value> items;
+        if (!Interp::iterate(v, items)) fail(k, "TypeError: spread needs an array, a string, a Map or a Set");
+        out.insert(out.end(), items.begin(), items.end());
     }
 
     // F.prototype of a function: made on first use for a plain function (ES5 constructors: F.prototype.m = function ...), the class's
@@ -2350,8 +2357,7 @@ Comp Evaluator::exec(const Node* n, EnvP& env) {
             std::vector<Value> items;
             if (it.type == Value::Obj) {
                 if (n->k == K::ForOf) {
-                    if (it.obj->kind != Object::Array) fail(n, "TypeError: for-of needs an array");
-                    items = it.obj->arr;
+                    if (!Interp::iterate(it, items)) fail(n, "TypeError: for-of needs an array, a string, a Map or a Set");
                 } else {
                     for (auto& k : Interp::own_keys(it)) items.push_back(Value(k));
                 }
@@ -2523,6 +2529,8 @@ std::string Interp::to_string(const Value& v) {
 
 static Value math1(double (*f)(double), std::vector<Value>& a) { return Value(f(a.empty() ? NAN : Interp::to_number(a[0]))); }
 
+static Value make_collection(Interp& ip, int kind, std::vector<Value>& args);
+
 Interp::Interp() {
     globals = std::make_shared<Env>();
     globals->function_scope = true;
@@ -2628,8 +2636,7 @@ Interp::Interp() {
     // Array.from(array | string | {length: n} [, (v, i) => ...])
     array_ctor->props["from"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
         std::vector<Value> items;
-        if (!a.empty() && a[0].type == Value::String) for (char c : a[0].str) items.push_back(Value(std::string(1, c)));
-        else if (!a.empty() && a[0].type == Value::Obj && a[0].obj->kind == Object::Array) items = a[0].obj->arr;
+        if (!a.empty() && Interp::iterate(a[0], items)) {}                  // array, string, Map, Set
         else if (!a.empty() && a[0].type == Value::Obj) {
             auto len = a[0].obj->props.find("length");
             const double n = len == a[0].obj->props.end() ? 0.0 : to_number(len->second);
@@ -2731,6 +2738,21 @@ Interp::Interp() {
         object_ctor->props[same] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return a.empty() ? Value() : a[0]; }));
     globals->vars["Object"] = Value(object_ctor);
     builtin_object = object_ctor;
+    globals->vars["Map"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return make_collection(ip, 1, a); }));
+    globals->vars["Set"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return make_collection(ip, 2, a); }));
+    globals->vars["WeakMap"] = globals->vars["Map"];
+    globals->vars["WeakSet"] = globals->vars["Set"];
+    // Float64Array(n | array): a plain array of numbers (no fixed length, no buffer views)
+    globals->vars["Float64Array"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) {
+        std::vector<Value> items;
+        if (!a.empty() && a[0].type == Value::Number) {
+            if (a[0].num < 0 || a[0].num > 1e7) throw JsError("RangeError: invalid typed array length");
+            items.assign((size_t)a[0].num, Value(0.0));
+        } else if (!a.empty() && Interp::iterate(a[0], items)) {
+            for (auto& v : items) v = Value(to_number(v));
+        }
+        return Value(make_array(items));
+    }));
     builtin_function = make_native([](Interp&, const Value&, std::vector<Value>&) -> Value { throw JsError("EvalError: the Function constructor is not available to metric scripts"); });
     globals->vars["Function"] = Value(builtin_function);
     // Error and its kinds: `new TypeError(msg)` -> {message, name}, `e instanceof Error`; errors the interpreter raises itself are
@@ -2792,6 +2814,78 @@ std::vector<std::string> Interp::own_keys(const Value& v) {
         } else if (!v.obj->hidden.count(kv.first)) keys.push_back(kv.first);
     }
     return keys;
+}
+
+bool Interp::iterate(const Value& v, std::vector<Value>& out) {
+    if (v.type == Value::String) { for (char c : v.str) out.push_back(Value(std::string(1, c))); return true; }
+    if (v.type != Value::Obj) return false;
+    if (v.obj->kind == Object::Array) { out = v.obj->arr; return true; }
+    if (v.obj->is_collection == 1) { for (auto& e : v.obj->entries) out.push_back(Value(make_array({e.first, e.second}))); return true; }
+    if (v.obj->is_collection == 2) { for (auto& e : v.obj->entries) out.push_back(e.first); return true; }
+    return false;
+}
+
+// SameValueZero: the key comparison of Map and Set (NaN equals NaN, +0 equals -0, objects by identity)
+static bool same_value_zero(const Value& a, const Value& b) {
+    if (a.type != b.type) return false;
+    switch (a.type) {
+        case Value::Undefined: case Value::Null: return true;
+        case Value::Bool: return a.b == b.b;
+        case Value::Number: return a.num == b.num || (std::isnan(a.num) && std::isnan(b.num));
+        case Value::String: return a.str == b.str;
+        case Value::Obj: return a.obj == b.obj;
+    }
+    return false;
+}
+
+// new Map([[k, v], ...]) / new Set([v, ...]): methods as own natives of the object (get / set / has / delete / clear / add / forEach / keys /
+// values / entries, `size` through a property hook); iteration through Interp::iterate
+static Value make_collection(Interp& ip, int kind, std::vector<Value>& args) {
+    auto o = Interp::make_object();
+    o->is_collection = kind;
+    std::weak_ptr<Object> weak = o;
+    auto find = [](Object& c, const Value& k) { for (size_t i = 0; i < c.entries.size(); i++) if (same_value_zero(c.entries[i].first, k)) return (long)i; return -1L; };
+    auto put = [find](Object& c, const Value& k, const Value& v) { long i = find(c, k); if (i >= 0) c.entries[(size_t)i].second = v; else c.entries.emplace_back(k, v); };
+    o->get_hook = [weak](Interp&, const std::string& key, Value& out) {
+        auto c = weak.lock();
+        if (key == "size" && c) { out = Value((double)c->entries.size()); return true; }
+        return false;
+    };
+    auto method = [&](const char* name, std::function<Value(Object&, Interp&, std::vector<Value>&)> fn) {
+        o->props[name] = Value(Interp::make_native([weak, fn](Interp& ip2, const Value&, std::vector<Value>& a) { auto c = weak.lock(); if (!c) throw JsError("TypeError: collection is gone"); return fn(*c, ip2, a); }));
+        o->hidden.insert(name);
+    };
+    method("has", [find](Object& c, Interp&, std::vector<Value>& a) { return Value(find(c, a.empty() ? Value() : a[0]) >= 0); });
+    method("delete", [find](Object& c, Interp&, std::vector<Value>& a) { long i = find(c, a.empty() ? Value() : a[0]); if (i < 0) return Value(false); c.entries.erase(c.entries.begin() + i); return Value(true); });
+    method("clear", [](Object& c, Interp&, std::vector<Value>&) { c.entries.clear(); return Value(); });
+    method("forEach", [kind](Object& c, Interp& ip2, std::vector<Value>& a) {
+        if (a.empty()) throw JsError("TypeError: callback required");
+        auto snapshot = c.entries;
+        for (auto& e : snapshot) ip2.call(a[0], Value(), {kind == 1 ? e.second : e.first, e.first});
+        return Value();
+    });
+    method("keys", [](Object& c, Interp&, std::vector<Value>&) { std::vector<Value> out; for (auto& e : c.entries) out.push_back(e.first); return Value(Interp::make_array(out)); });
+    method("values", [kind](Object& c, Interp&, std::vector<Value>&) { std::vector<Value> out; for (auto& e : c.entries) out.push_back(kind == 1 ? e.second : e.first); return Value(Interp::make_array(out)); });
+    method("entries", [kind](Object& c, Interp&, std::vector<Value>&) { std::vector<Value> out; for (auto& e : c.entries) out.push_back(Value(Interp::make_array({e.first, kind == 1 ? e.second : e.first}))); return Value(Interp::make_array(out)); });
+    if (kind == 1) {
+        method("get", [find](Object& c, Interp&, std::vector<Value>& a) { long i = find(c, a.empty() ? Value() : a[0]); return i < 0 ? Value() : c.entries[(size_t)i].second; });
+        o->props["set"] = Value(Interp::make_native([weak, put](Interp&, const Value&, std::vector<Value>& a) { auto c = weak.lock(); put(*c, a.empty() ? Value() : a[0], a.size() > 1 ? a[1] : Value()); return Value(c); }));
+        o->hidden.insert("set");
+    } else {
+        o->props["add"] = Value(Interp::make_native([weak, put](Interp&, const Value&, std::vector<Value>& a) { auto c = weak.lock(); put(*c, a.empty() ? Value() : a[0], Value()); return Value(c); }));
+        o->hidden.insert("add");
+    }
+    if (!args.empty() && !args[0].is_undefined() && args[0].type != Value::Null) {
+        std::vector<Value> items;
+        if (!Interp::iterate(args[0], items)) throw JsError("TypeError: the argument of a Map or Set constructor must be iterable");
+        for (auto& it : items) {
+            if (kind == 2) { put(*o, it, Value()); continue; }
+            if (it.type != Value::Obj || it.obj->kind != Object::Array) throw JsError("TypeError: a Map is built from [key, value] pairs");
+            put(*o, it.obj->arr.size() > 0 ? it.obj->arr[0] : Value(), it.obj->arr.size() > 1 ? it.obj->arr[1] : Value());
+        }
+    }
+    (void)ip;
+    return Value(o);
 }
 
 Value Interp::make_error_object(const std::string& what) {

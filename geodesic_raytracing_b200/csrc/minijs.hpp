@@ -162,6 +162,9 @@ struct Object {
     ObjP proto;                             // the prototype: where a property that is not the object's own is looked up (instances -> C.prototype -> B.prototype ...; a class -> its parent class, for statics)
     bool class_proto = false;               // a prototype object made by `class`: its members do not show in for-in
     std::set<std::string> hidden;           // own properties that do not enumerate (Object.defineProperty without enumerable: true)
+    // Map / Set: entries in insertion order (a Set keeps its values as keys); `is_collection` 1 = Map, 2 = Set
+    int is_collection = 0;
+    std::vector<std::pair<Value, Value>> entries;
     bool is_class = false;                  // a constructor made by `class`: props["prototype"] holds its methods
     // property hooks for Host objects (return true when handled)
     std::function<bool(Interp&, const std::string&, Value&)> get_hook;
@@ -209,6 +212,9 @@ struct Interp {
     // the object a `catch` binds for an error raised by the interpreter itself ("... TypeError: cannot read ..."): message, name, class
     Value make_error_object(const std::string& what);
     static std::vector<std::string> own_keys(const Value& v);   // enumerable own property names, JavaScript's order
+    // what for-of, spread and destructuring walk over: the elements of an array, the characters of a string, the [key, value] pairs of
+    // a Map, the values of a Set; false if the value is not iterable
+    static bool iterate(const Value& v, std::vector<Value>& out);
     std::vector<std::unique_ptr<Program>> programs;  // keep ASTs alive for closures
     std::unordered_map<std::string, std::function<Value(Interp&)>> global_getters;
     int call_depth = 0;

@@ -106,6 +106,11 @@ CASES["function constructor with prototype (ES5 classes)"] = "function P(a){ thi
 CASES["Object.create and getPrototypeOf"] = "const base={hi(){ return 7; }}; const o=Object.create(base); o.own=1; return [-1, o.hi()+0*x, Object.keys(o).length+0*y, (Object.getPrototypeOf(o)===base?1:0)+0*z];"
 CASES["JSON-free deep copy via spread and map"] = "const a=[{v:1},{v:2}]; const b=a.map(e=>({...e})); b[0].v=9; return [-1, a[0].v+0*x, b[0].v+0*y, 1+0*z];"
 CASES["getter on instance via defineProperty"] = "const o={}; Object.defineProperty(o,'v',{get(){ return 5; }, enumerable:false}); Object.defineProperty(o,'w',{value:6}); return [-1, o.v+0*x, o.w+0*y, Object.keys(o).length+1+0*z];"
+CASES["Map basics"] = "const m=new Map([['a',1],['b',2]]); m.set('c',3).set('a',10); const o={}; m.set(o,5); m.delete('b'); let s=0; for (const [k,v] of m) s+=v; return [-1, m.size+0*x, s+m.get('a')+(m.has('b')?100:0)+m.get(o)+0*y, [...m.keys()].length+[...m.values()][0]+0*z];"
+CASES["Set basics"] = "const s=new Set([1,2,2,3,NaN,NaN]); s.add(4).add(1); s.delete(2); let tt=0; s.forEach(v=>{ if(v===v) tt+=v; }); const u=[...new Set([3,1,3,2])]; return [-1, s.size+0*x, tt+(s.has(NaN)?100:0)+0*y, u.join('')*1+0*z];"
+CASES["Map of number objects and object keys"] = "const m=new Map(); const k1={id:1}, k2={id:1}; m.set(k1,x); m.set(k2,y); m.set(1,'n'); m.set('1','s'); return [-1, m.get(k1)*2, m.get(k2)+m.size, (m.get(1)=='n'?1:0)+(m.get('1')=='s'?10:0)+0*z];"
+CASES["Array.from Map Set and entries destructuring"] = "const m=new Map([[1,'a'],[2,'b']]); const a=Array.from(m); const b=Array.from(new Set('hello')); let n=0; m.forEach((v,k)=>{ n+=k*(v=='b'?10:1); }); return [-1, a.length*10+a[1][0]+0*x, b.length+0*y, n+0*z];"
+CASES["Float64Array"] = "const f=new Float64Array(3); f[1]=2.5; const g=new Float64Array([1,2,3]); return [-1, f.length+f[0]+f[1]+0*x, g.reduce((s,v)=>s+v,0)+0*y, g.map(v=>v*2)[2]+0*z];"
 SKIP = {"in operator and hasOwnProperty", "array holes length and join", "toString valueOf coercion on objects", "nested functions this binding", "json", "Math.random absent / Date"}
 out = {}
 for name, body in CASES.items():

@@ -267,6 +267,7 @@ REFUSED = {
     "shorthand default outside a pattern": ("function f(t,x,y,z){ var o = {q = 1}; return [-1,1,1,1]; }\nf", "shorthand property"),
     "field of a derived class without a top-level super": ("class A {}\nclass B extends A { n = 1; constructor() { if (true) { super(); } } }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "top-level statement"),
     "unary plus on a number object": ("function f(t,x,y,z){ return [-1, +x, 1, 1]; }\nf", "operator pos"),
+    "let redeclares a parameter": ("function f(t,x,y,z){ let x = 1; return [-1,1,1,1]; }\nf", "redefinition of parameter"),
     "class called without new": ("class A {}\nfunction f(t,x,y,z){ A(); return [-1,1,1,1]; }\nf", "'new'"),
 }
 
