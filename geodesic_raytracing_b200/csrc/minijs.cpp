@@ -52,7 +52,12 @@ static void read_escape(const std::string& src, size_t& pos, std::string& out, i
         case 'b': out += '\b'; break;
         case 'f': out += '\f'; break;
         case 'v': out += '\v'; break;
-        case '0': out += '\0'; break;
+        case '0': case '1': case '2': case '3': case '4': case '5': case '6': case '7': {      // \0, and legacy octal escapes \101
+            unsigned code = (unsigned)(e - '0');
+            for (int k = 0; k < 2 && pos < src.size() && src[pos] >= '0' && src[pos] <= '7' && code * 8 + (unsigned)(src[pos] - '0') <= 255; k++) code = code * 8 + (unsigned)(src[pos++] - '0');
+            utf8(code);
+            break;
+        }
         case '\n': line++; break;                                   // line continuation
         case 'x': if (hex(2, v)) utf8(v); else out += 'x'; break;
         case 'u':
@@ -130,6 +135,10 @@ struct Lexer {
                         any = true;
                     }
                     if (!any) fail("missing digits after the numeric prefix");
+                    t.num = v;
+                } else if (c == '0' && pos + 1 < src.size() && isdigit((unsigned char)src[pos + 1]) && [&] { size_t q = pos; while (q < src.size() && isdigit((unsigned char)src[q])) { if (src[q] > '7') return false; q++; } return q >= src.size() || (src[q] != '.' && src[q] != 'e' && src[q] != 'E'); }()) {
+                    double v = 0;                                    // 010: a legacy octal literal (sloppy mode, as the reference's engine reads scripts)
+                    for (; pos < src.size() && isdigit((unsigned char)src[pos]); pos++) v = v * 8 + (src[pos] - '0');
                     t.num = v;
                 } else {
                     // decimal: the text with its numeric separators removed (1_000.5e1_0)
@@ -511,7 +520,21 @@ struct Parser {
             b->kids.push_back(statement());
         }
         expect_punct("}");
+        check_lexical_redeclaration(b->kids);
         return b;
+    }
+
+    // two let / const / class declarations of one name in the same block (or one of them next to a function declaration of that name)
+    void check_lexical_redeclaration(const std::vector<NodeP>& body) {
+        std::set<std::string> lexical, functions;
+        for (auto& st : body) {
+            if (st->k == K::FuncDecl) { if (lexical.count(st->s)) throw JsError(name + ":" + std::to_string(st->line) + ": SyntaxError: invalid redefinition of lexical identifier '" + st->s + "'"); functions.insert(st->s); continue; }
+            std::vector<std::string> names;
+            if (st->k == K::VarDecl && st->s != "var") for (auto& d : st->kids) { if (d->s.compare(0, 1, "$") != 0 || d->s.find("$d") != 0) names.push_back(d->s); }
+            else if (st->k == K::Class && !st->s.empty()) names.push_back(st->s);
+            for (auto& nm : names)
+                if (!lexical.insert(nm).second || functions.count(nm)) throw JsError(name + ":" + std::to_string(st->line) + ": SyntaxError: invalid redefinition of lexical identifier '" + nm + "'");
+        }
     }
 
     NodeP var_decl(bool need_semicolon) {
@@ -706,6 +729,8 @@ struct Parser {
             if (c->s.empty()) fail("a class declaration needs a name");
             return c;
         }
+        if (t[p].type == Tok::Ident && t[p].text == "with" && t[p + 1].type == Tok::Punct && t[p + 1].text == "(")
+            fail("'with' statements are not supported by the metric script interpreter");
         if (t[p].type == Tok::Ident && (t[p].text == "async" || t[p].text == "yield" || t[p].text == "await") && t[p + 1].type != Tok::Punct)
             fail("'" + t[p].text + "' is not supported by the metric script interpreter");
         if (t[p].type == Tok::Ident && t[p + 1].type == Tok::Punct && t[p + 1].text == ":") {
@@ -823,7 +848,9 @@ struct Parser {
     }
 
     NodeP binary(int min_prec) {
+        const bool bare_unary = (t[p].type == Tok::Punct && (t[p].text == "-" || t[p].text == "+" || t[p].text == "!" || t[p].text == "~")) || is_kw("typeof") || is_kw("void") || is_kw("delete");
         auto lhs = unary();
+        if (bare_unary && is_punct("**")) fail("unparenthesized unary expression can't appear on the left-hand side of '**'");
         while (true) {
             int pr = prec(t[p]);
             if (pr < 0 || pr < min_prec) break;
@@ -919,6 +946,7 @@ struct Parser {
                 continue;
             }
             m.fn = function_rest(m.name);
+            if (m.accessor && (m.fn->params.size() != (m.accessor == 'g' ? 0u : 1u) || !m.fn->rest.empty())) fail("invalid number of arguments for getter or setter");
             c->members.push_back(std::move(m));
         }
         expect_punct("}");
@@ -994,6 +1022,7 @@ struct Parser {
     NodeP call_member() {
         NodeP e;
         if (is_kw("new")) {
+            if (t[p + 1].type == Tok::Punct && t[p + 1].text == ".") fail("new.target is not supported by the metric script interpreter");
             auto n = mk(K::New);
             p++;
             // callee without call parens
@@ -1144,6 +1173,7 @@ struct Parser {
                     key->s = std::string(which == 'g' ? "$get$" : "$set$") + property_name();
                     auto fnode = mk(K::Func);
                     fnode->fn = function_rest(key->s.substr(5));
+                    if (fnode->fn->params.size() != (which == 'g' ? 0u : 1u) || !fnode->fn->rest.empty()) fail("invalid number of arguments for getter or setter");
                     o->kids.push_back(std::move(key));
                     o->kids.push_back(std::move(fnode));
                     if (!eat_punct(",")) break;
@@ -1186,6 +1216,7 @@ struct Parser {
             expect_punct("}");
             return o;
         }
+        if (is_punct("/") || is_punct("/=")) fail("regular expression literals are not supported by the metric script interpreter");
         fail("unexpected token");
     }
 };
@@ -2062,6 +2093,10 @@ Value Evaluator::eval(const Node* n, EnvP& env) {
                 }
                 if (n->kids[i + 1]->k == K::Assign && n->kids[i + 1]->flag) fail(n->kids[i + 1].get(), "SyntaxError: invalid shorthand property initializer");
                 Value v = eval(n->kids[i + 1].get(), env);
+                if (n->kids[i]->s == "__proto__" && n->kids[i + 1]->k != K::Func) {   // {__proto__: base}: the prototype, not a property
+                    if (v.type == Value::Obj) o->proto = v.obj;
+                    continue;
+                }
                 if (n->kids[i]->s == "..." && n->kids[i + 1]->k != K::Str) {      // {...base}
                     if (v.type == Value::Obj) {
                         if (v.obj->kind == Object::Array) for (size_t k = 0; k < v.obj->arr.size(); k++) o->props[std::to_string(k)] = v.obj->arr[k];

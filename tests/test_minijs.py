@@ -268,6 +268,12 @@ REFUSED = {
     "field of a derived class without a top-level super": ("class A {}\nclass B extends A { n = 1; constructor() { if (true) { super(); } } }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "top-level statement"),
     "unary plus on a number object": ("function f(t,x,y,z){ return [-1, +x, 1, 1]; }\nf", "operator pos"),
     "let redeclares a parameter": ("function f(t,x,y,z){ let x = 1; return [-1,1,1,1]; }\nf", "redefinition of parameter"),
+    "regular expression literal": ("function f(t,x,y,z){ var r = /ab+c/.test('abc'); return [-1,1,1,1]; }\nf", "regular expression"),
+    "with statement": ("function f(t,x,y,z){ var o = {q: 1}; with (o) { var w = q; } return [-1,1,1,1]; }\nf", "'with'"),
+    "new.target": ("function F(){ return new.target; }\nfunction f(t,x,y,z){ return [-1,1,1,1]; }\nf", "new.target"),
+    "duplicate let": ("function f(t,x,y,z){ let a = 1; let a = 2; return [-1,1,1,1]; }\nf", "redefinition of lexical identifier"),
+    "getter with a parameter": ("function f(t,x,y,z){ var o = { get v(a) { return 1; } }; return [-1,1,1,1]; }\nf", "getter or setter"),
+    "unary minus under **": ("function f(t,x,y,z){ return [-1, -2 ** 2, 1, 1]; }\nf", "left-hand side of '**'"),
     "class called without new": ("class A {}\nfunction f(t,x,y,z){ A(); return [-1,1,1,1]; }\nf", "'new'"),
 }
 
