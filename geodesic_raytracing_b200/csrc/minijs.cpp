@@ -203,6 +203,7 @@ struct Lexer {
                         pos++;
                         flush();
                         push_punct("+");
+                        { Token k; k.type = Tok::Ident; k.text = "$$template_string"; k.line = line; toks.push_back(k); }      // ToString of the value: toString() before valueOf()
                         push_punct("(");
                         Lexer sub(inner, name);
                         sub.line = line;
@@ -1312,10 +1313,12 @@ struct Evaluator {
     Value to_primitive(const Node* n, const Value& v) {
         if (v.type != Value::Obj || v.obj->kind != Object::Plain) return v;
         for (const char* name : {"valueOf", "toString"}) {
-            auto it = v.obj->props.find(name);
-            if (it == v.obj->props.end() || it->second.type != Value::Obj || (it->second.obj->kind != Object::Function && it->second.obj->kind != Object::Native)) continue;
+            const Object* h = holder_of(v.obj.get(), name);           // its own or its class's
+            if (!h) continue;
+            const Value& fn = h->props.find(name)->second;
+            if (fn.type != Value::Obj || (fn.obj->kind != Object::Function && fn.obj->kind != Object::Native)) continue;
             std::vector<Value> none;
-            Value r = call_function(n, it->second, v, none);
+            Value r = call_function(n, fn, v, none);
             if (r.type != Value::Obj) return r;
         }
         return v;
@@ -2658,6 +2661,20 @@ Interp::Interp() {
     number_ctor->props["NaN"] = Value(NAN);
     globals->vars["Number"] = Value(number_ctor);
     globals->vars["String"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return Value(a.empty() ? std::string() : ip.to_string(a[0])); }));
+    // `${value}`: an object with its own toString() (then valueOf()) prints as that; number objects and everything else as in "" + value
+    globals->vars["$$template_string"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        if (a.empty()) return Value(std::string("undefined"));
+        if (a[0].type == Value::Obj && a[0].obj->kind == Object::Plain) {
+            for (const char* name : {"toString", "valueOf"}) {
+                Value fn;
+                for (const Object* c = a[0].obj.get(); c && fn.is_undefined(); c = c->proto.get()) { auto it = c->props.find(name); if (it != c->props.end()) fn = it->second; }
+                if (fn.type != Value::Obj || (fn.obj->kind != Object::Function && fn.obj->kind != Object::Native)) continue;
+                Value r = ip.call(fn, a[0], {});
+                if (r.type != Value::Obj) return Value(ip.to_string(r));
+            }
+        }
+        return a[0].type == Value::Obj && a[0].obj->kind == Object::Host ? a[0] : Value(ip.to_string(a[0]));
+    }));
     globals->vars["Boolean"] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return Value(!a.empty() && to_boolean(a[0])); }));
     auto array_ctor = make_native([](Interp&, const Value&, std::vector<Value>& a) {
         if (a.size() == 1 && a[0].type == Value::Number) {
