@@ -281,6 +281,7 @@ struct FuncDef {
     std::string rest;                     // `...rest`
     std::string source;                   // name of the script that defines the function (error messages of later calls)
     std::vector<NodeP> prologue;          // destructuring parameters: declarations run before the body
+    bool strict = false;                  // class code, or under a "use strict" directive: `this` of a plain call stays undefined
     std::vector<std::string> hoisted_vars;
     std::vector<const Node*> hoisted_funcs;
 };
@@ -375,6 +376,7 @@ struct Parser {
         auto prog = std::make_unique<Program>();
         prog->name = name;
         while (t[p].type != Tok::End) prog->body.push_back(statement());
+        if (starts_with_use_strict(prog->body)) for (auto& s : prog->body) mark_strict(s.get());      // "use strict" at the top of the script
         for (auto& s : prog->body) collect_hoisted(s.get(), prog->top, true);
         return prog;
     }
@@ -494,6 +496,10 @@ struct Parser {
         expect_punct(")");
     }
 
+    int strict_depth = 0;                 // > 0 inside class bodies and under "use strict"
+    static bool starts_with_use_strict(const std::vector<NodeP>& body) {
+        return !body.empty() && body[0]->k == K::ExprStmt && body[0]->kids[0]->k == K::Str && body[0]->kids[0]->s == "use strict";
+    }
     std::unique_ptr<FuncDef> function_rest(const std::string& fname) {
         auto f = std::make_unique<FuncDef>();
         f->name = fname;
@@ -510,7 +516,17 @@ struct Parser {
                     throw JsError(name + ":" + std::to_string(st->line) + ": SyntaxError: invalid redefinition of parameter name '" + d->s + "'");
         }
         collect_hoisted(f->body.get(), *f, true);
+        f->strict = strict_depth > 0 || starts_with_use_strict(f->body->kids);
+        if (f->strict && strict_depth == 0) mark_strict(f->body.get());          // "use strict" in this function: the functions inside it too
         return f;
+    }
+
+    // functions nested in a body that turned out to be strict (its directive is only seen after the body is parsed)
+    static void mark_strict(Node* n) {
+        if (!n) return;
+        if (n->fn) { n->fn->strict = true; mark_strict(n->fn->body.get()); for (auto& d : n->fn->defaults) mark_strict(d.get()); }
+        for (auto& m : n->members) if (m.fn) { m.fn->strict = true; mark_strict(m.fn->body.get()); }
+        for (auto& k : n->kids) mark_strict(k.get());
     }
 
     NodeP block() {
@@ -931,6 +947,8 @@ struct Parser {
         if (t[p].type == Tok::Ident && t[p].text == "extends") { p++; c->kids.push_back(call_member()); }
         else c->kids.push_back(mk(K::Empty));
         expect_punct("{");
+        strict_depth++;                                   // class code is strict
+        struct Leave { int& d; ~Leave() { d--; } } leave{strict_depth};
         while (!is_punct("}")) {
             if (eat_punct(";")) continue;
             Node::ClassMember m;
@@ -2042,6 +2060,10 @@ Value Evaluator::call_function(const Node* n, const Value& fn, const Value& self
     const FuncDef* def = fn.obj->def;
     EnvP env = new_env(fn.obj->env, true);
     env->this_val = fn.obj->is_arrow ? fn.obj->bound_this : self;
+    if (!fn.obj->is_arrow && !def->strict && (self.type == Value::Undefined || self.type == Value::Null)) {
+        auto g = in.globals->vars.find("globalThis");            // sloppy mode (scripts are not modules): a plain call sees the global object
+        if (g != in.globals->vars.end()) env->this_val = g->second;
+    }
     for (size_t i = 0; i < def->params.size(); i++) {
         Value v = i < args.size() ? args[i] : Value();
         if (v.is_undefined() && i < def->defaults.size() && def->defaults[i]) v = eval(def->defaults[i].get(), env);   // earlier parameters are in scope
@@ -2569,6 +2591,146 @@ static Value math1(double (*f)(double), std::vector<Value>& a) { return Value(f(
 
 static Value make_collection(Interp& ip, int kind, std::vector<Value>& args);
 
+// ---- JSON -------------------------------------------------------------------------------------
+namespace {
+struct JsonReader {
+    const std::string& s;
+    size_t p = 0;
+    [[noreturn]] void bad(const char* what) { throw JsError(std::string("SyntaxError: JSON.parse: ") + what + " at position " + std::to_string(p)); }
+    void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\t' || s[p] == '\n' || s[p] == '\r')) p++; }
+    Value value() {
+        ws();
+        if (p >= s.size()) bad("unexpected end of input");
+        const char c = s[p];
+        if (c == '{') {
+            p++;
+            auto o = Interp::make_object();
+            ws();
+            if (p < s.size() && s[p] == '}') { p++; return Value(o); }
+            for (;;) {
+                ws();
+                if (p >= s.size() || s[p] != '"') bad("expected a property name");
+                const std::string key = string();
+                ws();
+                if (p >= s.size() || s[p] != ':') bad("expected ':'");
+                p++;
+                o->props[key] = value();
+                ws();
+                if (p < s.size() && s[p] == ',') { p++; continue; }
+                if (p < s.size() && s[p] == '}') { p++; return Value(o); }
+                bad("expected ',' or '}'");
+            }
+        }
+        if (c == '[') {
+            p++;
+            std::vector<Value> items;
+            ws();
+            if (p < s.size() && s[p] == ']') { p++; return Value(Interp::make_array(items)); }
+            for (;;) {
+                items.push_back(value());
+                ws();
+                if (p < s.size() && s[p] == ',') { p++; continue; }
+                if (p < s.size() && s[p] == ']') { p++; return Value(Interp::make_array(items)); }
+                bad("expected ',' or ']'");
+            }
+        }
+        if (c == '"') return Value(string());
+        if (s.compare(p, 4, "true") == 0) { p += 4; return Value(true); }
+        if (s.compare(p, 5, "false") == 0) { p += 5; return Value(false); }
+        if (s.compare(p, 4, "null") == 0) { p += 4; return Value::null(); }
+        if (c == '-' || isdigit((unsigned char)c)) {
+            char* end = nullptr;
+            const double v = strtod(s.c_str() + p, &end);
+            if (end == s.c_str() + p) bad("bad number");
+            p = (size_t)(end - s.c_str());
+            return Value(v);
+        }
+        bad("unexpected token");
+    }
+    std::string string() {
+        p++;                         // opening quote
+        std::string out;
+        while (p < s.size() && s[p] != '"') {
+            if (s[p] == '\\' && p + 1 < s.size()) {
+                p++;
+                const char e = s[p];
+                if (e == 'u' || e == 'n' || e == 't' || e == 'r' || e == 'b' || e == 'f') { int line = 0; read_escape(s, p, out, line); }
+                else { out += e; p++; }          // \" \\ \/
+            } else out += s[p++];
+        }
+        if (p >= s.size()) bad("unterminated string");
+        p++;
+        return out;
+    }
+};
+
+void json_quote(const std::string& s, std::string& out) {
+    out += '"';
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\n': out += "\\n"; break;
+            case '\t': out += "\\t"; break;
+            case '\r': out += "\\r"; break;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if (c < 0x20) { char buf[8]; snprintf(buf, sizeof buf, "\\u%04x", c); out += buf; }
+                else out += (char)c;
+        }
+    }
+    out += '"';
+}
+
+// JSON.stringify(value [, null, indent]); undefined / functions are skipped in objects and become null in arrays
+bool json_write(Interp& ip, const Value& v, const std::string& indent, const std::string& cur, std::string& out, int depth) {
+    if (depth > 64) throw JsError("TypeError: cyclic object value");
+    switch (v.type) {
+        case Value::Undefined: return false;
+        case Value::Null: out += "null"; return true;
+        case Value::Bool: out += v.b ? "true" : "false"; return true;
+        case Value::Number: out += std::isfinite(v.num) ? ip.to_string(v) : "null"; return true;
+        case Value::String: json_quote(v.str, out); return true;
+        case Value::Obj: break;
+    }
+    if (v.obj->kind == Object::Function || v.obj->kind == Object::Native) return false;
+    const std::string inner = cur + indent;
+    const char* nl = indent.empty() ? "" : "\n";
+    if (v.obj->kind == Object::Array) {
+        if (v.obj->arr.empty()) { out += "[]"; return true; }
+        out += "[";
+        for (size_t i = 0; i < v.obj->arr.size(); i++) {
+            out += i ? "," : "";
+            out += nl + inner;
+            if (!json_write(ip, v.obj->arr[i], indent, inner, out, depth + 1)) out += "null";
+        }
+        out += nl + cur + "]";
+        return true;
+    }
+    {
+        auto tj = v.obj->props.find("toJSON");
+        if (tj != v.obj->props.end() && tj->second.type == Value::Obj) return json_write(ip, ip.call(tj->second, v, {}), indent, cur, out, depth + 1);
+    }
+    std::string body;
+    bool any = false;
+    for (auto& k : Interp::own_keys(v)) {
+        auto it = v.obj->props.find(k);
+        Value item = it != v.obj->props.end() ? it->second : Value();
+        std::string piece;
+        if (!json_write(ip, item, indent, inner, piece, depth + 1)) continue;
+        body += any ? "," : "";
+        body += nl + inner;
+        json_quote(k, body);
+        body += indent.empty() ? ":" : ": ";
+        body += piece;
+        any = true;
+    }
+    out += any ? "{" + body + nl + cur + "}" : "{}";
+    return true;
+}
+}  // namespace
+
 Interp::Interp() {
     globals = std::make_shared<Env>();
     globals->function_scope = true;
@@ -2790,6 +2952,24 @@ Interp::Interp() {
         object_ctor->props[same] = Value(make_native([](Interp&, const Value&, std::vector<Value>& a) { return a.empty() ? Value() : a[0]; }));
     globals->vars["Object"] = Value(object_ctor);
     builtin_object = object_ctor;
+    auto json = make_object();
+    json->props["parse"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        const std::string text = a.empty() ? "undefined" : ip.to_string(a[0]);
+        JsonReader r{text};
+        Value v = r.value();
+        r.ws();
+        if (r.p != text.size()) r.bad("unexpected characters after the value");
+        return v;
+    }));
+    json->props["stringify"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) {
+        std::string indent;
+        if (a.size() > 2 && a[2].type == Value::Number) indent.assign((size_t)std::max(0.0, std::min(10.0, a[2].num)), ' ');
+        else if (a.size() > 2 && a[2].type == Value::String) indent = a[2].str.substr(0, 10);
+        std::string out;
+        if (a.empty() || !json_write(ip, a[0], indent, "", out, 0)) return Value();
+        return Value(out);
+    }));
+    globals->vars["JSON"] = Value(json);
     globals->vars["Map"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return make_collection(ip, 1, a); }));
     globals->vars["Set"] = Value(make_native([](Interp& ip, const Value&, std::vector<Value>& a) { return make_collection(ip, 2, a); }));
     globals->vars["WeakMap"] = globals->vars["Map"];
