@@ -270,16 +270,17 @@ class Job:
             ctx.snapshot_geodesic(cfg["geodesic"]["speed"], True)
             ctx.set_camera_on_geodesic(cfg["geodesic"]["tau"])
         self.ctx = ctx
-        # Optionally (GRT_BENCH_BALANCE=1) the stripes are dealt by measured cost (sort-first with feedback: the trial steps of every half
-        # stripe of this view, rendered one by one during set-up - what an interactive host refreshes now and then).  Untimed; the
-        # numbers are a deterministic function of program, features and camera, so every rank measures the same profile itself.
+        # How the frame is shared out for N > 1 (GRT_BENCH_PARTITION): by measured cost - sort-first rendering with feedback.  The cost
+        # profile (trial steps of every half stripe of this view, rendered one by one) is a deterministic function of program, features
+        # and camera, so every rank measures the same profile itself; the feedback rounds all-gather what every rank's block cost.  All
+        # of it happens during set-up, untimed - what an interactive host refreshes now and then from frames it renders anyway.
         emu_world = int(os.environ.get("GRT_BENCH_EMULATE_WORLD", "0")) if self.world == 1 else 0
         part_world, part_rank = (emu_world, int(os.environ.get("GRT_BENCH_EMULATE_RANK", "0"))) if emu_world else (self.world, self.rank)
         # (emulation, diagnostic only: one GPU renders the stripes one rank of an N-GPU job would own - the per-rank pipeline without the delivery)
         self.stripe_costs = None
         self.partition = "interleaved"
         if part_world > 1 and partition == "contiguous":
-            # one block of rows per rank, boundaries at equal measured cost, then two rounds of feedback from what the blocks really cost
+            # one block of rows per rank, boundaries at equal measured cost, then REFINE_ROUNDS rounds of feedback from what the blocks really cost
             self.partition = "contiguous"
             self.stripe_costs = ctx.measure_stripe_costs(self.w, self.h, STRIPE_ROWS)
             bounds = grt.contiguous_bounds(self.h, part_world, self.stripe_costs, STRIPE_ROWS)
